@@ -1,0 +1,211 @@
+"""Generate golden fixtures by running the UNMODIFIED reference -- TEST INFRASTRUCTURE.
+
+Run in the build container only (needs /root/reference):
+
+    python oracle/gen_golden.py            # writes tests/golden/*.npz
+
+The reference has no golden vectors of its own for this path, so these
+fixtures -- outputs of the reference's own modules on seeded synthetic inputs -- are what pins
+the oracle (`oracle/gfdn_oracle.py`) and, through it, the CUDA kernels.
+Inputs follow SURVEY.md section 8(d) at sizes that keep each fixture well under 1 MB.
+"""
+import os
+import sys
+import tempfile
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import ref_shim  # noqa: E402
+
+ref_shim.install()
+
+from diff_gfdn.colorless_fdn.losses import amse_loss, mse_loss, sparsity_loss  # noqa: E402
+from diff_gfdn.config.config import (DiffGFDNConfig, FeedbackLoopConfig, OutputFilterConfig,  # noqa: E402
+                                     TrainerConfig)
+from diff_gfdn.losses import directional_edc_loss, edc_loss, edr_loss  # noqa: E402
+from diff_gfdn.model import DiffDirectionalFDNVarReceiverPos, DiffGFDNVarReceiverPos  # noqa: E402
+from diff_gfdn.trainer import DirectionalFDNVarReceiverPosTrainer, VarReceiverPosTrainer  # noqa: E402
+from diff_gfdn.utils import get_response  # noqa: E402
+import spaudiopy  # noqa: E402  (stub)
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+FS = 32000.0
+
+
+def synth_batch(nfft, bsz, seed, early=True, radius=1.0):
+    """Synthetic receiver batch: decaying-noise target RIRs, 20 ms early part."""
+    rng = np.random.default_rng(seed)
+    k = nfft // 2 + 1
+    w = np.fft.rfftfreq(nfft) * 2 * np.pi
+    z = torch.polar(torch.full((k, ), radius, dtype=torch.float64), torch.tensor(w))
+    pos = torch.tensor(rng.uniform(0, 1, (bsz, 3)))
+    t = np.arange(nfft // 2)
+    tau = rng.uniform(0.02, 0.05, (bsz, 1)) * FS
+    rir = rng.standard_normal((bsz, nfft // 2)) * np.exp(-t[None, :] / tau)
+    target = torch.tensor(np.fft.rfft(rir, n=nfft, axis=-1))
+    e = rir.copy()
+    e[:, 640:] = 0.0
+    e[:, 560:640] *= np.hanning(160)[80:][None, :]
+    d = torch.tensor(np.fft.rfft(e, n=nfft, axis=-1)) if early else torch.zeros(bsz, k, dtype=torch.complex128)
+    return dict(z_values=z, listener_position=pos, norm_listener_position=pos.clone(),
+                source_position=torch.zeros(bsz, 3, dtype=torch.float64), target_early_response=d,
+                target_rir_response=target)
+
+
+def np_state(net):
+    return {f"param/{k}": v.detach().cpu().numpy().copy() for k, v in net.state_dict().items()}
+
+
+def grads_of(net):
+    return {f"grad/{k}": p.grad.detach().cpu().numpy().copy() for k, p in net.named_parameters() if p.grad is not None}
+
+
+def make_trainer(cls, net, **kw):
+    tmp = tempfile.mkdtemp(prefix="dgfdn_golden_")
+    cfg = TrainerConfig(train_dir=os.path.join(tmp, "out"), ir_dir=os.path.join(tmp, "ir"), **kw)
+    return cls(net, cfg)
+
+
+def case_omni(name, n_lines, nfft, bsz, t60, seed, hidden, neurons, feats, radius=1.0, subband=False, steps=2):
+    cfg = DiffGFDNConfig(seed=235265, num_delay_lines=n_lines)
+    delays = cfg.delay_length_samps
+    torch.manual_seed(seed)
+    np.random.seed(seed)
+    net = DiffGFDNVarReceiverPos(FS, 3, delays, 'cpu', FeedbackLoopConfig(use_zero_coupling=False),
+                                 OutputFilterConfig(use_svfs=False, num_hidden_layers=hidden,
+                                                    num_neurons_per_layer=neurons, num_fourier_features=feats),
+                                 use_absorption_filters=False, common_decay_times=np.array([t60]),
+                                 use_colorless_loss=True)
+    data = synth_batch(nfft, bsz, seed + 1, radius=radius)
+    trainer = make_trainer(VarReceiverPosTrainer, net, use_colorless_loss=True, use_asym_spectral_loss=True,
+                           edc_loss_weight=10.0, num_freq_bins=nfft, io_lr=0.01, lr=0.01)
+    out = {"meta/delays": np.array(delays), "meta/nfft": nfft, "meta/fs": FS, "meta/t60": np.array(t60),
+           "meta/radius": radius, "meta/feats": feats, "meta/edc_w": 10.0, "meta/edr_w": 1.0,
+           "meta/max_ir_len_ms": float(np.max(t60) * 1e3)}
+    for key in ("listener_position", "norm_listener_position", "target_early_response", "target_rir_response"):
+        out[f"data/{key}"] = data[key].numpy()
+    out.update(np_state(net))
+
+    if subband:
+        k = nfft // 2 + 1
+        rng = np.random.default_rng(seed + 7)
+        fir = np.hanning(257) * np.sinc(np.linspace(-8, 8, 257)) * np.cos(np.linspace(-8, 8, 257) * 9.0)
+        filt = torch.fft.rfft(torch.tensor(fir + 0.01 * rng.standard_normal(257)), n=nfft)
+        assert filt.shape[0] == k
+        trainer.subband_process_config = types.SimpleNamespace()  # any non-None value enables trainer.py:457-461
+        trainer.subband_filter_freq_resp = filt
+        out["data/subband_filter"] = filt.numpy()
+
+    # forward + individual losses + backward, straight through the reference trainer code path
+    net.zero_grad()
+    H, (Hs, Hsd) = net(data)
+    Huse = H * trainer.subband_filter_freq_resp if subband else H
+    losses = trainer.calculate_losses(data, Huse, (Hs, Hsd))
+    total = sum(losses.values())
+    total.backward()
+    out["out/H"] = H.detach().numpy()
+    out["out/H_sub"] = Hs.detach().numpy()
+    out["out/H_sub_per_del_s16"] = Hsd.detach().numpy()[:, ::16, :]
+    out["out/A"] = net.feedback_loop.get_coupled_feedback_matrix().detach().numpy()
+    out["out/phi"] = net.feedback_loop.phi.detach().numpy()
+    out["out/s"] = net.output_scalars.gains.detach().numpy()
+    out["out/gamma"] = net.feedback_loop.delay_line_gains.detach().numpy()
+    for kk, v in losses.items():
+        out[f"loss/{kk}"] = float(v.detach())
+    out["loss/total"] = float(total.detach())
+    out.update(grads_of(net))
+    # stand-alone loss callables (no weights)
+    mx = float(np.max(t60) * 1e3)
+    out["loss/edc_raw"] = float(edc_loss(mx, FS)(data['target_rir_response'], Huse.detach()))
+    out["loss/edr_raw"] = float(edr_loss(FS)(data['target_rir_response'], Huse.detach()))
+    out["loss/mse_g0"] = float(mse_loss()(Hs.detach()[..., 0], torch.ones_like(Hs.detach()[..., 0])))
+    out["loss/amse_g0"] = float(amse_loss()(Hs.detach()[..., 0], torch.ones_like(Hs.detach()[..., 0])))
+    # masked EDC with an explicit index (the reference draws it from the global RNG: losses.py:221-223)
+    crit = edc_loss(mx, FS, use_mask=True)
+    torch.manual_seed(99)
+    masked = float(crit(data['target_rir_response'], Huse.detach()))
+    torch.manual_seed(99)
+    tlen = min(int(mx * 1e-3 * FS), nfft // 2 + 1) - 640
+    probs = torch.empty(tlen).uniform_(0, 1)
+    idx = torch.argwhere(torch.bernoulli(probs)).squeeze(-1)
+    out["data/edc_mask_index"] = idx.numpy()
+    out["loss/edc_masked_raw"] = masked
+    # time-domain response (utils.py:169)
+    _, _, h = get_response(data, net)
+    out["out/h_s8"] = h.numpy()[:, ::8]
+
+    # a few optimisation steps exactly as trainer.py:373-379 (normalize + train_step)
+    step_losses = []
+    for _ in range(steps):
+        trainer.normalize(data)
+        loss, _ = trainer.train_step(data)
+        step_losses.append(loss)
+    out["steps/loss"] = np.array(step_losses)
+    for kname, v in net.state_dict().items():
+        out[f"steps/param/{kname}"] = v.detach().numpy().copy()
+    np.savez_compressed(os.path.join(OUT, f"{name}.npz"), **out)
+    print(name, "total", out["loss/total"], {k: v for k, v in out.items() if k.startswith("loss/")}, step_losses)
+
+
+def case_directional(name, nfft, bsz, t60, seed, hidden, neurons, feats, skip):
+    ambi = 2
+    lsh = (ambi + 1)**2
+    cfg = DiffGFDNConfig(seed=235265, ambi_order=ambi)
+    delays = cfg.delay_length_samps
+    assert len(delays) == 3 * lsh
+    rng = np.random.default_rng(seed + 3)
+    nj = 12
+    ymat = (rng.standard_normal((nj, lsh)) / 3.0).astype(np.float32)
+    spaudiopy.sph.design_sph_filterbank = lambda *a, **k: (ymat, ymat.T)
+    torch.manual_seed(seed)
+    np.random.seed(seed)
+    dirs = rng.uniform(0, np.pi, (2, nj))
+    net = DiffDirectionalFDNVarReceiverPos(FS, 3, delays, 'cpu', FeedbackLoopConfig(use_zero_coupling=False),
+                                           OutputFilterConfig(use_svfs=False, num_hidden_layers=hidden,
+                                                              num_neurons_per_layer=neurons,
+                                                              num_fourier_features=feats,
+                                                              use_skip_connections=skip),
+                                           ambi, dirs, common_decay_times=np.array([t60]), use_colorless_loss=True)
+    with torch.no_grad():  # lift |H| so that the predicted EDC sits above the eps floor of utils.db
+        net.input_gains.mul_(6.0)
+        net.output_gains.mul_(6.0)
+    data = synth_batch(nfft, bsz, seed + 1, early=False)
+    amps = torch.tensor(rng.uniform(1e-4, 1.0, (bsz, nj, 3)))
+    data['target_common_slope_amps'] = amps
+    trainer = make_trainer(DirectionalFDNVarReceiverPosTrainer, net, use_colorless_loss=True,
+                           use_asym_spectral_loss=False, edc_loss_weight=2.0, num_freq_bins=nfft)
+    out = {"meta/delays": np.array(delays), "meta/nfft": nfft, "meta/fs": FS, "meta/t60": np.array(t60),
+           "meta/feats": feats, "meta/skip": skip, "meta/edc_w": 2.0, "meta/edc_len_ms": float(np.max(t60) * 1e3),
+           "data/Y": ymat, "data/amps": amps.numpy(), "data/norm_listener_position": data['norm_listener_position'].numpy()}
+    out.update(np_state(net))
+    net.zero_grad()
+    H_sh, (Hs, Hsd) = net(data)
+    H_dir = trainer.convert_ambi_rir_to_directional_rir(H_sh)
+    losses = trainer.calculate_losses(data, H_dir, (Hs, Hsd))
+    total = sum(losses.values())
+    total.backward()
+    out["out/H_sh"] = H_sh.detach().numpy()
+    out["out/H_dir_s4"] = H_dir.detach().numpy()[..., ::4]
+    out["out/H_sub"] = Hs.detach().numpy()
+    out["out/w"] = net.sh_output_scalars.weights.detach().numpy()
+    out["out/A"] = net.feedback_loop.get_coupled_feedback_matrix().detach().numpy()
+    out["out/envelopes_s16"] = trainer.criterion[0].envelopes.numpy()[:, ::16]
+    for kk, v in losses.items():
+        out[f"loss/{kk}"] = float(v.detach())
+    out["loss/total"] = float(total.detach())
+    out.update(grads_of(net))
+    np.savez_compressed(os.path.join(OUT, f"{name}.npz"), **out)
+    print(name, {k: v for k, v in out.items() if k.startswith("loss/")})
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    case_omni("omni_n12", 12, 8192, 4, [0.05, 0.08, 0.12], 11, 1, 32, 6)
+    case_omni("omni_n12_subband_r", 12, 8192, 3, [0.04, 0.09, 0.11], 12, 2, 16, 4, radius=1.00002, subband=True)
+    case_omni("omni_n24", 24, 4096, 3, [0.03, 0.05, 0.06], 13, 1, 16, 4, steps=1)
+    case_directional("directional_n27", 8192, 2, [0.05, 0.08, 0.1], 21, 1, 16, 4, skip=False)
+    case_directional("directional_n27_skip", 4096, 2, [0.03, 0.04, 0.05], 22, 2, 16, 4, skip=True)

@@ -1,0 +1,78 @@
+"""Helpers to load the reference-generated fixtures (tests/golden/*.npz) and run the oracle on them."""
+import os
+
+import numpy as np
+import torch
+
+from oracle import gfdn_oracle as O
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+OMNI_CASES = ["omni_n12", "omni_n12_subband_r", "omni_n24"]
+DIR_CASES = ["directional_n27", "directional_n27_skip"]
+
+
+def load(name):
+    return dict(np.load(os.path.join(GOLDEN, f"{name}.npz")))
+
+
+def params_of(g, prefix="param/", requires_grad=False):
+    p = {}
+    for k, v in g.items():
+        if k.startswith(prefix):
+            t = torch.tensor(v)
+            if t.is_floating_point():
+                t = t.to(torch.float64)
+                if requires_grad:
+                    t.requires_grad_(True)
+            p[k[len(prefix):]] = t
+    return p
+
+
+def oracle_omni(g, p):
+    """Forward + trainer loss composition of an omni golden case through the oracle. Returns dict of tensors."""
+    nfft = int(g["meta/nfft"])
+    fs = float(g["meta/fs"])
+    z = O.z_grid(nfft, float(g["meta/radius"]))
+    delays = torch.tensor(g["meta/delays"], dtype=torch.float64)
+    G = p["feedback_loop.M"].shape[0]
+    gamma = O.decay_times_to_gain_per_sample(g["meta/t60"], g["meta/delays"], fs, G)
+    A = O.coupled_feedback_matrix(p["feedback_loop.M"], p["feedback_loop.alpha"])
+    b = p["input_gains"].reshape(-1)
+    c = p["output_gains"].reshape(-1)
+    s = O.gains_from_mlp(torch.tensor(g["data/norm_listener_position"]), p, int(g["meta/feats"]), G)
+    d = torch.tensor(g["data/target_early_response"])
+    H = O.omni_response(z, delays, gamma, A, b, c, s, d)
+    Hs, Hsd = O.sub_fdn_output(z, delays, p["feedback_loop.M"], b, c)
+    Huse = H * torch.tensor(g["data/subband_filter"]) if "data/subband_filter" in g else H
+    tgt = torch.tensor(g["data/target_rir_response"])
+    edc = O.edc_loss(tgt, Huse, float(g["meta/max_ir_len_ms"]), fs)
+    edr = O.edr_loss(tgt, Huse)
+    spec, spars = O.colorless_losses(Hs, p["feedback_loop.M"], 1.0, 1.0, asym=True)
+    total = float(g["meta/edc_w"]) * edc + float(g["meta/edr_w"]) * edr + spec + spars
+    return dict(H=H, Huse=Huse, H_sub=Hs, H_sub_per_del=Hsd, A=A, s=s, gamma=gamma, edc=edc, edr=edr, spec=spec,
+                spars=spars, total=total, z=z, delays=delays, b=b, c=c, d=d, tgt=tgt)
+
+
+def oracle_directional(g, p):
+    nfft = int(g["meta/nfft"])
+    fs = float(g["meta/fs"])
+    z = O.z_grid(nfft)
+    delays = torch.tensor(g["meta/delays"], dtype=torch.float64)
+    G = p["feedback_loop.M"].shape[0]
+    L = p["feedback_loop.M"].shape[1]
+    gamma = O.decay_times_to_gain_per_sample(g["meta/t60"], g["meta/delays"], fs, G)
+    A = O.coupled_feedback_matrix(p["feedback_loop.M"], p["feedback_loop.alpha"])
+    b = p["input_gains"].reshape(-1)
+    c = p["output_gains"].reshape(-1)
+    w = O.sh_gains_from_mlp(torch.tensor(g["data/norm_listener_position"]), p, int(g["meta/feats"]), G, L,
+                            skip=bool(g["meta/skip"]))
+    H_sh = O.directional_response(z, delays, gamma, A, b, c, w)
+    Y = torch.tensor(g["data/Y"], dtype=torch.float64)
+    H_dir = O.sh_to_directional(H_sh, Y)
+    Hs, _ = O.sub_fdn_output(z, delays, p["feedback_loop.M"], b, c)
+    env = O.directional_envelopes(np.array([g["meta/t60"]]), float(g["meta/edc_len_ms"]), fs)
+    edc = O.directional_edc_loss(H_dir, torch.tensor(g["data/amps"]), env, O.ms_to_samps(float(g["meta/edc_len_ms"]), fs),
+                                 O.ms_to_samps(20.0, fs))
+    spec, spars = O.colorless_losses(Hs, p["feedback_loop.M"], 1.0, 1.0, asym=False)
+    total = float(g["meta/edc_w"]) * edc + spec + spars
+    return dict(H_sh=H_sh, H_dir=H_dir, H_sub=Hs, w=w, A=A, env=env, edc=edc, spec=spec, spars=spars, total=total)
