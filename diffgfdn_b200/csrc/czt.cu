@@ -1,0 +1,313 @@
+// K3a: windowed real inverse DFT of arbitrary length n via the chirp-z (Bluestein) identity, built on
+// power-of-two cuFFT C2C transforms.
+//
+// The reference's energy-decay losses call torch.fft.irfft(X, n = X.shape[-1]) (diff_gfdn/losses.py:207-213,
+// 442-445): with K = nfft/2+1 bins that is an ODD-length inverse real DFT (K = 65 537 is prime, 131 073 = 3 x
+// 43 691) that reads only bins 0..K/2 -- quirk Q3 of SURVEY.md. Only a window [t0, t0+tn) of its K output
+// samples is ever used (mixing time .. max RIR length). With k t = (k^2 + t^2 - (t-k)^2)/2:
+//
+//   out[t] = 1/n Re{ e^{i pi t^2/n} sum_k ( w_k X_k e^{i pi (k^2 + 2 k t0)/n} ) e^{-i pi (t-k)^2/n} },  t in [0,tn)
+//
+// i.e. one pre-chirp, one circular convolution of length mc >= n/2 + tn with a fixed chirp (two C2C FFTs and a
+// pointwise product with the precomputed spectrum), one post-chirp. All chirp phases are reduced with exact
+// integer arithmetic (k^2 mod 2n) before sincospi, so float32 storage is the only rounding (measured against
+// the float64 pocketfft result: 2e-7 of peak, < 1e-3 dB on a 108 dB EDC range).
+// The adjoint (for the backward pass) is the same pipeline run with conjugated chirps.
+#include <cufft.h>
+
+#include <map>
+#include <mutex>
+
+#include "common.cuh"
+
+struct dgfdn_czt_plan {
+  int64_t n, t0, tn, kh, mc;
+  bool even;
+  float2* pre;    // [kh+1]  w_k e^{i pi (k^2 + 2 k t0)/n}
+  float2* post;   // [tn]    e^{i pi t^2/n}
+  float2* vhat;   // [mc]    FFT(circular chirp) / (mc n)
+  std::map<int64_t, cufftHandle> plans;  // batch -> C2C plan
+  std::mutex mu;
+  int device;
+};
+
+namespace dgfdn {
+namespace {
+
+constexpr int kThreads = 256;
+
+#define DGFDN_CUFFT(call)                                                              \
+  do {                                                                                 \
+    cufftResult r__ = (call);                                                          \
+    if (r__ != CUFFT_SUCCESS) {                                                        \
+      dgfdn::set_error("%s failed: cufft error %d (%s:%d)", #call, (int)r__, __FILE__, __LINE__); \
+      return 1;                                                                        \
+    }                                                                                  \
+  } while (0)
+
+__device__ __forceinline__ double2 unit_phase(int64_t num, int64_t n) {
+  // e^{i pi num / n}, num already reduced modulo 2n
+  double s, c;
+  sincospi((double)num / (double)n, &s, &c);
+  return make_double2(c, s);
+}
+
+__global__ void build_tables_kernel(int64_t n, int64_t t0, int64_t tn, int64_t kh, int64_t mc, bool even, float2* pre,
+                                    float2* post, double2* vc) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t n2 = 2 * n;
+  if (i <= kh) {
+    int64_t num = ((i * i) % n2 + (2 * ((i * t0) % n)) % n2) % n2;
+    double2 p = unit_phase(num, n);
+    double w = (i == 0 || (even && i == kh)) ? 1.0 : 2.0;
+    pre[i] = make_float2((float)(w * p.x), (float)(w * p.y));
+  }
+  if (i < tn) {
+    double2 p = unit_phase((i * i) % n2, n);
+    post[i] = make_float2((float)p.x, (float)p.y);
+  }
+  if (i < mc) {
+    // circular chirp v_j = e^{-i pi j^2 / n} for j in [-kh, tn-1], stored at j mod mc; zero elsewhere
+    double2 v = make_double2(0.0, 0.0);
+    int64_t j = -1;
+    bool ok = false;
+    if (i < tn) {
+      j = i;
+      ok = true;
+    } else if (i >= mc - kh) {
+      j = mc - i;  // |j| for negative index (j^2 is what matters)
+      ok = true;
+    }
+    if (ok) {
+      double2 p = unit_phase((j * j) % n2, n);
+      v = make_double2(p.x, -p.y);
+    }
+    vc[i] = v;
+  }
+}
+
+__global__ void scale_to_c64_kernel(const double2* in, float2* out, int64_t m, double scale) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < m) out[i] = make_float2((float)(in[i].x * scale), (float)(in[i].y * scale));
+}
+
+// scratch[r, i] = pre[i] * P(filt[i] * x[r, i]) for i <= kh, 0 for kh < i < mc. Two elements per thread.
+__global__ void __launch_bounds__(kThreads) czt_pre_kernel(const float2* __restrict__ x, int64_t ldx,
+                                                           const float2* __restrict__ filt,
+                                                           const float2* __restrict__ pre, int64_t kh, int64_t mc,
+                                                           bool even, float2* __restrict__ scratch) {
+  const int64_t r = blockIdx.y;
+  const int64_t i0 = 2 * ((int64_t)blockIdx.x * kThreads + threadIdx.x);
+  if (i0 >= mc) return;
+  float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    const int64_t i = i0 + e;
+    if (i <= kh) {
+      float2 v = x[r * ldx + i];
+      if (filt != nullptr) v = cmulf(v, filt[i]);
+      if (i == 0 || (even && i == kh)) v.y = 0.f;
+      v = cmulf(v, pre[i]);
+      if (e == 0) {
+        o.x = v.x;
+        o.y = v.y;
+      } else {
+        o.z = v.x;
+        o.w = v.y;
+      }
+    }
+  }
+  *reinterpret_cast<float4*>(scratch + r * mc + i0) = o;  // mc is even and scratch rows are 16 B aligned
+}
+
+__global__ void __launch_bounds__(kThreads) czt_mul_kernel(float2* __restrict__ scratch,
+                                                           const float2* __restrict__ vhat, int64_t mc, bool conj) {
+  const int64_t r = blockIdx.y;
+  const int64_t i0 = 2 * ((int64_t)blockIdx.x * kThreads + threadIdx.x);
+  if (i0 >= mc) return;
+  float4* p = reinterpret_cast<float4*>(scratch + r * mc + i0);
+  float4 v = *p;
+  const float4 w = *reinterpret_cast<const float4*>(vhat + i0);
+  float2 a = make_float2(v.x, v.y), b = make_float2(v.z, v.w);
+  float2 wa = make_float2(w.x, conj ? -w.y : w.y), wb = make_float2(w.z, conj ? -w.w : w.w);
+  a = cmulf(a, wa);
+  b = cmulf(b, wb);
+  *p = make_float4(a.x, a.y, b.x, b.y);
+}
+
+__global__ void __launch_bounds__(kThreads) czt_post_kernel(const float2* __restrict__ scratch,
+                                                            const float2* __restrict__ post, int64_t tn, int64_t mc,
+                                                            float* __restrict__ out) {
+  const int64_t r = blockIdx.y;
+  const int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (t >= tn) return;
+  const float2 v = scratch[r * mc + t];
+  const float2 p = post[t];
+  out[r * tn + t] = p.x * v.x - p.y * v.y;
+}
+
+// adjoint of czt_post: scratch[r,t] = conj(post[t]) gout[r,t] (t < tn), 0 elsewhere
+__global__ void __launch_bounds__(kThreads) czt_post_adj_kernel(const float* __restrict__ gout,
+                                                                const float2* __restrict__ post, int64_t tn,
+                                                                int64_t mc, float2* __restrict__ scratch) {
+  const int64_t r = blockIdx.y;
+  const int64_t i0 = 2 * ((int64_t)blockIdx.x * kThreads + threadIdx.x);
+  if (i0 >= mc) return;
+  float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (i0 < tn) {
+    const float g = gout[r * tn + i0];
+    const float2 p = post[i0];
+    o.x = p.x * g;
+    o.y = -p.y * g;
+  }
+  if (i0 + 1 < tn) {
+    const float g = gout[r * tn + i0 + 1];
+    const float2 p = post[i0 + 1];
+    o.z = p.x * g;
+    o.w = -p.y * g;
+  }
+  *reinterpret_cast<float4*>(scratch + r * mc + i0) = o;
+}
+
+// adjoint of czt_pre: gx[r,i] = conj(filt[i]) P(conj(pre[i]) scratch[r,i]) for i <= kh; 0 for kh < i < kx
+__global__ void __launch_bounds__(kThreads) czt_pre_adj_kernel(const float2* __restrict__ scratch, int64_t mc,
+                                                               const float2* __restrict__ filt,
+                                                               const float2* __restrict__ pre, int64_t kh, bool even,
+                                                               float2* __restrict__ gx, int64_t ldx, int64_t kx) {
+  const int64_t r = blockIdx.y;
+  const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (i >= kx) return;
+  float2 v = make_float2(0.f, 0.f);
+  if (i <= kh) {
+    v = cmulcf(scratch[r * mc + i], pre[i]);
+    if (i == 0 || (even && i == kh)) v.y = 0.f;
+    if (filt != nullptr) v = cmulcf(v, filt[i]);
+  }
+  gx[r * ldx + i] = v;
+}
+
+int get_fft(dgfdn_czt_plan* p, int64_t rows, cufftHandle* out) {
+  std::lock_guard<std::mutex> lock(p->mu);
+  auto it = p->plans.find(rows);
+  if (it != p->plans.end()) {
+    *out = it->second;
+    return 0;
+  }
+  cufftHandle h;
+  int nn[1] = {(int)p->mc};
+  DGFDN_CUFFT(cufftPlanMany(&h, 1, nn, nullptr, 1, (int)p->mc, nullptr, 1, (int)p->mc, CUFFT_C2C, (int)rows));
+  p->plans[rows] = h;
+  *out = h;
+  return 0;
+}
+
+int convolve(dgfdn_czt_plan* p, float2* scratch, int64_t rows, bool conj, cudaStream_t st) {
+  cufftHandle h;
+  if (get_fft(p, rows, &h)) return 1;
+  DGFDN_CUFFT(cufftSetStream(h, st));
+  cufftComplex* s = reinterpret_cast<cufftComplex*>(scratch);
+  DGFDN_CUFFT(cufftExecC2C(h, s, s, CUFFT_FORWARD));
+  dim3 grid((unsigned)((p->mc / 2 + kThreads - 1) / kThreads), (unsigned)rows);
+  czt_mul_kernel<<<grid, kThreads, 0, st>>>(scratch, p->vhat, p->mc, conj);
+  DGFDN_LAUNCH_CHECK();
+  DGFDN_CUFFT(cufftExecC2C(h, s, s, CUFFT_INVERSE));
+  return 0;
+}
+
+}  // namespace
+}  // namespace dgfdn
+
+using namespace dgfdn;
+
+extern "C" int dgfdn_czt_plan_create(int64_t n, int64_t t0, int64_t tn, dgfdn_czt_plan** plan) {
+  DGFDN_CHECK(plan != nullptr, "czt_plan_create: null output");
+  DGFDN_CHECK(n >= 2 && t0 >= 0 && tn >= 1 && t0 + tn <= n, "czt_plan_create: need 0 <= t0, t0+tn <= n (n=%lld t0=%lld tn=%lld)",
+              (long long)n, (long long)t0, (long long)tn);
+  DGFDN_CHECK(n < ((int64_t)1 << 30), "czt_plan_create: n too large");
+  dgfdn_czt_plan* p = new dgfdn_czt_plan();
+  p->n = n;
+  p->t0 = t0;
+  p->tn = tn;
+  p->kh = n / 2;
+  p->even = (n % 2 == 0);
+  int64_t need = p->kh + tn;
+  int64_t mc = 16;
+  while (mc < need) mc <<= 1;
+  p->mc = mc;
+  DGFDN_CUDA(cudaGetDevice(&p->device));
+  double2 *vc = nullptr, *vf = nullptr;
+  DGFDN_CUDA(cudaMalloc(&p->pre, (size_t)(p->kh + 1) * sizeof(float2)));
+  DGFDN_CUDA(cudaMalloc(&p->post, (size_t)tn * sizeof(float2)));
+  DGFDN_CUDA(cudaMalloc(&p->vhat, (size_t)mc * sizeof(float2)));
+  DGFDN_CUDA(cudaMalloc(&vc, (size_t)mc * sizeof(double2)));
+  DGFDN_CUDA(cudaMalloc(&vf, (size_t)mc * sizeof(double2)));
+  int64_t m = mc > tn ? mc : tn;
+  if (p->kh + 1 > m) m = p->kh + 1;
+  build_tables_kernel<<<(unsigned)((m + 255) / 256), 256>>>(n, t0, tn, p->kh, mc, p->even, p->pre, p->post, vc);
+  DGFDN_LAUNCH_CHECK();
+  cufftHandle hz;
+  DGFDN_CUFFT(cufftPlan1d(&hz, (int)mc, CUFFT_Z2Z, 1));
+  DGFDN_CUFFT(cufftExecZ2Z(hz, reinterpret_cast<cufftDoubleComplex*>(vc), reinterpret_cast<cufftDoubleComplex*>(vf),
+                           CUFFT_FORWARD));
+  scale_to_c64_kernel<<<(unsigned)((mc + 255) / 256), 256>>>(vf, p->vhat, mc, 1.0 / ((double)mc * (double)n));
+  DGFDN_LAUNCH_CHECK();
+  DGFDN_CUDA(cudaDeviceSynchronize());
+  cufftDestroy(hz);
+  cudaFree(vc);
+  cudaFree(vf);
+  *plan = p;
+  return 0;
+}
+
+extern "C" int dgfdn_czt_plan_destroy(dgfdn_czt_plan* p) {
+  if (p == nullptr) return 0;
+  for (auto& kv : p->plans) cufftDestroy(kv.second);
+  cudaFree(p->pre);
+  cudaFree(p->post);
+  cudaFree(p->vhat);
+  delete p;
+  return 0;
+}
+
+extern "C" int64_t dgfdn_czt_plan_mc(const dgfdn_czt_plan* p) { return p ? p->mc : 0; }
+
+extern "C" int dgfdn_irfft_window_fwd(dgfdn_czt_plan* p, const void* x, int64_t ldx, int64_t rows, const void* filt,
+                                      void* scratch, float* out, void* stream) {
+  DGFDN_CHECK(p && x && scratch && out, "irfft_window_fwd: null pointer");
+  DGFDN_CHECK(ldx >= p->kh + 1, "irfft_window_fwd: rows hold %lld bins, need %lld", (long long)ldx,
+              (long long)(p->kh + 1));
+  if (rows == 0) return 0;
+  DGFDN_CHECK(rows > 0 && rows <= 65535, "irfft_window_fwd: rows=%lld out of range [0,65535]; tile the call",
+              (long long)rows);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float2* sc = static_cast<float2*>(scratch);
+  dim3 g1((unsigned)((p->mc / 2 + kThreads - 1) / kThreads), (unsigned)rows);
+  czt_pre_kernel<<<g1, kThreads, 0, st>>>(static_cast<const float2*>(x), ldx, static_cast<const float2*>(filt), p->pre,
+                                          p->kh, p->mc, p->even, sc);
+  DGFDN_LAUNCH_CHECK();
+  if (convolve(p, sc, rows, false, st)) return 1;
+  dim3 g2((unsigned)((p->tn + kThreads - 1) / kThreads), (unsigned)rows);
+  czt_post_kernel<<<g2, kThreads, 0, st>>>(sc, p->post, p->tn, p->mc, out);
+  DGFDN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int dgfdn_irfft_window_bwd(dgfdn_czt_plan* p, const float* gout, int64_t rows, const void* filt,
+                                      void* scratch, void* gx, int64_t ldx, int64_t kx, void* stream) {
+  DGFDN_CHECK(p && gout && scratch && gx, "irfft_window_bwd: null pointer");
+  DGFDN_CHECK(kx >= p->kh + 1 && ldx >= kx, "irfft_window_bwd: need kx >= n/2+1 and ldx >= kx");
+  if (rows == 0) return 0;
+  DGFDN_CHECK(rows > 0 && rows <= 65535, "irfft_window_bwd: rows=%lld out of range [0,65535]; tile the call",
+              (long long)rows);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float2* sc = static_cast<float2*>(scratch);
+  dim3 g1((unsigned)((p->mc / 2 + kThreads - 1) / kThreads), (unsigned)rows);
+  czt_post_adj_kernel<<<g1, kThreads, 0, st>>>(gout, p->post, p->tn, p->mc, sc);
+  DGFDN_LAUNCH_CHECK();
+  if (convolve(p, sc, rows, true, st)) return 1;
+  dim3 g2((unsigned)((kx + kThreads - 1) / kThreads), (unsigned)rows);
+  czt_pre_adj_kernel<<<g2, kThreads, 0, st>>>(sc, p->mc, static_cast<const float2*>(filt), p->pre, p->kh, p->even,
+                                              static_cast<float2*>(gx), ldx, kx);
+  DGFDN_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,133 @@
+// K6: block-recursive time-domain renderer of the Grouped FDN (late reverberation tail).
+//
+// The reference has no recursive renderer: it renders h = irfft(H) (diff_gfdn/utils.py:169) per receiver, sums
+// octave bands (run_subband_training_treble.py:316-358) and cross-fades block convolutions for a moving listener
+// (sound_examples.py:163-226). The transfer function it samples, H(z) = c^T (D Gamma^-1 - A)^-1 b, is the
+// recursion
+//     x_i[t] = gamma_i ( sum_j A_ij x_j[t - m_i] + b_i u[t - m_i] ),     q_g[t] = sum_{i in g} c_i x_i[t],
+// whose state is receiver independent; a listener only mixes the G group signals with its gains s[r,g].
+// With a block of L = min_i m_i samples every right-hand side refers to earlier blocks, so a block is one
+// dense (N x N) * (N x L) product. render_groups advances one CTA per (octave) band; render_mix streams the
+// listener outputs (4 B written per listener.sample, the only HBM-heavy part).
+#include "common.cuh"
+
+namespace dgfdn {
+namespace {
+
+constexpr int kThreads = 1024;
+
+__global__ void __launch_bounds__(kThreads) render_groups_kernel(int n, int g, int64_t tlen,
+                                                                 const int32_t* __restrict__ delays,
+                                                                 const float* __restrict__ a,
+                                                                 const float* __restrict__ gamma,
+                                                                 const float* __restrict__ b,
+                                                                 const float* __restrict__ c,
+                                                                 const float* __restrict__ u, float* hist,
+                                                                 float* __restrict__ q) {
+  __shared__ float s_a[DGFDN_MAX_LINES * DGFDN_MAX_LINES];
+  __shared__ float s_gamma[DGFDN_MAX_LINES], s_b[DGFDN_MAX_LINES], s_c[DGFDN_MAX_LINES];
+  __shared__ int s_m[DGFDN_MAX_LINES];
+  const int band = blockIdx.x;
+  const int l = n / g;
+  for (int i = threadIdx.x; i < n * n; i += kThreads) s_a[i] = a[(size_t)band * n * n + i];
+  for (int i = threadIdx.x; i < n; i += kThreads) {
+    s_gamma[i] = gamma ? gamma[band * n + i] : 1.f;
+    s_b[i] = b[band * n + i];
+    s_c[i] = c[band * n + i];
+    s_m[i] = delays[band * n + i];
+  }
+  __syncthreads();
+  int blk = s_m[0];
+  for (int i = 1; i < n; ++i) blk = min(blk, s_m[i]);
+  float* hb = hist + (size_t)band * tlen * n;
+  float* qb = q + (size_t)band * tlen * g;
+  for (int64_t s0 = 0; s0 < tlen; s0 += blk) {
+    const int len = (int)min((int64_t)blk, tlen - s0);
+    // one work item per (sample, line)
+    for (int w = threadIdx.x; w < len * n; w += kThreads) {
+      const int i = w % n;
+      const int64_t t = s0 + w / n;
+      const int64_t src = t - s_m[i];
+      float v = 0.f;
+      if (src >= 0) {
+        const float* xr = hb + src * n;
+        float acc = s_b[i] * (u ? u[src] : (src == 0 ? 1.f : 0.f));
+        for (int j = 0; j < n; ++j) acc = fmaf(s_a[i * n + j], xr[j], acc);
+        v = s_gamma[i] * acc;
+      }
+      hb[t * n + i] = v;
+    }
+    __syncthreads();  // block-scope ordering of the global writes above
+    for (int w = threadIdx.x; w < len * g; w += kThreads) {
+      const int gi = w % g;
+      const int64_t t = s0 + w / g;
+      float acc = 0.f;
+      for (int j = 0; j < l; ++j) acc = fmaf(s_c[gi * l + j], hb[t * n + gi * l + j], acc);
+      qb[t * g + gi] = acc;
+    }
+  }
+}
+
+// out[r,t] = sum_band sum_g s[band, traj[r, t/hop], g] q[band, t, g]; four samples per thread (128-bit stores).
+__global__ void __launch_bounds__(256) render_mix_kernel(int bands, int g, int64_t tlen, int64_t positions,
+                                                         int64_t hop, int64_t nhops, const float* __restrict__ s,
+                                                         const int32_t* __restrict__ traj,
+                                                         const float* __restrict__ q, float* __restrict__ out) {
+  const int64_t r = blockIdx.y;
+  const int64_t t0 = 4 * ((int64_t)blockIdx.x * 256 + threadIdx.x);
+  if (t0 >= tlen) return;
+  float v[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int64_t t = t0 + e;
+    if (t < tlen) {
+      const int64_t pos = traj[r * nhops + t / hop];
+      float acc = 0.f;
+      for (int bd = 0; bd < bands; ++bd) {
+        const float* sp = s + ((size_t)bd * positions + pos) * g;
+        const float* qp = q + ((size_t)bd * tlen + t) * g;
+        for (int gi = 0; gi < g; ++gi) acc = fmaf(__ldg(sp + gi), __ldg(qp + gi), acc);
+      }
+      v[e] = acc;
+    }
+  }
+  float* o = out + r * tlen + t0;
+  if (t0 + 3 < tlen && ((reinterpret_cast<uintptr_t>(o) & 15u) == 0)) {
+    st_stream(reinterpret_cast<float4*>(o), make_float4(v[0], v[1], v[2], v[3]));
+  } else {
+    for (int e = 0; e < 4 && t0 + e < tlen; ++e) o[e] = v[e];
+  }
+}
+
+}  // namespace
+}  // namespace dgfdn
+
+using namespace dgfdn;
+
+extern "C" int dgfdn_render_groups(int bands, int n, int g, int64_t t, const int32_t* delays, const float* a,
+                                   const float* gamma, const float* b, const float* c, const float* u, float* hist,
+                                   float* q, void* stream) {
+  DGFDN_CHECK(bands >= 1 && n >= 1 && n <= DGFDN_MAX_LINES && g >= 1 && n % g == 0 && t >= 1,
+              "render_groups: bad sizes");
+  DGFDN_CHECK(delays && a && b && c && hist && q, "render_groups: null pointer");
+  render_groups_kernel<<<bands, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(n, g, t, delays, a, gamma, b, c, u,
+                                                                                  hist, q);
+  DGFDN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int dgfdn_render_mix(int bands, int g, int64_t t, int64_t listeners, int64_t positions, int64_t hop,
+                                const float* s, const int32_t* traj, const float* q, float* out, void* stream) {
+  DGFDN_CHECK(bands >= 1 && g >= 1 && t >= 1 && listeners >= 0 && positions >= 1 && hop >= 1,
+              "render_mix: bad sizes");
+  DGFDN_CHECK(s && traj && q && out, "render_mix: null pointer");
+  if (listeners == 0) return 0;
+  DGFDN_CHECK(listeners <= 65535, "render_mix: listeners=%lld exceeds grid.y limit; tile the call",
+              (long long)listeners);
+  const int64_t nhops = (t + hop - 1) / hop;
+  dim3 grid((unsigned)((t + 1023) / 1024), (unsigned)listeners);
+  render_mix_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(bands, g, t, positions, hop, nhops, s, traj,
+                                                                         q, out);
+  DGFDN_LAUNCH_CHECK();
+  return 0;
+}

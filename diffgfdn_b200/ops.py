@@ -1,0 +1,436 @@
+"""torch.autograd bindings of the sm_100a kernels (called through the C ABI in include/diffgfdn_b200.h).
+
+Every op takes and returns CUDA tensors, runs on torch's current stream and raises on CPU tensors -- there is no
+CPU or eager fallback. Shapes follow the reference (orchidas/DiffGFDN): K frequency bins, N delay lines, G groups,
+R receivers (rows)."""
+import ctypes
+import math
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+C64 = torch.complex64
+C128 = torch.complex128
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _cuda(name, t: Optional[torch.Tensor], dtype=None, optional=False):
+    if t is None:
+        if optional:
+            return None
+        raise RuntimeError(f"{name}: tensor required")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: expected a CUDA tensor, got device {t.device} "
+                           "(diffgfdn_b200 has no CPU fallback)")
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    return t.contiguous()
+
+
+# ----------------------------------------------------------------------------------------------------------
+# K1: per-bin solve
+# ----------------------------------------------------------------------------------------------------------
+class _GFDNSolve(torch.autograd.Function):
+    """x_k = (diag(z_k^m / gamma) - A)^-1 b ;  y[k,g] = sum_{n in g} c_n x_k[n].
+
+    Replaces FeedbackLoop.forward + einsums (reference feedback_loop.py:326-391, model.py:615-619, 1083, 237-250)."""
+
+    @staticmethod
+    def forward(ctx, z, delays, a, gamma, b, c, num_groups, transpose_a, gamma_z):
+        z = _cuda("z", z, C128)
+        delays = _cuda("delays", delays, torch.int32)
+        a_ = _cuda("A", a, torch.float32)
+        gamma_ = _cuda("gamma", gamma, torch.float32, optional=True)
+        gamma_z_ = _cuda("gamma_z", gamma_z, C64, optional=True)
+        b_ = _cuda("b", b.reshape(-1), torch.float32)
+        c_ = _cuda("c", c.reshape(-1), torch.float32)
+        n = a_.shape[0]
+        k = z.shape[0]
+        if a_.shape != (n, n) or delays.numel() != n or b_.numel() != n or c_.numel() != n:
+            raise RuntimeError("gfdn_solve: inconsistent shapes")
+        if gamma_z_ is not None and tuple(gamma_z_.shape) != (n, k):
+            raise RuntimeError("gfdn_solve: gamma_z must be (N, K)")
+        x = torch.empty(k, n, dtype=C64, device=z.device)
+        y = torch.empty(k, num_groups, dtype=C64, device=z.device)
+        with torch.cuda.device(z.device):
+            _lib.call("dgfdn_solve_fwd", n, num_groups, k, _ptr(z), _ptr(delays), _ptr(a_), int(transpose_a),
+                      _ptr(gamma_), _ptr(gamma_z_), _ptr(b_), _ptr(c_), _ptr(x), _ptr(y), _stream())
+        ctx.save_for_backward(z, delays, a_, gamma_, gamma_z_, c_, x)
+        ctx.meta = (n, num_groups, k, int(transpose_a), b.shape, c.shape)
+        return x, y
+
+    @staticmethod
+    def backward(ctx, gx, gy):
+        z, delays, a_, gamma_, gamma_z_, c_, x = ctx.saved_tensors
+        n, g, k, tr, bshape, cshape = ctx.meta
+        if gx is None and gy is None:
+            return (None, ) * 9
+        gx_ = _cuda("gx", gx, C64, optional=True)
+        gy_ = _cuda("gy", gy, C64, optional=True)
+        dev = z.device
+        out = torch.empty(n * n + 3 * n, dtype=torch.float64, device=dev)
+        ga, gb, gc, gig = out[:n * n], out[n * n:n * n + n], out[n * n + n:n * n + 2 * n], out[n * n + 2 * n:]
+        with torch.cuda.device(dev):
+            ws = torch.empty(_lib.load().dgfdn_solve_bwd_ws_bytes(n) // 8, dtype=torch.float64, device=dev)
+            _lib.call("dgfdn_solve_bwd", n, g, k, _ptr(z), _ptr(delays), _ptr(a_), tr, _ptr(gamma_), _ptr(gamma_z_),
+                      _ptr(c_), _ptr(x), _ptr(gy_), _ptr(gx_), _ptr(ga), _ptr(gb), _ptr(gc), _ptr(gig), _ptr(ws),
+                      _stream())
+        g_a = ga.reshape(n, n).to(torch.float32) if ctx.needs_input_grad[2] else None
+        g_gamma = None
+        if gamma_ is not None and ctx.needs_input_grad[3]:
+            g_gamma = (-gig / gamma_.to(torch.float64)**2).to(torch.float32)
+        g_b = gb.to(torch.float32).reshape(bshape) if ctx.needs_input_grad[4] else None
+        g_c = gc.to(torch.float32).reshape(cshape) if ctx.needs_input_grad[5] else None
+        return None, None, g_a, g_gamma, g_b, g_c, None, None, None
+
+
+def gfdn_solve(z: torch.Tensor, delays: torch.Tensor, a: torch.Tensor, gamma: Optional[torch.Tensor],
+               b: torch.Tensor, c: torch.Tensor, num_groups: int, transpose_a: bool = False,
+               gamma_z: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Returns (x [K,N] c64, y [K,G] c64). Differentiable w.r.t. a, gamma (scalar gains), b, c."""
+    return _GFDNSolve.apply(z, delays, a, gamma, b, c, num_groups, transpose_a, gamma_z)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# K2: receiver projection
+# ----------------------------------------------------------------------------------------------------------
+class _ReceiverProject(torch.autograd.Function):
+    """H[r,k] = sum_g s[r,g] y[k,g] + d[r,k]  (reference model.py:583-619)."""
+
+    @staticmethod
+    def forward(ctx, s, y, d):
+        s_ = _cuda("s", s, torch.float32)
+        y_ = _cuda("y", y, C64)
+        d_ = _cuda("d", d, C64, optional=True)
+        rows, g = s_.shape
+        k = y_.shape[0]
+        if y_.shape[1] != g or (d_ is not None and tuple(d_.shape) != (rows, k)):
+            raise RuntimeError("receiver_project: inconsistent shapes")
+        h = torch.empty(rows, k, dtype=C64, device=s_.device)
+        with torch.cuda.device(s_.device):
+            _lib.call("dgfdn_project_fwd", g, rows, k, _ptr(s_), _ptr(y_), _ptr(d_), k, _ptr(h), k, _stream())
+        ctx.save_for_backward(s_, y_)
+        ctx.d_dtype = None if d is None else d.dtype
+        return h
+
+    @staticmethod
+    def backward(ctx, gh):
+        s_, y_ = ctx.saved_tensors
+        rows, g = s_.shape
+        k = y_.shape[0]
+        gh_ = _cuda("gh", gh, C64)
+        gs = torch.empty_like(s_) if ctx.needs_input_grad[0] else None
+        gy = torch.empty_like(y_) if ctx.needs_input_grad[1] else None
+        with torch.cuda.device(s_.device):
+            _lib.call("dgfdn_project_bwd", g, rows, k, _ptr(s_), _ptr(y_), _ptr(gh_), k, _ptr(gy), 0, _ptr(gs),
+                      _stream())
+        gd = gh_.to(ctx.d_dtype) if (ctx.d_dtype is not None and ctx.needs_input_grad[2]) else None
+        return gs, gy, gd
+
+
+def receiver_project(s: torch.Tensor, y: torch.Tensor, d: Optional[torch.Tensor] = None) -> torch.Tensor:
+    return _ReceiverProject.apply(s, y, d)
+
+
+class _SHProject(torch.autograd.Function):
+    """H_sh[r,l,k] = sum_g cw[r,g,l] x[k, gL+l]  (reference model.py:1056-1088)."""
+
+    @staticmethod
+    def forward(ctx, cw, x):
+        cw_ = _cuda("cw", cw, torch.float32)
+        x_ = _cuda("x", x, C64)
+        rows, g, l = cw_.shape
+        k = x_.shape[0]
+        if x_.shape[1] != g * l:
+            raise RuntimeError("sh_project: inconsistent shapes")
+        h = torch.empty(rows, l, k, dtype=C64, device=x_.device)
+        with torch.cuda.device(x_.device):
+            _lib.call("dgfdn_project_sh_fwd", g, l, rows, k, _ptr(cw_), _ptr(x_), _ptr(h), _stream())
+        ctx.save_for_backward(cw_, x_)
+        return h
+
+    @staticmethod
+    def backward(ctx, gh):
+        cw_, x_ = ctx.saved_tensors
+        rows, g, l = cw_.shape
+        k = x_.shape[0]
+        gh_ = _cuda("gh", gh, C64)
+        gcw = torch.empty_like(cw_) if ctx.needs_input_grad[0] else None
+        gx = torch.empty_like(x_) if ctx.needs_input_grad[1] else None
+        with torch.cuda.device(x_.device):
+            _lib.call("dgfdn_project_sh_bwd", g, l, rows, k, _ptr(cw_), _ptr(x_), _ptr(gh_), _ptr(gx), 0, _ptr(gcw),
+                      _stream())
+        return gcw, gx
+
+
+def sh_project(cw: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+    return _SHProject.apply(cw, x)
+
+
+class _MixChannels(torch.autograd.Function):
+    """out[r,j,k] = sum_l w[j,l] in[r,l,k]  (reference trainer.py:853-865); w is a constant matrix."""
+
+    @staticmethod
+    def forward(ctx, w, x):
+        w_ = _cuda("w", w, torch.float32)
+        x_ = _cuda("x", x, C64)
+        rows, cin, k = x_.shape
+        cout = w_.shape[0]
+        if w_.shape[1] != cin:
+            raise RuntimeError("mix_channels: inconsistent shapes")
+        out = torch.empty(rows, cout, k, dtype=C64, device=x_.device)
+        with torch.cuda.device(x_.device):
+            for r0 in range(0, rows, 32768):
+                r1 = min(rows, r0 + 32768)
+                _lib.call("dgfdn_mix_channels", cin, cout, r1 - r0, k, _ptr(w_), _ptr(x_[r0:r1]), _ptr(out[r0:r1]),
+                          _stream())
+        ctx.save_for_backward(w_)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        (w_, ) = ctx.saved_tensors
+        gx = _MixChannels.apply(w_.t().contiguous(), gout) if ctx.needs_input_grad[1] else None
+        return None, gx
+
+
+def mix_channels(w: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+    return _MixChannels.apply(w, x)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# K3a: windowed inverse real DFT of arbitrary length (chirp-z over cuFFT)
+# ----------------------------------------------------------------------------------------------------------
+class CZTPlan:
+    """Device-side plan for out[t] = irfft(X, n)[t0 + t], t in [0, tn). Owns the chirp tables and cuFFT plans."""
+
+    def __init__(self, n: int, t0: int, tn: int, device: torch.device):
+        self.n, self.t0, self.tn, self.device = int(n), int(t0), int(tn), torch.device(device)
+        self.num_bins = self.n // 2 + 1
+        h = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.call("dgfdn_czt_plan_create", self.n, self.t0, self.tn, ctypes.byref(h))
+        self._h = h
+        self.mc = int(_lib.load().dgfdn_czt_plan_mc(h))
+
+    @property
+    def handle(self):
+        return self._h
+
+    def rows_per_call(self, scratch_bytes: int = 1 << 30) -> int:
+        return int(max(1, min(32768, scratch_bytes // (self.mc * 8))))
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                _lib.load().dgfdn_czt_plan_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
+_PLANS = {}
+
+
+def get_czt_plan(n: int, t0: int, tn: int, device) -> CZTPlan:
+    device = torch.device(device)
+    if device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    key = (int(n), int(t0), int(tn), device.index)
+    plan = _PLANS.get(key)
+    if plan is None:
+        plan = CZTPlan(n, t0, tn, device)
+        _PLANS[key] = plan
+    return plan
+
+
+class _IrfftWindow(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, x, plan, filt):
+        x_ = _cuda("X", x, C64)
+        filt_ = _cuda("filt", filt, C64, optional=True)
+        kx = x_.shape[-1]
+        if kx < plan.num_bins:
+            raise RuntimeError(f"irfft_window: need at least {plan.num_bins} bins, got {kx}")
+        if filt_ is not None and filt_.numel() < plan.num_bins:
+            raise RuntimeError("irfft_window: filter shorter than the number of bins used")
+        lead = x_.shape[:-1]
+        x2 = x_.reshape(-1, kx)
+        rows = x2.shape[0]
+        out = torch.empty(rows, plan.tn, dtype=torch.float32, device=x_.device)
+        step = plan.rows_per_call()
+        with torch.cuda.device(x_.device):
+            scratch = torch.empty(min(step, rows) * plan.mc, dtype=C64, device=x_.device)
+            for r0 in range(0, rows, step):
+                r1 = min(rows, r0 + step)
+                _lib.call("dgfdn_irfft_window_fwd", plan.handle, _ptr(x2[r0:r1]), kx, r1 - r0, _ptr(filt_),
+                          _ptr(scratch), _ptr(out[r0:r1]), _stream())
+        ctx.plan = plan
+        ctx.kx = kx
+        ctx.lead = lead
+        ctx.save_for_backward(filt_)
+        return out.reshape(*lead, plan.tn)
+
+    @staticmethod
+    def backward(ctx, gout):
+        plan, kx = ctx.plan, ctx.kx
+        (filt_, ) = ctx.saved_tensors
+        g2 = _cuda("gout", gout, torch.float32).reshape(-1, plan.tn)
+        rows = g2.shape[0]
+        gx = torch.empty(rows, kx, dtype=C64, device=g2.device)
+        step = plan.rows_per_call()
+        with torch.cuda.device(g2.device):
+            scratch = torch.empty(min(step, rows) * plan.mc, dtype=C64, device=g2.device)
+            for r0 in range(0, rows, step):
+                r1 = min(rows, r0 + step)
+                _lib.call("dgfdn_irfft_window_bwd", plan.handle, _ptr(g2[r0:r1]), r1 - r0, _ptr(filt_), _ptr(scratch),
+                          _ptr(gx[r0:r1]), kx, kx, _stream())
+        return gx.reshape(*ctx.lead, kx), None, None
+
+
+def irfft_window(x: torch.Tensor, n: int, t0: int, tn: int, filt: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """torch.fft.irfft(filt * x, n)[..., t0:t0+tn] as float32, differentiable w.r.t. x (complex64 rows)."""
+    plan = get_czt_plan(n, t0, tn, x.device)
+    return _IrfftWindow.apply(x, plan, filt)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# K3b: energy decay curves and the dB loss
+# ----------------------------------------------------------------------------------------------------------
+def edc_db(h: torch.Tensor) -> torch.Tensor:
+    """10 log10(reverse-cumsum(h^2) + eps) clipped at -200 (reference losses.py:187-199 + utils.py:16-40). No grad."""
+    h_ = _cuda("h", h, torch.float32)
+    tn = h_.shape[-1]
+    h2 = h_.reshape(-1, tn)
+    out = torch.empty_like(h2)
+    with torch.cuda.device(h_.device):
+        _lib.call("dgfdn_edc_db", _ptr(h2), h2.shape[0], tn, _ptr(out), _stream())
+    return out.reshape(h_.shape)
+
+
+class _EDCLoss(torch.autograd.Function):
+    """sum_{r,t} mask[t] |target_db[r,t] - dB(EDC(h)[r,t])| as a float64 scalar."""
+
+    @staticmethod
+    def forward(ctx, h, target_db, mask):
+        h_ = _cuda("h", h, torch.float32)
+        t_ = _cuda("target_db", target_db, torch.float32)
+        m_ = _cuda("mask", mask, torch.float32, optional=True)
+        tn = h_.shape[-1]
+        h2 = h_.reshape(-1, tn)
+        t2 = t_.reshape(-1, tn)
+        if t2.shape != h2.shape or (m_ is not None and m_.numel() != tn):
+            raise RuntimeError("edc_loss: inconsistent shapes")
+        rows = h2.shape[0]
+        row_sum = torch.empty(rows, dtype=torch.float64, device=h_.device)
+        with torch.cuda.device(h_.device):
+            _lib.call("dgfdn_edc_loss_fwd", _ptr(h2), _ptr(t2), _ptr(m_), rows, tn, _ptr(row_sum), _stream())
+        ctx.save_for_backward(h2, t2, m_)
+        ctx.shape = h_.shape
+        return row_sum.sum()
+
+    @staticmethod
+    def backward(ctx, g):
+        h2, t2, m_ = ctx.saved_tensors
+        rows, tn = h2.shape
+        gh = torch.empty_like(h2)
+        with torch.cuda.device(h2.device):
+            # the upstream scalar is folded in afterwards to avoid a device->host sync here
+            _lib.call("dgfdn_edc_loss_bwd", _ptr(h2), _ptr(t2), _ptr(m_), rows, tn, 1.0, _ptr(gh), _stream())
+        return (gh * g.to(torch.float32)).reshape(ctx.shape), None, None
+
+
+def edc_abs_db_sum(h: torch.Tensor, target_db: torch.Tensor, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+    return _EDCLoss.apply(h, target_db, mask)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# colorless loss
+# ----------------------------------------------------------------------------------------------------------
+class _Colorless(torch.autograd.Function):
+    """loss[g] = mean_k (|H[k,g]| - 1)^p  (reference colorless_fdn/losses.py:20-73 with y_true = 1)."""
+
+    @staticmethod
+    def forward(ctx, h_sub, asym):
+        h_ = _cuda("h_sub", h_sub, C64)
+        k, g = h_.shape
+        loss = torch.empty(g, dtype=torch.float64, device=h_.device)
+        with torch.cuda.device(h_.device):
+            _lib.call("dgfdn_colorless_fwd", g, k, _ptr(h_), int(asym), _ptr(loss), _stream())
+        ctx.save_for_backward(h_)
+        ctx.asym = int(asym)
+        return loss
+
+    @staticmethod
+    def backward(ctx, gl):
+        (h_, ) = ctx.saved_tensors
+        k, g = h_.shape
+        coef = _cuda("coef", gl, torch.float64)
+        gh = torch.empty_like(h_)
+        with torch.cuda.device(h_.device):
+            _lib.call("dgfdn_colorless_bwd", g, k, _ptr(h_), ctx.asym, _ptr(coef), _ptr(gh), _stream())
+        return gh, None
+
+
+def colorless_loss_per_group(h_sub: torch.Tensor, asym: bool) -> torch.Tensor:
+    return _Colorless.apply(h_sub, asym)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# K6: renderer
+# ----------------------------------------------------------------------------------------------------------
+@torch.no_grad()
+def render_groups(delays: torch.Tensor, a: torch.Tensor, gamma: torch.Tensor, b: torch.Tensor, c: torch.Tensor,
+                  num_groups: int, num_samples: int, u: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Block-recursive FDN: returns q [bands, T, G] float32 (group signals, weighted by c). Inputs have a leading
+    band axis: delays [bands,N] int32, a [bands,N,N], gamma/b/c [bands,N]."""
+    a_ = _cuda("a", a, torch.float32)
+    bands, n, _ = a_.shape
+    delays_ = _cuda("delays", delays.reshape(bands, n), torch.int32)
+    gamma_ = _cuda("gamma", gamma.reshape(bands, n), torch.float32)
+    b_ = _cuda("b", b.reshape(bands, n), torch.float32)
+    c_ = _cuda("c", c.reshape(bands, n), torch.float32)
+    u_ = _cuda("u", u, torch.float32, optional=True)
+    if u_ is not None and u_.numel() < num_samples:
+        raise RuntimeError("render_groups: input signal shorter than num_samples")
+    hist = torch.empty(bands, num_samples, n, dtype=torch.float32, device=a_.device)
+    q = torch.empty(bands, num_samples, num_groups, dtype=torch.float32, device=a_.device)
+    with torch.cuda.device(a_.device):
+        _lib.call("dgfdn_render_groups", bands, n, num_groups, num_samples, _ptr(delays_), _ptr(a_), _ptr(gamma_),
+                  _ptr(b_), _ptr(c_), _ptr(u_), _ptr(hist), _ptr(q), _stream())
+    return q
+
+
+@torch.no_grad()
+def render_mix(s: torch.Tensor, traj: torch.Tensor, q: torch.Tensor, hop: int) -> torch.Tensor:
+    """out[r,t] = sum_band sum_g s[band, traj[r, t//hop], g] q[band,t,g]; s [bands,P,G], traj [R, ceil(T/hop)] int32."""
+    s_ = _cuda("s", s, torch.float32)
+    q_ = _cuda("q", q, torch.float32)
+    traj_ = _cuda("traj", traj, torch.int32)
+    bands, t, g = q_.shape
+    positions = s_.shape[1]
+    listeners = traj_.shape[0]
+    nhops = (t + hop - 1) // hop
+    if traj_.shape[1] != nhops or s_.shape[0] != bands or s_.shape[2] != g:
+        raise RuntimeError("render_mix: inconsistent shapes")
+    out = torch.empty(listeners, t, dtype=torch.float32, device=q_.device)
+    with torch.cuda.device(q_.device):
+        for r0 in range(0, listeners, 32768):
+            r1 = min(listeners, r0 + 32768)
+            _lib.call("dgfdn_render_mix", bands, g, t, r1 - r0, positions, hop, _ptr(s_), _ptr(traj_[r0:r1]), _ptr(q_),
+                      _ptr(out[r0:r1]), _stream())
+    return out
+
+
+def is_finite_scalar(x: float) -> bool:
+    return not (math.isnan(x) or math.isinf(x))

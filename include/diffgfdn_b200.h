@@ -1,0 +1,162 @@
+/*
+ * diffgfdn_b200 -- C ABI of the B200 (sm_100a) kernels for the DiffGFDN hot path.
+ *
+ * The reference (orchidas/DiffGFDN) is pure PyTorch: it has no FFI of its own. The entry points below
+ * are what a binding for its hot path would call; each one names the reference code it replaces
+ * (paths relative to /root/reference/src). INTEGRATION.md shows the ctypes stub on the reference side.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer on the current CUDA device unless its name ends in _host;
+ *   - complex64  = interleaved (re, im) float  pairs (torch.complex64 layout), "c64" below;
+ *   - complex128 = interleaved (re, im) double pairs (torch.complex128 layout), "c128";
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises
+ *     except the *_host entry points and plan creation;
+ *   - every function returns 0 on success, non-zero on error; dgfdn_last_error() returns the message
+ *     of the last failure on the calling thread. There is no CPU fallback anywhere.
+ *   - complex gradients follow the torch convention: g = dL/dRe + i dL/dIm.
+ */
+#ifndef DIFFGFDN_B200_H
+#define DIFFGFDN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define DGFDN_API __attribute__((visibility("default")))
+#else
+#define DGFDN_API
+#endif
+
+#define DGFDN_MAX_LINES 32  /* N: delay lines handled by one warp */
+#define DGFDN_MAX_GROUPS 8  /* G */
+
+DGFDN_API const char* dgfdn_last_error(void);
+DGFDN_API int dgfdn_version(void);
+/* number of SMs of the current device (grid sizing on the host side) */
+DGFDN_API int dgfdn_sm_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * K1: per-bin build + solve.   Replaces FeedbackLoop.forward (diff_gfdn/feedback_loop.py:326-391),
+ * the two einsums of DiffGFDNVarReceiverPos.forward (model.py:615-619) up to the receiver gains,
+ * the state of DiffDirectionalFDNVarReceiverPos.forward (model.py:1083, transpose_a = 1) and
+ * DiffGFDN.sub_fdn_output (model.py:209-252, with A = blockdiag(M_raw), gamma = NULL).
+ *
+ *   M_k = diag(z_k^{m_i} / gamma_i) - A            (transpose_a: - A^T)
+ *   x_k = M_k^{-1} b                               complex LU with partial pivoting, float64
+ *   y[k,g] = sum_{n in group g} c_n x_k[n]
+ *
+ * z       [K]    c128 sample points (dataloader.py:552-566)
+ * delays  [N]    int32
+ * a       [N,N]  float32 row-major
+ * gamma   [N]    float32 or NULL (= 1);  gamma_z [N,K] c64 or NULL (per-bin filter response, overrides gamma)
+ * b, c    [N]    float32
+ * x       [K,N]  c64 out (may be NULL)     y [K,G] c64 out (may be NULL)
+ */
+DGFDN_API int dgfdn_solve_fwd(int n, int g, int64_t k, const void* z, const int32_t* delays, const float* a,
+                    int transpose_a, const float* gamma, const void* gamma_z, const float* b, const float* c,
+                    void* x, void* y, void* stream);
+
+/* Adjoint of dgfdn_solve_fwd (replaces autograd through torch.linalg.inv + einsum, trainer.py:473-474).
+ *   lambda_k = M_k^{-H} (c o gy[k, g(.)] + gx[k, .])
+ *   ga  = Re sum_k lambda_k x_k^H (transposed back if transpose_a),  gb = Re sum_k lambda_k,
+ *   gc_n = Re sum_k conj(x_k[n]) gy[k,g(n)],   ginvgamma_i = -Re sum_k conj(z_k^{m_i}) lambda_k[i] conj(x_k[i])
+ * x [K,N] c64 is the state saved by the forward call; gy [K,G] c64 and gx [K,N] c64 may be NULL (not both).
+ * Outputs are float64: ga [N,N], gb [N], gc [N], ginvgamma [N] (gradient w.r.t. 1/gamma_i; ignored if NULL).
+ * ws: scratch of dgfdn_solve_bwd_ws_bytes(n) bytes. Reduction order is fixed (deterministic).
+ */
+DGFDN_API int64_t dgfdn_solve_bwd_ws_bytes(int n);
+DGFDN_API int dgfdn_solve_bwd(int n, int g, int64_t k, const void* z, const int32_t* delays, const float* a,
+                    int transpose_a, const float* gamma, const void* gamma_z, const float* c, const void* x,
+                    const void* gy, const void* gx, double* ga, double* gb, double* gc, double* ginvgamma,
+                    void* ws, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K2: receiver projection.  Replaces the (B,N,K) expansion + einsums of model.py:583-619.
+ *   H[r,k] = sum_g s[r,g] y[k,g] + d[r,k]
+ * s [R,G] float32, y [K,G] c64, d [R,K] c64 or NULL, h [R,K] c64 out (row stride ldh elements).
+ */
+DGFDN_API int dgfdn_project_fwd(int g, int64_t rows, int64_t k, const float* s, const void* y, const void* d, int64_t ldd,
+                      void* h, int64_t ldh, void* stream);
+/* Adjoint:  gy[k,g] (+)= sum_r s[r,g] gh[r,k] ;  gs[r,g] = Re sum_k conj(y[k,g]) gh[r,k].
+ * accumulate_gy != 0 adds into gy (receiver tiles processed one after another). gs/gy may be NULL. */
+DGFDN_API int dgfdn_project_bwd(int g, int64_t rows, int64_t k, const float* s, const void* y, const void* gh, int64_t ldh,
+                      void* gy, int accumulate_gy, float* gs, void* stream);
+
+/* Directional (SH) projection, model.py:1056-1088:
+ *   H_sh[r,l,k] = sum_g cw[r,g,l] x[k, g L + l]          cw = w o c  [R,G,L] float32, x [K,N] c64
+ * adjoint: gcw[r,g,l] = Re sum_k conj(x[k,gL+l]) gh[r,l,k] ; gx[k,gL+l] (+)= sum_r cw[r,g,l] gh[r,l,k] */
+DGFDN_API int dgfdn_project_sh_fwd(int g, int l, int64_t rows, int64_t k, const float* cw, const void* x, void* h_sh,
+                         void* stream);
+DGFDN_API int dgfdn_project_sh_bwd(int g, int l, int64_t rows, int64_t k, const float* cw, const void* x, const void* gh,
+                         void* gx, int accumulate_gx, float* gcw, void* stream);
+
+/* Channel mix, trainer.py:853-865 (SH -> directions):  out[r,j,k] = sum_l w[j,l] in[r,l,k].
+ * The adjoint is the same call with w transposed. w [cout,cin] float32 row-major, in/out c64. */
+DGFDN_API int dgfdn_mix_channels(int cin, int cout, int64_t rows, int64_t k, const float* w, const void* in, void* out,
+                       void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K3a: real inverse DFT of arbitrary length n on a time window, as a chirp-z transform over
+ * power-of-two cuFFT C2C passes.  Replaces torch.fft.irfft(X, n)[..., t0:t0+tn] at losses.py:207-213
+ * (n = K, quirk Q3), :344-346 (n = 2(K-1)) and :442-445, and utils.py:169.
+ *   out[r,t] = (1/n) Re sum_{k=0}^{n/2} w_k filt[k] X[r,k] e^{+2 pi i k (t0+t)/n},  w = 1 (DC, Nyquist) or 2
+ * Only bins 0..n/2 of each row are read; Im of DC (and Nyquist for even n) is ignored, as pocketfft/cuFFT C2R do.
+ */
+typedef struct dgfdn_czt_plan dgfdn_czt_plan;
+DGFDN_API int dgfdn_czt_plan_create(int64_t n, int64_t t0, int64_t tn, dgfdn_czt_plan** plan);
+DGFDN_API int dgfdn_czt_plan_destroy(dgfdn_czt_plan* plan);
+/* length (complex elements) of one scratch row; callers allocate rows * mc c64 of scratch */
+DGFDN_API int64_t dgfdn_czt_plan_mc(const dgfdn_czt_plan* plan);
+/* x [rows, ldx] c64 (>= n/2+1 valid bins per row); filt [n/2+1] c64 or NULL; scratch [rows, mc] c64;
+ * out [rows, tn] float32 */
+DGFDN_API int dgfdn_irfft_window_fwd(dgfdn_czt_plan* plan, const void* x, int64_t ldx, int64_t rows, const void* filt,
+                           void* scratch, float* out, void* stream);
+/* adjoint: gx[r,k] = conj(filt[k]) w_k/n sum_t gout[r,t] e^{-2 pi i k (t0+t)/n} for k <= n/2 (imag zeroed at DC /
+ * Nyquist), zero for n/2 < k < kx. gx [rows, ldx] c64 with kx columns written per row. */
+DGFDN_API int dgfdn_irfft_window_bwd(dgfdn_czt_plan* plan, const float* gout, int64_t rows, const void* filt, void* scratch,
+                           void* gx, int64_t ldx, int64_t kx, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K3b: Schroeder energy-decay curve + dB loss.  Replaces schroeder_backward_integral + db + mean|.|
+ * (losses.py:187-199, 217-238; utils.py:16-40) and losses.py:349-369.
+ *   EDC[r,t] = sum_{tau>=t} h[r,tau]^2 ;  dB = max(10 log10(EDC + eps_f32), -200)
+ */
+/* curve_db [rows, tn] float32 out */
+DGFDN_API int dgfdn_edc_db(const float* h, int64_t rows, int64_t tn, float* curve_db, void* stream);
+/* row_sum[r] = sum_t mask[t] | target_db[r,t] - dB(EDC[r,t]) |  (float64; mask [tn] float32 or NULL = all ones) */
+DGFDN_API int dgfdn_edc_loss_fwd(const float* h, const float* target_db, const float* mask, int64_t rows, int64_t tn,
+                       double* row_sum, void* stream);
+/* gh[r,t] = coef * d(sum_r row_sum[r]) / d h[r,t]   (gh [rows, tn] float32 out) */
+DGFDN_API int dgfdn_edc_loss_bwd(const float* h, const float* target_db, const float* mask, int64_t rows, int64_t tn,
+                       double coef, float* gh, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Colorless (spectral flatness) loss of the lossless sub-FDNs, colorless_fdn/losses.py:20-73 with
+ * y_true = 1:   loss[g] = mean_k (|H[k,g]| - 1)^p ,  p = 2, or 4 where |H|-1 > 1 when asym != 0.
+ * h_sub [K,G] c64; loss [G] float64 out. bwd: gh[k,g] = coef[g] * dloss[g]/dH[k,g]  (c64 out). */
+DGFDN_API int dgfdn_colorless_fwd(int g, int64_t k, const void* h_sub, int asym, double* loss, void* stream);
+DGFDN_API int dgfdn_colorless_bwd(int g, int64_t k, const void* h_sub, int asym, const double* coef, void* gh, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K6: block-recursive time-domain renderer (no reference implementation exists; ground truth is
+ * irfft(H), utils.py:169, and the band sum of run_subband_training_treble.py:316-358).
+ *   x_i[t] = gamma_i ( sum_j A_ij x_j[t - m_i] + b_i u[t - m_i] ),   q[band, t, g] = sum_{i in g} c_i x_i[t]
+ * One CTA per band advances min(m) samples per step with the state history in shared/global memory.
+ * a [bands,N,N], gamma/b/c [bands,N] float32, delays [bands,N] int32, u [T] float32 (NULL = unit impulse),
+ * hist: scratch [bands, T, N] float32, q [bands, T, G] float32 out.
+ */
+DGFDN_API int dgfdn_render_groups(int bands, int n, int g, int64_t t, const int32_t* delays, const float* a,
+                        const float* gamma, const float* b, const float* c, const float* u, float* hist, float* q,
+                        void* stream);
+/* listener mix: out[r,t] = sum_band sum_g s[band, pos(r,t), g] q[band,t,g]; pos = traj[r, t / hop] indexes the
+ * receiver-gain table s [bands, P, G]; traj [R, ceil(T/hop)] int32; out [R,T] float32. */
+DGFDN_API int dgfdn_render_mix(int bands, int g, int64_t t, int64_t listeners, int64_t positions, int64_t hop,
+                     const float* s, const int32_t* traj, const float* q, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIFFGFDN_B200_H */

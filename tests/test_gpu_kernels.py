@@ -1,0 +1,271 @@
+"""GPU parity tests of every C-ABI kernel against the CPU oracle (oracle/gfdn_oracle.py) on seeded inputs.
+
+Tolerances are the ones BASELINE.json states: |H| 1e-4 relative, EDC 0.01 dB, gradients 1e-3 relative,
+rendered samples 1e-5 of peak. All calls go through the C ABI (ctypes) via diffgfdn_b200.ops."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import gfdn_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+F64 = torch.float64
+
+
+def rel(a, b):
+    a = torch.as_tensor(a).detach().cpu()
+    b = torch.as_tensor(b).detach().cpu()
+    return float((a - b).abs().max() / b.abs().max())
+
+
+def make_system(n, g, nfft, seed, t60=(0.3, 0.8, 1.5), fs=32000.0, radius=1.0):
+    gen = torch.Generator().manual_seed(seed)
+    l = n // g
+    rng = np.random.default_rng(seed)
+    primes = [p for p in range(641, 1700) if all(p % q for q in range(2, int(p**0.5) + 1))]
+    delays = torch.tensor(rng.choice(primes, n, replace=False), dtype=torch.int32)
+    m_raw = ((2 * torch.rand(g, l, l, generator=gen) - 1) / np.sqrt(l)).to(torch.float32)
+    alpha = (np.pi / 4 * torch.rand(g * (g - 1) // 2, generator=gen)).to(torch.float32)
+    a = O.coupled_feedback_matrix(m_raw.to(F64), alpha.to(F64)).to(torch.float32)
+    gamma = O.decay_times_to_gain_per_sample(t60[:g], delays.tolist(), fs, g).to(torch.float32)
+    b = ((2 * torch.randn(n, generator=gen) - 1) / n).to(torch.float32)
+    c = ((2 * torch.randn(n, generator=gen) - 1) / n).to(torch.float32)
+    z = O.z_grid(nfft, radius)
+    return dict(n=n, g=g, l=l, delays=delays, m_raw=m_raw, alpha=alpha, a=a, gamma=gamma, b=b, c=c, z=z)
+
+
+def dev(t):
+    return t.cuda()
+
+
+@pytest.mark.parametrize("n,g,transpose", [(12, 3, False), (24, 3, False), (27, 3, True), (6, 2, False), (32, 4, False)])
+def test_solve_forward(n, g, transpose):
+    from diffgfdn_b200 import ops
+    sy = make_system(n, g, 2048, seed=n)
+    x, y = ops.gfdn_solve(dev(sy["z"]), dev(sy["delays"]), dev(sy["a"]), dev(sy["gamma"]), dev(sy["b"]), dev(sy["c"]),
+                          g, transpose_a=transpose)
+    p = O.feedback_loop_inverse(sy["z"], sy["delays"].to(F64), sy["gamma"].to(F64), sy["a"].to(F64))
+    if transpose:
+        xo = torch.einsum('knm,n->km', p, sy["b"].to(torch.complex128))
+    else:
+        xo = torch.einsum('knm,m->kn', p, sy["b"].to(torch.complex128))
+    yo = (xo * sy["c"].to(torch.complex128)).reshape(-1, g, n // g).sum(-1)
+    assert rel(x.cpu().to(torch.complex128), xo) < 2e-6
+    assert rel(y.cpu().to(torch.complex128), yo) < 2e-6
+
+
+def test_solve_forward_colorless_and_filter_absorption():
+    from diffgfdn_b200 import ops
+    sy = make_system(12, 3, 1024, seed=5)
+    # colorless sub-FDNs: A = blockdiag(M_raw), no absorption (reference model.py:209-252)
+    a_sub = torch.block_diag(*[sy["m_raw"][i] for i in range(3)])
+    xs, hs = ops.gfdn_solve(dev(sy["z"]), dev(sy["delays"]), dev(a_sub), None, dev(sy["b"]), dev(sy["c"]), 3)
+    ho, hpo = O.sub_fdn_output(sy["z"], sy["delays"].to(F64), sy["m_raw"].to(F64), sy["b"].to(F64), sy["c"].to(F64))
+    assert rel(hs.cpu().to(torch.complex128), ho) < 2e-6
+    # per-bin complex absorption Gamma_i(z_k) (reference feedback_loop.py:333-344, 378-381)
+    gen = torch.Generator().manual_seed(1)
+    k = sy["z"].numel()
+    gz = (0.5 + 0.4 * torch.rand(12, k, generator=gen)) * torch.exp(1j * 0.3 * torch.randn(12, k, generator=gen))
+    gz = gz.to(torch.complex64)
+    x, y = ops.gfdn_solve(dev(sy["z"]), dev(sy["delays"]), dev(sy["a"]), None, dev(sy["b"]), dev(sy["c"]), 3,
+                          gamma_z=dev(gz))
+    p = O.feedback_loop_inverse(sy["z"], sy["delays"].to(F64), gz.to(torch.complex128), sy["a"].to(F64))
+    xo = torch.einsum('knm,m->kn', p, sy["b"].to(torch.complex128))
+    assert rel(x.cpu().to(torch.complex128), xo) < 2e-6
+
+
+@pytest.mark.parametrize("n,g,transpose,radius", [(12, 3, False, 1.0), (24, 3, False, 1.00002), (27, 3, True, 1.0)])
+def test_solve_backward(n, g, transpose, radius):
+    from diffgfdn_b200 import ops
+    sy = make_system(n, g, 1024, seed=100 + n, radius=radius)
+    k = sy["z"].numel()
+    gen = torch.Generator().manual_seed(7)
+    wy = torch.randn(k, g, dtype=torch.complex128, generator=gen)
+    wx = torch.randn(k, n, dtype=torch.complex128, generator=gen)
+    # oracle (float64 autograd)
+    a = sy["a"].to(F64).requires_grad_(True)
+    gam = sy["gamma"].to(F64).requires_grad_(True)
+    b = sy["b"].to(F64).requires_grad_(True)
+    c = sy["c"].to(F64).requires_grad_(True)
+    p = O.feedback_loop_inverse(sy["z"], sy["delays"].to(F64), gam, a)
+    xo = torch.einsum('knm,n->km' if transpose else 'knm,m->kn', p, b.to(torch.complex128))
+    yo = (xo * c.to(torch.complex128)).reshape(-1, g, n // g).sum(-1)
+    lo = (yo * wy.conj()).real.sum() + (xo * wx.conj()).real.sum()
+    lo.backward()
+    # kernels
+    ad, gd, bd, cd = [dev(t).requires_grad_(True) for t in (sy["a"], sy["gamma"], sy["b"], sy["c"])]
+    x, y = ops.gfdn_solve(dev(sy["z"]), dev(sy["delays"]), ad, gd, bd, cd, g, transpose_a=transpose)
+    lk = (y.to(torch.complex128) * dev(wy).conj()).real.sum() + (x.to(torch.complex128) * dev(wx).conj()).real.sum()
+    lk.backward()
+    assert abs(float(lk) - float(lo)) < 1e-5 * abs(float(lo)) + 1e-6
+    assert rel(ad.grad, a.grad) < 1e-3
+    assert rel(gd.grad, gam.grad) < 1e-3
+    assert rel(bd.grad, b.grad) < 1e-3
+    assert rel(cd.grad, c.grad) < 1e-3
+
+
+@pytest.mark.parametrize("rows,k,g,with_d", [(5, 1025, 3, True), (17, 4097, 3, False), (3, 514, 1, True), (9, 333, 8, True)])
+def test_receiver_projection_forward_backward(rows, k, g, with_d):
+    from diffgfdn_b200 import ops
+    gen = torch.Generator().manual_seed(rows)
+    s = torch.randn(rows, g, generator=gen)
+    y = torch.randn(k, g, dtype=torch.complex64, generator=gen)
+    d = torch.randn(rows, k, dtype=torch.complex64, generator=gen) if with_d else None
+    w = torch.randn(rows, k, dtype=torch.complex128, generator=gen)
+    so = s.to(F64).requires_grad_(True)
+    yo = y.to(torch.complex128).requires_grad_(True)
+    ho = torch.einsum('rg,kg->rk', so.to(torch.complex128), yo) + (d.to(torch.complex128) if with_d else 0)
+    (ho * w.conj()).real.sum().backward()
+    sd = dev(s).requires_grad_(True)
+    yd = dev(y).requires_grad_(True)
+    h = ops.receiver_project(sd, yd, dev(d) if with_d else None)
+    (h.to(torch.complex128) * dev(w).conj()).real.sum().backward()
+    assert rel(h.cpu().to(torch.complex128), ho) < 1e-5
+    assert rel(sd.grad, so.grad) < 1e-4
+    assert rel(yd.grad.cpu().to(torch.complex128), yo.grad) < 1e-4
+
+
+def test_sh_projection_and_channel_mix():
+    from diffgfdn_b200 import ops
+    gen = torch.Generator().manual_seed(3)
+    rows, g, l, k, j = 4, 3, 9, 1025, 12
+    cw = torch.randn(rows, g, l, generator=gen)
+    x = torch.randn(k, g * l, dtype=torch.complex64, generator=gen)
+    ymat = torch.randn(j, l, generator=gen) / 3
+    w = torch.randn(rows, j, k, dtype=torch.complex128, generator=gen)
+    cwo = cw.to(F64).requires_grad_(True)
+    xo = x.to(torch.complex128).requires_grad_(True)
+    hsh = torch.einsum('rgl,kgl->rlk', cwo.to(torch.complex128), xo.reshape(k, g, l))
+    hdir = O.sh_to_directional(hsh, ymat.to(F64))
+    (hdir * w.conj()).real.sum().backward()
+    cwd = dev(cw).requires_grad_(True)
+    xd = dev(x).requires_grad_(True)
+    hk = ops.sh_project(cwd, xd)
+    hd = ops.mix_channels(dev(ymat), hk)
+    (hd.to(torch.complex128) * dev(w).conj()).real.sum().backward()
+    assert rel(hk.cpu().to(torch.complex128), hsh) < 1e-5
+    assert rel(hd.cpu().to(torch.complex128), hdir) < 1e-5
+    assert rel(cwd.grad, cwo.grad) < 1e-4
+    assert rel(xd.grad.cpu().to(torch.complex128), xo.grad) < 1e-4
+
+
+@pytest.mark.parametrize("kx,n,t0,tn", [(1025, 1025, 640, 300), (4097, 4097, 640, 3200), (1025, 2048, 0, 2048),
+                                         (1025, 2048, 640, 1000), (2050, 2050, 10, 2040), (65, 64, 0, 64)])
+def test_irfft_window_matches_pocketfft(kx, n, t0, tn):
+    """torch.fft.irfft(X, n)[t0:t0+tn] for odd n (quirk Q3), even n, and n = 2(K-1); plus the adjoint."""
+    from diffgfdn_b200 import ops
+    gen = torch.Generator().manual_seed(kx + n)
+    rows = 3
+    decay = torch.exp(-torch.arange(kx) / (kx / 3.0))
+    x = (torch.randn(rows, kx, dtype=torch.complex64, generator=gen) * decay).to(torch.complex64)
+    filt = torch.randn(kx, dtype=torch.complex64, generator=gen)
+    w = torch.randn(rows, tn, dtype=F64, generator=gen)
+    for f in (None, filt):
+        xo = x.to(torch.complex128).requires_grad_(True)
+        xin = xo if f is None else xo * f.to(torch.complex128)
+        ho = torch.fft.irfft(xin, n)[..., t0:t0 + tn]
+        (ho * w).sum().backward()
+        xd = dev(x).requires_grad_(True)
+        hk = ops.irfft_window(xd, n, t0, tn, None if f is None else dev(f))
+        (hk.to(F64) * dev(w)).sum().backward()
+        assert rel(hk.cpu().to(F64), ho) < 2e-5
+        assert rel(xd.grad.cpu().to(torch.complex128), xo.grad) < 2e-5
+
+
+def test_irfft_window_large_prime_length():
+    """K = 65537 (prime), the reference's full-band case: irfft(H, n=K)[640:48000]."""
+    from diffgfdn_b200 import ops
+    k = 65537
+    gen = torch.Generator().manual_seed(0)
+    env = torch.exp(-torch.arange(k) / 9000.0)
+    x = (torch.randn(2, k, dtype=torch.complex64, generator=gen) * env).to(torch.complex64)
+    ho = torch.fft.irfft(x.to(torch.complex128), k)[..., 640:48000]
+    hk = ops.irfft_window(dev(x), k, 640, 48000 - 640)
+    assert rel(hk.cpu().to(F64), ho) < 2e-5
+
+
+@pytest.mark.parametrize("rows,tn,masked", [(3, 300, False), (4, 5000, True), (2, 47360, False), (1, 4096, True)])
+def test_edc_loss_forward_backward(rows, tn, masked):
+    from diffgfdn_b200 import ops
+    gen = torch.Generator().manual_seed(tn)
+    t = torch.arange(tn, dtype=F64)
+    h = (torch.randn(rows, tn, dtype=F64, generator=gen) * torch.exp(-t / (tn / 6.0)) * 0.3).to(torch.float32)
+    ht = torch.randn(rows, tn, dtype=F64, generator=gen) * torch.exp(-t / (tn / 5.0)) * 0.3
+    tdb = O.db(O.schroeder(ht), is_squared=True)
+    mask = (torch.rand(tn, generator=gen) > 0.5).to(torch.float32) if masked else None
+    ho = h.to(F64).requires_grad_(True)
+    adb = O.db(O.schroeder(ho), is_squared=True)
+    diff = (tdb - adb).abs()
+    lo = (diff * mask.to(F64)).sum() if masked else diff.sum()
+    (lo * 0.37).backward()
+    curve = ops.edc_db(dev(h))
+    assert float((curve.cpu().to(F64) - adb.detach()).abs().max()) < 1e-3  # dB
+    hd = dev(h).requires_grad_(True)
+    lk = ops.edc_abs_db_sum(hd, dev(tdb.to(torch.float32)), None if mask is None else dev(mask))
+    (lk * 0.37).backward()
+    assert abs(float(lk) - float(lo)) < 1e-5 * float(lo)
+    assert rel(hd.grad, ho.grad) < 1e-3
+
+
+@pytest.mark.parametrize("asym", [False, True])
+def test_colorless_loss(asym):
+    from diffgfdn_b200 import ops
+    gen = torch.Generator().manual_seed(2)
+    k, g = 4097, 3
+    hs = (torch.randn(k, g, dtype=torch.complex64, generator=gen) * 1.5)
+    ho = hs.to(torch.complex128).requires_grad_(True)
+    lo = torch.stack([O.amse_loss(ho[:, i]) if asym else O.mse_loss(ho[:, i]) for i in range(g)])
+    wts = torch.tensor([1.0, 0.5, 2.0], dtype=F64)
+    (lo * wts).sum().backward()
+    hd = dev(hs).requires_grad_(True)
+    lk = ops.colorless_loss_per_group(hd, asym)
+    (lk * dev(wts)).sum().backward()
+    assert rel(lk, lo) < 1e-5
+    assert rel(hd.grad.cpu().to(torch.complex128), ho.grad) < 1e-4
+
+
+def test_renderer_matches_time_domain_recursion_and_irfft():
+    from diffgfdn_b200 import ops
+    fs = 8000.0
+    delays = [67, 71, 89, 97, 101, 113]
+    g = 3
+    gen = torch.Generator().manual_seed(3)
+    bands = 2
+    a, gam, b, c = [], [], [], []
+    for bd in range(bands):
+        m_raw = (2 * torch.rand(g, 2, 2, dtype=F64, generator=gen) - 1) / np.sqrt(2)
+        a.append(O.coupled_feedback_matrix(m_raw, torch.tensor([0.3, 0.2, 0.5], dtype=F64)))
+        gam.append(O.decay_times_to_gain_per_sample([0.02, 0.03, 0.04], delays, fs, g))
+        b.append(torch.randn(6, dtype=F64, generator=gen))
+        c.append(torch.randn(6, dtype=F64, generator=gen))
+    t = 4096
+    dl = torch.tensor([delays] * bands, dtype=torch.int32)
+    q = ops.render_groups(dev(dl), dev(torch.stack(a).float()), dev(torch.stack(gam).float()),
+                          dev(torch.stack(b).float()), dev(torch.stack(c).float()), g, t)
+    for bd in range(bands):
+        qo = O.fdn_time_domain(delays, gam[bd], a[bd], b[bd], c[bd], t).reshape(t, g, 2).sum(-1)
+        assert float((q[bd].cpu().to(F64) - qo).abs().max() / qo.abs().max()) < 1e-5
+    # moving listeners: gains switch every hop samples (sound_examples.py:87 uses 100 ms hops)
+    hop, listeners, positions = 512, 5, 7
+    s = torch.rand(bands, positions, g, generator=gen)
+    traj = torch.randint(0, positions, (listeners, (t + hop - 1) // hop), generator=gen, dtype=torch.int32)
+    out = ops.render_mix(dev(s), dev(traj), q, hop)
+    qc = q.cpu().to(F64)
+    ref = torch.zeros(listeners, t, dtype=F64)
+    for r in range(listeners):
+        for hb in range(traj.shape[1]):
+            sl = slice(hb * hop, min(t, (hb + 1) * hop))
+            ref[r, sl] = torch.einsum('bg,btg->t', s[:, traj[r, hb]].to(F64), qc[:, sl])
+    assert float((out.cpu().to(F64) - ref).abs().max() / ref.abs().max()) < 1e-5
+    # static listener == irfft(H) of the frequency-sampled model (nfft >= tail length)
+    H = O.omni_response(O.z_grid(t), torch.tensor(delays, dtype=F64), gam[0], a[0], b[0], c[0], s[0, :1].to(F64))
+    h = O.impulse_response(H)[0]
+    hr = torch.einsum('g,tg->t', s[0, 0].to(F64), qc[0])
+    assert float((hr - h).abs().max() / h.abs().max()) < 1e-5
+
+
+def test_no_cpu_fallback():
+    from diffgfdn_b200 import ops
+    with pytest.raises(RuntimeError):
+        ops.receiver_project(torch.zeros(2, 3), torch.zeros(8, 3, dtype=torch.complex64), None)
