@@ -40,9 +40,10 @@ struct SolveParams {
 
 // shared-memory carve-up (doubles). Block-wide: A (n*n), invgamma (n), b (n), c (n), delays as double (n).
 // Per warp: mat (2*n*n), rhs (2*n), xs (2*n), lam (2*n), acc (n*n, backward only).
-__host__ __device__ inline size_t block_doubles(int n) { return (size_t)n * n + 4 * (size_t)n; }
+// Both sizes are rounded up to an even count so that every double2 array stays 16-byte aligned for odd n.
+__host__ __device__ inline size_t block_doubles(int n) { return ((size_t)n * n + 4 * (size_t)n + 1) & ~(size_t)1; }
 __host__ __device__ inline size_t warp_doubles(int n, bool bwd) {
-  return 2 * (size_t)n * n + 6 * (size_t)n + (bwd ? (size_t)n * n : 0);
+  return (2 * (size_t)n * n + 6 * (size_t)n + (bwd ? (size_t)n * n : 0) + 1) & ~(size_t)1;
 }
 
 // z^m * invgamma for this lane's delay line, float64. Also returns z^m alone through zm.

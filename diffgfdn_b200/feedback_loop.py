@@ -1,0 +1,197 @@
+"""Feedback loop of the Grouped FDN: orthogonal coupled feedback matrix + the per-bin solve.
+
+Mirrors reference diff_gfdn/feedback_loop.py (class and parameter names, state_dict keys `M`, `alpha`). The
+parameter pre-processing (matrix exponential, Givens rotations, Kronecker mask) is O(N^2) and stays in PyTorch on
+the device, differentiable for free; the O(K N^3) part -- the reference's `torch.linalg.inv` over K dense matrices
+(feedback_loop.py:391) -- is the sm_100a kernel behind `ops.gfdn_solve`."""
+from typing import List, Optional
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import ops
+from .absorption_filters import decay_times_to_gain_per_sample
+from .config.config import CouplingMatrixType
+
+
+class Skew(nn.Module):
+
+    def forward(self, X: torch.Tensor) -> torch.Tensor:
+        A = X.triu(1)
+        return A - A.transpose(-1, -2)
+
+
+class MatrixExponential(nn.Module):
+
+    def forward(self, X: torch.Tensor) -> torch.Tensor:
+        return torch.matrix_exp(X)
+
+
+class ND_Unitary(nn.Module):
+    """N-D rotation from N(N-1)/2 Givens angles: U_n = R_{n-2}...R_0 [[U_{n-1},0],[0,1]] with R_i rotating the
+    (i, n-1) plane (reference feedback_loop.py:39-87). Built without in-place writes, on alpha's device."""
+
+    @staticmethod
+    def _unit(n, r, c, like):
+        e = torch.zeros(n, n, dtype=like.dtype, device=like.device)
+        e[r, c] = 1.0
+        return e
+
+    def forward(self, alpha: torch.Tensor, N: int) -> torch.Tensor:
+        assert len(alpha) == N * (N - 1) // 2
+        if N == 1:
+            return torch.ones(1, 1, dtype=alpha.dtype, device=alpha.device)
+        start = (N - 1) * (N - 2) // 2
+        cur = alpha[start:]
+        eye = torch.eye(N, dtype=alpha.dtype, device=alpha.device)
+        rot = eye
+        for i in range(N - 1):
+            c, s = torch.cos(cur[i]), torch.sin(cur[i])
+            diag = self._unit(N, i, i, alpha) + self._unit(N, N - 1, N - 1, alpha)
+            r = eye - diag + c * diag - s * self._unit(N, i, N - 1, alpha) + s * self._unit(N, N - 1, i, alpha)
+            rot = r @ rot
+        big = nn.functional.pad(self.forward(alpha[:start], N - 1), (0, 1, 0, 1)) + self._unit(N, N - 1, N - 1, alpha)
+        return rot @ big
+
+
+class FeedbackLoop(nn.Module):
+
+    def __init__(self,
+                 sample_rate: float,
+                 num_groups: int,
+                 num_delay_lines_per_group: int,
+                 delays: torch.Tensor,
+                 use_absorption_filters: bool,
+                 coupling_matrix_type: CouplingMatrixType = None,
+                 use_zero_coupling: bool = True,
+                 coupling_matrix_order: Optional[int] = None,
+                 colorless_feedback_matrix: Optional[torch.Tensor] = None,
+                 gains: Optional[torch.Tensor] = None,
+                 common_decay_times: Optional[List] = None,
+                 device: torch.device = 'cpu'):
+        super().__init__()
+        self.sample_rate = sample_rate
+        self.num_groups = num_groups
+        self.num_delay_lines_per_group = num_delay_lines_per_group
+        self.delays = torch.as_tensor(delays, dtype=torch.float32, device=device)
+        self.num_delays = len(self.delays)
+        self.use_absorption_filters = use_absorption_filters
+        self.use_zero_coupling = use_zero_coupling
+        self.device = device
+        self.coupling_matrix_type = coupling_matrix_type or CouplingMatrixType.SCALAR
+        self.coupling_matrix_order = coupling_matrix_order
+        if self.coupling_matrix_type != CouplingMatrixType.SCALAR:
+            raise NotImplementedError("only the scalar (unitary) coupling matrix is on the B200 hot path; "
+                                      "no shipped config uses filter/random coupling (SURVEY.md a-5)")
+        self._init_absorption(gains, common_decay_times)
+        self._init_feedback_matrix(colorless_feedback_matrix)
+
+    # ---- absorption (reference feedback_loop.py:193-258) -------------------------------------------------
+    def _init_absorption(self, gains, common_decay_times):
+        self.delay_line_gain_response = None  # (N, K) complex per-bin response when filters are used
+        if gains is None:
+            if self.use_absorption_filters:
+                raise NotImplementedError("learnable absorption filters do not exist in the reference either")
+            if common_decay_times is None:
+                t60 = 0.1 + 1.9 * torch.rand(self.num_groups)
+            else:
+                t60 = torch.as_tensor(np.asarray(common_decay_times).squeeze(), dtype=torch.float32)
+            self.common_decay_times = nn.Parameter(t60.to(self.device))
+            per = self.num_delay_lines_per_group
+            # computed once at construction like the reference (quirk Q9: never refreshed)
+            self.delay_line_gains = torch.cat([
+                decay_times_to_gain_per_sample(self.common_decay_times[i], self.delays[i * per:(i + 1) * per],
+                                               torch.tensor(self.sample_rate)) for i in range(self.num_groups)
+            ]).detach().to(self.device)
+        else:
+            if self.use_absorption_filters:
+                raise NotImplementedError(
+                    "frequency-dependent absorption: pass the per-bin responses Gamma_i(z_k) with "
+                    "set_absorption_response((N, K) complex); SOS/GEQ design is init-time host code outside the "
+                    "hot path (SURVEY.md section 8f rank 3)")
+            self.delay_line_gains = torch.as_tensor(gains, dtype=torch.float32, device=self.device)
+
+    def set_absorption_response(self, gamma_z: torch.Tensor):
+        """Use per-bin complex delay-line gains Gamma_i(z_k), shape (N, K) (reference feedback_loop.py:333-344)."""
+        self.delay_line_gain_response = gamma_z.to(torch.complex64)
+
+    # ---- feedback matrix (reference feedback_loop.py:260-324) --------------------------------------------
+    def _init_feedback_matrix(self, colorless_feedback_matrix):
+        self.ortho_param = nn.Sequential(Skew(), MatrixExponential())
+        L = self.num_delay_lines_per_group
+        if colorless_feedback_matrix is not None:
+            self.M = colorless_feedback_matrix.clone().detach().to(self.device)
+        else:
+            self.M = nn.Parameter(((2 * torch.rand(self.num_groups, L, L) - 1) / np.sqrt(L)).to(self.device))
+        self.nd_unitary = ND_Unitary()
+        n_alpha = self.num_groups * (self.num_groups - 1) // 2
+        if self.use_zero_coupling:
+            self.register_buffer("alpha", torch.zeros(n_alpha, device=self.device))
+        else:
+            self.alpha = nn.Parameter((np.pi / 4 * torch.rand(n_alpha, dtype=torch.float32)).to(self.device))
+
+    def _apply(self, fn, *args, **kwargs):
+        super()._apply(fn, *args, **kwargs)
+        self.delays = fn(self.delays)
+        self.delay_line_gains = fn(self.delay_line_gains)
+        if not isinstance(self.M, nn.Parameter):
+            self.M = fn(self.M)
+        if self.delay_line_gain_response is not None:
+            self.delay_line_gain_response = fn(self.delay_line_gain_response)
+        return self
+
+    def construct_block_mixing_matrix(self) -> torch.Tensor:
+        """block_M[i,j] = U_i U_j with U = expm(skew(M)); diagonal blocks are U_i^2 (reference :393-404, Q4)."""
+        U = self.ortho_param(self.M)  # (G, L, L)
+        G, L, _ = U.shape
+        blocks = torch.einsum('iab,jbc->iajc', U, U)  # (G, L, G, L)
+        return blocks.reshape(G * L, G * L)
+
+    def construct_coupling_matrix(self) -> torch.Tensor:
+        alpha = self.alpha.clamp(min=-np.pi, max=np.pi)
+        return self.nd_unitary(alpha, self.num_groups)
+
+    def coupled_feedback_matrix_real(self) -> torch.Tensor:
+        """A = block_M o (Phi (x) 1_{LxL}), real (N, N) float32 (reference :424-455 before to_complex)."""
+        block_M = self.construct_block_mixing_matrix()
+        self.phi = self.construct_coupling_matrix()
+        L = self.num_delay_lines_per_group
+        return block_M * torch.kron(self.phi, torch.ones(L, L, dtype=block_M.dtype, device=block_M.device))
+
+    def get_coupled_feedback_matrix(self) -> torch.Tensor:
+        a = self.coupled_feedback_matrix_real()
+        return torch.complex(a, torch.zeros_like(a))
+
+    def solve(self, z: torch.Tensor, b: torch.Tensor, c: torch.Tensor, transpose: bool = False):
+        """x_k = (D(z_k) Gamma^-1 - A)^-1 b and y[k,g] = sum_{n in g} c_n x_k[n] on the GPU (one warp per bin)."""
+        a = self.coupled_feedback_matrix_real()
+        self.coupled_feedback_matrix = a
+        gamma = None if self.delay_line_gain_response is not None else self.delay_line_gains
+        return ops.gfdn_solve(z, self.delays.to(torch.int32), a, gamma, b, c, self.num_groups, transpose_a=transpose,
+                              gamma_z=self.delay_line_gain_response)
+
+    def forward(self, z: torch.Tensor) -> torch.Tensor:
+        """Dense P[k] = (D Gamma^-1 - A)^-1, (K, N, N) complex64 -- API compatibility with reference :326-391.
+        The models never call this (they solve against b directly); it runs N single-RHS solves."""
+        n = self.num_delays
+        eye = torch.eye(n, dtype=torch.float32, device=self.delays.device)
+        cols = [self.solve(z, eye[j], eye[j])[0] for j in range(n)]
+        return torch.stack(cols, dim=-1)
+
+    def get_parameters(self):
+        M = [self.ortho_param(self.M[i]) for i in range(self.num_groups)]
+        coupled = self.get_coupled_feedback_matrix()
+        return (M, self.phi, None, None, coupled, self.delay_line_gains)
+
+    @torch.no_grad()
+    def get_param_dict(self):
+        coupled = self.get_coupled_feedback_matrix()
+        d = {'delay_line_gains': self.delay_line_gains, 'coupling_matrix': self.phi.squeeze().cpu().numpy(),
+             'individual_mixing_matrix': self.M.squeeze().cpu().numpy(),
+             'coupled_feedback_matrix': coupled.squeeze().cpu().numpy()}
+        if hasattr(self, 'common_decay_times'):
+            d['common_decay_times'] = self.common_decay_times
+        if not self.use_zero_coupling:
+            d['coupling_coefficient'] = self.alpha.squeeze().cpu().numpy()
+        return d

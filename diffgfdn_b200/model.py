@@ -1,0 +1,281 @@
+"""Differentiable Grouped-FDN models with the reference's nn.Module surface, on B200 kernels.
+
+Class names, constructor signatures, `forward(x: dict)` contract, parameter/buffer names (state_dict keys) and
+helper methods follow reference diff_gfdn/model.py; the arithmetic is restructured:
+
+    reference: P_k = inv(D_k Gamma^-1 - A) for every bin, expand receiver gains to (B, N, K), two einsums
+               -> O(B K N^2) work and several (B, N, K) complex temporaries (model.py:583-619)
+    here:      x_k = (D_k Gamma^-1 - A)^-1 b once per bin (b is shared by all receivers), fold c and the group
+               structure into y[k,g], then H[r,k] = sum_g s[r,g] y[k,g] + d[r,k] -- a length-G contraction
+               that streams at HBM bandwidth.
+
+Outputs are complex64 (the reference returns complex128 only because its `d` input is complex128, quirk Q6).
+Inputs that live on the host are copied to the module's device; the kernels themselves have no CPU path."""
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import ops
+from .absorption_filters import decay_times_to_gain_per_sample
+from .config.config import CouplingMatrixType, FeedbackLoopConfig, OutputFilterConfig
+from .feedback_loop import FeedbackLoop
+from .gain_filters import Gains_from_MLP
+from .sh_gains import Directional_Beamforming_Weights_from_MLP
+
+
+def _resolve_device(device) -> torch.device:
+    if device is None or str(device) in ("gpu", "cuda"):
+        return torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cuda")
+    return torch.device(device)
+
+
+class DiffGFDN(nn.Module):
+    """Parent module (reference model.py:24-299)."""
+
+    def __init__(self,
+                 sample_rate: int,
+                 num_groups: int,
+                 delays: List[int],
+                 device: torch.device,
+                 feedback_loop_config: FeedbackLoopConfig,
+                 use_absorption_filters: bool,
+                 learn_common_decay_times: bool,
+                 common_decay_times: Optional[List] = None,
+                 band_centre_hz: Optional[List] = None,
+                 colorless_fdn_params: Optional[List] = None,
+                 use_colorless_loss: bool = False):
+        super().__init__()
+        self.sample_rate = sample_rate
+        self.device = _resolve_device(device)
+        self.num_groups = num_groups
+        self.num_delay_lines = len(delays)
+        self.num_delay_lines_per_group = int(self.num_delay_lines / self.num_groups)
+        self.use_absorption_filters = use_absorption_filters
+        self.band_centre_hz = band_centre_hz
+        self.common_decay_times = common_decay_times
+        self.learn_common_decay_times = learn_common_decay_times
+        self.use_colorless_loss = use_colorless_loss
+        # whether forward() also builds the (N, K, G) per-delay-line tensor of reference model.py:243-246;
+        # nothing in the training path reads it, so the fused trainer switches it off
+        self.return_per_delay_outputs = True
+        self.delays = torch.tensor(delays, dtype=torch.float32, device=self.device)
+        self.register_buffer('delay_buffer', self.delays)
+        per = self.num_delay_lines_per_group
+        self.delays_by_group = [self.delays[i:i + per] for i in range(0, self.num_delay_lines, per)]
+        self._init_io_gains(colorless_fdn_params)
+        self._init_absorption(band_centre_hz)
+        self._init_feedback(feedback_loop_config, colorless_fdn_params)
+
+    def _apply(self, fn, *args, **kwargs):
+        super()._apply(fn, *args, **kwargs)
+        self.delays = self.delay_buffer
+        per = self.num_delay_lines_per_group
+        self.delays_by_group = [self.delays[i:i + per] for i in range(0, self.num_delay_lines, per)]
+        self.device = self.delay_buffer.device
+        return self
+
+    def _init_io_gains(self, colorless_fdn_params=None):
+        """reference model.py:95-122"""
+        n = self.num_delay_lines
+        if colorless_fdn_params is None:
+            self.input_gains = nn.Parameter(((2 * torch.randn(n, 1) - 1) / n).to(self.device))
+            self.output_gains = nn.Parameter(((2 * torch.randn(n, 1) - 1) / n).to(self.device))
+        else:
+            self.input_gains = torch.tensor([colorless_fdn_params[i].opt_input_gains.tolist()
+                                             for i in range(self.num_groups)], device=self.device).view(-1, 1)
+            self.output_gains = torch.tensor([colorless_fdn_params[i].opt_output_gains.tolist()
+                                              for i in range(self.num_groups)], device=self.device).view(-1, 1)
+
+    def _init_absorption(self, band_centre_hz=None):
+        """reference model.py:124-166 (broadband branch; GEQ filter design is init-time host code, see
+        FeedbackLoop.set_absorption_response)."""
+        if self.common_decay_times is None or self.learn_common_decay_times:
+            self.gain_per_sample = None
+            return
+        if self.use_absorption_filters:
+            raise NotImplementedError("GEQ absorption-filter design is outside the hot path; construct with "
+                                      "use_absorption_filters=False and call "
+                                      "feedback_loop.set_absorption_response(Gamma (N, K)) with the filter responses")
+        t60 = np.squeeze(np.asarray(self.common_decay_times))
+        gains = [decay_times_to_gain_per_sample(float(t60[i]), self.delays_by_group[i].cpu().numpy(),
+                                                self.sample_rate).tolist() for i in range(self.num_groups)]
+        self.gain_per_sample = torch.flatten(torch.tensor(gains, device=self.device)).to(torch.float32)
+        self.register_buffer('delay_filters', self.gain_per_sample)
+
+    def _init_feedback(self, feedback_loop_config: FeedbackLoopConfig, colorless_fdn_params=None):
+        """reference model.py:168-207"""
+        kw = dict(gains=self.gain_per_sample, use_zero_coupling=feedback_loop_config.use_zero_coupling,
+                  common_decay_times=self.common_decay_times,
+                  coupling_matrix_type=feedback_loop_config.coupling_matrix_type, device=self.device)
+        if colorless_fdn_params is None:
+            kw['coupling_matrix_order'] = feedback_loop_config.pu_matrix_order
+        else:
+            kw['colorless_feedback_matrix'] = torch.stack(
+                [torch.from_numpy(colorless_fdn_params[i].opt_feedback_matrix) for i in range(self.num_groups)], dim=0)
+        self.feedback_loop = FeedbackLoop(self.sample_rate, self.num_groups, self.num_delay_lines_per_group,
+                                          self.delays, self.use_absorption_filters, **kw)
+
+    # ---- helpers ---------------------------------------------------------------------------------------
+    def _on_device(self, t: torch.Tensor, dtype=None) -> torch.Tensor:
+        if t.device != self.device or (dtype is not None and t.dtype != dtype):
+            t = t.to(device=self.device, dtype=dtype, non_blocking=True)
+        return t
+
+    def _gains_vec(self, g) -> torch.Tensor:
+        return g.reshape(-1)
+
+    def sub_fdn_output(self, z: torch.Tensor) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+        """Response of each lossless sub-FDN, with the RAW mixing matrices M_g and no absorption (reference
+        model.py:209-252, quirk Q1): one block-diagonal solve. Returns Hout (K, G) and Hout_per_del (N, K, G)."""
+        z = self._on_device(z, torch.complex128)
+        a_sub = torch.block_diag(*self.feedback_loop.M)
+        xs, hout = ops.gfdn_solve(z, self.delays.to(torch.int32), a_sub, None, self._gains_vec(self.input_gains),
+                                  self._gains_vec(self.output_gains), self.num_groups)
+        if not self.return_per_delay_outputs:
+            return hout, None
+        per = (xs * self._gains_vec(self.output_gains).to(xs.dtype)).transpose(0, 1)  # (N, K)
+        onehot = torch.zeros(self.num_delay_lines, 1, self.num_groups, dtype=per.dtype, device=per.device)
+        idx = torch.arange(self.num_delay_lines, device=per.device)
+        onehot[idx, 0, idx // self.num_delay_lines_per_group] = 1.0
+        return hout, per.unsqueeze(-1) * onehot
+
+    @torch.no_grad()
+    def get_param_dict(self) -> Dict:
+        """reference model.py:254-299"""
+        fl = self.feedback_loop
+        d = {'delays': self.delays.squeeze().cpu().numpy(),
+             'gains_per_sample': fl.delay_line_gains.squeeze().cpu().numpy(),
+             'input_gains': self.input_gains.squeeze().cpu().numpy(),
+             'output_gains': self.output_gains.squeeze().cpu().numpy(),
+             'coupled_feedback_matrix': fl.get_coupled_feedback_matrix().squeeze().cpu().numpy(),
+             'individual_mixing_matrix': fl.M.squeeze().cpu().numpy(),
+             'coupling_matrix': fl.nd_unitary(fl.alpha, self.num_groups).squeeze().cpu().numpy()}
+        return d
+
+
+class DiffGFDNVarReceiverPos(DiffGFDN):
+    """GFDN for a grid of receiver positions with MLP-driven receiver gains (reference model.py:502-661)."""
+
+    def __init__(self,
+                 sample_rate: int,
+                 num_groups: int,
+                 delays: List[int],
+                 device: torch.device,
+                 feedback_loop_config: FeedbackLoopConfig,
+                 output_filter_config: OutputFilterConfig,
+                 use_absorption_filters: bool,
+                 learn_common_decay_times: Optional[bool] = False,
+                 common_decay_times: Optional[List] = None,
+                 band_centre_hz: Optional[List] = None,
+                 colorless_fdn_params: Optional[List] = None,
+                 use_colorless_loss: bool = False):
+        super().__init__(sample_rate, num_groups, delays, device, feedback_loop_config, use_absorption_filters,
+                         learn_common_decay_times, common_decay_times, band_centre_hz, colorless_fdn_params,
+                         use_colorless_loss)
+        self.use_svf_in_output = output_filter_config.use_svfs
+        self.input_scalars = torch.ones(self.num_groups, 1)
+        if self.use_svf_in_output:
+            raise NotImplementedError("SVF output filters (use_svfs=True) are the next row of the scope table "
+                                      "(SURVEY.md section 8f rank 3); use scalar receiver gains (use_svfs: False)")
+        self.output_scalars = Gains_from_MLP(self.num_groups, self.num_delay_lines_per_group,
+                                             output_filter_config.num_fourier_features,
+                                             output_filter_config.num_hidden_layers,
+                                             output_filter_config.num_neurons_per_layer,
+                                             output_filter_config.encoding_type, device=self.device).to(self.device)
+
+    def forward(self, x: Dict, output_scalars: Optional[torch.Tensor] = None):
+        """H(z) = c^T (D Gamma^-1 - A)^-1 b + d for every receiver of the batch and every bin.
+
+        x: 'z_values' (K,) complex, 'listener_position' (B,3), 'norm_listener_position' (B,3),
+           'target_early_response' (B,K) complex.  Returns H (B,K) complex64, or (H, (H_sub, H_sub_per_del))."""
+        z = self._on_device(x['z_values'], torch.complex128)
+        self.batch_size = x['listener_position'].shape[0]
+        if output_scalars is None:
+            s = self.output_scalars.gains(x)
+        else:
+            assert output_scalars.shape == (self.batch_size, self.num_groups)
+            s = self._on_device(output_scalars, torch.float32)
+        _, y = self.feedback_loop.solve(z, self._gains_vec(self.input_gains), self._gains_vec(self.output_gains))
+        d = x.get('target_early_response')
+        d = None if d is None else self._on_device(d, torch.complex64)
+        H = ops.receiver_project(s, y, d)
+        if self.use_colorless_loss:
+            return H, self.sub_fdn_output(z)
+        return H
+
+    @torch.no_grad()
+    def get_param_dict_inference(self, data: Dict) -> Dict:
+        return {'output_scalars': self.output_scalars.get_param_dict(data)['gains']}
+
+    @torch.no_grad()
+    def get_param_dict(self) -> Dict:
+        d = super().get_param_dict()
+        d['input_scalars'] = self.input_scalars.squeeze().cpu().numpy()
+        return d
+
+
+class DiffDirectionalFDNVarReceiverPos(DiffGFDN):
+    """Directional FDN: one delay line per (group, SH channel), MLP-driven SH gains (reference model.py:975-1126)."""
+
+    def __init__(self,
+                 sample_rate: int,
+                 num_groups: int,
+                 delays: List[int],
+                 device: torch.device,
+                 feedback_loop_config: FeedbackLoopConfig,
+                 output_filter_config: OutputFilterConfig,
+                 ambi_order: int,
+                 desired_directions: Optional[np.ndarray],
+                 use_absorption_filters: bool = False,
+                 learn_common_decay_times: Optional[bool] = False,
+                 common_decay_times: Optional[List] = None,
+                 band_centre_hz: Optional[List] = None,
+                 colorless_fdn_params: Optional[List] = None,
+                 use_colorless_loss: bool = False,
+                 analysis_matrix: Optional[np.ndarray] = None):
+        super().__init__(sample_rate, num_groups, delays, device, feedback_loop_config, use_absorption_filters,
+                         learn_common_decay_times, common_decay_times, band_centre_hz, colorless_fdn_params,
+                         use_colorless_loss)
+        self.ambi_order = ambi_order
+        assert self.num_delay_lines_per_group == (self.ambi_order + 1)**2, \
+            "Number of delay lines per group must be equal to the number of ambisonics channels"
+        self.input_scalars = torch.ones(self.num_groups, 1)
+        self.use_svf_in_output = False
+        self.sh_output_scalars = Directional_Beamforming_Weights_from_MLP(
+            self.num_groups, self.ambi_order, output_filter_config.num_fourier_features,
+            output_filter_config.num_hidden_layers, output_filter_config.num_neurons_per_layer,
+            desired_directions=desired_directions, device=self.device,
+            beamformer_type=output_filter_config.beamformer_type,
+            use_skip_connections=output_filter_config.use_skip_connections,
+            analysis_matrix=analysis_matrix).to(self.device)
+
+    def forward(self, x: Dict):
+        """H_sh[r,l,k] = sum_g w[r,g,l] c[g,l] (P_k^T b)[gL+l]  -> (B, (N_sp+1)^2, K) complex64.
+
+        The reference contracts the FIRST index of P with b here (einsum 'knm,bnk->bmk', model.py:1083), i.e. the
+        state is P^T b: the solve runs on A^T (quirk Q11 in DESIGN.md)."""
+        z = self._on_device(x['z_values'], torch.complex128)
+        self.batch_size = x['listener_position'].shape[0]
+        w = self.sh_output_scalars(x, normalise_weights=True)  # (B, G, L)
+        c = self._gains_vec(self.output_gains).reshape(1, self.num_groups, self.num_delay_lines_per_group)
+        xs, _ = self.feedback_loop.solve(z, self._gains_vec(self.input_gains), self._gains_vec(self.output_gains),
+                                         transpose=True)
+        H = ops.sh_project(w * c, xs)
+        if self.use_colorless_loss:
+            return H, self.sub_fdn_output(z)
+        return H
+
+    @torch.no_grad()
+    def get_param_dict_inference(self, data: Dict, normalise_weights: bool = False) -> Dict:
+        return {'output_scalars': self.sh_output_scalars.get_param_dict(data, normalise_weights)['beamformer_weights']}
+
+    @torch.no_grad()
+    def get_param_dict(self) -> Dict:
+        d = super().get_param_dict()
+        d['input_scalars'] = self.input_scalars.squeeze().cpu().numpy()
+        return d
+
+
+__all__ = ["DiffGFDN", "DiffGFDNVarReceiverPos", "DiffDirectionalFDNVarReceiverPos", "CouplingMatrixType"]

@@ -1,0 +1,226 @@
+"""Training-step contract of the reference (diff_gfdn/trainer.py) on the B200 kernels.
+
+Kept from the reference: Adam parameter groups by parameter name and StepLR(10, 0.1) (trainer.py:152-228), the
+per-step energy normalisation of b and c (trainer.py:317-332), the loss composition including its quirks
+(spectral loss `+=` over groups, sparsity loss `=` last group only: trainer.py:295-313, Q2), sub-band filtering of
+H before the losses (trainer.py:457-461, 804), the SH -> direction projection (trainer.py:853-865), per-epoch
+`state_dict` checkpoints (trainer.py:249-257) and early stopping. Not ported: wav export (`save_ir`) and the pyfar
+filterbank design -- the sub-band filter response is an input (`set_subband_filter`)."""
+import os
+from pathlib import Path
+import time
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import ops
+from .colorless_fdn.losses import amse_loss, mse_loss, sparsity_loss
+from .config.config import TrainerConfig
+from .losses import directional_edc_loss, edc_loss, edr_loss
+from .model import DiffGFDN
+
+
+class Trainer:
+
+    def __init__(self, net: DiffGFDN, trainer_config: TrainerConfig):
+        self.net = net
+        self.device = net.device
+        self.max_epochs = trainer_config.max_epochs
+        self.patience = 5
+        self.early_stop = 0
+        self.train_dir = Path(trainer_config.train_dir).resolve()
+        self.ir_dir = Path(trainer_config.ir_dir).resolve()
+        self.use_reg_loss = trainer_config.use_reg_loss
+        self.use_colorless_loss = trainer_config.use_colorless_loss
+        self.reduced_pole_radius = trainer_config.reduced_pole_radius
+        self.subband_process_config = trainer_config.subband_process_config
+        self.subband_filter_freq_resp = None
+        self.use_directional_fdn = getattr(self.net, "ambi_order", None) is not None
+        if self.use_reg_loss:
+            raise NotImplementedError("reg_loss belongs to the SVF output filters (out of scope this round)")
+        self.init_scheduler(trainer_config)
+        if self.net.common_decay_times is None:
+            max_ir_len_ms = 2000
+        else:
+            max_ir_len_ms = float(self.net.common_decay_times.max() * 1e3)
+        if self.use_directional_fdn:
+            self.criterion = [directional_edc_loss(self.net.common_decay_times, max_ir_len_ms, self.net.sample_rate,
+                                                   use_mask=trainer_config.use_edc_mask).to(self.device)]
+            self.loss_weights = [trainer_config.edc_loss_weight]
+        else:
+            self.criterion = [
+                edr_loss(self.net.sample_rate, reduced_pole_radius=self.reduced_pole_radius,
+                         use_erb_grouping=trainer_config.use_erb_edr_loss,
+                         use_weight_fn=trainer_config.use_frequency_weighting),
+                edc_loss(max_ir_len_ms, self.net.sample_rate, use_mask=trainer_config.use_edc_mask),
+            ]
+            self.loss_weights = [trainer_config.edr_loss_weight, trainer_config.edc_loss_weight]
+        if self.use_colorless_loss:
+            self.colorless_criterion = [amse_loss() if trainer_config.use_asym_spectral_loss else mse_loss(),
+                                        sparsity_loss()]
+            self.colorless_loss_weights = [trainer_config.spectral_loss_weight, trainer_config.sparsity_loss_weight]
+
+    def set_subband_filter(self, freq_resp: torch.Tensor):
+        """Frequency response F[k] of the octave-band filter applied to H before the losses (trainer.py:112-150
+        derive it from pyfar; here it is an input)."""
+        self.subband_filter_freq_resp = freq_resp.to(device=self.device, dtype=torch.complex64)
+
+    def init_scheduler(self, trainer_config: TrainerConfig):
+        """Adam with per-name learning rates + StepLR(10, 0.1) (reference trainer.py:152-228)."""
+        named = list(self.net.named_parameters())
+
+        def pick(pred):
+            return [p for n, p in named if pred(n)]
+
+        keys = ('feedback_loop.alpha', 'input_gains', 'output_gains', 'output_svf_params', 'output_scalars',
+                'sh_output_scalars', 'input_scalars')
+        groups = [
+            {'params': pick(lambda n: 'feedback_loop.alpha' in n), 'lr': trainer_config.coupling_angle_lr},
+            {'params': pick(lambda n: 'output_gains' in n), 'lr': trainer_config.io_lr},
+            {'params': pick(lambda n: 'input_gains' in n), 'lr': trainer_config.io_lr},
+            {'params': pick(lambda n: 'output_svf_params' in n), 'lr': trainer_config.io_lr},
+            {'params': pick(lambda n: 'input_scalars' in n), 'lr': trainer_config.io_lr},
+            {'params': pick(lambda n: 'output_scalars' in n or 'sh_output_scalars' in n), 'lr': trainer_config.io_lr},
+        ]
+        others = pick(lambda n: not any(k in n for k in keys))
+        if others:
+            groups.append({'params': others, 'lr': trainer_config.lr})
+        self.optimizer = torch.optim.Adam(groups)
+        self.scheduler = torch.optim.lr_scheduler.StepLR(self.optimizer, step_size=10, gamma=0.1)
+
+    def save_model(self, e: int):
+        d = os.path.join(self.train_dir, 'checkpoints')
+        os.makedirs(d, exist_ok=True)
+        torch.save(self.net.state_dict(), os.path.join(d, f'model_e{e}.pt'))
+
+    def apply_subband_filter(self, H: torch.Tensor) -> torch.Tensor:
+        if self.subband_process_config is not None or self.subband_filter_freq_resp is not None:
+            if self.subband_filter_freq_resp is None:
+                raise RuntimeError("subband_process_config is set: provide the filter with set_subband_filter()")
+            return H * self.subband_filter_freq_resp
+        return H
+
+    def calculate_losses(self, data: Dict, H: torch.Tensor, H_sub_fdn: Optional[Tuple] = None) -> Dict:
+        """reference trainer.py:259-315"""
+        if self.use_directional_fdn:
+            amps = data['target_common_slope_amps']
+            all_losses = {'edc_loss': self.loss_weights[0] * self.criterion[0](H, amps)}
+        else:
+            target = data['target_rir_response']
+            if not target.is_cuda:
+                target = target.to(self.device, non_blocking=True)
+            if target.dtype != torch.complex64:
+                target = self._as_c64(target)
+            edr_val = self.loss_weights[0] * self.criterion[0](target, H)
+            edc_val = self.loss_weights[1] * self.criterion[1](target, H)
+            all_losses = {'edc_loss': edc_val, 'edr_loss': edr_val}
+        if self.use_colorless_loss:
+            spectral = 0.0
+            sparsity = 0.0
+            per_group = ops.colorless_loss_per_group(H_sub_fdn[0], self.colorless_criterion[0].asym)
+            for k in range(self.net.num_groups):
+                spectral = spectral + self.colorless_loss_weights[0] * per_group[k]
+                # `=`, not `+=`: only the last group's sparsity survives (reference trainer.py:305, quirk Q2)
+                sparsity = self.colorless_loss_weights[1] * self.colorless_criterion[1](
+                    self.net.feedback_loop.ortho_param(self.net.feedback_loop.M[k]))
+            all_losses.update({'spectral_loss': spectral, 'sparsity_loss': sparsity})
+        return all_losses
+
+    def _as_c64(self, t: torch.Tensor) -> torch.Tensor:
+        """complex128 dataset tensors are converted once and remembered (targets are constant over training)."""
+        cache = self.__dict__.setdefault("_c64_cache", {})
+        key = (t.data_ptr(), tuple(t.shape), t._version)
+        out = cache.get(key)
+        if out is None:
+            if len(cache) > 64:
+                cache.clear()
+            out = t.to(torch.complex64)
+            cache[key] = out
+        return out
+
+    @torch.no_grad()
+    def normalize(self, data: Dict):
+        """Unit-energy normalisation of every sub-FDN: b_g, c_g /= (mean_k |H_sub[k,g]|^2)^(1/4) (reference
+        trainer.py:317-332). Only the receiver-independent colorless solve is needed, not a full forward."""
+        if not self.use_colorless_loss:
+            return
+        keep = self.net.return_per_delay_outputs
+        self.net.return_per_delay_outputs = False
+        try:
+            h_sub, _ = self.net.sub_fdn_output(data['z_values'])
+        finally:
+            self.net.return_per_delay_outputs = keep
+        energy = torch.mean(torch.abs(h_sub)**2, dim=0)  # (G,)
+        scale = torch.pow(energy, 0.25).repeat_interleave(self.net.num_delay_lines_per_group).view(-1, 1)
+        for name, prm in self.net.named_parameters():
+            if name in ('input_gains', 'output_gains'):
+                prm.data /= scale.to(prm.dtype)
+
+    def _forward_losses(self, data: Dict):
+        out = self.net(data)
+        H, H_sub = out if self.use_colorless_loss else (out, None)
+        H = self.apply_subband_filter(H)
+        if self.use_directional_fdn:
+            H = self.convert_ambi_rir_to_directional_rir(H)
+        return self.calculate_losses(data, H, H_sub)
+
+    def train_step(self, data: Dict):
+        """reference trainer.py:452-477 / 795-825"""
+        self.optimizer.zero_grad()
+        all_losses = self._forward_losses(data)
+        loss = sum(all_losses.values())
+        loss.backward()
+        self.optimizer.step()
+        return loss.item(), all_losses
+
+    @torch.no_grad()
+    def valid_step(self, data: Dict):
+        all_losses = self._forward_losses(data)
+        return sum(all_losses.values()).item(), all_losses
+
+    def convert_ambi_rir_to_directional_rir(self, H_sh: torch.Tensor) -> torch.Tensor:
+        """H_dir[b,j,k] = sum_l Y[j,l] H_sh[b,l,k] (reference trainer.py:853-865)."""
+        return ops.mix_channels(self.net.sh_output_scalars.analysis_matrix, H_sh)
+
+    def train(self, train_dataset, valid_dataset):
+        """Epoch loop of reference trainer.py:345-450 (without the wav export at the end)."""
+        self.train_loss, self.valid_loss = [], []
+        self.individual_train_loss, self.individual_valid_loss = [], []
+        st = time.time()
+        self.save_model(-1)
+        for epoch in range(self.max_epochs):
+            et = time.time()
+            tot, parts = 0.0, {}
+            for data in train_dataset:
+                self.normalize(data)
+                cur, cur_all = self.train_step(data)
+                tot += cur
+                for k, v in cur_all.items():
+                    parts[k] = parts.get(k, 0.0) + float(v)
+            vtot, vparts = 0.0, {}
+            for data in valid_dataset:
+                cur, cur_all = self.valid_step(data)
+                vtot += cur
+                for k, v in cur_all.items():
+                    vparts[k] = vparts.get(k, 0.0) + float(v)
+            self.scheduler.step()
+            self.train_loss.append(tot / max(1, len(train_dataset)))
+            self.individual_train_loss.append({k: v / max(1, len(train_dataset)) for k, v in parts.items()})
+            self.valid_loss.append(vtot / max(1, len(valid_dataset)))
+            self.individual_valid_loss.append({k: v / max(1, len(valid_dataset)) for k, v in vparts.items()})
+            self.save_model(epoch)
+            print(f"epoch {epoch:3d}, train_loss {self.train_loss[-1]:.4f}, valid_loss {self.valid_loss[-1]:.4f}, "
+                  f"time {time.time() - et:.3f}s")
+            if epoch >= 1:
+                self.early_stop = self.early_stop + 1 if abs(self.valid_loss[-2] - self.valid_loss[-1]) <= 1e-3 else 0
+            if self.early_stop == self.patience:
+                break
+        print(f"Training time: {time.time() - st:.3f}s")
+
+
+class VarReceiverPosTrainer(Trainer):
+    """Omni GFDN over a grid of receivers (reference trainer.py:338-564)."""
+
+
+class DirectionalFDNVarReceiverPosTrainer(Trainer):
+    """Directional FDN over a grid of receivers (reference trainer.py:690-921)."""

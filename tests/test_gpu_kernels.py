@@ -19,7 +19,7 @@ def rel(a, b):
     return float((a - b).abs().max() / b.abs().max())
 
 
-def make_system(n, g, nfft, seed, t60=(0.3, 0.8, 1.5), fs=32000.0, radius=1.0):
+def make_system(n, g, nfft, seed, t60=(0.3, 0.8, 1.5, 1.1, 0.6, 0.9, 0.4, 1.2), fs=32000.0, radius=1.0):
     gen = torch.Generator().manual_seed(seed)
     l = n // g
     rng = np.random.default_rng(seed)

@@ -1,0 +1,182 @@
+"""GPU parity of the drop-in nn.Module / loss / trainer surface against fixtures produced by the UNMODIFIED
+reference (tests/golden/*.npz) and against the CPU oracle.
+
+Tolerances (BASELINE.json): |H| 1e-4 relative, EDC 0.01 dB, gradients 1e-3 relative."""
+import numpy as np
+import pytest
+import torch
+
+from golden_util import load, oracle_directional, oracle_omni, params_of
+
+pytestmark = pytest.mark.gpu
+
+OMNI = {  # name: (hidden, neurons, fourier features, steps)
+    "omni_n12": (1, 32, 6, 2),
+    "omni_n12_subband_r": (2, 16, 4, 2),
+    "omni_n24": (1, 16, 4, 1),
+}
+DIRECTIONAL = {"directional_n27": (1, 16, 4, False), "directional_n27_skip": (2, 16, 4, True)}
+
+
+def rel(a, b):
+    a = torch.as_tensor(np.asarray(a.detach().cpu() if torch.is_tensor(a) else a))
+    b = torch.as_tensor(np.asarray(b.detach().cpu() if torch.is_tensor(b) else b))
+    return float((a - b).abs().max() / b.abs().max())
+
+
+def build_omni(g, hidden, neurons, feats):
+    from diffgfdn_b200.config import FeedbackLoopConfig, OutputFilterConfig
+    from diffgfdn_b200.model import DiffGFDNVarReceiverPos
+    net = DiffGFDNVarReceiverPos(float(g["meta/fs"]), 3, [int(v) for v in g["meta/delays"]], 'cuda',
+                                 FeedbackLoopConfig(use_zero_coupling=False),
+                                 OutputFilterConfig(use_svfs=False, num_hidden_layers=hidden,
+                                                    num_neurons_per_layer=neurons, num_fourier_features=feats),
+                                 use_absorption_filters=False, common_decay_times=np.array([g["meta/t60"]]),
+                                 use_colorless_loss=True)
+    state = {k[len("param/"):]: torch.tensor(v) for k, v in g.items() if k.startswith("param/")}
+    net.load_state_dict(state, strict=True)  # reference checkpoint layout must load unchanged
+    return net
+
+
+def omni_data(g):
+    from diffgfdn_b200.utils import unit_circle_grid
+    data = {k[len("data/"):]: torch.tensor(v) for k, v in g.items() if k.startswith("data/")}
+    data["z_values"] = unit_circle_grid(int(g["meta/nfft"]), float(g["meta/radius"]))
+    data["target_rir_response"] = data["target_rir_response"].cuda()
+    return data
+
+
+def make_trainer(cls, net, tmp_path, **kw):
+    from diffgfdn_b200.config import TrainerConfig
+    return cls(net, TrainerConfig(train_dir=str(tmp_path / "out"), ir_dir=str(tmp_path / "ir"), **kw))
+
+
+@pytest.mark.parametrize("name", list(OMNI))
+def test_omni_forward_losses_grads_match_reference(name, tmp_path):
+    from diffgfdn_b200.trainer import VarReceiverPosTrainer
+    g = load(name)
+    hidden, neurons, feats, _ = OMNI[name]
+    net = build_omni(g, hidden, neurons, feats)
+    data = omni_data(g)
+    trainer = make_trainer(VarReceiverPosTrainer, net, tmp_path, use_colorless_loss=True, use_asym_spectral_loss=True,
+                           edc_loss_weight=10.0, num_freq_bins=int(g["meta/nfft"]))
+    if "subband_filter" in data:
+        trainer.set_subband_filter(data["subband_filter"])
+    net.zero_grad()
+    H, (Hs, Hsd) = net(data)
+    d = g["data/target_early_response"]
+    assert H.dtype == torch.complex64 and tuple(H.shape) == d.shape
+    late_ref = g["out/H"] - d
+    assert rel(H.cpu().to(torch.complex128).numpy() - d, late_ref) < 1e-4
+    assert rel(np.abs(H.cpu().numpy()), np.abs(g["out/H"])) < 1e-4
+    assert rel(Hs, g["out/H_sub"]) < 1e-4
+    assert rel(Hsd.cpu().numpy()[:, ::16, :], g["out/H_sub_per_del_s16"]) < 1e-4
+    assert rel(net.feedback_loop.coupled_feedback_matrix_real(), np.real(g["out/A"])) < 1e-4
+    losses = trainer.calculate_losses(data, trainer.apply_subband_filter(H), (Hs, Hsd))
+    total = sum(losses.values())
+    total.backward()
+    w_edc = float(g["meta/edc_w"])
+    assert abs(float(losses["edc_loss"]) / w_edc - g["loss/edc_raw"]) < 0.01  # dB
+    assert abs(float(losses["edr_loss"]) - g["loss/edr_loss"]) < 2e-3 * g["loss/edr_loss"]
+    assert abs(float(losses["spectral_loss"]) - g["loss/spectral_loss"]) < 1e-4 * g["loss/spectral_loss"]
+    assert abs(float(losses["sparsity_loss"]) - g["loss/sparsity_loss"]) < 1e-5
+    assert abs(float(total) - g["loss/total"]) < 2e-3 * g["loss/total"]
+    for k, p in net.named_parameters():
+        assert rel(p.grad, g[f"grad/{k}"]) < 1e-3, k
+
+
+@pytest.mark.parametrize("name", list(OMNI))
+def test_omni_loss_callables_and_mask(name):
+    from diffgfdn_b200.colorless_fdn.losses import amse_loss, mse_loss
+    from diffgfdn_b200.losses import edc_loss, edr_loss
+    g = load(name)
+    o = oracle_omni(g, params_of(g))
+    H = o["Huse"].to(torch.complex64).cuda()
+    tgt = o["tgt"].to(torch.complex64).cuda()
+    mx, fs = float(g["meta/max_ir_len_ms"]), float(g["meta/fs"])
+    assert abs(float(edc_loss(mx, fs)(tgt, H)) - g["loss/edc_raw"]) < 0.01
+    idx = torch.tensor(g["data/edc_mask_index"])
+    assert abs(float(edc_loss(mx, fs)(tgt, H, mask_index=idx)) - g["loss/edc_masked_raw"]) < 0.01
+    assert abs(float(edr_loss(fs)(tgt, H)) - g["loss/edr_raw"]) < 2e-3 * g["loss/edr_raw"]
+    hs = o["H_sub"][:, 0].to(torch.complex64).cuda()
+    assert abs(float(mse_loss()(hs, torch.ones_like(hs))) - g["loss/mse_g0"]) < 1e-5
+    assert abs(float(amse_loss()(hs, torch.ones_like(hs))) - g["loss/amse_g0"]) < 1e-5
+    # the random mask path draws from torch's CPU generator exactly like the reference (losses.py:221-223)
+    torch.manual_seed(99)
+    masked = float(edc_loss(mx, fs, use_mask=True)(tgt, H))
+    assert abs(masked - g["loss/edc_masked_raw"]) < 0.01
+
+
+@pytest.mark.parametrize("name", list(OMNI))
+def test_omni_normalize_and_adam_steps_match_reference(name, tmp_path):
+    from diffgfdn_b200.trainer import VarReceiverPosTrainer
+    g = load(name)
+    hidden, neurons, feats, steps = OMNI[name]
+    net = build_omni(g, hidden, neurons, feats)
+    data = omni_data(g)
+    trainer = make_trainer(VarReceiverPosTrainer, net, tmp_path, use_colorless_loss=True, use_asym_spectral_loss=True,
+                           edc_loss_weight=10.0, num_freq_bins=int(g["meta/nfft"]), io_lr=0.01, lr=0.01)
+    if "subband_filter" in data:
+        trainer.set_subband_filter(data["subband_filter"])
+    got = []
+    for _ in range(steps):
+        trainer.normalize(data)
+        loss, _ = trainer.train_step(data)
+        got.append(loss)
+    assert np.allclose(got, g["steps/loss"], rtol=2e-3)
+    for k, v in net.state_dict().items():
+        ref = g[f"steps/param/{k}"]
+        assert float(np.abs(v.cpu().numpy() - ref).max()) < 5e-3 * max(1e-3, float(np.abs(ref).max())) + 2e-4, k
+
+
+@pytest.mark.parametrize("name", list(DIRECTIONAL))
+def test_directional_forward_losses_grads_match_reference(name, tmp_path):
+    from diffgfdn_b200.config import FeedbackLoopConfig, OutputFilterConfig
+    from diffgfdn_b200.model import DiffDirectionalFDNVarReceiverPos
+    from diffgfdn_b200.trainer import DirectionalFDNVarReceiverPosTrainer
+    from diffgfdn_b200.utils import unit_circle_grid
+    g = load(name)
+    hidden, neurons, feats, skip = DIRECTIONAL[name]
+    net = DiffDirectionalFDNVarReceiverPos(float(g["meta/fs"]), 3, [int(v) for v in g["meta/delays"]], 'cuda',
+                                           FeedbackLoopConfig(use_zero_coupling=False),
+                                           OutputFilterConfig(use_svfs=False, num_hidden_layers=hidden,
+                                                              num_neurons_per_layer=neurons,
+                                                              num_fourier_features=feats, use_skip_connections=skip),
+                                           2, None, common_decay_times=np.array([g["meta/t60"]]),
+                                           use_colorless_loss=True, analysis_matrix=g["data/Y"])
+    net.load_state_dict({k[len("param/"):]: torch.tensor(v) for k, v in g.items() if k.startswith("param/")},
+                        strict=True)
+    pos = torch.tensor(g["data/norm_listener_position"])
+    data = dict(z_values=unit_circle_grid(int(g["meta/nfft"])), listener_position=pos, norm_listener_position=pos,
+                target_common_slope_amps=torch.tensor(g["data/amps"]))
+    trainer = make_trainer(DirectionalFDNVarReceiverPosTrainer, net, tmp_path, use_colorless_loss=True,
+                           use_asym_spectral_loss=False, edc_loss_weight=float(g["meta/edc_w"]),
+                           num_freq_bins=int(g["meta/nfft"]))
+    net.zero_grad()
+    H_sh, (Hs, _) = net(data)
+    assert rel(H_sh, g["out/H_sh"]) < 1e-4
+    H_dir = trainer.convert_ambi_rir_to_directional_rir(H_sh)
+    assert rel(H_dir.cpu().numpy()[..., ::4], g["out/H_dir_s4"]) < 1e-4
+    losses = trainer.calculate_losses(data, H_dir, (Hs, None))
+    total = sum(losses.values())
+    total.backward()
+    assert abs(float(losses["edc_loss"]) - g["loss/edc_loss"]) < 0.01 * float(g["meta/edc_w"])
+    assert abs(float(total) - g["loss/total"]) < 1e-3 * g["loss/total"]
+    for k, p in net.named_parameters():
+        assert rel(p.grad, g[f"grad/{k}"]) < 1e-3, k
+    # oracle agrees on the same inputs (ties the oracle, the reference fixture and the kernels together)
+    o = oracle_directional(g, params_of(g))
+    assert rel(H_sh, o["H_sh"]) < 1e-4
+
+
+def test_feedback_loop_dense_inverse_api():
+    """FeedbackLoop.forward(z) keeps the reference's (K, N, N) inverse for API compatibility."""
+    from oracle import gfdn_oracle as O
+    g = load("omni_n12")
+    net = build_omni(g, *OMNI["omni_n12"][:3])
+    z = O.z_grid(256)
+    P = net.feedback_loop(z.cuda())
+    a = net.feedback_loop.coupled_feedback_matrix_real().detach().cpu().to(torch.float64)
+    Po = O.feedback_loop_inverse(z, torch.tensor(g["meta/delays"], dtype=torch.float64),
+                                 net.feedback_loop.delay_line_gains.cpu().to(torch.float64), a)
+    assert rel(P, Po) < 1e-5
