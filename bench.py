@@ -1,0 +1,399 @@
+"""Benchmark of the DiffGFDN hot path on B200: receiver.bin evals/s of one fwd+bwd training step.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[3], per-GPU shard): N = 24 delay lines in G = 3 groups, nfft = 2^18
+(K = 2^17 + 1 bins), 12 500 receivers per GPU (100 000 on 8 GPUs -> weak scaling), scalar absorption, MLP receiver
+gains, EDC (weight 10) + colorless losses, fs = 32 kHz, T60 = (0.3, 0.8, 1.5) s. One step = forward (MLP gains,
+per-bin solve, colorless sub-FDN solve, projection of every receiver over every bin, irfft, EDC loss, colorless
+loss) + backward to every parameter gradient (+ NCCL all-reduce of the flat gradient when N > 1).
+
+`value`  : inputs (early responses d, target EDC curves) resident in HBM, timed with CUDA events.
+`e2e`    : the same step with its inputs streamed from pinned host memory every step (early + target responses,
+           complex64) and the loss read back -- host<->device copies inside the timed region.
+`--impl reference`: the CPU port of the reference algorithm (oracle/gfdn_oracle.py) on the host cores, on a
+           bounded sample of the same workload.
+Prints ONE JSON line on rank 0."""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FS = 32000.0
+T60 = (0.3, 0.8, 1.5)
+N_LINES, N_GROUPS = 24, 3
+NFFT = 2**18
+ALGO_BYTES_PER_EVAL = 64.0  # algorithmic HBM bytes per receiver.bin, fwd+bwd
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--receivers", type=int, default=12500, help="receivers per GPU")
+    ap.add_argument("--nfft", type=int, default=NFFT)
+    ap.add_argument("--tile-rows", type=int, default=int(os.environ.get("DGFDN_TILE_ROWS", "128")))
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-receivers", type=int, default=4)
+    ap.add_argument("--profile-stages", action="store_true", help="per-kernel CUDA-event breakdown (extra output key)")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+# ------------------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons of one GPU while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.samples, self._stop = index, [], threading.Event()
+        self._t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(s) > 2 + i and s[2 + i].lower() == "active"
+                                                         for s in self.samples)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------------------
+# workload
+# ------------------------------------------------------------------------------------------------------------
+def delays_for(n_lines):
+    from diffgfdn_b200.config import DiffGFDNConfig
+    return DiffGFDNConfig(seed=235265, num_delay_lines=n_lines).delay_length_samps
+
+
+def build_net(device, seed=1234):
+    from diffgfdn_b200.config import FeedbackLoopConfig, OutputFilterConfig
+    from diffgfdn_b200.model import DiffGFDNVarReceiverPos
+    torch.manual_seed(seed)
+    return DiffGFDNVarReceiverPos(FS, N_GROUPS, delays_for(N_LINES), device, FeedbackLoopConfig(use_zero_coupling=False),
+                                  OutputFilterConfig(use_svfs=False), use_absorption_filters=False,
+                                  common_decay_times=np.array([T60]), use_colorless_loss=True)
+
+
+def synth_responses(rows, nfft, device, seed):
+    """Synthetic targets: 1 s of exponentially decaying noise per receiver -> rfft; the early
+    response is the first 20 ms with a fade-out. Generated on the device in chunks. Returns complex64 tensors."""
+    gen = torch.Generator(device=device).manual_seed(seed)
+    k = nfft // 2 + 1
+    tlen = int(FS)
+    t = torch.arange(tlen, device=device, dtype=torch.float32)
+    fade = torch.ones(640, device=device)
+    fade[560:] = torch.hann_window(160, periodic=False, device=device)[80:]
+    tgt = torch.empty(rows, k, dtype=torch.complex64, device=device)
+    early = torch.empty(rows, k, dtype=torch.complex64, device=device)
+    for r0 in range(0, rows, 256):
+        r1 = min(rows, r0 + 256)
+        tau = (0.1 + 0.2 * torch.rand(r1 - r0, 1, device=device, generator=gen)) * FS
+        rir = torch.randn(r1 - r0, tlen, device=device, generator=gen) * torch.exp(-t / tau)
+        tgt[r0:r1] = torch.fft.rfft(rir, n=nfft)
+        early[r0:r1] = torch.fft.rfft(rir[:, :640] * fade, n=nfft)
+    return early, tgt
+
+
+def timed_steps(fn, steps, barrier):
+    barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    out = None
+    for _ in range(steps):
+        out = fn()
+    e1.record()
+    torch.cuda.synchronize()
+    barrier()
+    return e0.elapsed_time(e1) / steps, out
+
+
+def stage_profile(step, pool_d, tdb):
+    """CUDA-event duration of every stage of one tile (kernel-level roofline evidence; see profiles/ for ncu)."""
+    import ctypes
+    from diffgfdn_b200 import _lib
+    from diffgfdn_b200.fused import _p
+    b = step._bufs
+    r = b["h_tile"].shape[0]
+    g = step.net.num_groups
+    k, kx, tn = step.k, step.kx, step.tn
+    with torch.no_grad():
+        s = step.net.output_scalars.gains({'norm_listener_position': step.positions}).detach().contiguous()
+        _, y = step.net.feedback_loop.solve(step.z, step.net.input_gains.reshape(-1), step.net.output_gains.reshape(-1))
+        y = y.detach().contiguous()
+    gy = torch.zeros_like(y)
+    gs = torch.empty_like(s)
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    dt = None if pool_d is None else pool_d[:r]
+    stages = [
+        ("project_fwd", 16.0 * r * k, lambda: _lib.call("dgfdn_project_fwd", g, r, k, _p(s[:r]), _p(y), _p(dt), k,
+                                                        _p(b["h_tile"]), k, st)),
+        ("irfft_window_fwd(czt+cuFFT)", (8.0 * kx + 4.0 * tn) * r,
+         lambda: _lib.call("dgfdn_irfft_window_fwd", step.plan.handle, _p(b["h_tile"]), k, r, None, _p(b["scratch"]),
+                           _p(b["h"]), st)),
+        ("edc_loss_fwd", 8.0 * r * tn, lambda: _lib.call("dgfdn_edc_loss_fwd", _p(b["h"]), _p(tdb[:r]), None, r, tn,
+                                                         _p(b["row_sum"][:r]), st)),
+        ("edc_loss_bwd", 12.0 * r * tn, lambda: _lib.call("dgfdn_edc_loss_bwd", _p(b["h"]), _p(tdb[:r]), None, r, tn,
+                                                          ctypes.c_double(1e-6), _p(b["gh"]), st)),
+        ("irfft_window_bwd(czt+cuFFT)", (8.0 * kx + 4.0 * tn) * r,
+         lambda: _lib.call("dgfdn_irfft_window_bwd", step.plan.handle, _p(b["gh"]), r, None, _p(b["scratch"]),
+                           _p(b["g_tile"]), kx, kx, st)),
+        ("project_bwd", 8.0 * r * kx, lambda: _lib.call("dgfdn_project_bwd", g, r, kx, _p(s[:r]), _p(y),
+                                                        _p(b["g_tile"]), kx, _p(gy), 1, _p(gs[:r]), st)),
+    ]
+    res = []
+    for name, nbytes, fn in stages:
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 5
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        res.append({"stage": name, "ms": round(ms, 4), "algorithmic_GBps": round(nbytes / ms / 1e6, 1)})
+    return res
+
+
+# ------------------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle (port of the reference algorithm) on the host cores
+# ------------------------------------------------------------------------------------------------------------
+def cpu_reference_step(nfft, receivers, seed=7):
+    """One fwd + EDC/colorless loss + bwd of the reference algorithm (float64 CPU port, reference batching
+    B <= 32), returning seconds and receiver.bin evals."""
+    from oracle import gfdn_oracle as O
+    torch.manual_seed(seed)
+    g, n = N_GROUPS, N_LINES
+    l = n // g
+    delays = torch.tensor(delays_for(n), dtype=torch.float64)
+    m_raw = ((2 * torch.rand(g, l, l, dtype=torch.float64) - 1) / np.sqrt(l)).requires_grad_(True)
+    alpha = (np.pi / 4 * torch.rand(3, dtype=torch.float64)).requires_grad_(True)
+    b = ((2 * torch.randn(n, dtype=torch.float64) - 1) / n).requires_grad_(True)
+    c = ((2 * torch.randn(n, dtype=torch.float64) - 1) / n).requires_grad_(True)
+    s = (2 * torch.rand(receivers, g, dtype=torch.float64) - 1).requires_grad_(True)
+    k = nfft // 2 + 1
+    z = O.z_grid(nfft)
+    rng = np.random.default_rng(seed)
+    tlen = int(FS)
+    rir = rng.standard_normal((receivers, tlen)) * np.exp(-np.arange(tlen)[None, :] / (0.2 * FS))
+    target = torch.tensor(np.fft.rfft(rir, n=nfft, axis=-1))
+    d = torch.tensor(np.fft.rfft(rir[:, :640], n=nfft, axis=-1))
+    gamma = O.decay_times_to_gain_per_sample(T60, delays.tolist(), FS, g)
+    t0 = time.perf_counter()
+    a = O.coupled_feedback_matrix(m_raw, alpha)
+    H = O.omni_response(z, delays, gamma, a, b, c, s, d)
+    h_sub, _ = O.sub_fdn_output(z, delays, m_raw, b, c)
+    loss = 10.0 * O.edc_loss(target, H, max(T60) * 1e3, FS)
+    spec, spars = O.colorless_losses(h_sub, m_raw, 1.0, 1.0, asym=True)
+    (loss + spec + spars).backward()
+    return time.perf_counter() - t0, receivers * k
+
+
+def cpu_baseline(nfft, receivers):
+    torch.set_num_threads(os.cpu_count() or 1)
+    secs, evals = cpu_reference_step(nfft, receivers)
+    return {"value": evals / secs, "unit": "receiver*bin evals/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{receivers} receivers x {nfft // 2 + 1} bins, N={N_LINES}, one fwd+loss+bwd of "
+                      f"oracle/gfdn_oracle.py (float64 torch-CPU port of the reference), {secs:.1f} s"}
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    torch.set_num_threads(os.cpu_count() or 1)
+    times = []
+    evals = 0
+    for i in range(args.warmup + args.steps):
+        secs, evals = cpu_reference_step(args.nfft, args.cpu_sample_receivers, seed=7 + i)
+        if i >= args.warmup:
+            times.append(secs)
+    ms = 1e3 * float(np.mean(times))
+    val = evals / (ms / 1e3)
+    base = {"value": val, "unit": "receiver*bin evals/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"each step = {args.cpu_sample_receivers} receivers x {args.nfft // 2 + 1} bins (bounded sample "
+                      f"of the per-GPU shard of {args.receivers}), oracle/gfdn_oracle.py"}
+    print(json.dumps({
+        "impl": "reference", "metric": "DiffGFDN receiver*bin evals/s fwd+bwd", "value": val,
+        "unit": "receiver*bin evals/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": workload_config(args), "cpu_baseline": base,
+        "e2e": {"value": val, "unit": "receiver*bin evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+def workload_config(args):
+    return {"workload": f"BASELINE configs[3] per-GPU shard: N={N_LINES} lines, G={N_GROUPS} groups, "
+                        f"{args.receivers} receivers/GPU x {args.nfft // 2 + 1} bins (nfft={args.nfft}), "
+                        "EDC(w=10)+colorless losses, fwd+bwd",
+            "receivers_per_gpu": args.receivers, "bins": args.nfft // 2 + 1, "delay_lines": N_LINES,
+            "groups": N_GROUPS, "tile_rows": args.tile_rows, "parallelism": f"receiver-sharded dp{args.gpus}",
+            "l2_policy": "inputs larger than L2 (per-step working set >> 126 MB), no explicit flush"}
+
+
+# ------------------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    import torch.distributed as dist
+    from diffgfdn_b200 import _lib, build
+    build.build()
+    _lib.load()
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the kernels have no CPU fallback")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    barrier = (lambda: dist.barrier()) if world > 1 else (lambda: None)
+
+    from diffgfdn_b200.fused import ShardedEDCStep
+    from diffgfdn_b200.utils import unit_circle_grid
+    net = build_net(device)
+    if world > 1:  # identical parameters on every rank
+        for p in net.parameters():
+            dist.broadcast(p.data, 0)
+    step = ShardedEDCStep(net, max(T60) * 1e3, tile_rows=args.tile_rows, edc_weight=10.0, world_size=world,
+                          total_receivers=args.receivers * world)
+    k = args.nfft // 2 + 1
+    z = unit_circle_grid(args.nfft, device=device)
+    gen = torch.Generator(device=device).manual_seed(100 + rank)
+    positions = torch.rand(args.receivers, 3, device=device, generator=gen)
+    step.attach(z, positions, None, None)
+    # resident inputs: early responses d and target EDC curves, built from a pool of synthetic RIRs
+    pool_rows = min(args.receivers, 1024)
+    early_pool, target_pool = synth_responses(pool_rows, args.nfft, device, 200 + rank)
+    tdb_pool = step.precompute_target_db(target_pool)
+    reps = (args.receivers + pool_rows - 1) // pool_rows
+    d = early_pool.repeat(reps, 1)[:args.receivers].contiguous()  # resident (B, K) complex64
+    target_db = tdb_pool.repeat(reps, 1)[:args.receivers].contiguous()
+    step.attach(z, positions, d, target_db)
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3)
+
+    def one_step():
+        losses = step.step()
+        opt.step()
+        return losses
+
+    for _ in range(args.warmup):
+        one_step()
+    step.kernel_launches = 0
+    with ClockSampler(local) as clocks:
+        ms, losses = timed_steps(one_step, args.steps, barrier)
+    launches = step.kernel_launches
+    t = torch.tensor([ms], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    evals_per_step = float(args.receivers) * world * k
+    value = evals_per_step / (ms / 1e3)
+    loss_val = float(sum(v for v in losses.values()))
+
+    # end-to-end: inputs from pinned host memory every step, loss read back
+    e2e = None
+    if not args.no_e2e:
+        host_d = early_pool.cpu().pin_memory()
+        host_t = target_pool.cpu().pin_memory()
+
+        def e2e_step():
+            ls = step.step(host_d=host_d, host_target=host_t)
+            opt.step()
+            return float(sum(v for v in ls.values()))  # device -> host read of the loss
+
+        e2e_step()
+        barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        te = torch.tensor([(time.perf_counter() - t0) / args.e2e_steps], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": evals_per_step / float(te.item()), "unit": "receiver*bin evals/s",
+               "h2d_bytes_per_step": int(step.h2d_bytes) + int(positions.numel() * 4), "d2h_bytes_per_step": 8,
+               "ms_per_step": 1e3 * float(te.item()),
+               "note": "early + target responses (complex64) streamed from a pinned host pool every step, target EDC "
+                       "rebuilt on the device, loss read back"}
+
+    if rank == 0:
+        hbm, how = peaks()
+        achieved = value / world * ALGO_BYTES_PER_EVAL / 1e9  # GB/s per GPU
+        out = {
+            "metric": "DiffGFDN receiver*bin evals/s fwd+bwd", "value": value, "unit": "receiver*bin evals/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32 storage / f64 per-bin solve and scans",
+            "data": "synthetic", "config": workload_config(args), "loss": loss_val, "clocks": clocks.summary(),
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
+                         "traffic": None, "peak_source": how,
+                         "kernel": "whole tile pipeline (project -> chirp-z irfft -> EDC fwd/bwd -> irfft^T -> "
+                                   "project^T) at 64 algorithmic B per receiver.bin"},
+            "e2e": e2e,
+        }
+        if args.profile_stages:
+            out["stages"] = stage_profile(step, d, target_db)
+        if not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(args.nfft, args.cpu_sample_receivers)
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

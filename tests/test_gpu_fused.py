@@ -1,0 +1,105 @@
+"""The receiver-tiled fused step (diffgfdn_b200/fused.py) must give the same losses and gradients as the
+autograd module path, for any tile size, in resident and in host-streamed mode."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def setup(nfft=4096, rows=11, seed=0):
+    from diffgfdn_b200.config import DiffGFDNConfig, FeedbackLoopConfig, OutputFilterConfig
+    from diffgfdn_b200.model import DiffGFDNVarReceiverPos
+    from diffgfdn_b200.utils import unit_circle_grid
+    torch.manual_seed(seed)
+    t60 = [0.03, 0.05, 0.06]
+    delays = DiffGFDNConfig(seed=235265, num_delay_lines=12).delay_length_samps
+    net = DiffGFDNVarReceiverPos(32000.0, 3, delays, 'cuda', FeedbackLoopConfig(use_zero_coupling=False),
+                                 OutputFilterConfig(use_svfs=False, num_hidden_layers=1, num_neurons_per_layer=16,
+                                                    num_fourier_features=4), use_absorption_filters=False,
+                                 common_decay_times=np.array([t60]), use_colorless_loss=True)
+    rng = np.random.default_rng(seed)
+    rir = rng.standard_normal((rows, nfft // 2)) * np.exp(-np.arange(nfft // 2)[None, :] / 500.0)
+    target = torch.tensor(np.fft.rfft(rir, n=nfft, axis=-1)).to(torch.complex64).cuda()
+    early = torch.tensor(np.fft.rfft(rir[:, :640], n=nfft, axis=-1)).to(torch.complex64).cuda()
+    pos = torch.tensor(rng.uniform(0, 1, (rows, 3))).cuda()
+    return net, t60, unit_circle_grid(nfft).cuda(), pos, early, target
+
+
+def module_path(net, t60, z, pos, early, target):
+    from diffgfdn_b200 import ops
+    from diffgfdn_b200.losses import edc_loss
+    net.zero_grad()
+    data = dict(z_values=z, listener_position=pos, norm_listener_position=pos, target_early_response=early)
+    H, (Hs, _) = net(data)
+    edc = 10.0 * edc_loss(max(t60) * 1e3, 32000.0)(target, H)
+    spec = ops.colorless_loss_per_group(Hs, True).sum()
+    a = net.feedback_loop.ortho_param(net.feedback_loop.M[2])
+    spars = -(a.abs().sum() - 4 * 2.0) / (4 * (2.0 - 1))
+    (edc + spec + spars).backward()
+    return float(edc), {k: p.grad.clone() for k, p in net.named_parameters()}
+
+
+@pytest.mark.parametrize("tile", [4, 11, 64])
+def test_fused_step_equals_module_path(tile):
+    from diffgfdn_b200.fused import ShardedEDCStep
+    net, t60, z, pos, early, target = setup()
+    edc_ref, g_ref = module_path(net, t60, z, pos, early, target)
+    step = ShardedEDCStep(net, max(t60) * 1e3, tile_rows=tile, edc_weight=10.0)
+    step.attach(z, pos, None, None)
+    step.attach(z, pos, early, step.precompute_target_db(target))
+    out = step.step()
+    assert abs(float(out["edc_loss"]) - edc_ref) < 1e-4 * abs(edc_ref)
+    for k, p in net.named_parameters():
+        err = float((p.grad - g_ref[k]).abs().max() / g_ref[k].abs().max())
+        assert err < 1e-3, (k, err)
+    # host-streamed (end-to-end) mode: same numbers
+    hd, ht = early.cpu().pin_memory(), target.cpu().pin_memory()
+    out2 = step.step(host_d=hd, host_target=ht)
+    assert abs(float(out2["edc_loss"]) - edc_ref) < 1e-4 * abs(edc_ref)
+    for k, p in net.named_parameters():
+        err = float((p.grad - g_ref[k]).abs().max() / g_ref[k].abs().max())
+        assert err < 1e-3, (k, err)
+    assert step.h2d_bytes == 2 * pos.shape[0] * z.numel() * 8
+
+
+def test_full_size_invariants():
+    """BASELINE full size (K = 2^17+1, N = 24): size-independent properties -- linearity of the projection in the
+    receiver gains, H bins above K/2 do not influence the EDC loss (quirk Q3), adjoint dot-product identity."""
+    from diffgfdn_b200 import ops
+    from diffgfdn_b200.config import DiffGFDNConfig
+    from oracle import gfdn_oracle as O
+    nfft = 2**18
+    k = nfft // 2 + 1
+    torch.manual_seed(1)
+    delays = torch.tensor(DiffGFDNConfig(seed=235265, num_delay_lines=24).delay_length_samps, dtype=torch.int32).cuda()
+    m_raw = (2 * torch.rand(3, 8, 8, dtype=torch.float64) - 1) / np.sqrt(8)
+    a = O.coupled_feedback_matrix(m_raw, torch.tensor([0.2, 0.4, 0.1], dtype=torch.float64)).float().cuda()
+    gamma = O.decay_times_to_gain_per_sample([0.3, 0.8, 1.5], delays.tolist(), 32000.0, 3).float().cuda()
+    b = (torch.randn(24) / 24).cuda()
+    c = (torch.randn(24) / 24).cuda()
+    z = O.z_grid(nfft).cuda()
+    x, y = ops.gfdn_solve(z, delays, a, gamma, b, c, 3)
+    assert torch.isfinite(torch.view_as_real(y)).all()
+    # spot-check 64 random bins against the oracle
+    idx = torch.randint(0, k, (64, ))
+    p = O.feedback_loop_inverse(z.cpu()[idx], delays.cpu().double(), gamma.cpu().double(), a.cpu().double())
+    xo = torch.einsum('knm,m->kn', p, b.cpu().to(torch.complex128))
+    assert float((x.cpu()[idx].to(torch.complex128) - xo).abs().max() / xo.abs().max()) < 2e-6
+    s1, s2 = torch.randn(3, 3).cuda(), torch.randn(3, 3).cuda()
+    h1, h2, h12 = ops.receiver_project(s1, y), ops.receiver_project(s2, y), ops.receiver_project(s1 + 2 * s2, y)
+    assert float((h12 - (h1 + 2 * h2)).abs().max() / h12.abs().max()) < 1e-5
+    n_t, t0, tn = k, 640, 48000 - 640
+    ha = ops.irfft_window(h1, n_t, t0, tn)
+    hb = h1.clone()
+    hb[:, k // 2 + 1:] = 0  # bins the odd-length irfft never reads
+    assert torch.equal(ha, ops.irfft_window(hb, n_t, t0, tn))
+    ho = torch.fft.irfft(h1.cpu().to(torch.complex128), n_t)[..., t0:t0 + tn]
+    assert float((ha.cpu().double() - ho).abs().max() / ho.abs().max()) < 2e-5
+    # <irfft(X), g> == <X, irfft^T(g)> (real inner product over re/im parts)
+    xin = h1.detach().clone().requires_grad_(True)
+    gvec = torch.randn(3, tn, device='cuda')
+    (ops.irfft_window(xin, n_t, t0, tn) * gvec).sum().backward()
+    lhs = float((ha * gvec).sum())
+    rhs = float((xin.grad.conj() * h1).real.sum())
+    assert abs(lhs - rhs) < 1e-3 * abs(lhs)
