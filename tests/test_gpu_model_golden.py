@@ -66,8 +66,12 @@ def test_omni_forward_losses_grads_match_reference(name, tmp_path):
     H, (Hs, Hsd) = net(data)
     d = g["data/target_early_response"]
     assert H.dtype == torch.complex64 and tuple(H.shape) == d.shape
-    late_ref = g["out/H"] - d
-    assert rel(H.detach().cpu().to(torch.complex128).numpy() - d, late_ref) < 1e-4
+    # the late (GFDN) part alone: forward without the direct path d (complex64 H cannot resolve a late part that
+    # sits 1e5 below |d|, which is the case in this fixture; the reference keeps H in complex128 only because its
+    # d input is complex128, quirk Q6)
+    with torch.no_grad():
+        H_late, _ = net({k: v for k, v in data.items() if k != "target_early_response"})
+    assert rel(H_late.cpu().to(torch.complex128).numpy(), g["out/H"] - d) < 1e-4
     assert rel(np.abs(H.detach().cpu().numpy()), np.abs(g["out/H"])) < 1e-4
     assert rel(Hs, g["out/H_sub"]) < 1e-4
     assert rel(Hsd.detach().cpu().numpy()[:, ::16, :], g["out/H_sub_per_del_s16"]) < 1e-4
