@@ -10,9 +10,16 @@ gains, EDC (weight 10) + colorless losses, fs = 32 kHz, T60 = (0.3, 0.8, 1.5) s.
 per-bin solve, colorless sub-FDN solve, projection of every receiver over every bin, irfft, EDC loss, colorless
 loss) + backward to every parameter gradient (+ NCCL all-reduce of the flat gradient when N > 1).
 
-`value`  : inputs (early responses d, target EDC curves) resident in HBM, timed with CUDA events.
-`e2e`    : the same step with its inputs streamed from pinned host memory every step (early + target responses,
-           complex64) and the loss read back -- host<->device copies inside the timed region.
+The step never forms H per receiver: the per-bin system is solved once per bin, the inverse DFT runs on G rows, and
+every receiver is handled in the time domain (diffgfdn_b200/fused.py) -- same loss and
+gradients as the reference's project-then-irfft formulation (tests/test_gpu_fused.py).
+
+`value`  : inputs resident in HBM in the data layer's device format (early-response windows hd = irfft(d)[window]
+           and target EDC curves in dB, both float32 (B, tn), built once from the frequency-domain responses),
+           timed with CUDA events.
+`e2e`    : the same step with its inputs streamed every step from pinned host memory in the reference's layout
+           (early + target responses, (B, K) complex64) and the loss read back -- host<->device copies and the
+           per-receiver transforms inside the timed region.
 `--impl reference`: the CPU port of the reference algorithm (oracle/gfdn_oracle.py) on the host cores, on a
            bounded sample of the same workload.
 Prints ONE JSON line on rank 0."""
@@ -34,7 +41,8 @@ FS = 32000.0
 T60 = (0.3, 0.8, 1.5)
 N_LINES, N_GROUPS = 24, 3
 NFFT = 2**18
-ALGO_BYTES_PER_EVAL = 64.0  # algorithmic HBM bytes per receiver.bin, fwd+bwd
+SURVEY_BYTES_PER_EVAL = 64.0  # bytes per receiver.bin of the un-restructured pipeline
+TD_BYTES_PER_SAMPLE = 8.0  # td_edc_step reads hd (4 B) + target dB (4 B) per receiver.sample
 
 
 def parse():
@@ -45,12 +53,12 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--receivers", type=int, default=12500, help="receivers per GPU")
     ap.add_argument("--nfft", type=int, default=NFFT)
-    ap.add_argument("--tile-rows", type=int, default=int(os.environ.get("DGFDN_TILE_ROWS", "128")))
+    ap.add_argument("--tile-rows", type=int, default=int(os.environ.get("DGFDN_TILE_ROWS", "296")))
+    ap.add_argument("--e2e-tile-rows", type=int, default=int(os.environ.get("DGFDN_E2E_TILE_ROWS", "128")))
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-receivers", type=int, default=4)
-    ap.add_argument("--profile-stages", action="store_true", help="per-kernel CUDA-event breakdown (extra output key)")
     return ap.parse_args()
 
 
@@ -156,54 +164,14 @@ def timed_steps(fn, steps, barrier):
     return e0.elapsed_time(e1) / steps, out
 
 
-def stage_profile(step, pool_d, tdb):
-    """CUDA-event duration of every stage of one tile (kernel-level roofline evidence; see profiles/ for ncu)."""
-    import ctypes
-    from diffgfdn_b200 import _lib
-    from diffgfdn_b200.fused import _p
-    b = step._bufs
-    r = b["h_tile"].shape[0]
-    g = step.net.num_groups
-    k, kx, tn = step.k, step.kx, step.tn
-    with torch.no_grad():
-        s = step.net.output_scalars.gains({'norm_listener_position': step.positions}).detach().contiguous()
-        _, y = step.net.feedback_loop.solve(step.z, step.net.input_gains.reshape(-1), step.net.output_gains.reshape(-1))
-        y = y.detach().contiguous()
-    gy = torch.zeros_like(y)
-    gs = torch.empty_like(s)
-    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-    dt = None if pool_d is None else pool_d[:r]
-    stages = [
-        ("project_fwd", 16.0 * r * k, lambda: _lib.call("dgfdn_project_fwd", g, r, k, _p(s[:r]), _p(y), _p(dt), k,
-                                                        _p(b["h_tile"]), k, st)),
-        ("irfft_window_fwd(czt+cuFFT)", (8.0 * kx + 4.0 * tn) * r,
-         lambda: _lib.call("dgfdn_irfft_window_fwd", step.plan.handle, _p(b["h_tile"]), k, r, None, _p(b["scratch"]),
-                           _p(b["h"]), st)),
-        ("edc_loss_fwd", 8.0 * r * tn, lambda: _lib.call("dgfdn_edc_loss_fwd", _p(b["h"]), _p(tdb[:r]), None, r, tn,
-                                                         _p(b["row_sum"][:r]), st)),
-        ("edc_loss_bwd", 12.0 * r * tn, lambda: _lib.call("dgfdn_edc_loss_bwd", _p(b["h"]), _p(tdb[:r]), None, r, tn,
-                                                          ctypes.c_double(1e-6), _p(b["gh"]), st)),
-        ("irfft_window_bwd(czt+cuFFT)", (8.0 * kx + 4.0 * tn) * r,
-         lambda: _lib.call("dgfdn_irfft_window_bwd", step.plan.handle, _p(b["gh"]), r, None, _p(b["scratch"]),
-                           _p(b["g_tile"]), kx, kx, st)),
-        ("project_bwd", 8.0 * r * kx, lambda: _lib.call("dgfdn_project_bwd", g, r, kx, _p(s[:r]), _p(y),
-                                                        _p(b["g_tile"]), kx, _p(gy), 1, _p(gs[:r]), st)),
-    ]
-    res = []
-    for name, nbytes, fn in stages:
-        for _ in range(2):
-            fn()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 5
-        e0.record()
-        for _ in range(reps):
-            fn()
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / reps
-        res.append({"stage": name, "ms": round(ms, 4), "algorithmic_GBps": round(nbytes / ms / 1e6, 1)})
-    return res
+def event_breakdown(events, steps):
+    """Per-step device time of each instrumented kernel / section from the CUDA events recorded inside the timed
+    region (same stream as the launches)."""
+    out = {}
+    for name, pairs in events.items():
+        ms = sum(a.elapsed_time(b) for a, b in pairs)
+        out[name] = {"ms_per_step": ms / steps, "launches_per_step": len(pairs) / steps}
+    return out
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -278,7 +246,8 @@ def workload_config(args):
                         "EDC(w=10)+colorless losses, fwd+bwd",
             "receivers_per_gpu": args.receivers, "bins": args.nfft // 2 + 1, "delay_lines": N_LINES,
             "groups": N_GROUPS, "tile_rows": args.tile_rows, "parallelism": f"receiver-sharded dp{args.gpus}",
-            "l2_policy": "inputs larger than L2 (per-step working set >> 126 MB), no explicit flush"}
+            "l2_policy": "inputs larger than L2 (resident hd + target dB = 2 x receivers x tn x 4 B >> 126 MB, "
+                         "streamed once per step), no explicit flush"}
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -309,20 +278,22 @@ def main():
         for p in net.parameters():
             dist.broadcast(p.data, 0)
     step = ShardedEDCStep(net, max(T60) * 1e3, tile_rows=args.tile_rows, edc_weight=10.0, world_size=world,
-                          total_receivers=args.receivers * world)
+                          total_receivers=args.receivers * world, e2e_tile_rows=args.e2e_tile_rows)
     k = args.nfft // 2 + 1
     z = unit_circle_grid(args.nfft, device=device)
     gen = torch.Generator(device=device).manual_seed(100 + rank)
     positions = torch.rand(args.receivers, 3, device=device, generator=gen)
     step.attach(z, positions, None, None)
-    # resident inputs: early responses d and target EDC curves, built from a pool of synthetic RIRs
+    # resident inputs: early-response windows and target EDC curves (float32 (B, tn)), built once from a pool of
+    # synthetic frequency-domain responses
     pool_rows = min(args.receivers, 1024)
     early_pool, target_pool = synth_responses(pool_rows, args.nfft, device, 200 + rank)
     tdb_pool = step.precompute_target_db(target_pool)
+    hd_pool = step.precompute_early_window(early_pool)
     reps = (args.receivers + pool_rows - 1) // pool_rows
-    d = early_pool.repeat(reps, 1)[:args.receivers].contiguous()  # resident (B, K) complex64
+    hd = hd_pool.repeat(reps, 1)[:args.receivers].contiguous()
     target_db = tdb_pool.repeat(reps, 1)[:args.receivers].contiguous()
-    step.attach(z, positions, d, target_db)
+    step.attach(z, positions, hd, target_db)
     opt = torch.optim.Adam(net.parameters(), lr=1e-3)
 
     def one_step():
@@ -333,9 +304,12 @@ def main():
     for _ in range(args.warmup):
         one_step()
     step.kernel_launches = 0
+    step.events = {}
     with ClockSampler(local) as clocks:
         ms, losses = timed_steps(one_step, args.steps, barrier)
     launches = step.kernel_launches
+    stages = event_breakdown(step.events, args.steps)
+    step.events = None
     t = torch.tensor([ms], device=device, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -368,12 +342,16 @@ def main():
         e2e = {"value": evals_per_step / float(te.item()), "unit": "receiver*bin evals/s",
                "h2d_bytes_per_step": int(step.h2d_bytes) + int(positions.numel() * 4), "d2h_bytes_per_step": 8,
                "ms_per_step": 1e3 * float(te.item()),
-               "note": "early + target responses (complex64) streamed from a pinned host pool every step, target EDC "
-                       "rebuilt on the device, loss read back"}
+               "note": "early + target responses ((B, K) complex64, reference layout) streamed from a pinned host pool "
+                       "every step (bins 0..K/2, the ones irfft(X, n=K) reads), early window + target EDC rebuilt on "
+                       "the device, loss read back"}
 
     if rank == 0:
         hbm, how = peaks()
-        achieved = value / world * ALGO_BYTES_PER_EVAL / 1e9  # GB/s per GPU
+        # dominant receiver-scaling kernel: td_edc_step, 8 algorithmic bytes per receiver.sample
+        td = stages["td_edc_step"]
+        td_bytes = TD_BYTES_PER_SAMPLE * args.receivers * step.tn  # per step, this rank
+        achieved = td_bytes / (td["ms_per_step"] * 1e-3) / 1e9
         out = {
             "metric": "DiffGFDN receiver*bin evals/s fwd+bwd", "value": value, "unit": "receiver*bin evals/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
@@ -382,12 +360,18 @@ def main():
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
                          "traffic": None, "peak_source": how,
-                         "kernel": "whole tile pipeline (project -> chirp-z irfft -> EDC fwd/bwd -> irfft^T -> "
-                                   "project^T) at 64 algorithmic B per receiver.bin"},
+                         "kernel": "td_edc_step_kernel<3,true> (mix + EDC + dB loss + backward per receiver row)",
+                         "algorithmic_bytes_per_launch": TD_BYTES_PER_SAMPLE * min(args.tile_rows, args.receivers) * step.tn,
+                         "avg_launch_ms": td["ms_per_step"] / td["launches_per_step"],
+                         "share_of_step": td["ms_per_step"] / ms,
+                         "note": "8 B per receiver.sample (hd 4 + target dB 4); tn = %d samples per receiver" % step.tn},
+            # the same throughput expressed with SURVEY.md 8(d)'s 64 B per receiver.bin of the project-then-irfft
+            # pipeline this design replaces (can exceed 1: those bytes are no longer moved)
+            "survey_64B_equivalent": {"GBps": value / world * SURVEY_BYTES_PER_EVAL / 1e9,
+                                      "frac_of_peak": value / world * SURVEY_BYTES_PER_EVAL / 1e9 / hbm},
+            "stages": stages,
             "e2e": e2e,
         }
-        if args.profile_stages:
-            out["stages"] = stage_profile(step, d, target_db)
         if not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(args.nfft, args.cpu_sample_receivers)
         print(json.dumps(out))

@@ -15,6 +15,7 @@ SIGNATURES = {
     "dgfdn_last_error": (c_char_p, []),
     "dgfdn_version": (c_int, []),
     "dgfdn_sm_count": (c_int, []),
+    "dgfdn_copy_rows_h2d": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p]),
     "dgfdn_solve_fwd": (c_int, [c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dgfdn_solve_bwd_ws_bytes": (c_int64, [c_int]),
@@ -38,6 +39,13 @@ SIGNATURES = {
     "dgfdn_edc_db": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
     "dgfdn_edc_loss_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
     "dgfdn_edc_loss_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_double, c_void_p, c_void_p]),
+    "dgfdn_td_edc_step": (c_int, [c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64,
+                                  c_void_p, c_double, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "dgfdn_td_mix": (c_int, [c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64,
+                             c_void_p]),
+    "dgfdn_td_contract_ws_bytes": (c_int64, [c_int, c_int64, c_int64]),
+    "dgfdn_td_contract": (c_int, [c_int, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int, c_void_p,
+                                  c_void_p]),
     "dgfdn_colorless_fwd": (c_int, [c_int, c_int64, c_void_p, c_int, c_void_p, c_void_p]),
     "dgfdn_colorless_bwd": (c_int, [c_int, c_int64, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "dgfdn_render_groups": (c_int, [c_int, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

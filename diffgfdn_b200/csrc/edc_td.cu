@@ -1,0 +1,553 @@
+// K3c: receiver step in the TIME domain -- mix, energy-decay curve, dB loss and its whole backward in one kernel.
+//
+// The reference evaluates, per receiver r, H_r = sum_g s[r,g] y_g + d_r over every bin (diff_gfdn/model.py:583-619),
+// takes irfft(H_r, n=K)[mix:max_len] and compares Schroeder EDCs in dB (losses.py:187-238). The inverse DFT is
+// linear and the receiver enters only through the G real gains s[r,:], so
+//
+//     h_r[t] = sum_g s[r,g] hy_g[t] + hd_r[t],     hy_g = irfft(y_g)[window],   hd_r = irfft(d_r)[window]
+//
+// where hy is G rows per step (receiver independent) and hd_r is a constant of the data set (like the target
+// EDC), precomputed once. Per receiver and step nothing is left in the frequency domain: this kernel reads
+// hd_r and the target EDC in dB (4 B + 4 B per sample), and produces the row loss, dL/ds[r,:] and dL/dh_r.
+// The adjoint closes with one G-row contraction (td_contract) and one G-row inverse-DFT adjoint.
+//
+// Persistent kernel, one CTA per SM, one receiver row at a time per CTA. Pass 1 walks the row late -> early in
+// chunks of 8192 samples: h (kept in shared memory), suffix scan of h^2 (float32 inside a thread's 4-sample
+// segment, float64 across threads and chunks), dB, |target - achieved|, dL/dEDC. Pass 2 walks early -> late: prefix
+// scan of dL/dEDC, dL/dh = 2 h cumsum, dot products with hy for dL/ds; it reads no HBM, so it prefetches the CTA's
+// next row into L2 meanwhile. Reduction order is fixed (deterministic).
+#include <type_traits>
+
+#include "common.cuh"
+
+namespace dgfdn {
+namespace {
+
+constexpr int kThreads = 1024;
+constexpr int kWarps = kThreads / 32;
+constexpr int kSeg = 4;                    // samples per thread and segment (one 128-bit access)
+constexpr int kHalf = kThreads * kSeg;     // 4096 samples: one segment per thread
+constexpr int kChunk = 2 * kHalf;          // two segments per thread and iteration share one block scan
+constexpr float kEpsF = 1.1920928955078125e-07f;   // torch.finfo(float32).eps (reference utils.py:35)
+constexpr float kDbPerLog2 = 3.0102999566398120f;  // 10 / log2(10)
+constexpr double kDbFactor = 4.342944819032518;    // 10 / ln(10)
+
+struct ScanSmem {
+  double in[2][kWarps];
+  double out[2][kWarps];
+};
+
+// Exclusive scans over the thread index of TWO independent values per thread (they share the barriers).
+// REVERSE: sum over threads with a HIGHER index. Returns the exclusive offsets in a/b and the block totals.
+template <bool REVERSE>
+__device__ __forceinline__ void block_scan2(double& a, double& b, ScanSmem& sm, double* tot_a, double* tot_b) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double ia = a, ib = b;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double ta = REVERSE ? __shfl_down_sync(0xffffffffu, ia, o) : __shfl_up_sync(0xffffffffu, ia, o);
+    const double tb = REVERSE ? __shfl_down_sync(0xffffffffu, ib, o) : __shfl_up_sync(0xffffffffu, ib, o);
+    if (REVERSE ? (lane + o < 32) : (lane >= o)) {
+      ia += ta;
+      ib += tb;
+    }
+  }
+  if (lane == (REVERSE ? 0 : 31)) {
+    sm.in[0][warp] = ia;
+    sm.in[1][warp] = ib;
+  }
+  __syncthreads();
+  if (warp < 2) {  // warp 0 scans the warp totals of a, warp 1 those of b (kWarps == 32)
+    double w = sm.in[warp][lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double t = REVERSE ? __shfl_down_sync(0xffffffffu, w, o) : __shfl_up_sync(0xffffffffu, w, o);
+      if (REVERSE ? (lane + o < 32) : (lane >= o)) w += t;
+    }
+    sm.out[warp][lane] = w;
+  }
+  __syncthreads();
+  double wa, wb;
+  if (REVERSE) {
+    wa = (warp < kWarps - 1) ? sm.out[0][warp + 1] : 0.0;
+    wb = (warp < kWarps - 1) ? sm.out[1][warp + 1] : 0.0;
+    *tot_a = sm.out[0][0];
+    *tot_b = sm.out[1][0];
+  } else {
+    wa = (warp > 0) ? sm.out[0][warp - 1] : 0.0;
+    wb = (warp > 0) ? sm.out[1][warp - 1] : 0.0;
+    *tot_a = sm.out[0][kWarps - 1];
+    *tot_b = sm.out[1][kWarps - 1];
+  }
+  a = wa + ia - a;
+  b = wb + ib - b;
+  __syncthreads();  // sm reusable by the next call
+}
+
+struct TdParams {
+  int64_t rows;
+  int tn;
+  const float* s;     // [rows, G]
+  const float* hy;    // [G, tn]
+  const float* hd;    // [rows, ldhd] or null
+  int64_t ldhd;
+  const float* tdb;   // [rows, ldt]
+  int64_t ldt;
+  const float* mask;  // [tn] or null
+  double coef;
+  double* row_sum;    // [rows]
+  float* gs;          // [rows, G]
+  float* gh;          // [rows, ldg]
+  int64_t ldg;
+};
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// One segment (4 consecutive samples starting at t) of a row-major float array; samples at or beyond tn read as 0.
+// VEC: tn % 4 == 0 and every row is 16-byte aligned, so a segment is either fully inside or fully outside.
+template <bool VEC, bool STREAM>
+__device__ __forceinline__ float4 load_seg(const float* __restrict__ p, int t, int tn) {
+  if (VEC) {
+    if (t >= tn) return make_float4(0.f, 0.f, 0.f, 0.f);
+    return STREAM ? ld_stream(reinterpret_cast<const float4*>(p + t)) : __ldcg(reinterpret_cast<const float4*>(p + t));
+  }
+  float4 v;
+  v.x = (t < tn) ? __ldcg(p + t) : 0.f;
+  v.y = (t + 1 < tn) ? __ldcg(p + t + 1) : 0.f;
+  v.z = (t + 2 < tn) ? __ldcg(p + t + 2) : 0.f;
+  v.w = (t + 3 < tn) ? __ldcg(p + t + 3) : 0.f;
+  return v;
+}
+
+template <bool VEC>
+__device__ __forceinline__ void store_seg(float* __restrict__ p, int t, int tn, float4 v) {
+  if (VEC) {
+    if (t < tn) __stcg(reinterpret_cast<float4*>(p + t), v);
+    return;
+  }
+  if (t < tn) __stcg(p + t, v.x);
+  if (t + 1 < tn) __stcg(p + t + 1, v.y);
+  if (t + 2 < tn) __stcg(p + t + 2, v.z);
+  if (t + 3 < tn) __stcg(p + t + 3, v.w);
+}
+
+// h of one segment: sum_g s_g hy_g[t..t+3] + hd[t..t+3]
+template <int G, bool VEC>
+__device__ __forceinline__ float4 mix_seg(const TdParams& p, const float* hdr, const float (&sv)[G], int t) {
+  float4 h = hdr ? load_seg<VEC, true>(hdr, t, p.tn) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    const float4 y = load_seg<VEC, false>(p.hy + (int64_t)g * p.tn, t, p.tn);
+    h.x = fmaf(sv[g], y.x, h.x);
+    h.y = fmaf(sv[g], y.y, h.y);
+    h.z = fmaf(sv[g], y.z, h.z);
+    h.w = fmaf(sv[g], y.w, h.w);
+  }
+  return h;
+}
+
+// dB of the EDC samples of one segment, masked |target - dB| and dL/dEDC. `suf` holds the suffix sums of h^2 inside
+// the segment, `off` everything later than the segment. 10 log10(EDC + eps) >= -69.2 dB, so the reference's clip
+// at -200 dB (utils.py:38-40) can never bind and is not evaluated.
+__device__ __forceinline__ float4 db_loss_seg(float4 suf, float off, float4 td, float4 mk, float cf, float& acc) {
+  float4 ge;
+#define DGFDN_DB_ONE(C)                                                 \
+  {                                                                     \
+    const float x = suf.C + off + kEpsF;                                \
+    const float diff = td.C - kDbPerLog2 * __log2f(x);                  \
+    acc = fmaf(mk.C, fabsf(diff), acc);                                 \
+    const float g = __fdividef(mk.C * cf, x);                           \
+    ge.C = diff > 0.f ? -g : (diff < 0.f ? g : 0.f);                    \
+  }
+  DGFDN_DB_ONE(x) DGFDN_DB_ONE(y) DGFDN_DB_ONE(z) DGFDN_DB_ONE(w)
+#undef DGFDN_DB_ONE
+  return ge;
+}
+
+// Persistent: CTA b handles rows b, b + gridDim.x, ...  H_IN_SMEM keeps the row's h (tn floats) in shared memory
+// between the two passes; otherwise pass 2 rebuilds it from hd and hy.
+template <int G, bool H_IN_SMEM, bool VEC>
+__global__ void __launch_bounds__(kThreads, 1) td_edc_step_kernel(TdParams p) {
+  extern __shared__ float4 s_h4[];  // [ceil(tn/4)] segments when H_IN_SMEM
+  __shared__ ScanSmem sm;
+  __shared__ double red[kWarps][G + 1];
+  const int tn = p.tn;
+  const int tid = threadIdx.x;
+  const int nchunks = (tn + kChunk - 1) / kChunk;
+  const float cf = (float)(p.coef * kDbFactor);
+
+  for (int64_t r = blockIdx.x; r < p.rows; r += gridDim.x) {
+    float sv[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) sv[g] = p.s[r * G + g];
+    const float* hdr = p.hd ? p.hd + r * p.ldhd : nullptr;
+    const float* tr = p.tdb + r * p.ldt;
+    float* gr = p.gh + r * p.ldg;
+    // the row this CTA handles next: its inputs are pulled into L2 while pass 2 (which reads no HBM) runs
+    const int64_t rn = r + gridDim.x;
+    const float* hdn = (rn < p.rows && p.hd) ? p.hd + rn * p.ldhd : nullptr;
+    const float* trn = (rn < p.rows) ? p.tdb + rn * p.ldt : nullptr;
+
+    // ---- pass 1, late -> early: EDC[t] = sum_{tau >= t} h^2, loss, dL/dEDC -> gr
+    double carry = 0.0;
+    float acc = 0.f;
+    for (int c = nchunks - 1; c >= 0; --c) {
+      const int ta = c * kChunk + tid * kSeg;  // earlier segment
+      const int tb = ta + kHalf;               // later segment
+      if (c > 0) {  // next iteration's HBM inputs (no effect if the previous row's pass 2 already fetched them)
+        if (hdr) {
+          prefetch_l2(hdr + ta - kChunk);
+          prefetch_l2(hdr + tb - kChunk);
+        }
+        prefetch_l2(tr + ta - kChunk);
+        prefetch_l2(tr + tb - kChunk);
+      }
+      const float4 ha = mix_seg<G, VEC>(p, hdr, sv, ta);
+      const float4 hb = mix_seg<G, VEC>(p, hdr, sv, tb);
+      if (H_IN_SMEM) {
+        if (ta < tn) s_h4[ta >> 2] = ha;  // samples beyond tn inside the last segment are zero
+        if (tb < tn) s_h4[tb >> 2] = hb;
+      }
+      float4 sa, sb;  // suffix sums of h^2 inside each segment
+      sa.w = ha.w * ha.w;
+      sa.z = fmaf(ha.z, ha.z, sa.w);
+      sa.y = fmaf(ha.y, ha.y, sa.z);
+      sa.x = fmaf(ha.x, ha.x, sa.y);
+      sb.w = hb.w * hb.w;
+      sb.z = fmaf(hb.z, hb.z, sb.w);
+      sb.y = fmaf(hb.y, hb.y, sb.z);
+      sb.x = fmaf(hb.x, hb.x, sb.y);
+      double oa = (double)sa.x, ob = (double)sb.x, tot_a, tot_b;
+      block_scan2<true>(oa, ob, sm, &tot_a, &tot_b);
+      const float offb = (float)(ob + carry);
+      const float offa = (float)(oa + tot_b + carry);
+      const float4 tda = load_seg<VEC, true>(tr, ta, tn), tdb4 = load_seg<VEC, true>(tr, tb, tn);
+      float4 ma = make_float4(1.f, 1.f, 1.f, 1.f), mb = ma;
+      if (p.mask != nullptr) {
+        ma = load_seg<VEC, false>(p.mask, ta, tn);
+        mb = load_seg<VEC, false>(p.mask, tb, tn);
+      }
+      if (!VEC) {  // a ragged last segment: samples beyond tn must not contribute
+        if (ta + 1 >= tn) ma.y = 0.f;
+        if (ta + 2 >= tn) ma.z = 0.f;
+        if (ta + 3 >= tn) ma.w = 0.f;
+        if (tb + 1 >= tn) mb.y = 0.f;
+        if (tb + 2 >= tn) mb.z = 0.f;
+        if (tb + 3 >= tn) mb.w = 0.f;
+      }
+      if (ta >= tn) ma = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (tb >= tn) mb = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 ga = db_loss_seg(sa, offa, tda, ma, cf, acc);
+      const float4 gb = db_loss_seg(sb, offb, tdb4, mb, cf, acc);
+      store_seg<VEC>(gr, ta, tn, ga);
+      store_seg<VEC>(gr, tb, tn, gb);
+      carry += tot_a + tot_b;
+    }
+    if (H_IN_SMEM) __syncthreads();
+
+    // ---- pass 2, early -> late: dL/dh[tau] = 2 h[tau] sum_{t <= tau} dL/dEDC[t]; dL/ds_g = <dL/dh, hy_g>
+    float gsacc[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) gsacc[g] = 0.f;
+    carry = 0.0;
+    for (int c = 0; c < nchunks; ++c) {
+      const int ta = c * kChunk + tid * kSeg;
+      const int tb = ta + kHalf;
+      {  // pull the chunk of the next row that its pass 1 will consume at the mirrored position
+        const int cn = nchunks - 1 - c;
+        const int pa = cn * kChunk + tid * kSeg, pb = pa + kHalf;
+        if (trn != nullptr) {
+          if (pa < tn) prefetch_l2(trn + pa);
+          if (pb < tn) prefetch_l2(trn + pb);
+        }
+        if (hdn != nullptr) {
+          if (pa < tn) prefetch_l2(hdn + pa);
+          if (pb < tn) prefetch_l2(hdn + pb);
+        }
+      }
+      const float4 ga = load_seg<VEC, false>(gr, ta, tn);  // written by this same thread in pass 1
+      const float4 gb = load_seg<VEC, false>(gr, tb, tn);
+      float4 pa4, pb4;  // prefix sums inside each segment
+      pa4.x = ga.x;
+      pa4.y = pa4.x + ga.y;
+      pa4.z = pa4.y + ga.z;
+      pa4.w = pa4.z + ga.w;
+      pb4.x = gb.x;
+      pb4.y = pb4.x + gb.y;
+      pb4.z = pb4.y + gb.z;
+      pb4.w = pb4.z + gb.w;
+      double oa = (double)pa4.w, ob = (double)pb4.w, tot_a, tot_b;
+      block_scan2<false>(oa, ob, sm, &tot_a, &tot_b);
+      const float offa = (float)(oa + carry);
+      const float offb = (float)(ob + tot_a + carry);
+      float4 ha, hb;
+      if (H_IN_SMEM) {
+        ha = (ta < tn) ? s_h4[ta >> 2] : make_float4(0.f, 0.f, 0.f, 0.f);
+        hb = (tb < tn) ? s_h4[tb >> 2] : make_float4(0.f, 0.f, 0.f, 0.f);
+      } else {
+        ha = mix_seg<G, VEC>(p, hdr, sv, ta);
+        hb = mix_seg<G, VEC>(p, hdr, sv, tb);
+      }
+      float4 oa4, ob4;
+      oa4.x = 2.f * ha.x * (pa4.x + offa);
+      oa4.y = 2.f * ha.y * (pa4.y + offa);
+      oa4.z = 2.f * ha.z * (pa4.z + offa);
+      oa4.w = 2.f * ha.w * (pa4.w + offa);
+      ob4.x = 2.f * hb.x * (pb4.x + offb);
+      ob4.y = 2.f * hb.y * (pb4.y + offb);
+      ob4.z = 2.f * hb.z * (pb4.z + offb);
+      ob4.w = 2.f * hb.w * (pb4.w + offb);
+      store_seg<VEC>(gr, ta, tn, oa4);
+      store_seg<VEC>(gr, tb, tn, ob4);
+      if (p.gs != nullptr) {
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          const float4 ya = load_seg<VEC, false>(p.hy + (int64_t)g * tn, ta, tn);
+          const float4 yb = load_seg<VEC, false>(p.hy + (int64_t)g * tn, tb, tn);
+          float a = gsacc[g];
+          a = fmaf(oa4.x, ya.x, a);
+          a = fmaf(oa4.y, ya.y, a);
+          a = fmaf(oa4.z, ya.z, a);
+          a = fmaf(oa4.w, ya.w, a);
+          a = fmaf(ob4.x, yb.x, a);
+          a = fmaf(ob4.y, yb.y, a);
+          a = fmaf(ob4.z, yb.z, a);
+          a = fmaf(ob4.w, yb.w, a);
+          gsacc[g] = a;
+        }
+      }
+      carry += tot_a + tot_b;
+    }
+
+    // ---- block reduction of the row loss and of dL/ds[r, :] (float64, fixed order)
+    const int lane = tid & 31, warp = tid >> 5;
+    {
+      const double v = warp_sum((double)acc);
+      if (lane == 0) red[warp][G] = v;
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      const double v = warp_sum((double)gsacc[g]);
+      if (lane == 0) red[warp][g] = v;
+    }
+    __syncthreads();
+    if (tid <= G) {
+      double v = 0.0;
+      for (int w = 0; w < kWarps; ++w) v += red[w][tid];
+      if (tid == G) {
+        if (p.row_sum) p.row_sum[r] = v;
+      } else if (p.gs != nullptr) {
+        p.gs[r * G + tid] = (float)v;
+      }
+    }
+    __syncthreads();  // red / s_h4 are reused by the next row
+  }
+}
+
+// h[r,t] = sum_g s[r,g] hy[g,t] + hd[r,t]  (the receiver's late RIR window itself; inference / validation)
+template <int G>
+__global__ void __launch_bounds__(256) td_mix_kernel(int64_t rows, int64_t tn, const float* __restrict__ s,
+                                                     const float* __restrict__ hy, const float* __restrict__ hd,
+                                                     int64_t ldhd, float* __restrict__ h, int64_t ldh) {
+  const int64_t r = blockIdx.y;
+  const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (t >= tn) return;
+  float acc = hd ? hd[r * ldhd + t] : 0.f;
+#pragma unroll
+  for (int g = 0; g < G; ++g) acc = fmaf(__ldg(s + r * G + g), __ldg(hy + (int64_t)g * tn + t), acc);
+  h[r * ldh + t] = acc;
+}
+
+// partial[split][g][t] = sum_{r in split} s[r,g] gh[r,t]; one thread per 4 samples, rows streamed once.
+constexpr int kCThreads = 256;
+constexpr int kCRows = 256;
+template <int G>
+__global__ void __launch_bounds__(kCThreads) td_contract_kernel(int64_t rows, int64_t tn, const float* __restrict__ s,
+                                                                const float* __restrict__ gh, int64_t ldg,
+                                                                float* __restrict__ partial, int64_t rows_per_split,
+                                                                bool vec) {
+  __shared__ float s_s[kCRows * G];
+  const int64_t t0 = 4 * ((int64_t)blockIdx.x * kCThreads + threadIdx.x);
+  const int64_t r_begin = (int64_t)blockIdx.y * rows_per_split;
+  const int64_t r_end = min(rows, r_begin + rows_per_split);
+  const bool active = t0 < tn;
+  const bool full = vec && (t0 + 4 <= tn);
+  float4 acc[G];
+#pragma unroll
+  for (int g = 0; g < G; ++g) acc[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int64_t rc = r_begin; rc < r_end; rc += kCRows) {
+    const int nr = (int)min((int64_t)kCRows, r_end - rc);
+    __syncthreads();
+    for (int i = threadIdx.x; i < nr * G; i += kCThreads) s_s[i] = s[rc * G + i];
+    __syncthreads();
+    if (active) {
+#pragma unroll 4
+      for (int r = 0; r < nr; ++r) {
+        const float* gp = gh + (rc + r) * ldg + t0;
+        float4 v;
+        if (full) {
+          v = ld_stream(reinterpret_cast<const float4*>(gp));
+        } else {
+          v.x = gp[0];
+          v.y = (t0 + 1 < tn) ? gp[1] : 0.f;
+          v.z = (t0 + 2 < tn) ? gp[2] : 0.f;
+          v.w = (t0 + 3 < tn) ? gp[3] : 0.f;
+        }
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          const float sv = s_s[r * G + g];
+          acc[g].x = fmaf(sv, v.x, acc[g].x);
+          acc[g].y = fmaf(sv, v.y, acc[g].y);
+          acc[g].z = fmaf(sv, v.z, acc[g].z);
+          acc[g].w = fmaf(sv, v.w, acc[g].w);
+        }
+      }
+    }
+  }
+  if (!active) return;
+  float* out = partial + (int64_t)blockIdx.y * G * tn;
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    float* o = out + (int64_t)g * tn + t0;
+    o[0] = acc[g].x;
+    if (t0 + 1 < tn) o[1] = acc[g].y;
+    if (t0 + 2 < tn) o[2] = acc[g].z;
+    if (t0 + 3 < tn) o[3] = acc[g].w;
+  }
+}
+
+__global__ void td_contract_reduce_kernel(int64_t total, int nsplit, const float* __restrict__ partial,
+                                          float* __restrict__ ghy, int accumulate) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  float v = accumulate ? ghy[i] : 0.f;
+  for (int sp = 0; sp < nsplit; ++sp) v += partial[(int64_t)sp * total + i];
+  ghy[i] = v;
+}
+
+template <typename F>
+int dispatch_g(int g, F&& f) {
+  switch (g) {
+    case 1: f(std::integral_constant<int, 1>{}); return 0;
+    case 2: f(std::integral_constant<int, 2>{}); return 0;
+    case 3: f(std::integral_constant<int, 3>{}); return 0;
+    case 4: f(std::integral_constant<int, 4>{}); return 0;
+    case 5: f(std::integral_constant<int, 5>{}); return 0;
+    case 6: f(std::integral_constant<int, 6>{}); return 0;
+    case 7: f(std::integral_constant<int, 7>{}); return 0;
+    case 8: f(std::integral_constant<int, 8>{}); return 0;
+    default: set_error("td: g=%d out of range [1,%d]", g, DGFDN_MAX_GROUPS); return 1;
+  }
+}
+
+inline bool aligned16(const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+int contract_splits(int64_t rows, int64_t tn) {
+  const int64_t tblocks = (tn + 4 * kCThreads - 1) / (4 * kCThreads);
+  int64_t want = (4 * (int64_t)sm_count() + tblocks - 1) / tblocks;
+  if (want > 64) want = 64;
+  const int64_t max_by_rows = (rows + 63) / 64;  // at least 64 rows per split
+  if (want > max_by_rows) want = max_by_rows;
+  return (int)(want < 1 ? 1 : want);
+}
+
+constexpr size_t kMaxHSmem = 200 * 1024;
+
+}  // namespace
+}  // namespace dgfdn
+
+using namespace dgfdn;
+
+extern "C" int dgfdn_td_edc_step(int g, int64_t rows, int64_t tn, const float* s, const float* hy, const float* hd,
+                                 int64_t ldhd, const float* target_db, int64_t ldt, const float* mask, double coef,
+                                 double* row_sum, float* gs, float* gh, int64_t ldg, void* stream) {
+  DGFDN_CHECK(rows >= 0 && tn >= 1 && s && hy && target_db && gh, "td_edc_step: bad arguments");
+  DGFDN_CHECK(tn < ((int64_t)1 << 30), "td_edc_step: tn too large");
+  DGFDN_CHECK(ldt >= tn && ldg >= tn && (hd == nullptr || ldhd >= tn), "td_edc_step: row stride smaller than tn");
+  if (rows == 0) return 0;
+  TdParams p{};
+  p.rows = rows;
+  p.tn = (int)tn;
+  p.s = s;
+  p.hy = hy;
+  p.hd = hd;
+  p.ldhd = ldhd;
+  p.tdb = target_db;
+  p.ldt = ldt;
+  p.mask = mask;
+  p.coef = coef;
+  p.row_sum = row_sum;
+  p.gs = gs;
+  p.gh = gh;
+  p.ldg = ldg;
+  const bool vec = aligned16(hy) && aligned16(hd) && aligned16(target_db) && aligned16(gh) && aligned16(mask) &&
+                   tn % 4 == 0 && ldt % 4 == 0 && ldg % 4 == 0 && (hd == nullptr || ldhd % 4 == 0);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t hbytes = (size_t)((tn + 3) / 4) * sizeof(float4);
+  const bool in_smem = hbytes <= kMaxHSmem;
+  const unsigned grid = (unsigned)(rows < (int64_t)sm_count() ? rows : sm_count());  // persistent, one CTA per SM
+  int rc = 0;
+  auto launch = [&](auto kern, size_t smem) {
+    if (smem > 48 * 1024 &&
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxHSmem) != cudaSuccess) {
+      set_error("td_edc_step: cannot raise the shared-memory limit");
+      rc = 1;
+      return;
+    }
+    kern<<<grid, kThreads, smem, st>>>(p);
+  };
+  if (dispatch_g(g, [&](auto gc) {
+        constexpr int G = decltype(gc)::value;
+        if (in_smem && vec) launch(td_edc_step_kernel<G, true, true>, hbytes);
+        else if (in_smem) launch(td_edc_step_kernel<G, true, false>, hbytes);
+        else if (vec) launch(td_edc_step_kernel<G, false, true>, 0);
+        else launch(td_edc_step_kernel<G, false, false>, 0);
+      }))
+    return 1;
+  if (rc) return rc;
+  DGFDN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int dgfdn_td_mix(int g, int64_t rows, int64_t tn, const float* s, const float* hy, const float* hd,
+                            int64_t ldhd, float* h, int64_t ldh, void* stream) {
+  DGFDN_CHECK(rows >= 0 && tn >= 1 && s && hy && h, "td_mix: bad arguments");
+  DGFDN_CHECK(ldh >= tn && (hd == nullptr || ldhd >= tn), "td_mix: row stride smaller than tn");
+  if (rows == 0) return 0;
+  DGFDN_CHECK(rows <= 65535, "td_mix: rows=%lld exceeds grid.y limit; tile the call", (long long)rows);
+  dim3 grid((unsigned)((tn + 255) / 256), (unsigned)rows);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dispatch_g(g, [&](auto gc) {
+        td_mix_kernel<decltype(gc)::value><<<grid, 256, 0, st>>>(rows, tn, s, hy, hd, ldhd, h, ldh);
+      }))
+    return 1;
+  DGFDN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int64_t dgfdn_td_contract_ws_bytes(int g, int64_t rows, int64_t tn) {
+  if (g < 1 || rows < 1 || tn < 1) return 0;
+  return (int64_t)contract_splits(rows, tn) * g * tn * (int64_t)sizeof(float);
+}
+
+extern "C" int dgfdn_td_contract(int g, int64_t rows, int64_t tn, const float* s, const float* gh, int64_t ldg,
+                                 float* ghy, int accumulate, void* ws, void* stream) {
+  DGFDN_CHECK(rows >= 0 && tn >= 1 && s && gh && ghy && ws, "td_contract: bad arguments");
+  DGFDN_CHECK(ldg >= tn, "td_contract: row stride smaller than tn");
+  if (rows == 0) return 0;
+  const int nsplit = contract_splits(rows, tn);
+  const int64_t rps = (rows + nsplit - 1) / nsplit;
+  const bool vec = aligned16(gh) && ldg % 4 == 0;
+  dim3 grid((unsigned)((tn + 4 * kCThreads - 1) / (4 * kCThreads)), (unsigned)nsplit);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* partial = static_cast<float*>(ws);
+  if (dispatch_g(g, [&](auto gc) {
+        td_contract_kernel<decltype(gc)::value><<<grid, kCThreads, 0, st>>>(rows, tn, s, gh, ldg, partial, rps, vec);
+      }))
+    return 1;
+  DGFDN_LAUNCH_CHECK();
+  const int64_t total = (int64_t)g * tn;
+  td_contract_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(total, nsplit, partial, ghy, accumulate);
+  DGFDN_LAUNCH_CHECK();
+  return 0;
+}

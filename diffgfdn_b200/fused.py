@@ -1,24 +1,34 @@
-"""Receiver-sharded, tiled training step for large receiver counts (BASELINE config 4: 100k receivers x 2^17 bins).
+"""Receiver-sharded training step for large receiver counts (BASELINE config 4: 100k receivers x 2^17 bins).
 
 The reference can only hold ~32 receivers per step because it materialises (B, N, K) complex tensors
-(model.py:583-619). Here the per-bin solve is receiver independent and the projection + loss pipeline streams over
-receivers, so a step walks the rank's receiver shard in tiles:
+(model.py:583-619) and runs one irfft per receiver (losses.py:207-213). Two linearities remove all per-receiver
+frequency-domain work:
 
-    s = MLP(positions)                      torch (cuBLAS), autograd graph kept            (B, G)
-    x, y = solve(z, A, gamma, b, c)         K1 kernel, autograd graph kept                 (K, G)
-    for each tile of R receivers:           raw C-ABI calls on preallocated buffers, no graph
-        H   = project(s, y, d)              K2          (R, K) -- full spectrum, as the reference's forward
-        h   = irfft(H, n=K)[mix:max_len]    K3a         chirp-z over cuFFT
-        l  += sum |EDC_dB(target) - EDC_dB(h)|          K3b forward
-        gh  = dl/dh                         K3b backward
-        gH  = irfft^T(gh)                   K3a adjoint (bins 0..K/2 only: the others have zero gradient, Q3)
-        gy += s^T gH ; gs = Re(gH y^H)      K2 adjoint
-    backward([y, s], [gy, gs]) + colorless losses -> parameter gradients     K1^T kernel + torch autograd
+  * b is shared by every receiver, so the per-bin system is solved ONCE per bin:  y[k,g] = c_g^T (D G^-1 - A)^-1 b;
+  * irfft is linear and receiver r enters H_r = sum_g s[r,g] y_g + d_r only through its G real gains, so
+        h_r = irfft(H_r)[window] = sum_g s[r,g] hy_g + hd_r,   hy_g = irfft(y_g)[window]   (G rows per step)
+    and hd_r = irfft(d_r)[window] is a constant of the data set, precomputed once like the target EDC.
+
+One step:
+
+    s  = MLP(positions)                        torch (cuBLAS), autograd graph kept            (B, G)
+    y  = solve(z, A, gamma, b, c)              K1 kernel, autograd graph kept                 (K, G)
+    hy = irfft(y^T, n=K)[mix:max_len]          K3a chirp-z, G rows, autograd graph kept       (G, tn)
+    for each tile of receivers:                raw C-ABI calls on preallocated buffers, no graph
+        row loss, dL/ds, dL/dh = td_edc_step(s, hy, hd, target_db)      K3c: mix + EDC + dB loss + backward
+        dL/dhy += s^T dL/dh                                             K3c contraction
+    backward([hy, s], [dL/dhy, dL/ds]) + colorless losses -> parameter gradients   K3a^T + K1^T + torch autograd
     all-reduce of the flat gradient bucket over NCCL when world_size > 1
 
-Losses are means over ALL receivers of the job, so every rank scales by 1/B_total; the colorless losses are
-receiver independent, computed on every rank and divided by world_size before the SUM all-reduce.
-Receivers are independent given the shared parameters: sharding needs no data-path collective (weak scaling)."""
+HBM traffic per receiver and time sample: hd 4 B + target dB 4 B (+ 4 B of dL/dh that stay in L2 when the tile is
+small). Losses are means over ALL receivers of the job, so every rank scales by 1/B_total; the colorless losses are
+receiver independent, computed on every rank and divided by world_size before the SUM all-reduce. Receivers are
+independent given the shared parameters: sharding needs no data-path collective (weak scaling).
+
+End-to-end mode (`step(host_d=..., host_target=...)`): the early and target responses arrive every step in the
+reference's layout -- (B, K) complex64 frequency-domain arrays in pinned host memory (dataloader.py:674-704) -- and
+are moved host -> device tile by tile on a copy stream (only bins 0..K/2, the ones irfft(X, n=K) reads), transformed
+with the chirp-z kernels and fed to the same time-domain kernels."""
 import ctypes
 from typing import Dict, Optional
 
@@ -39,31 +49,33 @@ def _p(t):
 class ShardedEDCStep:
     """One data-parallel training step (EDC + colorless losses) over this rank's receiver shard."""
 
-    def __init__(self, net: DiffGFDNVarReceiverPos, max_ir_len_ms: float, tile_rows: int = 128,
+    def __init__(self, net: DiffGFDNVarReceiverPos, max_ir_len_ms: float, tile_rows: int = 296,
                  edc_weight: float = 1.0, spectral_weight: float = 1.0, sparsity_weight: float = 1.0,
                  asym_spectral: bool = True, mixing_time_ms: float = 20.0, world_size: int = 1,
-                 total_receivers: Optional[int] = None, process_group=None):
+                 total_receivers: Optional[int] = None, process_group=None, e2e_tile_rows: int = 128):
         self.net = net
         self.dev = net.device
         self.crit = edc_loss(max_ir_len_ms, net.sample_rate, mixing_time_ms=mixing_time_ms)
         self.tile_rows = int(tile_rows)
+        self.e2e_tile_rows = int(e2e_tile_rows)
         self.w_edc, self.w_spec, self.w_spars = edc_weight, spectral_weight, sparsity_weight
         self.asym = asym_spectral
         self.world_size = world_size
         self.total_receivers = total_receivers
         self.pg = process_group
         self.kernel_launches = 0
+        self.h2d_bytes = 0
         self._bufs = None
-        self._flat = None
+        self.mask = None
+        self.events = None  # set to a dict of lists to collect per-kernel CUDA events (bench.py)
 
     # ---- data ------------------------------------------------------------------------------------------
-    def attach(self, z: torch.Tensor, positions: torch.Tensor, d: Optional[torch.Tensor],
+    def attach(self, z: torch.Tensor, positions: torch.Tensor, early_window: Optional[torch.Tensor],
                target_db: Optional[torch.Tensor]):
-        """Device-resident shard: z (K,) c128, positions (B,3), d (B,K) c64 or None, target_db (B,tn) f32."""
+        """Device-resident shard: z (K,) c128, positions (B,3), early_window (B,tn) f32 or None (= precompute_
+        early_window(d)), target_db (B,tn) f32 (= precompute_target_db(target))."""
         self.z = z.to(self.dev, torch.complex128)
         self.positions = positions.to(self.dev)
-        self.d = d
-        self.target_db = target_db
         self.k = self.z.numel()
         self.n_fft, self.t0, self.tn = self.crit.window(self.k)
         self.kx = self.n_fft // 2 + 1
@@ -71,87 +83,118 @@ class ShardedEDCStep:
         self.rows = self.positions.shape[0]
         if self.total_receivers is None:
             self.total_receivers = self.rows * self.world_size
-        r = min(self.tile_rows, self.rows)
+        for name, t in (("early_window", early_window), ("target_db", target_db)):
+            if t is not None and (tuple(t.shape) != (self.rows, self.tn) or t.dtype != torch.float32 or not t.is_cuda):
+                raise RuntimeError(f"attach: {name} must be a CUDA float32 tensor of shape ({self.rows}, {self.tn})")
+        self.hd = None if early_window is None else early_window.contiguous()
+        self.target_db = None if target_db is None else target_db.contiguous()
+        r = max(1, min(self.tile_rows, self.rows))
+        g = self.net.num_groups
         dev = self.dev
-        self._bufs = dict(h_tile=torch.empty(r, self.k, dtype=C64, device=dev),
-                          scratch=torch.empty(r * self.plan.mc, dtype=C64, device=dev),
-                          h=torch.empty(r, self.tn, dtype=torch.float32, device=dev),
-                          gh=torch.empty(r, self.tn, dtype=torch.float32, device=dev),
-                          g_tile=torch.empty(r, self.kx, dtype=C64, device=dev),
+        self._bufs = dict(gh=torch.empty(r, self.tn, dtype=torch.float32, device=dev),
+                          ws=ops.td_contract_workspace(g, r, self.tn, dev),
                           row_sum=torch.empty(self.rows, dtype=torch.float64, device=dev))
+
+    def _window_rows(self, resp: torch.Tensor, to_db: bool) -> torch.Tensor:
+        out = torch.empty(resp.shape[0], self.tn, dtype=torch.float32, device=self.dev)
+        step = self.plan.rows_per_call(1 << 29)
+        for r0 in range(0, resp.shape[0], step):
+            h = ops.irfft_window(resp[r0:r0 + step].to(self.dev, C64), self.n_fft, self.t0, self.tn)
+            out[r0:r0 + step] = ops.edc_db(h) if to_db else h
+        return out
 
     @torch.no_grad()
     def precompute_target_db(self, target_response: torch.Tensor) -> torch.Tensor:
-        """EDC of the targets in dB for the loss window (done once per dataset; targets never change)."""
-        out = torch.empty(target_response.shape[0], self.tn, dtype=torch.float32, device=self.dev)
-        step = self.plan.rows_per_call(1 << 29)
-        for r0 in range(0, target_response.shape[0], step):
-            h = ops.irfft_window(target_response[r0:r0 + step].to(self.dev, C64), self.n_fft, self.t0, self.tn)
-            out[r0:r0 + step] = ops.edc_db(h)
-        return out
+        """EDC of the targets in dB on the loss window (done once per data set; targets never change)."""
+        return self._window_rows(target_response, True)
 
-    # ---- the tile pipeline -----------------------------------------------------------------------------
     @torch.no_grad()
-    def _tile(self, r0, r1, s_d, y_d, d_tile, tdb_tile, gy_acc, gs, coef, stream, accumulate):
-        b = self._bufs
-        g = self.net.num_groups
-        rows = r1 - r0
-        k, kx, tn = self.k, self.kx, self.tn
-        lib_call = _lib.call
-        lib_call("dgfdn_project_fwd", g, rows, k, _p(s_d[r0:r1]), _p(y_d), _p(d_tile), k, _p(b["h_tile"]), k, stream)
-        lib_call("dgfdn_irfft_window_fwd", self.plan.handle, _p(b["h_tile"]), k, rows, None, _p(b["scratch"]),
-                 _p(b["h"]), stream)
-        lib_call("dgfdn_edc_loss_fwd", _p(b["h"]), _p(tdb_tile), None, rows, tn, _p(b["row_sum"][r0:r1]), stream)
-        lib_call("dgfdn_edc_loss_bwd", _p(b["h"]), _p(tdb_tile), None, rows, tn, ctypes.c_double(coef), _p(b["gh"]),
-                 stream)
-        lib_call("dgfdn_irfft_window_bwd", self.plan.handle, _p(b["gh"]), rows, None, _p(b["scratch"]),
-                 _p(b["g_tile"]), kx, kx, stream)
-        lib_call("dgfdn_project_bwd", g, rows, kx, _p(s_d[r0:r1]), _p(y_d), _p(b["g_tile"]), kx, _p(gy_acc),
-                 1 if accumulate else 0, _p(gs[r0:r1]), stream)
-        # own kernels per tile: project 1, czt fwd 3, edc fwd 1, edc bwd 1, czt bwd 3, project bwd 2 (+4 cuFFT)
-        self.kernel_launches += 11
+    def precompute_early_window(self, early_response: torch.Tensor) -> torch.Tensor:
+        """hd = irfft(d, n=K)[mix:max_len] of the early (direct-path) responses, (B, tn) float32. d is an input of
+        the data set ('target_early_response'), constant over training, so its window is too."""
+        return self._window_rows(early_response, False)
 
+    # ---- one step ----------------------------------------------------------------------------------------
     def step(self, host_d: Optional[torch.Tensor] = None, host_target: Optional[torch.Tensor] = None) -> Dict:
         """Forward + backward over the shard; leaves gradients in net.parameters().grad and returns the losses.
 
         With host_d / host_target (pinned host tensors, (P, K) complex64 pools that are cycled over the shard) the
-        step streams its inputs host -> device tile by tile on a copy stream and rebuilds the target EDC on the fly:
-        this is the end-to-end mode."""
+        step streams its inputs host -> device tile by tile on a copy stream and rebuilds the early window and the
+        target EDC on the fly: this is the end-to-end mode."""
         net = self.net
+        g = net.num_groups
         for p in net.parameters():
             p.grad = None
+        ev = self.events
+        sec = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if ev is not None else None
+        if sec:
+            sec[0].record()
         s = net.output_scalars.gains({'norm_listener_position': self.positions})
         _, y = net.feedback_loop.solve(self.z, net.input_gains.reshape(-1), net.output_gains.reshape(-1))
+        hy = ops.irfft_window(y.transpose(0, 1), self.n_fft, self.t0, self.tn)  # (G, tn)
         keep = net.return_per_delay_outputs
         net.return_per_delay_outputs = False
         h_sub, _ = net.sub_fdn_output(self.z)
         net.return_per_delay_outputs = keep
         per_group = ops.colorless_loss_per_group(h_sub, self.asym)
         spectral = self.w_spec * per_group.sum()
-        sparsity = self.w_spars * self._sparsity(net.feedback_loop.ortho_param(net.feedback_loop.M[net.num_groups - 1]))
-        self.kernel_launches += 2 + 1  # two solves, colorless forward
+        sparsity = self.w_spars * self._sparsity(net.feedback_loop.ortho_param(net.feedback_loop.M[g - 1]))
+        self.kernel_launches += 2 + 3 + 1  # two solves, chirp-z (pre, mul, post; + 2 cuFFT), colorless forward
 
         s_d = s.detach().contiguous()
-        y_d = y.detach().contiguous()
-        gy_acc = torch.zeros_like(y_d)
+        hy_d = hy.detach().contiguous()
+        ghy = torch.empty_like(hy_d)
         gs = torch.empty_like(s_d)
         coef = self.w_edc / (self.total_receivers * self.tn)
         stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-        r = self._bufs["h_tile"].shape[0]
+        if sec:
+            sec[1].record()
         if host_d is None:
+            if self.target_db is None:
+                raise RuntimeError("step: attach() a target_db (and early_window) first, or pass host buffers")
+            b = self._bufs
+            r = b["gh"].shape[0]
             for i, r0 in enumerate(range(0, self.rows, r)):
                 r1 = min(self.rows, r0 + r)
-                d_tile = None if self.d is None else self.d[r0:r1]
-                self._tile(r0, r1, s_d, y_d, d_tile, self.target_db[r0:r1], gy_acc, gs, coef, stream, i > 0)
+                self._td_tile(r0, r1, s_d, hy_d, None if self.hd is None else self.hd[r0:r1], self.target_db[r0:r1],
+                              b["gh"], b["ws"], ghy, gs, coef, stream, i > 0)
         else:
-            self._stream_tiles(host_d, host_target, s_d, y_d, gy_acc, gs, coef, stream, r)
+            self._stream_tiles(host_d, host_target, s_d, hy_d, ghy, gs, coef, stream)
+        if sec:
+            sec[2].record()
         edc = self._bufs["row_sum"].sum() * coef
         aux = (spectral + sparsity.to(spectral.dtype)) / self.world_size
-        torch.autograd.backward([y, s, aux], [gy_acc, gs, torch.ones_like(aux)])
-        self.kernel_launches += 2 * 2 + 1  # two adjoint solves (+ reduce each), colorless backward
+        torch.autograd.backward([hy, s, aux], [ghy, gs, torch.ones_like(aux)])
+        self.kernel_launches += 3 + 2 * 2 + 1  # chirp-z adjoint, two adjoint solves (+ reduce each), colorless bwd
         if self.world_size > 1:
             self.allreduce_grads()
+        if sec:
+            sec[3].record()
+            ev.setdefault("front(MLP+solves+irfft of G rows)", []).append((sec[0], sec[1]))
+            ev.setdefault("receiver tiles", []).append((sec[1], sec[2]))
+            ev.setdefault("back(irfft^T+adjoint solves+autograd)", []).append((sec[2], sec[3]))
         return {'edc_loss': edc, 'spectral_loss': spectral.detach(), 'sparsity_loss': sparsity.detach()}
+
+    @torch.no_grad()
+    def _td_tile(self, r0, r1, s_d, hy_d, hd_tile, tdb_tile, gh, ws, ghy, gs, coef, stream, accumulate):
+        g = self.net.num_groups
+        rows, tn = r1 - r0, self.tn
+        ev = self.events
+        if ev is not None:
+            marks = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            marks[0].record()
+        _lib.call("dgfdn_td_edc_step", g, rows, tn, _p(s_d[r0:r1]), _p(hy_d), _p(hd_tile), tn, _p(tdb_tile), tn,
+                  _p(self.mask), ctypes.c_double(coef), _p(self._bufs["row_sum"][r0:r1]), _p(gs[r0:r1]), _p(gh), tn,
+                  stream)
+        if ev is not None:
+            marks[1].record()
+        _lib.call("dgfdn_td_contract", g, rows, tn, _p(s_d[r0:r1]), _p(gh), tn, _p(ghy), 1 if accumulate else 0, _p(ws),
+                  stream)
+        if ev is not None:
+            marks[2].record()
+            ev.setdefault("td_edc_step", []).append((marks[0], marks[1]))
+            ev.setdefault("td_contract", []).append((marks[1], marks[2]))
+        self.kernel_launches += 3  # td_edc_step, td_contract, td_contract_reduce
 
     @staticmethod
     def _sparsity(a: torch.Tensor) -> torch.Tensor:
@@ -159,17 +202,28 @@ class ShardedEDCStep:
         return -(torch.sum(torch.abs(a)) - n * n**0.5) / (n * (n**0.5 - 1))
 
     # ---- end-to-end mode: inputs come from pinned host memory every step ---------------------------------
-    def _stream_tiles(self, host_d, host_target, s_d, y_d, gy_acc, gs, coef, stream, r):
+    def _stream_tiles(self, host_d, host_target, s_d, hy_d, ghy, gs, coef, stream):
         dev = self.dev
+        r = max(1, min(self.e2e_tile_rows, self.rows))
+        kx, tn, g = self.kx, self.tn, self.net.num_groups
+        for name, t in (("host_d", host_d), ("host_target", host_target)):
+            if t.dtype != C64 or t.dim() != 2 or t.shape[1] < kx or not t.is_pinned() or not t.is_contiguous():
+                raise RuntimeError(f"step: {name} must be a contiguous pinned complex64 (P, >= {kx}) host tensor")
         if "stage" not in self._bufs:
-            self._bufs["stage"] = [dict(d=torch.empty(r, self.k, dtype=C64, device=dev),
-                                        t=torch.empty(r, self.k, dtype=C64, device=dev),
-                                        tdb=torch.empty(r, self.tn, dtype=torch.float32, device=dev),
-                                        ht=torch.empty(r, self.tn, dtype=torch.float32, device=dev),
+            self._bufs["stage"] = [dict(d=torch.empty(r, kx, dtype=C64, device=dev),
+                                        t=torch.empty(r, kx, dtype=C64, device=dev),
                                         ready=torch.cuda.Event(), free=torch.cuda.Event()) for _ in range(2)]
             self._bufs["copy_stream"] = torch.cuda.Stream(device=dev)
+            self._bufs["e2e"] = dict(scratch=torch.empty(r * self.plan.mc, dtype=C64, device=dev),
+                                     hd=torch.empty(r, tn, dtype=torch.float32, device=dev),
+                                     ht=torch.empty(r, tn, dtype=torch.float32, device=dev),
+                                     tdb=torch.empty(r, tn, dtype=torch.float32, device=dev),
+                                     gh=torch.empty(r, tn, dtype=torch.float32, device=dev),
+                                     ws=ops.td_contract_workspace(g, r, tn, dev))
         stage = self._bufs["stage"]
+        e = self._bufs["e2e"]
         copy_stream = self._bufs["copy_stream"]
+        cs = ctypes.c_void_p(copy_stream.cuda_stream)
         main = torch.cuda.current_stream()
         pool = host_d.shape[0]
         self.h2d_bytes = 0
@@ -177,18 +231,17 @@ class ShardedEDCStep:
 
         def issue(i):
             r0 = tiles[i]
-            r1 = min(self.rows, r0 + r)
+            n = min(self.rows, r0 + r) - r0
             st = stage[i % 2]
             p0 = r0 % pool
-            n = r1 - r0
             if p0 + n > pool:
                 p0 = 0
-            with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(st["free"])
-                st["d"][:n].copy_(host_d[p0:p0 + n], non_blocking=True)
-                st["t"][:n].copy_(host_target[p0:p0 + n], non_blocking=True)
-                st["ready"].record(copy_stream)
-            self.h2d_bytes += 2 * n * self.k * 8
+            copy_stream.wait_event(st["free"])
+            for key, host in (("d", host_d), ("t", host_target)):
+                _lib.call("dgfdn_copy_rows_h2d", _p(st[key]), kx * 8, ctypes.c_void_p(host[p0].data_ptr()),
+                          host.shape[1] * 8, kx * 8, n, cs)
+            st["ready"].record(copy_stream)
+            self.h2d_bytes += 2 * n * kx * 8
 
         for st in stage:
             st["free"].record(main)
@@ -200,13 +253,15 @@ class ShardedEDCStep:
                 issue(i + 1)
             st = stage[i % 2]
             main.wait_event(st["ready"])
-            # target EDC of this tile, rebuilt every step in this mode
-            _lib.call("dgfdn_irfft_window_fwd", self.plan.handle, _p(st["t"]), self.k, n, None,
-                      _p(self._bufs["scratch"]), _p(st["ht"]), stream)
-            _lib.call("dgfdn_edc_db", _p(st["ht"]), n, self.tn, _p(st["tdb"]), stream)
-            self.kernel_launches += 4
-            self._tile(r0, r1, s_d, y_d, st["d"][:n], st["tdb"][:n], gy_acc, gs, coef, stream, i > 0)
+            # early window and target EDC of this tile, rebuilt every step in this mode
+            _lib.call("dgfdn_irfft_window_fwd", self.plan.handle, _p(st["d"]), kx, n, None, _p(e["scratch"]), _p(e["hd"]),
+                      stream)
+            _lib.call("dgfdn_irfft_window_fwd", self.plan.handle, _p(st["t"]), kx, n, None, _p(e["scratch"]), _p(e["ht"]),
+                      stream)
             st["free"].record(main)
+            _lib.call("dgfdn_edc_db", _p(e["ht"]), n, tn, _p(e["tdb"]), stream)
+            self.kernel_launches += 7
+            self._td_tile(r0, r1, s_d, hy_d, e["hd"], e["tdb"], e["gh"], e["ws"], ghy, gs, coef, stream, i > 0)
 
     # ---- data parallel -----------------------------------------------------------------------------------
     def allreduce_grads(self):

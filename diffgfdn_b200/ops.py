@@ -355,6 +355,82 @@ def edc_abs_db_sum(h: torch.Tensor, target_db: torch.Tensor, mask: Optional[torc
 
 
 # ----------------------------------------------------------------------------------------------------------
+# K3c: receiver step in the time domain (mix + EDC + dB loss + backward in one kernel)
+# ----------------------------------------------------------------------------------------------------------
+def td_contract_workspace(num_groups: int, rows: int, tn: int, device) -> torch.Tensor:
+    nbytes = int(_lib.load().dgfdn_td_contract_ws_bytes(num_groups, rows, tn))
+    return torch.empty(max(nbytes // 4, 1), dtype=torch.float32, device=device)
+
+
+@torch.no_grad()
+def td_mix(s: torch.Tensor, hy: torch.Tensor, hd: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """h[r,t] = sum_g s[r,g] hy[g,t] + hd[r,t]: late RIR window of every receiver (float32, no grad)."""
+    s_ = _cuda("s", s, torch.float32)
+    hy_ = _cuda("hy", hy, torch.float32)
+    hd_ = _cuda("hd", hd, torch.float32, optional=True)
+    rows, g = s_.shape
+    tn = hy_.shape[-1]
+    if hy_.shape[0] != g or (hd_ is not None and tuple(hd_.shape) != (rows, tn)):
+        raise RuntimeError("td_mix: inconsistent shapes")
+    out = torch.empty(rows, tn, dtype=torch.float32, device=s_.device)
+    with torch.cuda.device(s_.device):
+        for r0 in range(0, rows, 32768):
+            r1 = min(rows, r0 + 32768)
+            _lib.call("dgfdn_td_mix", g, r1 - r0, tn, _ptr(s_[r0:r1]), _ptr(hy_), _ptr(None if hd_ is None else hd_[r0:r1]),
+                      tn, _ptr(out[r0:r1]), tn, _stream())
+    return out
+
+
+class _TDEDCLoss(torch.autograd.Function):
+    """sum_{r,t} mask[t] |target_db[r,t] - dB(EDC(sum_g s[r,g] hy[g,:] + hd[r,:])[t])| as a float64 scalar.
+
+    Same value as edc_abs_db_sum(irfft_window(receiver_project(s, y, d))) of the frequency-domain path (reference
+    model.py:583-619 + losses.py:207-238), by linearity of the inverse DFT; differentiable w.r.t. s and hy."""
+
+    @staticmethod
+    def forward(ctx, s, hy, hd, target_db, mask, tile_rows):
+        s_ = _cuda("s", s, torch.float32)
+        hy_ = _cuda("hy", hy, torch.float32)
+        hd_ = _cuda("hd", hd, torch.float32, optional=True)
+        t_ = _cuda("target_db", target_db, torch.float32)
+        m_ = _cuda("mask", mask, torch.float32, optional=True)
+        rows, g = s_.shape
+        tn = hy_.shape[-1]
+        if hy_.shape[0] != g or tuple(t_.shape) != (rows, tn) or (hd_ is not None and tuple(hd_.shape) != (rows, tn)) \
+                or (m_ is not None and m_.numel() != tn):
+            raise RuntimeError("td_edc_loss: inconsistent shapes")
+        dev = s_.device
+        tile = max(1, min(int(tile_rows), rows))
+        row_sum = torch.empty(rows, dtype=torch.float64, device=dev)
+        gs = torch.empty(rows, g, dtype=torch.float32, device=dev)
+        ghy = torch.empty(g, tn, dtype=torch.float32, device=dev)
+        gh = torch.empty(tile, tn, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            ws = td_contract_workspace(g, tile, tn, dev)
+            for i, r0 in enumerate(range(0, rows, tile)):
+                r1 = min(rows, r0 + tile)
+                _lib.call("dgfdn_td_edc_step", g, r1 - r0, tn, _ptr(s_[r0:r1]), _ptr(hy_),
+                          _ptr(None if hd_ is None else hd_[r0:r1]), tn, _ptr(t_[r0:r1]), tn, _ptr(m_), 1.0,
+                          _ptr(row_sum[r0:r1]), _ptr(gs[r0:r1]), _ptr(gh), tn, _stream())
+                _lib.call("dgfdn_td_contract", g, r1 - r0, tn, _ptr(s_[r0:r1]), _ptr(gh), tn, _ptr(ghy), int(i > 0),
+                          _ptr(ws), _stream())
+        ctx.save_for_backward(gs, ghy)
+        return row_sum.sum()
+
+    @staticmethod
+    def backward(ctx, g):
+        gs, ghy = ctx.saved_tensors
+        gf = g.to(torch.float32)
+        return (gs * gf if ctx.needs_input_grad[0] else None, ghy * gf if ctx.needs_input_grad[1] else None, None, None,
+                None, None)
+
+
+def td_edc_abs_db_sum(s: torch.Tensor, hy: torch.Tensor, hd: Optional[torch.Tensor], target_db: torch.Tensor,
+                      mask: Optional[torch.Tensor] = None, tile_rows: int = 296) -> torch.Tensor:
+    return _TDEDCLoss.apply(s, hy, hd, target_db, mask, tile_rows)
+
+
+# ----------------------------------------------------------------------------------------------------------
 # colorless loss
 # ----------------------------------------------------------------------------------------------------------
 class _Colorless(torch.autograd.Function):

@@ -37,6 +37,11 @@ DGFDN_API const char* dgfdn_last_error(void);
 DGFDN_API int dgfdn_version(void);
 /* number of SMs of the current device (grid sizing on the host side) */
 DGFDN_API int dgfdn_sm_count(void);
+/* Strided host -> device copy on `stream`: the first width_bytes of each of `rows` rows of a (pinned) host array
+ * (cudaMemcpy2DAsync). The end-to-end path uses it to ship only bins 0..K/2 of the reference-layout (B, K) arrays
+ * produced by the data loader (dataloader.py:250,320-325, 674-704) -- the bins irfft(X, n=K) reads (quirk Q3). */
+DGFDN_API int dgfdn_copy_rows_h2d(void* dst, int64_t dst_pitch_bytes, const void* src_host, int64_t src_pitch_bytes,
+                        int64_t width_bytes, int64_t rows, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K1: per-bin build + solve.   Replaces FeedbackLoop.forward (diff_gfdn/feedback_loop.py:326-391),
@@ -132,6 +137,31 @@ DGFDN_API int dgfdn_edc_loss_fwd(const float* h, const float* target_db, const f
 /* gh[r,t] = coef * d(sum_r row_sum[r]) / d h[r,t]   (gh [rows, tn] float32 out) */
 DGFDN_API int dgfdn_edc_loss_bwd(const float* h, const float* target_db, const float* mask, int64_t rows, int64_t tn,
                        double coef, float* gh, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K3c: receiver step in the time domain.  irfft is linear and a receiver enters H_r = sum_g s[r,g] y_g + d_r
+ * (model.py:583-619) only through its G real gains, so irfft(H_r)[window] = sum_g s[r,g] hy[g,:] + hd[r,:] with
+ * hy = irfft(y_g)[window] (G rows per step, dgfdn_irfft_window_fwd) and hd[r,:] = irfft(d_r)[window] a constant of
+ * the data set. dgfdn_td_edc_step replaces, per receiver, model.py:583-619 + losses.py:207-238 and their autograd
+ * backward: it reads hd and the target EDC in dB (8 B per receiver.sample) and never touches the frequency domain.
+ *   h[r,t]   = sum_g s[r,g] hy[g,t] + hd[r,t]                     (hd may be NULL)
+ *   row_sum[r] = sum_t mask[t] | target_db[r,t] - dB(EDC(h[r,:])[t]) |        float64
+ *   gh[r,t]  = coef * d(sum_r row_sum[r]) / d h[r,t]               float32 [rows, ldg]
+ *   gs[r,g]  = sum_t gh[r,t] hy[g,t]                               float32 (may be NULL)
+ * s [rows,G], hy [G,tn], hd [rows,ldhd], target_db [rows,ldt], mask [tn] or NULL (= ones).
+ */
+DGFDN_API int dgfdn_td_edc_step(int g, int64_t rows, int64_t tn, const float* s, const float* hy, const float* hd,
+                      int64_t ldhd, const float* target_db, int64_t ldt, const float* mask, double coef,
+                      double* row_sum, float* gs, float* gh, int64_t ldg, void* stream);
+/* h[r,t] = sum_g s[r,g] hy[g,t] + hd[r,t]: the late RIR window of each receiver (utils.py:169 get_response +
+ * irfft, restricted to the window), float32 [rows, ldh]. */
+DGFDN_API int dgfdn_td_mix(int g, int64_t rows, int64_t tn, const float* s, const float* hy, const float* hd, int64_t ldhd,
+                 float* h, int64_t ldh, void* stream);
+/* ghy[g,t] (+)= sum_r s[r,g] gh[r,t]  (adjoint of the mix w.r.t. hy; fixed-order two-stage reduction).
+ * ws: scratch of dgfdn_td_contract_ws_bytes(g, rows, tn) bytes. */
+DGFDN_API int64_t dgfdn_td_contract_ws_bytes(int g, int64_t rows, int64_t tn);
+DGFDN_API int dgfdn_td_contract(int g, int64_t rows, int64_t tn, const float* s, const float* gh, int64_t ldg, float* ghy,
+                      int accumulate, void* ws, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Colorless (spectral flatness) loss of the lossless sub-FDNs, colorless_fdn/losses.py:20-73 with

@@ -1,5 +1,6 @@
-"""The receiver-tiled fused step (diffgfdn_b200/fused.py) must give the same losses and gradients as the
-autograd module path, for any tile size, in resident and in host-streamed mode."""
+"""The receiver-tiled fused step (diffgfdn_b200/fused.py: solve once per bin, inverse DFT of G rows, everything per
+receiver in the time domain) must give the same losses and gradients as the autograd module path (project every
+receiver over every bin, one inverse DFT per receiver), for any tile size, in resident and in host-streamed mode."""
 import numpy as np
 import pytest
 import torch
@@ -47,7 +48,7 @@ def test_fused_step_equals_module_path(tile):
     edc_ref, g_ref = module_path(net, t60, z, pos, early, target)
     step = ShardedEDCStep(net, max(t60) * 1e3, tile_rows=tile, edc_weight=10.0)
     step.attach(z, pos, None, None)
-    step.attach(z, pos, early, step.precompute_target_db(target))
+    step.attach(z, pos, step.precompute_early_window(early), step.precompute_target_db(target))
     out = step.step()
     assert abs(float(out["edc_loss"]) - edc_ref) < 1e-4 * abs(edc_ref)
     for k, p in net.named_parameters():
@@ -60,7 +61,44 @@ def test_fused_step_equals_module_path(tile):
     for k, p in net.named_parameters():
         err = float((p.grad - g_ref[k]).abs().max() / g_ref[k].abs().max())
         assert err < 1e-3, (k, err)
-    assert step.h2d_bytes == 2 * pos.shape[0] * z.numel() * 8
+    # only the bins irfft(X, n=K) reads (0..K/2, quirk Q3) cross the bus
+    assert step.h2d_bytes == 2 * pos.shape[0] * (z.numel() // 2 + 1) * 8
+
+
+def test_time_domain_step_kernel_vs_torch_fp64():
+    """dgfdn_td_edc_step / dgfdn_td_contract / dgfdn_td_mix against a float64 torch restatement of
+    h = s hy + hd -> flip(cumsum(flip(h^2))) -> 10 log10(. + eps) -> sum mask |target - .| and its autograd
+    (reference losses.py:187-238, utils.py:16-40). Ragged sizes: tn not a multiple of the chunk, 4 or 8."""
+    from diffgfdn_b200 import ops
+    gen = torch.Generator().manual_seed(3)
+    for rows, g, tn, use_hd, use_mask in [(5, 3, 9001, True, True), (3, 2, 16384, False, False), (7, 3, 777, True, False),
+                                          (2, 1, 52000, True, True), (1, 4, 8, True, False)]:
+        decay = torch.exp(-torch.arange(tn, dtype=torch.float64) / (0.15 * tn))
+        hy = torch.randn(g, tn, generator=gen, dtype=torch.float64) * decay
+        hd = torch.randn(rows, tn, generator=gen, dtype=torch.float64) * decay * 0.3 if use_hd else None
+        s = torch.randn(rows, g, generator=gen, dtype=torch.float64)
+        tgt = torch.randn(rows, tn, generator=gen, dtype=torch.float64) * decay
+        tdb = 10 * torch.log10(torch.flip(torch.cumsum(torch.flip(tgt**2, [-1]), -1), [-1]) + 1.1920928955078125e-07)
+        mask = (torch.rand(tn, generator=gen) < 0.5).double() if use_mask else None
+        s_r = s.clone().float().double().requires_grad_(True)
+        hy_r = hy.clone().float().double().requires_grad_(True)
+        h = s_r @ hy_r + (hd.float().double() if use_hd else 0.0)
+        edc = torch.flip(torch.cumsum(torch.flip(h**2, [-1]), -1), [-1])
+        db = torch.clamp(10 * torch.log10(edc + 1.1920928955078125e-07), min=-200.0)
+        diff = (tdb.float().double() - db).abs()
+        ref = (diff * mask).sum() if use_mask else diff.sum()
+        ref.backward()
+        s_c = s.float().cuda().requires_grad_(True)
+        hy_c = hy.float().cuda().requires_grad_(True)
+        hd_c = hd.float().cuda() if use_hd else None
+        out = ops.td_edc_abs_db_sum(s_c, hy_c, hd_c, tdb.float().cuda(), None if mask is None else mask.float().cuda(),
+                                    tile_rows=3)
+        out.backward()
+        assert abs(float(out) - float(ref)) < 2e-5 * abs(float(ref)) + 1e-3, (rows, g, tn)
+        assert float((s_c.grad.cpu().double() - s_r.grad).abs().max() / s_r.grad.abs().max()) < 1e-3, (rows, g, tn)
+        assert float((hy_c.grad.cpu().double() - hy_r.grad).abs().max() / hy_r.grad.abs().max()) < 1e-3, (rows, g, tn)
+        hm = ops.td_mix(s_c.detach(), hy_c.detach(), hd_c)
+        assert float((hm.cpu().double() - h.detach()).abs().max() / h.detach().abs().max()) < 1e-6
 
 
 def test_full_size_invariants():
