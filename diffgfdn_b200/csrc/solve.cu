@@ -1,4 +1,4 @@
-// K1 / K1^T: per-bin build + complex solve of the Grouped-FDN feedback loop, one warp per bin.
+// K1 / K1^T: per-bin build + complex solve of the Grouped-FDN feedback loop.
 //
 //   M_k = diag(z_k^{m_i} / gamma_i) - A      x_k = M_k^{-1} b      y[k,g] = sum_{n in g} c_n x_k[n]
 //
@@ -7,14 +7,21 @@
 // :237-250. The reference inverts, then contracts with c (per receiver!) and b; b is shared by every
 // receiver, so one solve per bin is all that is needed and the (K,N,N) inverse never exists.
 //
-// Layout: lane i of the warp owns row i of the system in REGISTERS (NP complex doubles, NP = N rounded up to a
-// multiple of 4, all loops unrolled so every index is static). Gauss-Jordan elimination with partial pivoting:
-// the pivot lane is found with a shuffle arg-max, it publishes its row through a small shared-memory line and
-// every other lane eliminates against the broadcast values. Rows are never swapped -- a lane remembers which
-// column it was pivot for and ends up holding that component of the solution.
+// Layout: a group of W lanes (W = 4, 8, 16 or 32, the power of two >= the padded system size NP) owns one system;
+// a warp therefore works on 32/W systems at once (the G lossless 8x8 sub-FDN systems of a bin pack four to a
+// warp). Lane i of the group holds row i in REGISTERS (NP complex doubles, every loop unrolled so each index is
+// static). Gauss-Jordan elimination with partial pivoting: the pivot lane is found with ONE warp-reduce
+// (REDUX.MAX on a key made of the high word of |m|^2 and the lane number; a log2(W)-step shuffle butterfly for
+// sub-warp groups), it publishes its row through a double-buffered shared-memory line and every other lane
+// eliminates against it. Rows are never swapped -- a lane remembers which column it was pivot for and ends up
+// holding that component of the solution. z^m is formed by binary powering in float64 (22 complex products,
+// relative error < 1e-12 for m < 4096).
 // Arithmetic is float64 (the reference inverts in complex128, feedback_loop.py:391); outputs are complex64 like
 // the reference's P. The adjoint kernel solves M^H lambda = g the same way and reduces the parameter gradients
 // with a fixed-order two-stage reduction (deterministic).
+//
+// "Group mode" (nsys = G > 1) solves the G independent LxL systems diag(z^{m_g}) - M_g of
+// DiffGFDN.sub_fdn_output (model.py:209-252) instead of one block-diagonal NxN system: 1/G^2 of the flops.
 #include "common.cuh"
 
 namespace dgfdn {
@@ -23,11 +30,14 @@ namespace {
 constexpr int kWarps = 4;
 
 struct SolveParams {
-  int n, g, l;
+  int n;      // rows of one system (N in coupled mode, L in group mode)
+  int nsys;   // systems per bin (1 in coupled mode, G in group mode)
+  int ntot;   // total number of delay lines N = n * nsys
+  int g, l;   // groups and lines per group (for y)
   int64_t k;
   const double2* z;
   const int32_t* delays;
-  const float* a;
+  const float* a;  // coupled: [N,N]; group mode: [G,L,L]
   int transpose_a;
   const float* gamma;
   const float2* gamma_z;
@@ -43,40 +53,53 @@ struct SolveParams {
   double* ws;
 };
 
-// Shared memory (in doubles). Block-wide constants: A_eff row-major [NP*NP], A_eff transposed [NP*NP],
-// invgamma/b/c/delay [4*NP]. Per warp: pivot row line 2*(NP+1), solution line 2*NP, saved-x line 2*NP and (backward)
-// the gradient accumulator NP*NP.
+// Shared memory (in doubles). Block-wide constants per system type q: A_eff row-major [NP*NP] and transposed
+// [NP*NP]; invgamma/b/c/delay [4*ntot_pad]. Per lane group: two pivot lines of (NP+1) double2, and (backward)
+// lambda[NP], x[NP] double2 and the gradient accumulator NP*NP.
 template <int NP>
 struct Smem {
-  static constexpr size_t kBlock = 2 * (size_t)NP * NP + 4 * NP;
-  static constexpr size_t kWarpFwd = 2 * (NP + 1) + 4 * NP;
-  static constexpr size_t kWarpBwd = kWarpFwd + (size_t)NP * NP;
-  static_assert(kBlock % 2 == 0 && kWarpFwd % 2 == 0 && kWarpBwd % 2 == 0, "double2 alignment");
+  static constexpr size_t kConstPerSys = 2 * (size_t)NP * NP + 4 * NP;
+  static constexpr size_t kGroupFwd = 2 * 2 * (NP + 1);
+  static constexpr size_t kGroupBwd = kGroupFwd + 4 * NP + (size_t)NP * NP;
 };
 
-// z^m * invgamma for this lane's delay line, float64. Also returns z^m alone through zm.
-__device__ __forceinline__ double2 diag_entry(const SolveParams& p, int64_t bin, int line, double invg, double delay,
-                                              double2* zm) {
-  const double2 zk = p.z[bin];
-  const double r = hypot(zk.x, zk.y);
-  const double th = atan2(zk.y, zk.x);
-  const double mag = (fabs(r - 1.0) < 4e-16) ? 1.0 : pow(r, delay);
-  double sn, cs;
-  sincos(delay * th, &sn, &cs);
-  const double2 v = make_double2(mag * cs, mag * sn);
-  *zm = v;
-  if (p.gamma_z != nullptr) {
-    const float2 gz = p.gamma_z[(int64_t)line * p.k + bin];
-    return cdiv(v, make_double2((double)gz.x, (double)gz.y));
-  }
-  return make_double2(v.x * invg, v.y * invg);
+__device__ __forceinline__ double fast_rcp(double d) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+  r = r * (2.0 - d * r);
+  r = r * (2.0 - d * r);
+  return r;
+}
+__device__ __forceinline__ double2 fast_cinv(double2 b) {
+  const double s = fast_rcp(b.x * b.x + b.y * b.y);
+  return make_double2(b.x * s, -b.y * s);
 }
 
-// Gauss-Jordan with partial pivoting on a register-resident system: lane `lane` holds row `lane` in m[] and its
-// right-hand side in rhs. Returns the solution component this lane ends up owning; *col is its index
-// (a permutation of 0..NP-1 over the lanes < NP; lanes >= NP return col = -1).
-// The elimination step is a template over the column so that every register-array index is a compile-time
-// constant (a plain `#pragma unroll` over the column left the array in local memory for NP = 20, 24, 28).
+// z^m by binary powering; nbits = bit length of the largest exponent in the warp (uniform trip count).
+__device__ __forceinline__ double2 cpow_int(double2 z, int m, int nbits) {
+  double2 r = make_double2(1.0, 0.0);
+  double2 p = z;
+  for (int bit = 0; bit < nbits; ++bit) {
+    if (m & (1 << bit)) r = cmul(r, p);
+    p = cmul(p, p);
+  }
+  return r;
+}
+
+template <int W>
+__device__ __forceinline__ int pivot_sublane(unsigned key) {
+  if (W == 32) {
+    key = __reduce_max_sync(0xffffffffu, key);
+  } else {
+#pragma unroll
+    for (int o = W / 2; o > 0; o >>= 1) {
+      const unsigned other = __shfl_xor_sync(0xffffffffu, key, o);
+      key = other > key ? other : key;
+    }
+  }
+  return (W - 1) - (int)(key & (unsigned)(W - 1));
+}
+
 struct GJState {
   double2 rhs;
   double2 diag;
@@ -84,22 +107,18 @@ struct GJState {
   bool used;
 };
 
-template <int NP, int K>
+// One elimination step per template instance, so that every register-array index is a compile-time constant.
+template <int NP, int W, int K>
 struct GJStep {
-  static __device__ __forceinline__ void run(double2 (&m)[NP], GJState& st, int lane, double2* line) {
-    double key = st.used ? -1.0 : cnorm(m[K]);
-    int idx = lane;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const double ok = __shfl_xor_sync(0xffffffffu, key, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
-      if (ok > key || (ok == key && oi < idx)) {
-        key = ok;
-        idx = oi;
-      }
+  static __device__ __forceinline__ void run(double2 (&m)[NP], GJState& st, int sl, double2* line0, double2* line1) {
+    double2* line = (K & 1) ? line1 : line0;
+    unsigned key = 0u;
+    if (!st.used) {
+      const unsigned hi = (unsigned)__double2hiint(cnorm(m[K]));  // monotone in |m|^2 for non-negative doubles
+      key = 0x80000000u | (hi & ~(unsigned)(W - 1)) | (unsigned)(W - 1 - sl);
     }
-    const int piv = idx;
-    if (lane == piv) {
+    const int piv = pivot_sublane<W>(key);
+    if (sl == piv) {
 #pragma unroll
       for (int j = K; j < NP; ++j) line[j] = m[j];
       line[NP] = st.rhs;
@@ -108,8 +127,8 @@ struct GJStep {
       st.diag = m[K];
     }
     __syncwarp();
-    if (lane != piv && lane < NP) {
-      const double2 f = cmul(m[K], cinv(line[K]));
+    if (sl != piv && sl < NP) {
+      const double2 f = cmul(m[K], fast_cinv(line[K]));
 #pragma unroll
       for (int j = K + 1; j < NP; ++j) {
         const double2 pj = line[j];
@@ -120,163 +139,259 @@ struct GJStep {
       st.rhs.x -= f.x * pr.x - f.y * pr.y;
       st.rhs.y -= f.x * pr.y + f.y * pr.x;
     }
-    __syncwarp();
-    if constexpr (K + 1 < NP) GJStep<NP, K + 1>::run(m, st, lane, line);
+    // no second barrier: step K+1 writes the other line; step K+2 reuses this one only after the barrier of K+1
+    if constexpr (K + 1 < NP) GJStep<NP, W, K + 1>::run(m, st, sl, line0, line1);
   }
 };
 
-template <int NP>
-__device__ __forceinline__ double2 gauss_jordan(double2 (&m)[NP], double2 rhs, int lane, double2* line, int* col) {
+// Returns the solution component this lane ends up owning; *col is its index (a permutation of 0..NP-1 over the
+// sub-lanes < NP; sub-lanes >= NP return col = -1).
+template <int NP, int W>
+__device__ __forceinline__ double2 gauss_jordan(double2 (&m)[NP], double2 rhs, int sl, double2* line0, double2* line1,
+                                                int* col) {
   GJState st;
   st.rhs = rhs;
   st.diag = make_double2(1.0, 0.0);
   st.mycol = -1;
-  st.used = lane >= NP;
-  GJStep<NP, 0>::run(m, st, lane, line);
+  st.used = sl >= NP;
+  GJStep<NP, W, 0>::run(m, st, sl, line0, line1);
+  __syncwarp();  // the lines may be rewritten by the caller's next system
   *col = st.mycol;
-  return cdiv(st.rhs, st.diag);
+  return cmul(st.rhs, fast_cinv(st.diag));
 }
 
 template <int NP>
-__device__ __forceinline__ void load_block_constants(const SolveParams& p, double* s_a, double* s_at, double* s_invg,
-                                                     double* s_b, double* s_c, double* s_delay) {
+__device__ __forceinline__ void load_block_constants(const SolveParams& p, double* s_const, double* s_vec) {
   const int n = p.n;
-  for (int i = threadIdx.x; i < NP * NP; i += blockDim.x) {
-    const int r = i / NP, c = i % NP;
+  for (int i = threadIdx.x; i < p.nsys * NP * NP; i += blockDim.x) {
+    const int q = i / (NP * NP), rc = i % (NP * NP);
+    const int r = rc / NP, c = rc % NP;
     double v = 0.0;
-    if (r < n && c < n) v = (double)(p.transpose_a ? p.a[c * n + r] : p.a[r * n + c]);
-    s_a[r * NP + c] = v;
-    s_at[c * NP + r] = v;
+    if (r < n && c < n) {
+      const float* aq = p.a + (size_t)q * n * n;
+      v = (double)(p.transpose_a ? aq[c * n + r] : aq[r * n + c]);
+    }
+    double* base = s_const + (size_t)q * 2 * NP * NP;
+    base[r * NP + c] = v;            // A_eff row-major
+    base[NP * NP + c * NP + r] = v;  // A_eff transposed
   }
-  for (int i = threadIdx.x; i < NP; i += blockDim.x) {
-    const bool in = i < n;
-    s_invg[i] = (in && p.gamma) ? 1.0 / (double)p.gamma[i] : 1.0;
-    s_b[i] = (in && p.b) ? (double)p.b[i] : 0.0;
-    s_c[i] = (in && p.c) ? (double)p.c[i] : 0.0;
-    s_delay[i] = in ? (double)p.delays[i] : 0.0;
+  // per delay line: invgamma, b, c, delay  (index q*NP + i)
+  for (int i = threadIdx.x; i < p.nsys * NP; i += blockDim.x) {
+    const int q = i / NP, r = i % NP;
+    const bool in = r < n;
+    const int line = q * n + r;
+    s_vec[0 * p.nsys * NP + i] = (in && p.gamma) ? 1.0 / (double)p.gamma[line] : 1.0;
+    s_vec[1 * p.nsys * NP + i] = (in && p.b) ? (double)p.b[line] : 0.0;
+    s_vec[2 * p.nsys * NP + i] = (in && p.c) ? (double)p.c[line] : 0.0;
+    s_vec[3 * p.nsys * NP + i] = in ? (double)p.delays[line] : 0.0;
   }
 }
 
-// Row `lane` of M (adjoint = false) or of M^H (adjoint = true). Padded rows/columns (>= n) form an identity block.
+// Row `sl` of M (adjoint = false) or of M^H (adjoint = true). Padded rows/columns (>= n) form an identity block.
 template <int NP>
-__device__ __forceinline__ void build_row(double2 (&m)[NP], const double* s_a, const double* s_at, int n, int lane,
+__device__ __forceinline__ void build_row(double2 (&m)[NP], const double* s_a, const double* s_at, int n, int sl,
                                           double2 dz, bool adjoint) {
-  // M[i][j] = delta_ij dz_i - A[i][j]          -> needs A[lane][j]  = s_at[j*NP + lane]  (lane-contiguous)
-  // M^H[i][j] = delta_ij conj(dz_i) - A[j][i]  -> needs A[j][lane]  = s_a [j*NP + lane]
+  // M[i][j] = delta_ij dz_i - A[i][j]          -> needs A[sl][j]  = s_at[j*NP + sl]  (lane-contiguous)
+  // M^H[i][j] = delta_ij conj(dz_i) - A[j][i]  -> needs A[j][sl]  = s_a [j*NP + sl]
   const double* src = adjoint ? s_a : s_at;
-  const int li = lane < NP ? lane : 0;
-  const double dre = lane < n ? dz.x : 1.0;
-  const double dim = lane < n ? (adjoint ? -dz.y : dz.y) : 0.0;
+  const int li = sl < NP ? sl : 0;
+  const double dre = sl < n ? dz.x : 1.0;
+  const double dim = sl < n ? (adjoint ? -dz.y : dz.y) : 0.0;
 #pragma unroll
   for (int j = 0; j < NP; ++j) {
-    const bool on_diag = (j == lane);
+    const bool on_diag = (j == sl);
     m[j] = make_double2((on_diag ? dre : 0.0) - src[j * NP + li], on_diag ? dim : 0.0);
   }
 }
 
-template <int NP>
-__global__ void __launch_bounds__(kWarps * 32) solve_fwd_kernel(SolveParams p) {
-  extern __shared__ double smem[];
-  const int n = p.n;
-  double* s_a = smem;
-  double* s_at = s_a + NP * NP;
-  double* s_invg = s_at + NP * NP;
-  double* s_b = s_invg + NP;
-  double* s_c = s_b + NP;
-  double* s_delay = s_c + NP;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  double* wbase = smem + Smem<NP>::kBlock + (size_t)warp * Smem<NP>::kWarpFwd;
-  double2* line = reinterpret_cast<double2*>(wbase);
-
-  load_block_constants<NP>(p, s_a, s_at, s_invg, s_b, s_c, s_delay);
-  __syncthreads();
-  const int li = lane < NP ? lane : 0;
-  const double my_invg = s_invg[li], my_delay = s_delay[li], my_b = s_b[li];
-
-  for (int64_t bin = (int64_t)blockIdx.x * kWarps + warp; bin < p.k; bin += (int64_t)gridDim.x * kWarps) {
-    double2 zm;
-    double2 dz = make_double2(0.0, 0.0);
-    if (lane < n) dz = diag_entry(p, bin, lane, my_invg, my_delay, &zm);
-    double2 m[NP];
-    build_row<NP>(m, s_a, s_at, n, lane, dz, false);
-    int col;
-    const double2 xr = gauss_jordan<NP>(m, make_double2(my_b, 0.0), lane, line, &col);
-    const bool live = col >= 0 && col < n;
-    if (p.x != nullptr && live) p.x[bin * n + col] = make_float2((float)xr.x, (float)xr.y);
-    if (p.y != nullptr) {
-      const double cr = live ? s_c[col] : 0.0;
-      const int grp = live ? col / p.l : -1;
-      for (int gi = 0; gi < p.g; ++gi) {
-        const double re = warp_sum(grp == gi ? cr * xr.x : 0.0);
-        const double im = warp_sum(grp == gi ? cr * xr.y : 0.0);
-        if (lane == 0) p.y[bin * p.g + gi] = make_float2((float)re, (float)im);
-      }
-    }
+// z^{m_i} / gamma_i for this lane's delay line; also returns z^m alone through zm.
+__device__ __forceinline__ double2 diag_entry(const SolveParams& p, int64_t bin, int line, double invg, int delay,
+                                              int nbits, double2* zm) {
+  const double2 v = cpow_int(p.z[bin], delay, nbits);
+  *zm = v;
+  if (p.gamma_z != nullptr) {
+    const float2 gz = p.gamma_z[(int64_t)line * p.k + bin];
+    return cmul(v, fast_cinv(make_double2((double)gz.x, (double)gz.y)));
   }
+  return make_double2(v.x * invg, v.y * invg);
 }
 
-// Backward: adjoint solve per bin + accumulation of the parameter gradients. Each block writes one row of partial
-// sums to ws; solve_bwd_reduce_kernel adds the rows in a fixed order.
-template <int NP>
+// Lane-group bookkeeping shared by both kernels: which system type q this group serves and which bins.
+template <int W>
+struct GroupIndex {
+  int sl, q;
+  int64_t sgid, bin0, bin_stride;
+  __device__ __forceinline__ GroupIndex(const SolveParams& p) {
+    constexpr int kSpw = 32 / W;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    sl = lane % W;
+    sgid = ((int64_t)blockIdx.x * kWarps + warp) * kSpw + lane / W;
+    const int64_t total = (int64_t)gridDim.x * kWarps * kSpw;
+    q = (int)(sgid % p.nsys);
+    bin0 = sgid / p.nsys;
+    bin_stride = (total - q + p.nsys - 1) / p.nsys;  // number of lane groups serving system type q
+  }
+};
+
+template <int NP, int W>
+__global__ void __launch_bounds__(kWarps * 32) solve_fwd_kernel(SolveParams p) {
+  extern __shared__ double smem[];
+  constexpr int kSpw = 32 / W;
+  const int n = p.n;
+  double* s_const = smem;
+  double* s_vec = s_const + (size_t)p.nsys * 2 * NP * NP;
+  double* s_groups = s_vec + (size_t)p.nsys * 4 * NP;
+  const GroupIndex<W> gi(p);
+  const int sl = gi.sl, q = gi.q;
+  const int lg = (threadIdx.x >> 5) * kSpw + (threadIdx.x & 31) / W;  // lane group inside the block
+  double2* line0 = reinterpret_cast<double2*>(s_groups + (size_t)lg * Smem<NP>::kGroupFwd);
+  double2* line1 = line0 + (NP + 1);
+
+  load_block_constants<NP>(p, s_const, s_vec);
+  __syncthreads();
+  const double* s_a = s_const + (size_t)q * 2 * NP * NP;
+  const double* s_at = s_a + NP * NP;
+  const int li = q * NP + (sl < NP ? sl : 0);
+  const double my_invg = s_vec[li], my_b = s_vec[p.nsys * NP + li], my_c = s_vec[2 * p.nsys * NP + li];
+  const int my_delay = (int)s_vec[3 * p.nsys * NP + li];
+  const int my_line = q * n + sl;
+  const int nbits = 32 - __clz((int)__reduce_max_sync(0xffffffffu, (unsigned)(sl < n ? my_delay : 0)));
+
+  // every lane of a warp runs the same number of iterations (shuffles are warp wide); idle groups clamp the bin
+  const int64_t iters = (p.k + gi.bin_stride - 1) / gi.bin_stride;
+  int64_t iters_max = iters;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const int64_t other = __shfl_xor_sync(0xffffffffu, iters_max, o);
+    iters_max = other > iters_max ? other : iters_max;
+  }
+  for (int64_t it = 0; it < iters_max; ++it) {
+    int64_t bin = gi.bin0 + it * gi.bin_stride;
+    const bool live_bin = bin < p.k;
+    if (!live_bin) bin = p.k - 1;
+    double2 zm;
+    double2 dz = make_double2(0.0, 0.0);
+    if (sl < n) dz = diag_entry(p, bin, my_line, my_invg, my_delay, nbits, &zm);
+    double2 m[NP];
+    build_row<NP>(m, s_a, s_at, n, sl, dz, false);
+    int col;
+    const double2 xr = gauss_jordan<NP, W>(m, make_double2(my_b, 0.0), sl, line0, line1, &col);
+    const bool live = col >= 0 && col < n;
+    if (p.x != nullptr && live && live_bin) p.x[bin * p.ntot + q * n + col] = make_float2((float)xr.x, (float)xr.y);
+    if (p.y != nullptr) {
+      // c_col x_col through the (now idle) pivot line; one lane per output group adds its entries in order
+      if (live) {
+        const double cr = s_vec[2 * p.nsys * NP + q * NP + col];
+        line0[col] = make_double2(cr * xr.x, cr * xr.y);
+      }
+      __syncwarp();
+      if (p.nsys == 1) {
+        if (sl < p.g && live_bin) {
+          double re = 0.0, im = 0.0;
+          for (int j = 0; j < p.l; ++j) {
+            const double2 v = line0[sl * p.l + j];
+            re += v.x;
+            im += v.y;
+          }
+          p.y[bin * p.g + sl] = make_float2((float)re, (float)im);
+        }
+      } else if (sl == 0 && live_bin) {
+        double re = 0.0, im = 0.0;
+        for (int j = 0; j < n; ++j) {
+          const double2 v = line0[j];
+          re += v.x;
+          im += v.y;
+        }
+        p.y[bin * p.g + q] = make_float2((float)re, (float)im);
+      }
+      __syncwarp();
+    }
+  }
+  (void)my_c;
+}
+
+// Backward: adjoint solve per bin + accumulation of the parameter gradients. Each lane group writes one row of
+// partial sums to ws; solve_bwd_reduce_kernel adds the rows of each system type in a fixed order.
+template <int NP, int W>
 __global__ void __launch_bounds__(kWarps * 32) solve_bwd_kernel(SolveParams p) {
   extern __shared__ double smem[];
+  constexpr int kSpw = 32 / W;
   const int n = p.n;
-  double* s_a = smem;
-  double* s_at = s_a + NP * NP;
-  double* s_invg = s_at + NP * NP;
-  double* s_b = s_invg + NP;
-  double* s_c = s_b + NP;
-  double* s_delay = s_c + NP;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  double* wbase = smem + Smem<NP>::kBlock + (size_t)warp * Smem<NP>::kWarpBwd;
-  double2* line = reinterpret_cast<double2*>(wbase);
-  double2* lam = line + (NP + 1);
+  double* s_const = smem;
+  double* s_vec = s_const + (size_t)p.nsys * 2 * NP * NP;
+  double* s_groups = s_vec + (size_t)p.nsys * 4 * NP;
+  const GroupIndex<W> gi(p);
+  const int sl = gi.sl, q = gi.q;
+  const int lg = (threadIdx.x >> 5) * kSpw + (threadIdx.x & 31) / W;
+  double* gbase = s_groups + (size_t)lg * Smem<NP>::kGroupBwd;
+  double2* line0 = reinterpret_cast<double2*>(gbase);
+  double2* line1 = line0 + (NP + 1);
+  double2* lam = line1 + (NP + 1);
   double2* xs = lam + NP;
   double* acc = reinterpret_cast<double*>(xs + NP);
 
-  load_block_constants<NP>(p, s_a, s_at, s_invg, s_b, s_c, s_delay);
-  for (int i = lane; i < NP * NP; i += 32) acc[i] = 0.0;
+  load_block_constants<NP>(p, s_const, s_vec);
+  if (sl < NP)
+    for (int j = 0; j < NP; ++j) acc[sl + NP * j] = 0.0;
   __syncthreads();
-  const int li = lane < NP ? lane : 0;
-  const double my_invg = s_invg[li], my_delay = s_delay[li], my_c = s_c[li];
+  const double* s_a = s_const + (size_t)q * 2 * NP * NP;
+  const double* s_at = s_a + NP * NP;
+  const int li = q * NP + (sl < NP ? sl : 0);
+  const double my_invg = s_vec[li], my_c = s_vec[2 * p.nsys * NP + li];
+  const int my_delay = (int)s_vec[3 * p.nsys * NP + li];
+  const int my_line = q * n + sl;
+  const int my_group = p.nsys == 1 ? sl / p.l : q;
+  const int nbits = 32 - __clz((int)__reduce_max_sync(0xffffffffu, (unsigned)(sl < n ? my_delay : 0)));
 
+  const int64_t iters = (p.k + gi.bin_stride - 1) / gi.bin_stride;
+  int64_t iters_max = iters;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const int64_t other = __shfl_xor_sync(0xffffffffu, iters_max, o);
+    iters_max = other > iters_max ? other : iters_max;
+  }
   double gb_acc = 0.0, gc_acc = 0.0, gig_acc = 0.0;
-  for (int64_t bin = (int64_t)blockIdx.x * kWarps + warp; bin < p.k; bin += (int64_t)gridDim.x * kWarps) {
+  for (int64_t it = 0; it < iters_max; ++it) {
+    int64_t bin = gi.bin0 + it * gi.bin_stride;
+    const bool live_bin = bin < p.k;
+    if (!live_bin) bin = p.k - 1;
     double2 zm = make_double2(0.0, 0.0);
     double2 dz = make_double2(0.0, 0.0);
     double2 xr = make_double2(0.0, 0.0);
     double2 gyr = make_double2(0.0, 0.0);
     double2 rhs = make_double2(0.0, 0.0);
-    if (lane < n) {
-      dz = diag_entry(p, bin, lane, my_invg, my_delay, &zm);
-      const float2 xv = p.xin[bin * n + lane];
-      xr = make_double2((double)xv.x, (double)xv.y);
-      if (p.gy != nullptr) {
-        const float2 gv = p.gy[bin * p.g + lane / p.l];
-        gyr = make_double2((double)gv.x, (double)gv.y);
-        rhs.x = my_c * gyr.x;
-        rhs.y = my_c * gyr.y;
-      }
-      if (p.gx != nullptr) {
-        const float2 gv = p.gx[bin * n + lane];
-        rhs.x += (double)gv.x;
-        rhs.y += (double)gv.y;
+    if (sl < n) {
+      dz = diag_entry(p, bin, my_line, my_invg, my_delay, nbits, &zm);
+      if (live_bin) {
+        const float2 xv = p.xin[bin * p.ntot + my_line];
+        xr = make_double2((double)xv.x, (double)xv.y);
+        if (p.gy != nullptr) {
+          const float2 gv = p.gy[bin * p.g + my_group];
+          gyr = make_double2((double)gv.x, (double)gv.y);
+          rhs.x = my_c * gyr.x;
+          rhs.y = my_c * gyr.y;
+        }
+        if (p.gx != nullptr) {
+          const float2 gv = p.gx[bin * p.ntot + my_line];
+          rhs.x += (double)gv.x;
+          rhs.y += (double)gv.y;
+        }
       }
     }
-    if (lane < NP) xs[lane] = xr;
+    if (sl < NP) xs[sl] = xr;
     double2 m[NP];
-    build_row<NP>(m, s_a, s_at, n, lane, dz, true);
+    build_row<NP>(m, s_a, s_at, n, sl, dz, true);
     int col;
-    const double2 sol = gauss_jordan<NP>(m, rhs, lane, line, &col);
+    const double2 sol = gauss_jordan<NP, W>(m, rhs, sl, line0, line1, &col);
     if (col >= 0) lam[col] = sol;
     __syncwarp();
-    if (lane < n) {
-      const double2 lr = lam[lane];
+    if (sl < n) {  // a dead bin contributes zeros: its rhs and x are zero
+      const double2 lr = lam[sl];
       // dL/dA_eff[i][j] = Re(lambda_i conj(x_j)); the reduce kernel transposes back when A_eff = A^T.
 #pragma unroll 4
       for (int j = 0; j < n; ++j) {
         const double2 o = xs[j];
-        acc[lane + NP * j] += lr.x * o.x + lr.y * o.y;
+        acc[sl + NP * j] += lr.x * o.x + lr.y * o.y;
       }
       gb_acc += lr.x;
       gc_acc += xr.x * gyr.x + xr.y * gyr.y;
@@ -286,43 +401,28 @@ __global__ void __launch_bounds__(kWarps * 32) solve_bwd_kernel(SolveParams p) {
     }
     __syncwarp();
   }
-  // block reduction: warp partials -> ws[blockIdx.x]
-  __syncthreads();
+  // this lane group's partial sums -> ws[sgid]
   const size_t per = (size_t)n * n + 3 * (size_t)n;
-  double* out = p.ws + (size_t)blockIdx.x * per;
-  double* acc0 = smem + Smem<NP>::kBlock + Smem<NP>::kWarpFwd;  // warp 0 accumulator
-  for (int i = threadIdx.x; i < n * n; i += blockDim.x) {
-    const int row = i % n, colj = i / n;
-    double s = 0.0;
-#pragma unroll
-    for (int w = 0; w < kWarps; ++w) s += acc0[(size_t)w * Smem<NP>::kWarpBwd + row + NP * colj];
-    out[i] = s;  // index row + n*col of dL/dA_eff
-  }
-  double* stash = reinterpret_cast<double*>(line);  // 2(NP+1) + 4 NP doubles available per warp
-  if (lane < n) {
-    stash[lane] = gb_acc;
-    stash[n + lane] = gc_acc;
-    stash[2 * n + lane] = gig_acc;
-  }
-  __syncthreads();
-  double* stash0 = smem + Smem<NP>::kBlock;
-  for (int i = threadIdx.x; i < 3 * n; i += blockDim.x) {
-    double s = 0.0;
-#pragma unroll
-    for (int w = 0; w < kWarps; ++w) s += stash0[(size_t)w * Smem<NP>::kWarpBwd + i];
-    out[(size_t)n * n + i] = s;
+  double* out = p.ws + (size_t)gi.sgid * per;
+  if (sl < n) {
+    for (int j = 0; j < n; ++j) out[sl + n * j] = acc[sl + NP * j];  // index row + n*col of dL/dA_eff
+    out[(size_t)n * n + sl] = gb_acc;
+    out[(size_t)n * n + n + sl] = gc_acc;
+    out[(size_t)n * n + 2 * n + sl] = gig_acc;
   }
 }
 
-// One warp per output element: lanes stride over the per-block partial rows, fixed-order shuffle reduction.
-__global__ void solve_bwd_reduce_kernel(const double* ws, int nblocks, int n, int transpose_a, double* ga, double* gb,
-                                        double* gc, double* gig) {
+// One warp per output element: lanes stride over the partial rows of the lane groups that served system type q
+// (sgid = q, q + nsys, ...), fixed-order shuffle reduction.
+__global__ void solve_bwd_reduce_kernel(const double* ws, int64_t ngroups, int n, int nsys, int transpose_a, double* ga,
+                                        double* gb, double* gc, double* gig) {
   const int per = n * n + 3 * n;
   const int lane = threadIdx.x & 31;
-  const int i = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-  if (i >= per) return;
+  const int idx = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (idx >= per * nsys) return;
+  const int q = idx / per, i = idx % per;
   double s = 0.0;
-  for (int b = lane; b < nblocks; b += 32) s += ws[(size_t)b * per + i];
+  for (int64_t sg = q + (int64_t)lane * nsys; sg < ngroups; sg += 32 * (int64_t)nsys) s += ws[(size_t)sg * per + i];
   s = warp_sum(s);
   if (lane != 0) return;
   if (i < n * n) {
@@ -332,47 +432,63 @@ __global__ void solve_bwd_reduce_kernel(const double* ws, int nblocks, int n, in
       row = col;
       col = t;
     }
-    if (ga) ga[row * n + col] = s;
+    if (ga) ga[(size_t)q * n * n + row * n + col] = s;
   } else {
     const int j = i - n * n;
     if (j < n) {
-      if (gb) gb[j] = s;
+      if (gb) gb[q * n + j] = s;
     } else if (j < 2 * n) {
-      if (gc) gc[j - n] = s;
+      if (gc) gc[q * n + j - n] = s;
     } else {
-      if (gig) gig[j - 2 * n] = s;
+      if (gig) gig[q * n + j - 2 * n] = s;
     }
   }
 }
 
-int grid_blocks(int64_t k) {
-  int64_t want = (k + kWarps - 1) / kWarps;
+constexpr int lanes_for(int np) { return np <= 4 ? 4 : (np <= 8 ? 8 : (np <= 16 ? 16 : 32)); }
+
+int grid_blocks(int64_t systems, int w) {
+  const int per_block = kWarps * (32 / w);
+  int64_t want = (systems + per_block - 1) / per_block;
   int64_t cap = (int64_t)sm_count() * 4;
   return (int)(want < cap ? (want < 1 ? 1 : want) : cap);
 }
 
-int check_common(int n, int g, int64_t k) {
+int check_common(int n, int nsys, int g, int64_t k) {
   DGFDN_CHECK(n >= 1 && n <= DGFDN_MAX_LINES, "solve: n=%d out of range [1,%d]", n, DGFDN_MAX_LINES);
-  DGFDN_CHECK(g >= 1 && g <= DGFDN_MAX_GROUPS && n % g == 0, "solve: g=%d must divide n=%d and be <= %d", g, n,
-              DGFDN_MAX_GROUPS);
+  DGFDN_CHECK(nsys >= 1 && n * nsys <= DGFDN_MAX_LINES, "solve: %d systems of %d lines exceed %d lines", nsys, n,
+              DGFDN_MAX_LINES);
+  DGFDN_CHECK(g >= 1 && g <= DGFDN_MAX_GROUPS && (n * nsys) % g == 0, "solve: g=%d must divide N=%d and be <= %d", g,
+              n * nsys, DGFDN_MAX_GROUPS);
+  DGFDN_CHECK(nsys == 1 || nsys == g, "solve: group mode needs one system per group");
   DGFDN_CHECK(k >= 1, "solve: k=%lld must be positive", (long long)k);
   return 0;
 }
 
 template <int NP>
+size_t smem_bytes(const SolveParams& p, bool bwd) {
+  constexpr int W = lanes_for(NP);
+  const size_t groups = kWarps * (32 / W);
+  return ((size_t)p.nsys * Smem<NP>::kConstPerSys + groups * (bwd ? Smem<NP>::kGroupBwd : Smem<NP>::kGroupFwd)) *
+         sizeof(double);
+}
+
+template <int NP>
 int launch_fwd(const SolveParams& p, cudaStream_t st) {
-  const size_t smem = (Smem<NP>::kBlock + kWarps * Smem<NP>::kWarpFwd) * sizeof(double);
-  DGFDN_CUDA(cudaFuncSetAttribute(solve_fwd_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  solve_fwd_kernel<NP><<<grid_blocks(p.k), kWarps * 32, smem, st>>>(p);
+  constexpr int W = lanes_for(NP);
+  const size_t smem = smem_bytes<NP>(p, false);
+  DGFDN_CUDA(cudaFuncSetAttribute(solve_fwd_kernel<NP, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  solve_fwd_kernel<NP, W><<<grid_blocks(p.k * p.nsys, W), kWarps * 32, smem, st>>>(p);
   DGFDN_LAUNCH_CHECK();
   return 0;
 }
 
 template <int NP>
 int launch_bwd(const SolveParams& p, int blocks, cudaStream_t st) {
-  const size_t smem = (Smem<NP>::kBlock + kWarps * Smem<NP>::kWarpBwd) * sizeof(double);
-  DGFDN_CUDA(cudaFuncSetAttribute(solve_bwd_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  solve_bwd_kernel<NP><<<blocks, kWarps * 32, smem, st>>>(p);
+  constexpr int W = lanes_for(NP);
+  const size_t smem = smem_bytes<NP>(p, true);
+  DGFDN_CUDA(cudaFuncSetAttribute(solve_bwd_kernel<NP, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  solve_bwd_kernel<NP, W><<<blocks, kWarps * 32, smem, st>>>(p);
   DGFDN_LAUNCH_CHECK();
   return 0;
 }
@@ -404,21 +520,15 @@ int dispatch_bwd(const SolveParams& p, int blocks, cudaStream_t st) {
 #undef CALL_BWD
 }
 
-}  // namespace
-}  // namespace dgfdn
+int lanes_runtime(int n) { return lanes_for((n + 3) & ~3); }
 
-using namespace dgfdn;
-
-extern "C" int dgfdn_solve_fwd(int n, int g, int64_t k, const void* z, const int32_t* delays, const float* a,
-                               int transpose_a, const float* gamma, const void* gamma_z, const float* b,
-                               const float* c, void* x, void* y, void* stream) {
-  if (check_common(n, g, k)) return 1;
-  DGFDN_CHECK(z && delays && a && b, "solve_fwd: null input pointer");
-  DGFDN_CHECK(y == nullptr || c != nullptr, "solve_fwd: y requested without c");
-  SolveParams p{};
+int fill_params(SolveParams& p, int n, int nsys, int g, int64_t k, const void* z, const int32_t* delays, const float* a,
+                int transpose_a, const float* gamma, const void* gamma_z, const float* b, const float* c) {
   p.n = n;
+  p.nsys = nsys;
+  p.ntot = n * nsys;
   p.g = g;
-  p.l = n / g;
+  p.l = p.ntot / g;
   p.k = k;
   p.z = static_cast<const double2*>(z);
   p.delays = delays;
@@ -428,45 +538,89 @@ extern "C" int dgfdn_solve_fwd(int n, int g, int64_t k, const void* z, const int
   p.gamma_z = static_cast<const float2*>(gamma_z);
   p.b = b;
   p.c = c;
+  return 0;
+}
+
+int64_t bwd_groups(int n, int nsys, int64_t k) {
+  const int w = lanes_runtime(n);
+  return (int64_t)grid_blocks(k * nsys, w) * kWarps * (32 / w);
+}
+
+}  // namespace
+}  // namespace dgfdn
+
+using namespace dgfdn;
+
+static int solve_fwd_impl(int n, int nsys, int g, int64_t k, const void* z, const int32_t* delays, const float* a,
+                          int transpose_a, const float* gamma, const void* gamma_z, const float* b, const float* c,
+                          void* x, void* y, void* stream) {
+  if (check_common(n, nsys, g, k)) return 1;
+  DGFDN_CHECK(z && delays && a && b, "solve_fwd: null input pointer");
+  DGFDN_CHECK(y == nullptr || c != nullptr, "solve_fwd: y requested without c");
+  SolveParams p{};
+  fill_params(p, n, nsys, g, k, z, delays, a, transpose_a, gamma, gamma_z, b, c);
   p.x = static_cast<float2*>(x);
   p.y = static_cast<float2*>(y);
   return dispatch_fwd(p, static_cast<cudaStream_t>(stream));
 }
 
-extern "C" int64_t dgfdn_solve_bwd_ws_bytes(int n) {
-  return (int64_t)sm_count() * 4 * ((int64_t)n * n + 3 * (int64_t)n) * (int64_t)sizeof(double);
+static int solve_bwd_impl(int n, int nsys, int g, int64_t k, const void* z, const int32_t* delays, const float* a,
+                          int transpose_a, const float* gamma, const void* gamma_z, const float* c, const void* x,
+                          const void* gy, const void* gx, double* ga, double* gb, double* gc, double* ginvgamma,
+                          void* ws, void* stream) {
+  if (check_common(n, nsys, g, k)) return 1;
+  DGFDN_CHECK(z && delays && a && x && ws, "solve_bwd: null input pointer");
+  DGFDN_CHECK(gy || gx, "solve_bwd: need gy or gx");
+  DGFDN_CHECK(gy == nullptr || c != nullptr, "solve_bwd: gy given without c");
+  SolveParams p{};
+  fill_params(p, n, nsys, g, k, z, delays, a, transpose_a, gamma, gamma_z, nullptr, c);
+  p.xin = static_cast<const float2*>(x);
+  p.gy = static_cast<const float2*>(gy);
+  p.gx = static_cast<const float2*>(gx);
+  p.ws = static_cast<double*>(ws);
+  const int w = lanes_runtime(n);
+  const int blocks = grid_blocks(k * nsys, w);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dispatch_bwd(p, blocks, st)) return 1;
+  const int per = (n * n + 3 * n) * nsys;
+  solve_bwd_reduce_kernel<<<(per * 32 + 255) / 256, 256, 0, st>>>(p.ws, bwd_groups(n, nsys, k), n, nsys, transpose_a, ga,
+                                                                 gb, gc, ginvgamma);
+  DGFDN_LAUNCH_CHECK();
+  return 0;
 }
+
+extern "C" int dgfdn_solve_fwd(int n, int g, int64_t k, const void* z, const int32_t* delays, const float* a,
+                               int transpose_a, const float* gamma, const void* gamma_z, const float* b,
+                               const float* c, void* x, void* y, void* stream) {
+  return solve_fwd_impl(n, 1, g, k, z, delays, a, transpose_a, gamma, gamma_z, b, c, x, y, stream);
+}
+
+// one row of (n^2 + 3n) doubles per lane group of the largest grid the backward kernel launches
+static int64_t bwd_ws_bytes(int n) {
+  if (n < 1 || n > DGFDN_MAX_LINES) return 0;
+  const int64_t groups = (int64_t)sm_count() * 4 * kWarps * (32 / lanes_runtime(n));
+  return groups * ((int64_t)n * n + 3 * (int64_t)n) * (int64_t)sizeof(double);
+}
+
+extern "C" int64_t dgfdn_solve_bwd_ws_bytes(int n) { return bwd_ws_bytes(n); }
+extern "C" int64_t dgfdn_solve_groups_bwd_ws_bytes(int l) { return bwd_ws_bytes(l); }
 
 extern "C" int dgfdn_solve_bwd(int n, int g, int64_t k, const void* z, const int32_t* delays, const float* a,
                                int transpose_a, const float* gamma, const void* gamma_z, const float* c,
                                const void* x, const void* gy, const void* gx, double* ga, double* gb, double* gc,
                                double* ginvgamma, void* ws, void* stream) {
-  if (check_common(n, g, k)) return 1;
-  DGFDN_CHECK(z && delays && a && x && ws, "solve_bwd: null input pointer");
-  DGFDN_CHECK(gy || gx, "solve_bwd: need gy or gx");
-  DGFDN_CHECK(gy == nullptr || c != nullptr, "solve_bwd: gy given without c");
-  SolveParams p{};
-  p.n = n;
-  p.g = g;
-  p.l = n / g;
-  p.k = k;
-  p.z = static_cast<const double2*>(z);
-  p.delays = delays;
-  p.a = a;
-  p.transpose_a = transpose_a;
-  p.gamma = gamma;
-  p.gamma_z = static_cast<const float2*>(gamma_z);
-  p.b = nullptr;
-  p.c = c;
-  p.xin = static_cast<const float2*>(x);
-  p.gy = static_cast<const float2*>(gy);
-  p.gx = static_cast<const float2*>(gx);
-  p.ws = static_cast<double*>(ws);
-  const int blocks = grid_blocks(k);
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (dispatch_bwd(p, blocks, st)) return 1;
-  const int per = n * n + 3 * n;
-  solve_bwd_reduce_kernel<<<(per * 32 + 255) / 256, 256, 0, st>>>(p.ws, blocks, n, transpose_a, ga, gb, gc, ginvgamma);
-  DGFDN_LAUNCH_CHECK();
-  return 0;
+  return solve_bwd_impl(n, 1, g, k, z, delays, a, transpose_a, gamma, gamma_z, c, x, gy, gx, ga, gb, gc, ginvgamma, ws,
+                        stream);
+}
+
+extern "C" int dgfdn_solve_groups_fwd(int l, int g, int64_t k, const void* z, const int32_t* delays, const float* m_raw,
+                                      const float* gamma, const float* b, const float* c, void* x, void* y,
+                                      void* stream) {
+  return solve_fwd_impl(l, g, g, k, z, delays, m_raw, 0, gamma, nullptr, b, c, x, y, stream);
+}
+
+extern "C" int dgfdn_solve_groups_bwd(int l, int g, int64_t k, const void* z, const int32_t* delays, const float* m_raw,
+                                      const float* gamma, const float* c, const void* x, const void* gy, const void* gx,
+                                      double* gm, double* gb, double* gc, double* ginvgamma, void* ws, void* stream) {
+  return solve_bwd_impl(l, g, g, k, z, delays, m_raw, 0, gamma, nullptr, c, x, gy, gx, gm, gb, gc, ginvgamma, ws, stream);
 }

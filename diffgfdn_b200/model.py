@@ -128,11 +128,10 @@ class DiffGFDN(nn.Module):
 
     def sub_fdn_output(self, z: torch.Tensor) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
         """Response of each lossless sub-FDN, with the RAW mixing matrices M_g and no absorption (reference
-        model.py:209-252, quirk Q1): one block-diagonal solve. Returns Hout (K, G) and Hout_per_del (N, K, G)."""
+        model.py:209-252, quirk Q1): G small solves per bin (group mode of K1). Returns Hout (K, G) and Hout_per_del (N, K, G)."""
         z = self._on_device(z, torch.complex128)
-        a_sub = torch.block_diag(*self.feedback_loop.M)
-        xs, hout = ops.gfdn_solve(z, self.delays.to(torch.int32), a_sub, None, self._gains_vec(self.input_gains),
-                                  self._gains_vec(self.output_gains), self.num_groups)
+        xs, hout = ops.gfdn_solve_groups(z, self.delays.to(torch.int32), self.feedback_loop.M, None,
+                                         self._gains_vec(self.input_gains), self._gains_vec(self.output_gains))
         if not self.return_per_delay_outputs:
             return hout, None
         per = (xs * self._gains_vec(self.output_gains).to(xs.dtype)).transpose(0, 1)  # (N, K)

@@ -100,6 +100,65 @@ def gfdn_solve(z: torch.Tensor, delays: torch.Tensor, a: torch.Tensor, gamma: Op
     return _GFDNSolve.apply(z, delays, a, gamma, b, c, num_groups, transpose_a, gamma_z)
 
 
+class _GFDNSolveGroups(torch.autograd.Function):
+    """G independent LxL systems per bin: x[k, gL+i] = ((diag(z_k^{m_g}/gamma_g) - M_g)^-1 b_g)[i],
+    y[k,g] = sum_i c[gL+i] x[k, gL+i]  -- DiffGFDN.sub_fdn_output (reference model.py:209-252)."""
+
+    @staticmethod
+    def forward(ctx, z, delays, m, gamma, b, c):
+        z = _cuda("z", z, C128)
+        delays = _cuda("delays", delays, torch.int32)
+        m_ = _cuda("M", m, torch.float32)
+        gamma_ = _cuda("gamma", gamma, torch.float32, optional=True)
+        b_ = _cuda("b", b.reshape(-1), torch.float32)
+        c_ = _cuda("c", c.reshape(-1), torch.float32)
+        if m_.dim() != 3 or m_.shape[1] != m_.shape[2]:
+            raise RuntimeError("gfdn_solve_groups: M must be (G, L, L)")
+        g, l, _ = m_.shape
+        n, k = g * l, z.shape[0]
+        if delays.numel() != n or b_.numel() != n or c_.numel() != n or (gamma_ is not None and gamma_.numel() != n):
+            raise RuntimeError("gfdn_solve_groups: inconsistent shapes")
+        x = torch.empty(k, n, dtype=C64, device=z.device)
+        y = torch.empty(k, g, dtype=C64, device=z.device)
+        with torch.cuda.device(z.device):
+            _lib.call("dgfdn_solve_groups_fwd", l, g, k, _ptr(z), _ptr(delays), _ptr(m_), _ptr(gamma_), _ptr(b_),
+                      _ptr(c_), _ptr(x), _ptr(y), _stream())
+        ctx.save_for_backward(z, delays, m_, gamma_, c_, x)
+        ctx.meta = (g, l, k, b.shape, c.shape)
+        return x, y
+
+    @staticmethod
+    def backward(ctx, gx, gy):
+        z, delays, m_, gamma_, c_, x = ctx.saved_tensors
+        g, l, k, bshape, cshape = ctx.meta
+        if gx is None and gy is None:
+            return (None, ) * 6
+        gx_ = _cuda("gx", gx, C64, optional=True)
+        gy_ = _cuda("gy", gy, C64, optional=True)
+        n = g * l
+        dev = z.device
+        out = torch.empty(g * l * l + 3 * n, dtype=torch.float64, device=dev)
+        gm, gb, gc, gig = out[:g * l * l], out[g * l * l:g * l * l + n], out[g * l * l + n:g * l * l + 2 * n], \
+            out[g * l * l + 2 * n:]
+        with torch.cuda.device(dev):
+            ws = torch.empty(_lib.load().dgfdn_solve_groups_bwd_ws_bytes(l) // 8, dtype=torch.float64, device=dev)
+            _lib.call("dgfdn_solve_groups_bwd", l, g, k, _ptr(z), _ptr(delays), _ptr(m_), _ptr(gamma_), _ptr(c_), _ptr(x),
+                      _ptr(gy_), _ptr(gx_), _ptr(gm), _ptr(gb), _ptr(gc), _ptr(gig), _ptr(ws), _stream())
+        g_m = gm.reshape(g, l, l).to(torch.float32) if ctx.needs_input_grad[2] else None
+        g_gamma = None
+        if gamma_ is not None and ctx.needs_input_grad[3]:
+            g_gamma = (-gig / gamma_.to(torch.float64)**2).to(torch.float32)
+        g_b = gb.to(torch.float32).reshape(bshape) if ctx.needs_input_grad[4] else None
+        g_c = gc.to(torch.float32).reshape(cshape) if ctx.needs_input_grad[5] else None
+        return None, None, g_m, g_gamma, g_b, g_c
+
+
+def gfdn_solve_groups(z: torch.Tensor, delays: torch.Tensor, m: torch.Tensor, gamma: Optional[torch.Tensor],
+                      b: torch.Tensor, c: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Returns (x [K, G*L] c64, y [K, G] c64) of the G decoupled systems. Differentiable w.r.t. m, gamma, b, c."""
+    return _GFDNSolveGroups.apply(z, delays, m, gamma, b, c)
+
+
 # ----------------------------------------------------------------------------------------------------------
 # K2: receiver projection
 # ----------------------------------------------------------------------------------------------------------

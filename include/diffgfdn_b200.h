@@ -50,11 +50,11 @@ DGFDN_API int dgfdn_copy_rows_h2d(void* dst, int64_t dst_pitch_bytes, const void
  * DiffGFDN.sub_fdn_output (model.py:209-252, with A = blockdiag(M_raw), gamma = NULL).
  *
  *   M_k = diag(z_k^{m_i} / gamma_i) - A            (transpose_a: - A^T)
- *   x_k = M_k^{-1} b                               complex LU with partial pivoting, float64
+ *   x_k = M_k^{-1} b                               Gauss-Jordan with partial pivoting, float64
  *   y[k,g] = sum_{n in group g} c_n x_k[n]
  *
  * z       [K]    c128 sample points (dataloader.py:552-566)
- * delays  [N]    int32
+ * delays  [N]    int32, 0 <= m_i < 2^30 (z^m is formed by binary powering)
  * a       [N,N]  float32 row-major
  * gamma   [N]    float32 or NULL (= 1);  gamma_z [N,K] c64 or NULL (per-bin filter response, overrides gamma)
  * b, c    [N]    float32
@@ -77,6 +77,19 @@ DGFDN_API int dgfdn_solve_bwd(int n, int g, int64_t k, const void* z, const int3
                     int transpose_a, const float* gamma, const void* gamma_z, const float* c, const void* x,
                     const void* gy, const void* gx, double* ga, double* gb, double* gc, double* ginvgamma,
                     void* ws, void* stream);
+
+/* Group mode of K1: the G independent lossless LxL systems of DiffGFDN.sub_fdn_output (model.py:209-252, quirk Q1:
+ * RAW mixing matrices, normally no absorption) solved as G small systems per bin -- four 8x8 systems to a warp --
+ * instead of one block-diagonal NxN system.
+ *   x[k, g L + i] = ((diag(z_k^{m_g} / gamma_g) - M_g)^{-1} b_g)[i],   y[k,g] = sum_i c[g L + i] x[k, g L + i]
+ * m_raw [G,L,L] float32; delays, gamma (or NULL), b, c [G*L]; x [K, G*L] c64 (may be NULL), y [K,G] c64.
+ * The adjoint returns gm [G,L,L], gb, gc, ginvgamma [G*L] (float64); ws: dgfdn_solve_groups_bwd_ws_bytes(l) bytes. */
+DGFDN_API int dgfdn_solve_groups_fwd(int l, int g, int64_t k, const void* z, const int32_t* delays, const float* m_raw,
+                           const float* gamma, const float* b, const float* c, void* x, void* y, void* stream);
+DGFDN_API int64_t dgfdn_solve_groups_bwd_ws_bytes(int l);
+DGFDN_API int dgfdn_solve_groups_bwd(int l, int g, int64_t k, const void* z, const int32_t* delays, const float* m_raw,
+                           const float* gamma, const float* c, const void* x, const void* gy, const void* gx,
+                           double* gm, double* gb, double* gc, double* ginvgamma, void* ws, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K2: receiver projection.  Replaces the (B,N,K) expansion + einsums of model.py:583-619.

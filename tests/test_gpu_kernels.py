@@ -105,6 +105,42 @@ def test_solve_backward(n, g, transpose, radius):
     assert rel(cd.grad, c.grad) < 1e-3
 
 
+@pytest.mark.parametrize("n,g,k_bins", [(12, 3, 1024), (24, 3, 2048), (27, 3, 700), (8, 2, 513), (32, 1, 300), (5, 5, 64)])
+def test_solve_groups_forward_backward(n, g, k_bins):
+    """Group mode of K1 (G decoupled LxL lossless systems per bin, packed 32/W to a warp) against the oracle's
+    sub_fdn_output (reference model.py:209-252, raw M_g, no absorption) and its float64 autograd."""
+    from diffgfdn_b200 import ops
+    sy = make_system(n, g, 2 * (k_bins - 1), seed=300 + n)
+    # raw M with spectral radius < 1 keeps the lossless systems well conditioned on the unit circle
+    m_raw = 0.6 * sy["m_raw"]
+    k = sy["z"].numel()
+    gen = torch.Generator().manual_seed(11)
+    wy = torch.randn(k, g, dtype=torch.complex128, generator=gen)
+    wx = torch.randn(k, n, dtype=torch.complex128, generator=gen)
+    mo = m_raw.to(F64).requires_grad_(True)
+    bo = sy["b"].to(F64).requires_grad_(True)
+    co = sy["c"].to(F64).requires_grad_(True)
+    ho, hpo = O.sub_fdn_output(sy["z"], sy["delays"].to(F64), mo, bo, co)
+    # per-line states x = Hout_per_del / c (oracle returns c_n x_n per delay line, (N, K, G) one-hot over groups)
+    xo = hpo.sum(-1).transpose(0, 1) / co.to(torch.complex128)
+    lo = (ho * wy.conj()).real.sum() + (xo * wx.conj()).real.sum()
+    lo.backward()
+    md, bd, cd = [dev(t).requires_grad_(True) for t in (m_raw, sy["b"], sy["c"])]
+    x, y = ops.gfdn_solve_groups(dev(sy["z"]), dev(sy["delays"]), md, None, bd, cd)
+    assert rel(y.cpu().to(torch.complex128), ho.detach()) < 2e-6
+    assert rel(x.cpu().to(torch.complex128), xo.detach()) < 2e-6
+    lk = (y.to(torch.complex128) * dev(wy).conj()).real.sum() + (x.to(torch.complex128) * dev(wx).conj()).real.sum()
+    lk.backward()
+    assert abs(float(lk) - float(lo)) < 1e-5 * abs(float(lo)) + 1e-6
+    assert rel(md.grad, mo.grad) < 1e-3
+    assert rel(bd.grad, bo.grad) < 1e-3
+    assert rel(cd.grad, co.grad) < 1e-3
+    # same numbers as the block-diagonal coupled solve
+    a_sub = torch.block_diag(*[m_raw[i] for i in range(g)])
+    x2, y2 = ops.gfdn_solve(dev(sy["z"]), dev(sy["delays"]), dev(a_sub), None, dev(sy["b"]), dev(sy["c"]), g)
+    assert rel(y.cpu(), y2.cpu()) < 1e-6
+
+
 @pytest.mark.parametrize("rows,k,g,with_d", [(5, 1025, 3, True), (17, 4097, 3, False), (3, 514, 1, True), (9, 333, 8, True)])
 def test_receiver_projection_forward_backward(rows, k, g, with_d):
     from diffgfdn_b200 import ops
