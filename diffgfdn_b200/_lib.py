@@ -16,6 +16,8 @@ SIGNATURES = {
     "dgfdn_version": (c_int, []),
     "dgfdn_sm_count": (c_int, []),
     "dgfdn_copy_rows_h2d": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p]),
+    "dgfdn_skew_expm_fwd": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "dgfdn_skew_expm_bwd": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dgfdn_solve_fwd": (c_int, [c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dgfdn_solve_bwd_ws_bytes": (c_int64, [c_int]),

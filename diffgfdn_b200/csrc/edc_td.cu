@@ -33,55 +33,61 @@ constexpr float kDbPerLog2 = 3.0102999566398120f;  // 10 / log2(10)
 constexpr double kDbFactor = 4.342944819032518;    // 10 / ln(10)
 
 struct ScanSmem {
-  double in[2][kWarps];
-  double out[2][kWarps];
+  double in[2][2][kWarps];   // [parity][value][warp]
+  double out[2][2][kWarps];
 };
 
-// Exclusive scans over the thread index of TWO independent values per thread (they share the barriers).
-// REVERSE: sum over threads with a HIGHER index. Returns the exclusive offsets in a/b and the block totals.
+// Exclusive scans over the thread index of the TWO per-thread segment totals va (earlier segment) and vb (later
+// segment, kHalf samples further on), sharing two barriers. Inside a warp the scan runs in float32 (128 samples),
+// across warps and chunks in float64. REVERSE sums over later samples (suffix), otherwise over earlier ones.
+// Returns the offsets to add to the in-segment partial sums; `carry` holds everything outside the chunk and is
+// advanced by the chunk total. `parity` alternates between calls (double-buffered shared memory, no third barrier).
 template <bool REVERSE>
-__device__ __forceinline__ void block_scan2(double& a, double& b, ScanSmem& sm, double* tot_a, double* tot_b) {
+__device__ __forceinline__ void block_scan2(float va, float vb, ScanSmem& sm, int parity, double& carry, float& offa,
+                                            float& offb) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double ia = a, ib = b;
+  float ia = va, ib = vb;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
-    const double ta = REVERSE ? __shfl_down_sync(0xffffffffu, ia, o) : __shfl_up_sync(0xffffffffu, ia, o);
-    const double tb = REVERSE ? __shfl_down_sync(0xffffffffu, ib, o) : __shfl_up_sync(0xffffffffu, ib, o);
+    const float ta = REVERSE ? __shfl_down_sync(0xffffffffu, ia, o) : __shfl_up_sync(0xffffffffu, ia, o);
+    const float tb = REVERSE ? __shfl_down_sync(0xffffffffu, ib, o) : __shfl_up_sync(0xffffffffu, ib, o);
     if (REVERSE ? (lane + o < 32) : (lane >= o)) {
       ia += ta;
       ib += tb;
     }
   }
   if (lane == (REVERSE ? 0 : 31)) {
-    sm.in[0][warp] = ia;
-    sm.in[1][warp] = ib;
+    sm.in[parity][0][warp] = (double)ia;
+    sm.in[parity][1][warp] = (double)ib;
   }
   __syncthreads();
   if (warp < 2) {  // warp 0 scans the warp totals of a, warp 1 those of b (kWarps == 32)
-    double w = sm.in[warp][lane];
+    double w = sm.in[parity][warp][lane];
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const double t = REVERSE ? __shfl_down_sync(0xffffffffu, w, o) : __shfl_up_sync(0xffffffffu, w, o);
       if (REVERSE ? (lane + o < 32) : (lane >= o)) w += t;
     }
-    sm.out[warp][lane] = w;
+    sm.out[parity][warp][lane] = w;
   }
   __syncthreads();
-  double wa, wb;
+  double wa, wb, tot_a, tot_b;
   if (REVERSE) {
-    wa = (warp < kWarps - 1) ? sm.out[0][warp + 1] : 0.0;
-    wb = (warp < kWarps - 1) ? sm.out[1][warp + 1] : 0.0;
-    *tot_a = sm.out[0][0];
-    *tot_b = sm.out[1][0];
+    wa = (warp < kWarps - 1) ? sm.out[parity][0][warp + 1] : 0.0;
+    wb = (warp < kWarps - 1) ? sm.out[parity][1][warp + 1] : 0.0;
+    tot_a = sm.out[parity][0][0];
+    tot_b = sm.out[parity][1][0];
+    offa = (float)(wa + tot_b + carry) + (ia - va);
+    offb = (float)(wb + carry) + (ib - vb);
   } else {
-    wa = (warp > 0) ? sm.out[0][warp - 1] : 0.0;
-    wb = (warp > 0) ? sm.out[1][warp - 1] : 0.0;
-    *tot_a = sm.out[0][kWarps - 1];
-    *tot_b = sm.out[1][kWarps - 1];
+    wa = (warp > 0) ? sm.out[parity][0][warp - 1] : 0.0;
+    wb = (warp > 0) ? sm.out[parity][1][warp - 1] : 0.0;
+    tot_a = sm.out[parity][0][kWarps - 1];
+    tot_b = sm.out[parity][1][kWarps - 1];
+    offa = (float)(wa + carry) + (ia - va);
+    offb = (float)(wb + tot_a + carry) + (ib - vb);
   }
-  a = wa + ia - a;
-  b = wb + ib - b;
-  __syncthreads();  // sm reusable by the next call
+  carry += tot_a + tot_b;
 }
 
 struct TdParams {
@@ -103,13 +109,17 @@ struct TdParams {
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
+enum LoadKind { kStream, kShared, kRead };  // read-once HBM stream / re-read of this thread's own store / read-only
+
 // One segment (4 consecutive samples starting at t) of a row-major float array; samples at or beyond tn read as 0.
 // VEC: tn % 4 == 0 and every row is 16-byte aligned, so a segment is either fully inside or fully outside.
-template <bool VEC, bool STREAM>
+// FULL: the caller guarantees t + 4 <= tn (implies VEC): no bounds logic at all.
+template <bool VEC, bool FULL, LoadKind KIND>
 __device__ __forceinline__ float4 load_seg(const float* __restrict__ p, int t, int tn) {
   if (VEC) {
-    if (t >= tn) return make_float4(0.f, 0.f, 0.f, 0.f);
-    return STREAM ? ld_stream(reinterpret_cast<const float4*>(p + t)) : __ldcg(reinterpret_cast<const float4*>(p + t));
+    if (!FULL && t >= tn) return make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4* q = reinterpret_cast<const float4*>(p + t);
+    return KIND == kStream ? ld_stream(q) : (KIND == kShared ? __ldcg(q) : __ldg(q));
   }
   float4 v;
   v.x = (t < tn) ? __ldcg(p + t) : 0.f;
@@ -119,10 +129,10 @@ __device__ __forceinline__ float4 load_seg(const float* __restrict__ p, int t, i
   return v;
 }
 
-template <bool VEC>
+template <bool VEC, bool FULL>
 __device__ __forceinline__ void store_seg(float* __restrict__ p, int t, int tn, float4 v) {
   if (VEC) {
-    if (t < tn) __stcg(reinterpret_cast<float4*>(p + t), v);
+    if (FULL || t < tn) __stcg(reinterpret_cast<float4*>(p + t), v);
     return;
   }
   if (t < tn) __stcg(p + t, v.x);
@@ -132,12 +142,12 @@ __device__ __forceinline__ void store_seg(float* __restrict__ p, int t, int tn, 
 }
 
 // h of one segment: sum_g s_g hy_g[t..t+3] + hd[t..t+3]
-template <int G, bool VEC>
+template <int G, bool VEC, bool FULL>
 __device__ __forceinline__ float4 mix_seg(const TdParams& p, const float* hdr, const float (&sv)[G], int t) {
-  float4 h = hdr ? load_seg<VEC, true>(hdr, t, p.tn) : make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 h = hdr ? load_seg<VEC, FULL, kStream>(hdr, t, p.tn) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
   for (int g = 0; g < G; ++g) {
-    const float4 y = load_seg<VEC, false>(p.hy + (int64_t)g * p.tn, t, p.tn);
+    const float4 y = load_seg<VEC, FULL, kRead>(p.hy + (int64_t)g * p.tn, t, p.tn);
     h.x = fmaf(sv[g], y.x, h.x);
     h.y = fmaf(sv[g], y.y, h.y);
     h.z = fmaf(sv[g], y.z, h.z);
@@ -146,22 +156,157 @@ __device__ __forceinline__ float4 mix_seg(const TdParams& p, const float* hdr, c
   return h;
 }
 
+__device__ __forceinline__ float4 suffix4(float4 h) {  // suffix sums of h^2 inside a segment
+  float4 s;
+  s.w = h.w * h.w;
+  s.z = fmaf(h.z, h.z, s.w);
+  s.y = fmaf(h.y, h.y, s.z);
+  s.x = fmaf(h.x, h.x, s.y);
+  return s;
+}
+__device__ __forceinline__ float4 prefix4(float4 g) {
+  float4 p;
+  p.x = g.x;
+  p.y = p.x + g.y;
+  p.z = p.y + g.z;
+  p.w = p.z + g.w;
+  return p;
+}
+
 // dB of the EDC samples of one segment, masked |target - dB| and dL/dEDC. `suf` holds the suffix sums of h^2 inside
 // the segment, `off` everything later than the segment. 10 log10(EDC + eps) >= -69.2 dB, so the reference's clip
 // at -200 dB (utils.py:38-40) can never bind and is not evaluated.
+template <bool MASKED>
 __device__ __forceinline__ float4 db_loss_seg(float4 suf, float off, float4 td, float4 mk, float cf, float& acc) {
   float4 ge;
-#define DGFDN_DB_ONE(C)                                                 \
-  {                                                                     \
-    const float x = suf.C + off + kEpsF;                                \
-    const float diff = td.C - kDbPerLog2 * __log2f(x);                  \
-    acc = fmaf(mk.C, fabsf(diff), acc);                                 \
-    const float g = __fdividef(mk.C * cf, x);                           \
-    ge.C = diff > 0.f ? -g : (diff < 0.f ? g : 0.f);                    \
+#define DGFDN_DB_ONE(C)                                                                   \
+  {                                                                                       \
+    const float x = suf.C + off + kEpsF;                                                  \
+    const float diff = td.C - kDbPerLog2 * __log2f(x);                                    \
+    const float w = MASKED ? mk.C : 1.f;                                                  \
+    acc = fmaf(w, fabsf(diff), acc);                                                      \
+    const float g = __fdividef(MASKED ? w * cf : cf, x);                                  \
+    /* -sign(diff) g: flip the sign of g where diff > 0 */                                \
+    const float sg = __int_as_float(__float_as_int(g) ^ (~__float_as_int(diff) & 0x80000000));  \
+    ge.C = diff == 0.f ? 0.f : sg;                                                        \
   }
   DGFDN_DB_ONE(x) DGFDN_DB_ONE(y) DGFDN_DB_ONE(z) DGFDN_DB_ONE(w)
 #undef DGFDN_DB_ONE
   return ge;
+}
+
+template <int G, bool H_IN_SMEM, bool VEC, bool FULL>
+__device__ __forceinline__ void pass1_chunk(const TdParams& p, const float* hdr, const float* tr, float* gr,
+                                            const float (&sv)[G], int c, float cf, float4* s_h4, ScanSmem& sm,
+                                            double& carry, float& acc) {
+  const int tn = p.tn;
+  const int ta = c * kChunk + threadIdx.x * kSeg;  // earlier segment
+  const int tb = ta + kHalf;                       // later segment
+  if (c > 0) {  // next iteration's HBM inputs (no effect if the previous row's pass 2 already fetched them)
+    if (hdr) {
+      prefetch_l2(hdr + ta - kChunk);
+      prefetch_l2(hdr + tb - kChunk);
+    }
+    prefetch_l2(tr + ta - kChunk);
+    prefetch_l2(tr + tb - kChunk);
+  }
+  const float4 ha = mix_seg<G, VEC, FULL>(p, hdr, sv, ta);
+  const float4 hb = mix_seg<G, VEC, FULL>(p, hdr, sv, tb);
+  const float4 tda = load_seg<VEC, FULL, kStream>(tr, ta, tn), tdb4 = load_seg<VEC, FULL, kStream>(tr, tb, tn);
+  if (H_IN_SMEM) {
+    if (FULL || ta < tn) s_h4[ta >> 2] = ha;  // samples beyond tn inside the last segment are zero
+    if (FULL || tb < tn) s_h4[tb >> 2] = hb;
+  }
+  const float4 sa = suffix4(ha), sb = suffix4(hb);
+  float offa, offb;
+  block_scan2<true>(sa.x, sb.x, sm, c & 1, carry, offa, offb);
+  float4 ga, gb;
+  if (FULL && p.mask == nullptr) {
+    const float4 one = make_float4(1.f, 1.f, 1.f, 1.f);
+    ga = db_loss_seg<false>(sa, offa, tda, one, cf, acc);
+    gb = db_loss_seg<false>(sb, offb, tdb4, one, cf, acc);
+  } else {
+    float4 ma = make_float4(1.f, 1.f, 1.f, 1.f), mb = ma;
+    if (p.mask != nullptr) {
+      ma = load_seg<VEC, FULL, kRead>(p.mask, ta, tn);
+      mb = load_seg<VEC, FULL, kRead>(p.mask, tb, tn);
+    }
+    if (!FULL) {  // samples beyond tn must not contribute
+      if (ta >= tn) ma.x = 0.f;
+      if (ta + 1 >= tn) ma.y = 0.f;
+      if (ta + 2 >= tn) ma.z = 0.f;
+      if (ta + 3 >= tn) ma.w = 0.f;
+      if (tb >= tn) mb.x = 0.f;
+      if (tb + 1 >= tn) mb.y = 0.f;
+      if (tb + 2 >= tn) mb.z = 0.f;
+      if (tb + 3 >= tn) mb.w = 0.f;
+    }
+    ga = db_loss_seg<true>(sa, offa, tda, ma, cf, acc);
+    gb = db_loss_seg<true>(sb, offb, tdb4, mb, cf, acc);
+  }
+  store_seg<VEC, FULL>(gr, ta, tn, ga);
+  store_seg<VEC, FULL>(gr, tb, tn, gb);
+}
+
+template <int G, bool H_IN_SMEM, bool VEC, bool FULL>
+__device__ __forceinline__ void pass2_chunk(const TdParams& p, const float* hdr, float* gr, const float* hdn,
+                                            const float* trn, const float (&sv)[G], int c, int nchunks,
+                                            const float4* s_h4, ScanSmem& sm, double& carry, float (&gsacc)[G]) {
+  const int tn = p.tn;
+  const int ta = c * kChunk + threadIdx.x * kSeg;
+  const int tb = ta + kHalf;
+  {  // pull the chunk of the CTA's next row that its pass 1 will consume at the mirrored position into L2
+    const int pa = (nchunks - 1 - c) * kChunk + threadIdx.x * kSeg, pb = pa + kHalf;
+    if (trn != nullptr) {
+      if (pa < tn) prefetch_l2(trn + pa);
+      if (pb < tn) prefetch_l2(trn + pb);
+    }
+    if (hdn != nullptr) {
+      if (pa < tn) prefetch_l2(hdn + pa);
+      if (pb < tn) prefetch_l2(hdn + pb);
+    }
+  }
+  const float4 ga = load_seg<VEC, FULL, kShared>(gr, ta, tn);  // written by this same thread in pass 1
+  const float4 gb = load_seg<VEC, FULL, kShared>(gr, tb, tn);
+  float4 ha, hb;
+  if (H_IN_SMEM) {
+    ha = (FULL || ta < tn) ? s_h4[ta >> 2] : make_float4(0.f, 0.f, 0.f, 0.f);
+    hb = (FULL || tb < tn) ? s_h4[tb >> 2] : make_float4(0.f, 0.f, 0.f, 0.f);
+  } else {
+    ha = mix_seg<G, VEC, FULL>(p, hdr, sv, ta);
+    hb = mix_seg<G, VEC, FULL>(p, hdr, sv, tb);
+  }
+  const float4 pa4 = prefix4(ga), pb4 = prefix4(gb);
+  float offa, offb;
+  block_scan2<false>(pa4.w, pb4.w, sm, c & 1, carry, offa, offb);
+  float4 oa4, ob4;
+  oa4.x = 2.f * ha.x * (pa4.x + offa);
+  oa4.y = 2.f * ha.y * (pa4.y + offa);
+  oa4.z = 2.f * ha.z * (pa4.z + offa);
+  oa4.w = 2.f * ha.w * (pa4.w + offa);
+  ob4.x = 2.f * hb.x * (pb4.x + offb);
+  ob4.y = 2.f * hb.y * (pb4.y + offb);
+  ob4.z = 2.f * hb.z * (pb4.z + offb);
+  ob4.w = 2.f * hb.w * (pb4.w + offb);
+  store_seg<VEC, FULL>(gr, ta, tn, oa4);
+  store_seg<VEC, FULL>(gr, tb, tn, ob4);
+  if (p.gs != nullptr) {
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      const float4 ya = load_seg<VEC, FULL, kRead>(p.hy + (int64_t)g * tn, ta, tn);
+      const float4 yb = load_seg<VEC, FULL, kRead>(p.hy + (int64_t)g * tn, tb, tn);
+      float a = gsacc[g];
+      a = fmaf(oa4.x, ya.x, a);
+      a = fmaf(oa4.y, ya.y, a);
+      a = fmaf(oa4.z, ya.z, a);
+      a = fmaf(oa4.w, ya.w, a);
+      a = fmaf(ob4.x, yb.x, a);
+      a = fmaf(ob4.y, yb.y, a);
+      a = fmaf(ob4.z, yb.z, a);
+      a = fmaf(ob4.w, yb.w, a);
+      gsacc[g] = a;
+    }
+  }
 }
 
 // Persistent: CTA b handles rows b, b + gridDim.x, ...  H_IN_SMEM keeps the row's h (tn floats) in shared memory
@@ -174,6 +319,7 @@ __global__ void __launch_bounds__(kThreads, 1) td_edc_step_kernel(TdParams p) {
   const int tn = p.tn;
   const int tid = threadIdx.x;
   const int nchunks = (tn + kChunk - 1) / kChunk;
+  const int nfull = VEC ? tn / kChunk : 0;  // chunks that need no bounds logic
   const float cf = (float)(p.coef * kDbFactor);
 
   for (int64_t r = blockIdx.x; r < p.rows; r += gridDim.x) {
@@ -192,58 +338,12 @@ __global__ void __launch_bounds__(kThreads, 1) td_edc_step_kernel(TdParams p) {
     double carry = 0.0;
     float acc = 0.f;
     for (int c = nchunks - 1; c >= 0; --c) {
-      const int ta = c * kChunk + tid * kSeg;  // earlier segment
-      const int tb = ta + kHalf;               // later segment
-      if (c > 0) {  // next iteration's HBM inputs (no effect if the previous row's pass 2 already fetched them)
-        if (hdr) {
-          prefetch_l2(hdr + ta - kChunk);
-          prefetch_l2(hdr + tb - kChunk);
-        }
-        prefetch_l2(tr + ta - kChunk);
-        prefetch_l2(tr + tb - kChunk);
-      }
-      const float4 ha = mix_seg<G, VEC>(p, hdr, sv, ta);
-      const float4 hb = mix_seg<G, VEC>(p, hdr, sv, tb);
-      if (H_IN_SMEM) {
-        if (ta < tn) s_h4[ta >> 2] = ha;  // samples beyond tn inside the last segment are zero
-        if (tb < tn) s_h4[tb >> 2] = hb;
-      }
-      float4 sa, sb;  // suffix sums of h^2 inside each segment
-      sa.w = ha.w * ha.w;
-      sa.z = fmaf(ha.z, ha.z, sa.w);
-      sa.y = fmaf(ha.y, ha.y, sa.z);
-      sa.x = fmaf(ha.x, ha.x, sa.y);
-      sb.w = hb.w * hb.w;
-      sb.z = fmaf(hb.z, hb.z, sb.w);
-      sb.y = fmaf(hb.y, hb.y, sb.z);
-      sb.x = fmaf(hb.x, hb.x, sb.y);
-      double oa = (double)sa.x, ob = (double)sb.x, tot_a, tot_b;
-      block_scan2<true>(oa, ob, sm, &tot_a, &tot_b);
-      const float offb = (float)(ob + carry);
-      const float offa = (float)(oa + tot_b + carry);
-      const float4 tda = load_seg<VEC, true>(tr, ta, tn), tdb4 = load_seg<VEC, true>(tr, tb, tn);
-      float4 ma = make_float4(1.f, 1.f, 1.f, 1.f), mb = ma;
-      if (p.mask != nullptr) {
-        ma = load_seg<VEC, false>(p.mask, ta, tn);
-        mb = load_seg<VEC, false>(p.mask, tb, tn);
-      }
-      if (!VEC) {  // a ragged last segment: samples beyond tn must not contribute
-        if (ta + 1 >= tn) ma.y = 0.f;
-        if (ta + 2 >= tn) ma.z = 0.f;
-        if (ta + 3 >= tn) ma.w = 0.f;
-        if (tb + 1 >= tn) mb.y = 0.f;
-        if (tb + 2 >= tn) mb.z = 0.f;
-        if (tb + 3 >= tn) mb.w = 0.f;
-      }
-      if (ta >= tn) ma = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (tb >= tn) mb = make_float4(0.f, 0.f, 0.f, 0.f);
-      const float4 ga = db_loss_seg(sa, offa, tda, ma, cf, acc);
-      const float4 gb = db_loss_seg(sb, offb, tdb4, mb, cf, acc);
-      store_seg<VEC>(gr, ta, tn, ga);
-      store_seg<VEC>(gr, tb, tn, gb);
-      carry += tot_a + tot_b;
+      if (c < nfull)
+        pass1_chunk<G, H_IN_SMEM, VEC, VEC>(p, hdr, tr, gr, sv, c, cf, s_h4, sm, carry, acc);
+      else
+        pass1_chunk<G, H_IN_SMEM, VEC, false>(p, hdr, tr, gr, sv, c, cf, s_h4, sm, carry, acc);
     }
-    if (H_IN_SMEM) __syncthreads();
+    __syncthreads();  // s_h4 complete; scan buffers of either parity idle
 
     // ---- pass 2, early -> late: dL/dh[tau] = 2 h[tau] sum_{t <= tau} dL/dEDC[t]; dL/ds_g = <dL/dh, hy_g>
     float gsacc[G];
@@ -251,72 +351,10 @@ __global__ void __launch_bounds__(kThreads, 1) td_edc_step_kernel(TdParams p) {
     for (int g = 0; g < G; ++g) gsacc[g] = 0.f;
     carry = 0.0;
     for (int c = 0; c < nchunks; ++c) {
-      const int ta = c * kChunk + tid * kSeg;
-      const int tb = ta + kHalf;
-      {  // pull the chunk of the next row that its pass 1 will consume at the mirrored position
-        const int cn = nchunks - 1 - c;
-        const int pa = cn * kChunk + tid * kSeg, pb = pa + kHalf;
-        if (trn != nullptr) {
-          if (pa < tn) prefetch_l2(trn + pa);
-          if (pb < tn) prefetch_l2(trn + pb);
-        }
-        if (hdn != nullptr) {
-          if (pa < tn) prefetch_l2(hdn + pa);
-          if (pb < tn) prefetch_l2(hdn + pb);
-        }
-      }
-      const float4 ga = load_seg<VEC, false>(gr, ta, tn);  // written by this same thread in pass 1
-      const float4 gb = load_seg<VEC, false>(gr, tb, tn);
-      float4 pa4, pb4;  // prefix sums inside each segment
-      pa4.x = ga.x;
-      pa4.y = pa4.x + ga.y;
-      pa4.z = pa4.y + ga.z;
-      pa4.w = pa4.z + ga.w;
-      pb4.x = gb.x;
-      pb4.y = pb4.x + gb.y;
-      pb4.z = pb4.y + gb.z;
-      pb4.w = pb4.z + gb.w;
-      double oa = (double)pa4.w, ob = (double)pb4.w, tot_a, tot_b;
-      block_scan2<false>(oa, ob, sm, &tot_a, &tot_b);
-      const float offa = (float)(oa + carry);
-      const float offb = (float)(ob + tot_a + carry);
-      float4 ha, hb;
-      if (H_IN_SMEM) {
-        ha = (ta < tn) ? s_h4[ta >> 2] : make_float4(0.f, 0.f, 0.f, 0.f);
-        hb = (tb < tn) ? s_h4[tb >> 2] : make_float4(0.f, 0.f, 0.f, 0.f);
-      } else {
-        ha = mix_seg<G, VEC>(p, hdr, sv, ta);
-        hb = mix_seg<G, VEC>(p, hdr, sv, tb);
-      }
-      float4 oa4, ob4;
-      oa4.x = 2.f * ha.x * (pa4.x + offa);
-      oa4.y = 2.f * ha.y * (pa4.y + offa);
-      oa4.z = 2.f * ha.z * (pa4.z + offa);
-      oa4.w = 2.f * ha.w * (pa4.w + offa);
-      ob4.x = 2.f * hb.x * (pb4.x + offb);
-      ob4.y = 2.f * hb.y * (pb4.y + offb);
-      ob4.z = 2.f * hb.z * (pb4.z + offb);
-      ob4.w = 2.f * hb.w * (pb4.w + offb);
-      store_seg<VEC>(gr, ta, tn, oa4);
-      store_seg<VEC>(gr, tb, tn, ob4);
-      if (p.gs != nullptr) {
-#pragma unroll
-        for (int g = 0; g < G; ++g) {
-          const float4 ya = load_seg<VEC, false>(p.hy + (int64_t)g * tn, ta, tn);
-          const float4 yb = load_seg<VEC, false>(p.hy + (int64_t)g * tn, tb, tn);
-          float a = gsacc[g];
-          a = fmaf(oa4.x, ya.x, a);
-          a = fmaf(oa4.y, ya.y, a);
-          a = fmaf(oa4.z, ya.z, a);
-          a = fmaf(oa4.w, ya.w, a);
-          a = fmaf(ob4.x, yb.x, a);
-          a = fmaf(ob4.y, yb.y, a);
-          a = fmaf(ob4.z, yb.z, a);
-          a = fmaf(ob4.w, yb.w, a);
-          gsacc[g] = a;
-        }
-      }
-      carry += tot_a + tot_b;
+      if (c < nfull)
+        pass2_chunk<G, H_IN_SMEM, VEC, VEC>(p, hdr, gr, hdn, trn, sv, c, nchunks, s_h4, sm, carry, gsacc);
+      else
+        pass2_chunk<G, H_IN_SMEM, VEC, false>(p, hdr, gr, hdn, trn, sv, c, nchunks, s_h4, sm, carry, gsacc);
     }
 
     // ---- block reduction of the row loss and of dL/ds[r, :] (float64, fixed order)
@@ -340,7 +378,7 @@ __global__ void __launch_bounds__(kThreads, 1) td_edc_step_kernel(TdParams p) {
         p.gs[r * G + tid] = (float)v;
       }
     }
-    __syncthreads();  // red / s_h4 are reused by the next row
+    __syncthreads();  // red / s_h4 / scan buffers are reused by the next row
   }
 }
 

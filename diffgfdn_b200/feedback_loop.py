@@ -28,6 +28,19 @@ class MatrixExponential(nn.Module):
         return torch.matrix_exp(X)
 
 
+class OrthoParam(nn.Sequential):
+    """Skew() -> MatrixExponential(), the reference's `ortho_param` (feedback_loop.py:270). CUDA inputs with
+    L <= 16 take the fused, host-sync-free kernel (ops.skew_expm); anything else the stock torch sequence."""
+
+    def __init__(self):
+        super().__init__(Skew(), MatrixExponential())
+
+    def forward(self, X: torch.Tensor) -> torch.Tensor:
+        if X.is_cuda and X.dtype == torch.float32 and X.shape[-1] <= ops.SKEW_EXPM_MAX_L:
+            return ops.skew_expm(X)
+        return super().forward(X)
+
+
 class ND_Unitary(nn.Module):
     """N-D rotation from N(N-1)/2 Givens angles: U_n = R_{n-2}...R_0 [[U_{n-1},0],[0,1]] with R_i rotating the
     (i, n-1) plane (reference feedback_loop.py:39-87). Built without in-place writes, on alpha's device."""
@@ -118,7 +131,7 @@ class FeedbackLoop(nn.Module):
 
     # ---- feedback matrix (reference feedback_loop.py:260-324) --------------------------------------------
     def _init_feedback_matrix(self, colorless_feedback_matrix):
-        self.ortho_param = nn.Sequential(Skew(), MatrixExponential())
+        self.ortho_param = OrthoParam()
         L = self.num_delay_lines_per_group
         if colorless_feedback_matrix is not None:
             self.M = colorless_feedback_matrix.clone().detach().to(self.device)

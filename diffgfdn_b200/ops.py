@@ -37,6 +37,45 @@ def _cuda(name, t: Optional[torch.Tensor], dtype=None, optional=False):
 
 
 # ----------------------------------------------------------------------------------------------------------
+# orthogonal parametrisation (matrix exponential of the skew part), sync free
+# ----------------------------------------------------------------------------------------------------------
+SKEW_EXPM_MAX_L = 16
+
+
+class _SkewExpm(torch.autograd.Function):
+    """U = expm(triu(M,1) - triu(M,1)^T) for a batch (G, L, L) of raw mixing matrices (reference
+    feedback_loop.py:16-36). Same value as torch.matrix_exp(Skew(M)) without its device->host read-backs."""
+
+    @staticmethod
+    def forward(ctx, m):
+        m_ = _cuda("M", m, torch.float32)
+        if m_.dim() < 2 or m_.shape[-1] != m_.shape[-2] or m_.shape[-1] > SKEW_EXPM_MAX_L:
+            raise RuntimeError(f"skew_expm: expected (..., L, L) with L <= {SKEW_EXPM_MAX_L}")
+        l = m_.shape[-1]
+        g = m_.numel() // (l * l)
+        u = torch.empty_like(m_)
+        with torch.cuda.device(m_.device):
+            _lib.call("dgfdn_skew_expm_fwd", g, l, _ptr(m_), _ptr(u), _stream())
+        ctx.save_for_backward(m_)
+        return u
+
+    @staticmethod
+    def backward(ctx, gu):
+        (m_, ) = ctx.saved_tensors
+        l = m_.shape[-1]
+        g = m_.numel() // (l * l)
+        gu_ = _cuda("gU", gu, torch.float32)
+        gm = torch.empty_like(m_)
+        with torch.cuda.device(m_.device):
+            _lib.call("dgfdn_skew_expm_bwd", g, l, _ptr(m_), _ptr(gu_), _ptr(gm), _stream())
+        return gm
+
+
+def skew_expm(m: torch.Tensor) -> torch.Tensor:
+    return _SkewExpm.apply(m)
+
+
+# ----------------------------------------------------------------------------------------------------------
 # K1: per-bin solve
 # ----------------------------------------------------------------------------------------------------------
 class _GFDNSolve(torch.autograd.Function):

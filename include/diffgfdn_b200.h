@@ -44,6 +44,14 @@ DGFDN_API int dgfdn_copy_rows_h2d(void* dst, int64_t dst_pitch_bytes, const void
                         int64_t width_bytes, int64_t rows, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Orthogonal parametrisation of the mixing matrices.  Replaces Skew + MatrixExponential (torch.matrix_exp) of
+ * feedback_loop.py:16-36, 270, 401-403, which synchronises with the host twice per step:
+ *   U_g = expm(triu(M_g,1) - triu(M_g,1)^T),   m, u [G,L,L] float32, 2 L <= 32, one CTA per matrix, float64 inside.
+ * bwd: gm = d<gu, U>/dM  (adjoint of the Frechet derivative through the 2L x 2L block identity). */
+DGFDN_API int dgfdn_skew_expm_fwd(int g, int l, const float* m, float* u, void* stream);
+DGFDN_API int dgfdn_skew_expm_bwd(int g, int l, const float* m, const float* gu, float* gm, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * K1: per-bin build + solve.   Replaces FeedbackLoop.forward (diff_gfdn/feedback_loop.py:326-391),
  * the two einsums of DiffGFDNVarReceiverPos.forward (model.py:615-619) up to the receiver gains,
  * the state of DiffDirectionalFDNVarReceiverPos.forward (model.py:1083, transpose_a = 1) and

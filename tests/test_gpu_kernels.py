@@ -105,6 +105,26 @@ def test_solve_backward(n, g, transpose, radius):
     assert rel(cd.grad, c.grad) < 1e-3
 
 
+@pytest.mark.parametrize("g,l,scale", [(3, 4, 1.0), (3, 8, 1.0), (3, 9, 3.0), (1, 16, 0.2), (5, 1, 1.0), (2, 6, 25.0)])
+def test_skew_expm_forward_backward(g, l, scale):
+    """Fused Skew + matrix exponential against torch.matrix_exp in float64 (reference feedback_loop.py:16-36)."""
+    from diffgfdn_b200 import ops
+    gen = torch.Generator().manual_seed(g * 100 + l)
+    m = (scale * (2 * torch.rand(g, l, l, generator=gen) - 1) / np.sqrt(l)).to(torch.float32)
+    w = torch.randn(g, l, l, generator=gen, dtype=F64)
+    mo = m.to(F64).requires_grad_(True)
+    t = mo.triu(1)
+    uo = torch.matrix_exp(t - t.transpose(-1, -2))
+    (uo * w).sum().backward()
+    md = dev(m).requires_grad_(True)
+    u = ops.skew_expm(md)
+    (u.to(F64) * dev(w)).sum().backward()
+    assert float((u.cpu().to(F64) - uo.detach()).abs().max()) < 5e-7
+    assert float((u.cpu().to(F64) @ u.cpu().to(F64).transpose(-1, -2) - torch.eye(l, dtype=F64)).abs().max()) < 1e-6
+    assert float((md.grad.cpu().to(F64) - mo.grad).abs().max()) < 2e-6 * max(1.0, float(mo.grad.abs().max()))
+    assert float(md.grad.cpu().tril().abs().max()) == 0.0  # only the strict upper triangle of M is used
+
+
 @pytest.mark.parametrize("n,g,k_bins", [(12, 3, 1024), (24, 3, 2048), (27, 3, 700), (8, 2, 513), (32, 1, 300), (5, 5, 64)])
 def test_solve_groups_forward_backward(n, g, k_bins):
     """Group mode of K1 (G decoupled LxL lossless systems per bin, packed 32/W to a warp) against the oracle's
