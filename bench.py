@@ -57,6 +57,7 @@ def parse():
     ap.add_argument("--e2e-tile-rows", type=int, default=int(os.environ.get("DGFDN_E2E_TILE_ROWS", "128")))
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time eager steps instead of CUDA-graph replays")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-receivers", type=int, default=4)
     return ap.parse_args()
@@ -294,22 +295,33 @@ def main():
     hd = hd_pool.repeat(reps, 1)[:args.receivers].contiguous()
     target_db = tdb_pool.repeat(reps, 1)[:args.receivers].contiguous()
     step.attach(z, positions, hd, target_db)
-    opt = torch.optim.Adam(net.parameters(), lr=1e-3)
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3, capturable=True)
 
-    def one_step():
+    def eager_step():
         losses = step.step()
         opt.step()
         return losses
 
     for _ in range(args.warmup):
+        eager_step()
+    # (1) instrumented eager steps: CUDA events around the receiver kernels and the step sections (same stream),
+    #     used for the per-kernel roofline and the stage breakdown
+    step.events = {}
+    ms_eager, _ = timed_steps(eager_step, args.steps, barrier)
+    stages = event_breakdown(step.events, args.steps)
+    step.events = None
+    # (2) the headline: the same step (+ Adam) captured once in a CUDA graph and replayed -- no host work per step
+    if args.no_graph:
+        one_step = eager_step
+    else:
+        step.capture(optimizer=opt, warmup=1)
+        one_step = step.replay
+    for _ in range(args.warmup):
         one_step()
     step.kernel_launches = 0
-    step.events = {}
     with ClockSampler(local) as clocks:
         ms, losses = timed_steps(one_step, args.steps, barrier)
     launches = step.kernel_launches
-    stages = event_breakdown(step.events, args.steps)
-    step.events = None
     t = torch.tensor([ms], device=device, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -364,12 +376,15 @@ def main():
                          "algorithmic_bytes_per_launch": TD_BYTES_PER_SAMPLE * min(args.tile_rows, args.receivers) * step.tn,
                          "avg_launch_ms": td["ms_per_step"] / td["launches_per_step"],
                          "share_of_step": td["ms_per_step"] / ms,
+                         "timing": "CUDA events around every launch of this kernel during %d instrumented eager steps "
+                                   "of the same workload (events cannot be recorded inside a graph replay)" % args.steps,
                          "note": "8 B per receiver.sample (hd 4 + target dB 4); tn = %d samples per receiver" % step.tn},
             # the same throughput expressed with SURVEY.md 8(d)'s 64 B per receiver.bin of the project-then-irfft
             # pipeline this design replaces (can exceed 1: those bytes are no longer moved)
             "survey_64B_equivalent": {"GBps": value / world * SURVEY_BYTES_PER_EVAL / 1e9,
                                       "frac_of_peak": value / world * SURVEY_BYTES_PER_EVAL / 1e9 / hbm},
-            "stages": stages,
+            "stages": stages, "ms_per_step_eager_instrumented": ms_eager,
+            "cuda_graph": not args.no_graph,
             "e2e": e2e,
         }
         if not args.no_cpu_baseline:

@@ -43,13 +43,29 @@ class OrthoParam(nn.Sequential):
 
 class ND_Unitary(nn.Module):
     """N-D rotation from N(N-1)/2 Givens angles: U_n = R_{n-2}...R_0 [[U_{n-1},0],[0,1]] with R_i rotating the
-    (i, n-1) plane (reference feedback_loop.py:39-87). Built without in-place writes, on alpha's device."""
+    (i, n-1) plane (reference feedback_loop.py:39-87). Built without in-place writes, on alpha's device; the constant
+    selector matrices are cached per (N, device, dtype) so a step issues no host->device copies (CUDA-graph safe)."""
 
-    @staticmethod
-    def _unit(n, r, c, like):
-        e = torch.zeros(n, n, dtype=like.dtype, device=like.device)
-        e[r, c] = 1.0
-        return e
+    def __init__(self):
+        super().__init__()
+        self._consts = {}
+
+    def _constants(self, n, like):
+        key = (n, like.device, like.dtype)
+        c = self._consts.get(key)
+        if c is None:
+            eye = torch.eye(n)
+            diag, up, lo = torch.zeros(n - 1, n, n), torch.zeros(n - 1, n, n), torch.zeros(n - 1, n, n)
+            for i in range(n - 1):
+                diag[i, i, i] = 1.0
+                diag[i, n - 1, n - 1] = 1.0
+                up[i, i, n - 1] = 1.0
+                lo[i, n - 1, i] = 1.0
+            corner = torch.zeros(n, n)
+            corner[n - 1, n - 1] = 1.0
+            c = tuple(t.to(device=like.device, dtype=like.dtype) for t in (eye, diag, up, lo, corner))
+            self._consts[key] = c
+        return c
 
     def forward(self, alpha: torch.Tensor, N: int) -> torch.Tensor:
         assert len(alpha) == N * (N - 1) // 2
@@ -57,14 +73,13 @@ class ND_Unitary(nn.Module):
             return torch.ones(1, 1, dtype=alpha.dtype, device=alpha.device)
         start = (N - 1) * (N - 2) // 2
         cur = alpha[start:]
-        eye = torch.eye(N, dtype=alpha.dtype, device=alpha.device)
+        eye, diag, up, lo, corner = self._constants(N, alpha)
+        cs, sn = torch.cos(cur), torch.sin(cur)
         rot = eye
         for i in range(N - 1):
-            c, s = torch.cos(cur[i]), torch.sin(cur[i])
-            diag = self._unit(N, i, i, alpha) + self._unit(N, N - 1, N - 1, alpha)
-            r = eye - diag + c * diag - s * self._unit(N, i, N - 1, alpha) + s * self._unit(N, N - 1, i, alpha)
+            r = eye - diag[i] + cs[i] * diag[i] - sn[i] * up[i] + sn[i] * lo[i]
             rot = r @ rot
-        big = nn.functional.pad(self.forward(alpha[:start], N - 1), (0, 1, 0, 1)) + self._unit(N, N - 1, N - 1, alpha)
+        big = nn.functional.pad(self.forward(alpha[:start], N - 1), (0, 1, 0, 1)) + corner
         return rot @ big
 
 
@@ -168,9 +183,10 @@ class FeedbackLoop(nn.Module):
     def coupled_feedback_matrix_real(self) -> torch.Tensor:
         """A = block_M o (Phi (x) 1_{LxL}), real (N, N) float32 (reference :424-455 before to_complex)."""
         block_M = self.construct_block_mixing_matrix()
-        self.phi = self.construct_coupling_matrix()
+        phi = self.construct_coupling_matrix()
+        self.phi = phi.detach()  # kept for get_parameters()/get_param_dict(); detached (no graph outlives the step)
         L = self.num_delay_lines_per_group
-        return block_M * torch.kron(self.phi, torch.ones(L, L, dtype=block_M.dtype, device=block_M.device))
+        return block_M * torch.kron(phi, torch.ones(L, L, dtype=block_M.dtype, device=block_M.device))
 
     def get_coupled_feedback_matrix(self) -> torch.Tensor:
         a = self.coupled_feedback_matrix_real()
@@ -179,7 +195,7 @@ class FeedbackLoop(nn.Module):
     def solve(self, z: torch.Tensor, b: torch.Tensor, c: torch.Tensor, transpose: bool = False):
         """x_k = (D(z_k) Gamma^-1 - A)^-1 b and y[k,g] = sum_{n in g} c_n x_k[n] on the GPU (one warp per bin)."""
         a = self.coupled_feedback_matrix_real()
-        self.coupled_feedback_matrix = a
+        self.coupled_feedback_matrix = a.detach()
         gamma = None if self.delay_line_gain_response is not None else self.delay_line_gains
         return ops.gfdn_solve(z, self.delays.to(torch.int32), a, gamma, b, c, self.num_groups, transpose_a=transpose,
                               gamma_z=self.delay_line_gain_response)

@@ -175,6 +175,42 @@ class ShardedEDCStep:
             ev.setdefault("back(irfft^T+adjoint solves+autograd)", []).append((sec[2], sec[3]))
         return {'edc_loss': edc, 'spectral_loss': spectral.detach(), 'sparsity_loss': sparsity.detach()}
 
+    # ---- CUDA graph: the whole resident step (+ optimizer) as one launch ----------------------------------
+    def capture(self, optimizer: Optional[torch.optim.Optimizer] = None, warmup: int = 3):
+        """Capture step() (+ optimizer.step()) of the resident mode into a CUDA graph. Every kernel of the step --
+        cuBLAS MLP, expm, per-bin solves, cuFFT, the receiver kernels, the NCCL all-reduce -- is stream ordered and
+        free of host synchronisation, so a replay costs one launch. The optimizer must be capturable (e.g.
+        torch.optim.Adam(..., capturable=True)). Gradients live in the graph's memory pool: parameters keep
+        pointing at them, so code that reads p.grad after replay() sees the fresh values."""
+        if self.target_db is None:
+            raise RuntimeError("capture: attach() resident inputs first")
+        self.events = None
+        side = torch.cuda.Stream(device=self.dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):
+                self.step()
+                if optimizer is not None:
+                    optimizer.step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize(self.dev)
+        before = self.kernel_launches
+        self._graph = torch.cuda.CUDAGraph()
+        # same stream as the warm-up: the parameters' AccumulateGrad nodes are bound to the stream they were
+        # created on, and a backward that crosses streams would invalidate the capture
+        with torch.cuda.graph(self._graph, stream=side):
+            self._static_losses = self.step()
+            if optimizer is not None:
+                optimizer.step()
+        self.launches_per_replay = self.kernel_launches - before
+        return self._graph
+
+    def replay(self) -> Dict:
+        """Run the captured step once; returns the (static) loss tensors, overwritten by every replay."""
+        self._graph.replay()
+        self.kernel_launches += self.launches_per_replay
+        return self._static_losses
+
     @torch.no_grad()
     def _td_tile(self, r0, r1, s_d, hy_d, hd_tile, tdb_tile, gh, ws, ghy, gs, coef, stream, accumulate):
         g = self.net.num_groups

@@ -47,8 +47,9 @@ class Gains_from_MLP(nn.Module):
         position = position.to(param.device)
         self.batch_size = position.shape[0]
         out = self.mlp(self.encoder(position))
-        self.gains_ = self.scaled_sigmoid(out.view(-1)).view(self.batch_size, self.num_groups)
-        return self.gains_
+        gains = self.scaled_sigmoid(out.view(-1)).view(self.batch_size, self.num_groups)
+        self.gains_ = gains.detach()  # for get_parameters(); detached so no autograd graph outlives the step
+        return gains
 
     def forward(self, x: Dict) -> torch.Tensor:
         """(B, N, K) expansion with the reference's shape; a view, nothing is materialised."""
