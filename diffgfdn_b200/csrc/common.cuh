@@ -33,7 +33,7 @@ int sm_count();
 
 // ---- complex arithmetic on double2 / float2 -------------------------------------------------
 __host__ __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
-  return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+  return make_double2(fma(a.x, b.x, -(a.y * b.y)), fma(a.x, b.y, a.y * b.x));
 }
 __host__ __device__ __forceinline__ double2 cmulc(double2 a, double2 b) {  // a * conj(b)
   return make_double2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);

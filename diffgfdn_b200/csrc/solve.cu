@@ -129,15 +129,16 @@ struct GJStep {
     __syncwarp();
     if (sl != piv && sl < NP) {
       const double2 f = cmul(m[K], fast_cinv(line[K]));
+      const double nfx = -f.x, nfy = -f.y;
 #pragma unroll
-      for (int j = K + 1; j < NP; ++j) {
+      for (int j = K + 1; j < NP; ++j) {  // m[j] -= f * p[j]: four fused multiply-adds per complex element
         const double2 pj = line[j];
-        m[j].x -= f.x * pj.x - f.y * pj.y;
-        m[j].y -= f.x * pj.y + f.y * pj.x;
+        m[j].x = fma(f.y, pj.y, fma(nfx, pj.x, m[j].x));
+        m[j].y = fma(nfy, pj.x, fma(nfx, pj.y, m[j].y));
       }
       const double2 pr = line[NP];
-      st.rhs.x -= f.x * pr.x - f.y * pr.y;
-      st.rhs.y -= f.x * pr.y + f.y * pr.x;
+      st.rhs.x = fma(f.y, pr.y, fma(nfx, pr.x, st.rhs.x));
+      st.rhs.y = fma(nfy, pr.x, fma(nfx, pr.y, st.rhs.y));
     }
     // no second barrier: step K+1 writes the other line; step K+2 reuses this one only after the barrier of K+1
     if constexpr (K + 1 < NP) GJStep<NP, W, K + 1>::run(m, st, sl, line0, line1);
@@ -234,7 +235,7 @@ struct GroupIndex {
 };
 
 template <int NP, int W>
-__global__ void __launch_bounds__(kWarps * 32) solve_fwd_kernel(SolveParams p) {
+__global__ void __launch_bounds__(kWarps * 32, (NP <= 24 ? 3 : 2)) solve_fwd_kernel(SolveParams p) {
   extern __shared__ double smem[];
   constexpr int kSpw = 32 / W;
   const int n = p.n;
@@ -313,7 +314,7 @@ __global__ void __launch_bounds__(kWarps * 32) solve_fwd_kernel(SolveParams p) {
 // Backward: adjoint solve per bin + accumulation of the parameter gradients. Each lane group writes one row of
 // partial sums to ws; solve_bwd_reduce_kernel adds the rows of each system type in a fixed order.
 template <int NP, int W>
-__global__ void __launch_bounds__(kWarps * 32) solve_bwd_kernel(SolveParams p) {
+__global__ void __launch_bounds__(kWarps * 32, (NP <= 24 ? 3 : 2)) solve_bwd_kernel(SolveParams p) {
   extern __shared__ double smem[];
   constexpr int kSpw = 32 / W;
   const int n = p.n;
