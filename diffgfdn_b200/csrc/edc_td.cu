@@ -11,9 +11,10 @@
 // hd_r and the target EDC in dB (4 B + 4 B per sample), and produces the row loss, dL/ds[r,:] and dL/dh_r.
 // The adjoint closes with one G-row contraction (td_contract) and one G-row inverse-DFT adjoint.
 //
-// Persistent kernel, one CTA per SM, one receiver row at a time per CTA. Pass 1 walks the row late -> early in
-// chunks of 8192 samples: h (kept in shared memory), suffix scan of h^2 (float32 inside a thread's 4-sample
-// segment, float64 across threads and chunks), dB, |target - achieved|, dL/dEDC. Pass 2 walks early -> late: prefix
+// Persistent kernel, one CTA (512 threads) per SM, one receiver row at a time per CTA. Pass 1 walks the row late ->
+// early in chunks of 8192 samples (four independent 4-sample segments per thread): h (kept in shared memory),
+// suffix scan of h^2 (float32 inside a segment and a warp, float64 across warps and chunks), dB,
+// |target - achieved|, dL/dEDC. Pass 2 walks early -> late: prefix
 // scan of dL/dEDC, dL/dh = 2 h cumsum, dot products with hy for dL/ds; it reads no HBM, so it prefetches the CTA's
 // next row into L2 meanwhile. Reduction order is fixed (deterministic).
 #include <type_traits>
@@ -23,71 +24,74 @@
 namespace dgfdn {
 namespace {
 
-constexpr int kThreads = 1024;
+constexpr int kThreads = 512;
 constexpr int kWarps = kThreads / 32;
-constexpr int kSeg = 4;                    // samples per thread and segment (one 128-bit access)
-constexpr int kHalf = kThreads * kSeg;     // 4096 samples: one segment per thread
-constexpr int kChunk = 2 * kHalf;          // two segments per thread and iteration share one block scan
+constexpr int kSeg = 4;                    // samples per segment (one 128-bit access)
+constexpr int kNSeg = 4;                   // segments per thread and iteration (independent chains: ILP)
+constexpr int kSub = kThreads * kSeg;      // 2048 samples: one segment of every thread
+constexpr int kChunk = kNSeg * kSub;       // 8192 samples per iteration, one block scan
 constexpr float kEpsF = 1.1920928955078125e-07f;   // torch.finfo(float32).eps (reference utils.py:35)
 constexpr float kDbPerLog2 = 3.0102999566398120f;  // 10 / log2(10)
 constexpr double kDbFactor = 4.342944819032518;    // 10 / ln(10)
 
 struct ScanSmem {
-  double in[2][2][kWarps];   // [parity][value][warp]
-  double out[2][2][kWarps];
+  double in[2][kNSeg][kWarps];   // [parity][segment][warp]
+  double out[2][kNSeg][kWarps];
 };
 
-// Exclusive scans over the thread index of the TWO per-thread segment totals va (earlier segment) and vb (later
-// segment, kHalf samples further on), sharing two barriers. Inside a warp the scan runs in float32 (128 samples),
-// across warps and chunks in float64. REVERSE sums over later samples (suffix), otherwise over earlier ones.
-// Returns the offsets to add to the in-segment partial sums; `carry` holds everything outside the chunk and is
-// advanced by the chunk total. `parity` alternates between calls (double-buffered shared memory, no third barrier).
+// Exclusive scan over the samples of one chunk, given the per-thread totals v[j] of the thread's kNSeg segments
+// (segment j covers samples [j kSub + 4 tid, +4) of the chunk). Inside a warp the scan runs in float32 (128
+// samples), across warps, sub-chunks and chunks in float64; all kNSeg scans share two barriers. REVERSE sums over
+// later samples (suffix), otherwise over earlier ones. off[j] is what to add to the partial sums inside segment j;
+// `carry` holds everything outside the chunk and is advanced by the chunk total. `parity` alternates between
+// consecutive calls (double-buffered shared memory instead of a third barrier).
 template <bool REVERSE>
-__device__ __forceinline__ void block_scan2(float va, float vb, ScanSmem& sm, int parity, double& carry, float& offa,
-                                            float& offb) {
+__device__ __forceinline__ void block_scan_n(const float (&v)[kNSeg], ScanSmem& sm, int parity, double& carry,
+                                             float (&off)[kNSeg]) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float ia = va, ib = vb;
+  float inc[kNSeg];
+#pragma unroll
+  for (int j = 0; j < kNSeg; ++j) inc[j] = v[j];
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
-    const float ta = REVERSE ? __shfl_down_sync(0xffffffffu, ia, o) : __shfl_up_sync(0xffffffffu, ia, o);
-    const float tb = REVERSE ? __shfl_down_sync(0xffffffffu, ib, o) : __shfl_up_sync(0xffffffffu, ib, o);
-    if (REVERSE ? (lane + o < 32) : (lane >= o)) {
-      ia += ta;
-      ib += tb;
+    const bool take = REVERSE ? (lane + o < 32) : (lane >= o);
+#pragma unroll
+    for (int j = 0; j < kNSeg; ++j) {
+      const float t = REVERSE ? __shfl_down_sync(0xffffffffu, inc[j], o) : __shfl_up_sync(0xffffffffu, inc[j], o);
+      if (take) inc[j] += t;
     }
   }
   if (lane == (REVERSE ? 0 : 31)) {
-    sm.in[parity][0][warp] = (double)ia;
-    sm.in[parity][1][warp] = (double)ib;
+#pragma unroll
+    for (int j = 0; j < kNSeg; ++j) sm.in[parity][j][warp] = (double)inc[j];
   }
   __syncthreads();
-  if (warp < 2) {  // warp 0 scans the warp totals of a, warp 1 those of b (kWarps == 32)
-    double w = sm.in[parity][warp][lane];
+  if (warp < kNSeg) {  // warp j scans the kWarps warp totals of segment j
+    double w = lane < kWarps ? sm.in[parity][warp][lane] : 0.0;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
+    for (int o = 1; o < kWarps; o <<= 1) {
       const double t = REVERSE ? __shfl_down_sync(0xffffffffu, w, o) : __shfl_up_sync(0xffffffffu, w, o);
       if (REVERSE ? (lane + o < 32) : (lane >= o)) w += t;
     }
-    sm.out[parity][warp][lane] = w;
+    if (lane < kWarps) sm.out[parity][warp][lane] = w;
   }
   __syncthreads();
-  double wa, wb, tot_a, tot_b;
-  if (REVERSE) {
-    wa = (warp < kWarps - 1) ? sm.out[parity][0][warp + 1] : 0.0;
-    wb = (warp < kWarps - 1) ? sm.out[parity][1][warp + 1] : 0.0;
-    tot_a = sm.out[parity][0][0];
-    tot_b = sm.out[parity][1][0];
-    offa = (float)(wa + tot_b + carry) + (ia - va);
-    offb = (float)(wb + carry) + (ib - vb);
-  } else {
-    wa = (warp > 0) ? sm.out[parity][0][warp - 1] : 0.0;
-    wb = (warp > 0) ? sm.out[parity][1][warp - 1] : 0.0;
-    tot_a = sm.out[parity][0][kWarps - 1];
-    tot_b = sm.out[parity][1][kWarps - 1];
-    offa = (float)(wa + carry) + (ia - va);
-    offb = (float)(wb + tot_a + carry) + (ib - vb);
+  double base = carry;
+#pragma unroll
+  for (int jj = 0; jj < kNSeg; ++jj) {
+    const int j = REVERSE ? kNSeg - 1 - jj : jj;  // sub-chunks in scan order
+    double w, tot;
+    if (REVERSE) {
+      w = (warp < kWarps - 1) ? sm.out[parity][j][warp + 1] : 0.0;
+      tot = sm.out[parity][j][0];
+    } else {
+      w = (warp > 0) ? sm.out[parity][j][warp - 1] : 0.0;
+      tot = sm.out[parity][j][kWarps - 1];
+    }
+    off[j] = (float)(w + base) + (inc[j] - v[j]);
+    base += tot;
   }
-  carry += tot_a + tot_b;
+  carry = base;
 }
 
 struct TdParams {
@@ -107,53 +111,41 @@ struct TdParams {
   int64_t ldg;
 };
 
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// One instruction pulls `bytes` (multiple of 16) starting at p (16-byte aligned) into L2.
+__device__ __forceinline__ void prefetch_l2_bulk(const void* p, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
 
-enum LoadKind { kStream, kShared, kRead };  // read-once HBM stream / re-read of this thread's own store / read-only
+enum LoadKind { kStream, kOwn, kRead };  // read-once HBM stream / re-read of this thread's own store / read-only
 
-// One segment (4 consecutive samples starting at t) of a row-major float array; samples at or beyond tn read as 0.
+// One segment (4 consecutive samples) at q[0..3]; `t` is its first sample index. Samples at or beyond tn read as 0.
 // VEC: tn % 4 == 0 and every row is 16-byte aligned, so a segment is either fully inside or fully outside.
 // FULL: the caller guarantees t + 4 <= tn (implies VEC): no bounds logic at all.
 template <bool VEC, bool FULL, LoadKind KIND>
-__device__ __forceinline__ float4 load_seg(const float* __restrict__ p, int t, int tn) {
+__device__ __forceinline__ float4 load_seg(const float* __restrict__ q, int t, int tn) {
   if (VEC) {
     if (!FULL && t >= tn) return make_float4(0.f, 0.f, 0.f, 0.f);
-    const float4* q = reinterpret_cast<const float4*>(p + t);
-    return KIND == kStream ? ld_stream(q) : (KIND == kShared ? __ldcg(q) : __ldg(q));
+    const float4* q4 = reinterpret_cast<const float4*>(q);
+    return KIND == kStream ? ld_stream(q4) : (KIND == kOwn ? __ldcg(q4) : __ldg(q4));
   }
   float4 v;
-  v.x = (t < tn) ? __ldcg(p + t) : 0.f;
-  v.y = (t + 1 < tn) ? __ldcg(p + t + 1) : 0.f;
-  v.z = (t + 2 < tn) ? __ldcg(p + t + 2) : 0.f;
-  v.w = (t + 3 < tn) ? __ldcg(p + t + 3) : 0.f;
+  v.x = (t < tn) ? __ldcg(q) : 0.f;
+  v.y = (t + 1 < tn) ? __ldcg(q + 1) : 0.f;
+  v.z = (t + 2 < tn) ? __ldcg(q + 2) : 0.f;
+  v.w = (t + 3 < tn) ? __ldcg(q + 3) : 0.f;
   return v;
 }
 
 template <bool VEC, bool FULL>
-__device__ __forceinline__ void store_seg(float* __restrict__ p, int t, int tn, float4 v) {
+__device__ __forceinline__ void store_seg(float* __restrict__ q, int t, int tn, float4 v) {
   if (VEC) {
-    if (FULL || t < tn) __stcg(reinterpret_cast<float4*>(p + t), v);
+    if (FULL || t < tn) __stcg(reinterpret_cast<float4*>(q), v);
     return;
   }
-  if (t < tn) __stcg(p + t, v.x);
-  if (t + 1 < tn) __stcg(p + t + 1, v.y);
-  if (t + 2 < tn) __stcg(p + t + 2, v.z);
-  if (t + 3 < tn) __stcg(p + t + 3, v.w);
-}
-
-// h of one segment: sum_g s_g hy_g[t..t+3] + hd[t..t+3]
-template <int G, bool VEC, bool FULL>
-__device__ __forceinline__ float4 mix_seg(const TdParams& p, const float* hdr, const float (&sv)[G], int t) {
-  float4 h = hdr ? load_seg<VEC, FULL, kStream>(hdr, t, p.tn) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-  for (int g = 0; g < G; ++g) {
-    const float4 y = load_seg<VEC, FULL, kRead>(p.hy + (int64_t)g * p.tn, t, p.tn);
-    h.x = fmaf(sv[g], y.x, h.x);
-    h.y = fmaf(sv[g], y.y, h.y);
-    h.z = fmaf(sv[g], y.z, h.z);
-    h.w = fmaf(sv[g], y.w, h.w);
-  }
-  return h;
+  if (t < tn) __stcg(q, v.x);
+  if (t + 1 < tn) __stcg(q + 1, v.y);
+  if (t + 2 < tn) __stcg(q + 2, v.z);
+  if (t + 3 < tn) __stcg(q + 3, v.w);
 }
 
 __device__ __forceinline__ float4 suffix4(float4 h) {  // suffix sums of h^2 inside a segment
@@ -174,136 +166,154 @@ __device__ __forceinline__ float4 prefix4(float4 g) {
 }
 
 // dB of the EDC samples of one segment, masked |target - dB| and dL/dEDC. `suf` holds the suffix sums of h^2 inside
-// the segment, `off` everything later than the segment. 10 log10(EDC + eps) >= -69.2 dB, so the reference's clip
-// at -200 dB (utils.py:38-40) can never bind and is not evaluated.
+// the segment, `offe` everything later than the segment plus eps. 10 log10(EDC + eps) >= -69.2 dB, so the
+// reference's clip at -200 dB (utils.py:38-40) can never bind and is not evaluated.
 template <bool MASKED>
-__device__ __forceinline__ float4 db_loss_seg(float4 suf, float off, float4 td, float4 mk, float cf, float& acc) {
+__device__ __forceinline__ float4 db_loss_seg(float4 suf, float offe, float4 td, float4 mk, float cf, float& acc) {
   float4 ge;
-#define DGFDN_DB_ONE(C)                                                                   \
-  {                                                                                       \
-    const float x = suf.C + off + kEpsF;                                                  \
-    const float diff = td.C - kDbPerLog2 * __log2f(x);                                    \
-    const float w = MASKED ? mk.C : 1.f;                                                  \
-    acc = fmaf(w, fabsf(diff), acc);                                                      \
-    const float g = __fdividef(MASKED ? w * cf : cf, x);                                  \
-    /* -sign(diff) g: flip the sign of g where diff > 0 */                                \
+#define DGFDN_DB_ONE(C)                                                                         \
+  {                                                                                             \
+    const float x = suf.C + offe;                                                               \
+    const float diff = td.C - kDbPerLog2 * __log2f(x);                                          \
+    const float w = MASKED ? mk.C : 1.f;                                                        \
+    acc = fmaf(w, fabsf(diff), acc);                                                            \
+    const float g = __fdividef(MASKED ? w * cf : cf, x);                                        \
+    /* -sign(diff) g: flip the sign of g where diff > 0 */                                      \
     const float sg = __int_as_float(__float_as_int(g) ^ (~__float_as_int(diff) & 0x80000000));  \
-    ge.C = diff == 0.f ? 0.f : sg;                                                        \
+    ge.C = diff == 0.f ? 0.f : sg;                                                              \
   }
   DGFDN_DB_ONE(x) DGFDN_DB_ONE(y) DGFDN_DB_ONE(z) DGFDN_DB_ONE(w)
 #undef DGFDN_DB_ONE
   return ge;
 }
 
-template <int G, bool H_IN_SMEM, bool VEC, bool FULL>
-__device__ __forceinline__ void pass1_chunk(const TdParams& p, const float* hdr, const float* tr, float* gr,
-                                            const float (&sv)[G], int c, float cf, float4* s_h4, ScanSmem& sm,
-                                            double& carry, float& acc) {
-  const int tn = p.tn;
-  const int ta = c * kChunk + threadIdx.x * kSeg;  // earlier segment
-  const int tb = ta + kHalf;                       // later segment
-  if (c > 0) {  // next iteration's HBM inputs (no effect if the previous row's pass 2 already fetched them)
-    if (hdr) {
-      prefetch_l2(hdr + ta - kChunk);
-      prefetch_l2(hdr + tb - kChunk);
+// Per-row, per-thread base pointers (already offset by 4 tid); chunk c / segment j add c kChunk + j kSub floats.
+template <int G>
+struct RowPtrs {
+  const float* hd;  // may be null
+  const float* td;
+  float* gr;
+  const float* hy[G];
+  const float* mask;  // may be null
+};
+
+template <int G, bool VEC, bool FULL>
+__device__ __forceinline__ void mix_chunk(const RowPtrs<G>& rp, const float (&sv)[G], int base, int t0, int tn,
+                                          float4 (&h)[kNSeg]) {
+#pragma unroll
+  for (int j = 0; j < kNSeg; ++j)
+    h[j] = rp.hd ? load_seg<VEC, FULL, kStream>(rp.hd + base + j * kSub, t0 + j * kSub, tn)
+                 : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+#pragma unroll
+    for (int j = 0; j < kNSeg; ++j) {
+      const float4 y = load_seg<VEC, FULL, kRead>(rp.hy[g] + base + j * kSub, t0 + j * kSub, tn);
+      h[j].x = fmaf(sv[g], y.x, h[j].x);
+      h[j].y = fmaf(sv[g], y.y, h[j].y);
+      h[j].z = fmaf(sv[g], y.z, h[j].z);
+      h[j].w = fmaf(sv[g], y.w, h[j].w);
     }
-    prefetch_l2(tr + ta - kChunk);
-    prefetch_l2(tr + tb - kChunk);
   }
-  const float4 ha = mix_seg<G, VEC, FULL>(p, hdr, sv, ta);
-  const float4 hb = mix_seg<G, VEC, FULL>(p, hdr, sv, tb);
-  const float4 tda = load_seg<VEC, FULL, kStream>(tr, ta, tn), tdb4 = load_seg<VEC, FULL, kStream>(tr, tb, tn);
-  if (H_IN_SMEM) {
-    if (FULL || ta < tn) s_h4[ta >> 2] = ha;  // samples beyond tn inside the last segment are zero
-    if (FULL || tb < tn) s_h4[tb >> 2] = hb;
-  }
-  const float4 sa = suffix4(ha), sb = suffix4(hb);
-  float offa, offb;
-  block_scan2<true>(sa.x, sb.x, sm, c & 1, carry, offa, offb);
-  float4 ga, gb;
-  if (FULL && p.mask == nullptr) {
-    const float4 one = make_float4(1.f, 1.f, 1.f, 1.f);
-    ga = db_loss_seg<false>(sa, offa, tda, one, cf, acc);
-    gb = db_loss_seg<false>(sb, offb, tdb4, one, cf, acc);
-  } else {
-    float4 ma = make_float4(1.f, 1.f, 1.f, 1.f), mb = ma;
-    if (p.mask != nullptr) {
-      ma = load_seg<VEC, FULL, kRead>(p.mask, ta, tn);
-      mb = load_seg<VEC, FULL, kRead>(p.mask, tb, tn);
-    }
-    if (!FULL) {  // samples beyond tn must not contribute
-      if (ta >= tn) ma.x = 0.f;
-      if (ta + 1 >= tn) ma.y = 0.f;
-      if (ta + 2 >= tn) ma.z = 0.f;
-      if (ta + 3 >= tn) ma.w = 0.f;
-      if (tb >= tn) mb.x = 0.f;
-      if (tb + 1 >= tn) mb.y = 0.f;
-      if (tb + 2 >= tn) mb.z = 0.f;
-      if (tb + 3 >= tn) mb.w = 0.f;
-    }
-    ga = db_loss_seg<true>(sa, offa, tda, ma, cf, acc);
-    gb = db_loss_seg<true>(sb, offb, tdb4, mb, cf, acc);
-  }
-  store_seg<VEC, FULL>(gr, ta, tn, ga);
-  store_seg<VEC, FULL>(gr, tb, tn, gb);
 }
 
 template <int G, bool H_IN_SMEM, bool VEC, bool FULL>
-__device__ __forceinline__ void pass2_chunk(const TdParams& p, const float* hdr, float* gr, const float* hdn,
-                                            const float* trn, const float (&sv)[G], int c, int nchunks,
+__device__ __forceinline__ void pass1_chunk(const RowPtrs<G>& rp, const float (&sv)[G], int c, int tn, float cf,
+                                            float4* s_h4, ScanSmem& sm, double& carry, float& acc) {
+  const int base = c * kChunk;                // offset of the chunk from the per-thread row pointers
+  const int t0 = base + threadIdx.x * kSeg;   // first sample of segment 0
+  if (VEC && c > 0 && threadIdx.x == 0) {     // next iteration's HBM inputs -> L2 (one bulk prefetch per stream)
+    if (rp.hd) prefetch_l2_bulk(rp.hd + base - kChunk, kChunk * 4);
+    prefetch_l2_bulk(rp.td + base - kChunk, kChunk * 4);
+  }
+  float4 h[kNSeg], td[kNSeg];
+  mix_chunk<G, VEC, FULL>(rp, sv, base, t0, tn, h);
+#pragma unroll
+  for (int j = 0; j < kNSeg; ++j) td[j] = load_seg<VEC, FULL, kStream>(rp.td + base + j * kSub, t0 + j * kSub, tn);
+  float4 suf[kNSeg];
+  float tot[kNSeg], off[kNSeg];
+#pragma unroll
+  for (int j = 0; j < kNSeg; ++j) {
+    if (H_IN_SMEM && (FULL || t0 + j * kSub < tn)) s_h4[(t0 + j * kSub) >> 2] = h[j];  // zeros beyond tn in a ragged tail
+    suf[j] = suffix4(h[j]);
+    tot[j] = suf[j].x;
+  }
+  block_scan_n<true>(tot, sm, c & 1, carry, off);
+#pragma unroll
+  for (int j = 0; j < kNSeg; ++j) {
+    const int t = t0 + j * kSub;
+    float4 ge;
+    if (FULL && rp.mask == nullptr) {
+      ge = db_loss_seg<false>(suf[j], off[j] + kEpsF, td[j], td[j], cf, acc);
+    } else {
+      float4 mk = make_float4(1.f, 1.f, 1.f, 1.f);
+      if (rp.mask != nullptr) mk = load_seg<VEC, FULL, kRead>(rp.mask + base + j * kSub, t, tn);
+      if (!FULL) {  // samples beyond tn must not contribute
+        if (t >= tn) mk.x = 0.f;
+        if (t + 1 >= tn) mk.y = 0.f;
+        if (t + 2 >= tn) mk.z = 0.f;
+        if (t + 3 >= tn) mk.w = 0.f;
+      }
+      ge = db_loss_seg<true>(suf[j], off[j] + kEpsF, td[j], mk, cf, acc);
+    }
+    store_seg<VEC, FULL>(rp.gr + base + j * kSub, t, tn, ge);
+  }
+}
+
+template <int G, bool H_IN_SMEM, bool VEC, bool FULL>
+__device__ __forceinline__ void pass2_chunk(const RowPtrs<G>& rp, const float* hdn, const float* tdn,
+                                            const float (&sv)[G], int c, int nchunks, int tn, bool want_gs,
                                             const float4* s_h4, ScanSmem& sm, double& carry, float (&gsacc)[G]) {
-  const int tn = p.tn;
-  const int ta = c * kChunk + threadIdx.x * kSeg;
-  const int tb = ta + kHalf;
-  {  // pull the chunk of the CTA's next row that its pass 1 will consume at the mirrored position into L2
-    const int pa = (nchunks - 1 - c) * kChunk + threadIdx.x * kSeg, pb = pa + kHalf;
-    if (trn != nullptr) {
-      if (pa < tn) prefetch_l2(trn + pa);
-      if (pb < tn) prefetch_l2(trn + pb);
-    }
-    if (hdn != nullptr) {
-      if (pa < tn) prefetch_l2(hdn + pa);
-      if (pb < tn) prefetch_l2(hdn + pb);
-    }
+  const int base = c * kChunk;
+  const int t0 = base + threadIdx.x * kSeg;
+  if (VEC && threadIdx.x == 0) {
+    // pull the chunk of the CTA's NEXT row that its pass 1 will consume at the mirrored position into L2
+    // (hdn / tdn are that row's un-offset pointers; pass 2 itself reads no HBM)
+    const int pb = (nchunks - 1 - c) * kChunk;
+    const unsigned bytes = (unsigned)(min(kChunk, tn - pb) * 4);
+    if (tdn != nullptr) prefetch_l2_bulk(tdn + pb, bytes);
+    if (hdn != nullptr) prefetch_l2_bulk(hdn + pb, bytes);
   }
-  const float4 ga = load_seg<VEC, FULL, kShared>(gr, ta, tn);  // written by this same thread in pass 1
-  const float4 gb = load_seg<VEC, FULL, kShared>(gr, tb, tn);
-  float4 ha, hb;
+  float4 ge[kNSeg], h[kNSeg], pre[kNSeg];
+  float tot[kNSeg], off[kNSeg];
+#pragma unroll
+  for (int j = 0; j < kNSeg; ++j)  // written by this same thread in pass 1
+    ge[j] = load_seg<VEC, FULL, kOwn>(rp.gr + base + j * kSub, t0 + j * kSub, tn);
   if (H_IN_SMEM) {
-    ha = (FULL || ta < tn) ? s_h4[ta >> 2] : make_float4(0.f, 0.f, 0.f, 0.f);
-    hb = (FULL || tb < tn) ? s_h4[tb >> 2] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < kNSeg; ++j)
+      h[j] = (FULL || t0 + j * kSub < tn) ? s_h4[(t0 + j * kSub) >> 2] : make_float4(0.f, 0.f, 0.f, 0.f);
   } else {
-    ha = mix_seg<G, VEC, FULL>(p, hdr, sv, ta);
-    hb = mix_seg<G, VEC, FULL>(p, hdr, sv, tb);
+    mix_chunk<G, VEC, FULL>(rp, sv, base, t0, tn, h);
   }
-  const float4 pa4 = prefix4(ga), pb4 = prefix4(gb);
-  float offa, offb;
-  block_scan2<false>(pa4.w, pb4.w, sm, c & 1, carry, offa, offb);
-  float4 oa4, ob4;
-  oa4.x = 2.f * ha.x * (pa4.x + offa);
-  oa4.y = 2.f * ha.y * (pa4.y + offa);
-  oa4.z = 2.f * ha.z * (pa4.z + offa);
-  oa4.w = 2.f * ha.w * (pa4.w + offa);
-  ob4.x = 2.f * hb.x * (pb4.x + offb);
-  ob4.y = 2.f * hb.y * (pb4.y + offb);
-  ob4.z = 2.f * hb.z * (pb4.z + offb);
-  ob4.w = 2.f * hb.w * (pb4.w + offb);
-  store_seg<VEC, FULL>(gr, ta, tn, oa4);
-  store_seg<VEC, FULL>(gr, tb, tn, ob4);
-  if (p.gs != nullptr) {
+#pragma unroll
+  for (int j = 0; j < kNSeg; ++j) {
+    pre[j] = prefix4(ge[j]);
+    tot[j] = pre[j].w;
+  }
+  block_scan_n<false>(tot, sm, c & 1, carry, off);
+#pragma unroll
+  for (int j = 0; j < kNSeg; ++j) {
+    float4 o;
+    o.x = 2.f * h[j].x * (pre[j].x + off[j]);
+    o.y = 2.f * h[j].y * (pre[j].y + off[j]);
+    o.z = 2.f * h[j].z * (pre[j].z + off[j]);
+    o.w = 2.f * h[j].w * (pre[j].w + off[j]);
+    store_seg<VEC, FULL>(rp.gr + base + j * kSub, t0 + j * kSub, tn, o);
+    h[j] = o;  // keep dL/dh for the dot products below
+  }
+  if (want_gs) {
 #pragma unroll
     for (int g = 0; g < G; ++g) {
-      const float4 ya = load_seg<VEC, FULL, kRead>(p.hy + (int64_t)g * tn, ta, tn);
-      const float4 yb = load_seg<VEC, FULL, kRead>(p.hy + (int64_t)g * tn, tb, tn);
       float a = gsacc[g];
-      a = fmaf(oa4.x, ya.x, a);
-      a = fmaf(oa4.y, ya.y, a);
-      a = fmaf(oa4.z, ya.z, a);
-      a = fmaf(oa4.w, ya.w, a);
-      a = fmaf(ob4.x, yb.x, a);
-      a = fmaf(ob4.y, yb.y, a);
-      a = fmaf(ob4.z, yb.z, a);
-      a = fmaf(ob4.w, yb.w, a);
+#pragma unroll
+      for (int j = 0; j < kNSeg; ++j) {
+        const float4 y = load_seg<VEC, FULL, kRead>(rp.hy[g] + base + j * kSub, t0 + j * kSub, tn);
+        a = fmaf(h[j].x, y.x, a);
+        a = fmaf(h[j].y, y.y, a);
+        a = fmaf(h[j].z, y.z, a);
+        a = fmaf(h[j].w, y.w, a);
+      }
       gsacc[g] = a;
     }
   }
@@ -324,24 +334,29 @@ __global__ void __launch_bounds__(kThreads, 1) td_edc_step_kernel(TdParams p) {
 
   for (int64_t r = blockIdx.x; r < p.rows; r += gridDim.x) {
     float sv[G];
+    RowPtrs<G> rp;
 #pragma unroll
-    for (int g = 0; g < G; ++g) sv[g] = p.s[r * G + g];
-    const float* hdr = p.hd ? p.hd + r * p.ldhd : nullptr;
-    const float* tr = p.tdb + r * p.ldt;
-    float* gr = p.gh + r * p.ldg;
+    for (int g = 0; g < G; ++g) {
+      sv[g] = p.s[r * G + g];
+      rp.hy[g] = p.hy + (int64_t)g * tn + tid * kSeg;
+    }
+    rp.hd = p.hd ? p.hd + r * p.ldhd + tid * kSeg : nullptr;
+    rp.td = p.tdb + r * p.ldt + tid * kSeg;
+    rp.gr = p.gh + r * p.ldg + tid * kSeg;
+    rp.mask = p.mask ? p.mask + tid * kSeg : nullptr;
     // the row this CTA handles next: its inputs are pulled into L2 while pass 2 (which reads no HBM) runs
     const int64_t rn = r + gridDim.x;
     const float* hdn = (rn < p.rows && p.hd) ? p.hd + rn * p.ldhd : nullptr;
-    const float* trn = (rn < p.rows) ? p.tdb + rn * p.ldt : nullptr;
+    const float* tdn = (rn < p.rows) ? p.tdb + rn * p.ldt : nullptr;
 
     // ---- pass 1, late -> early: EDC[t] = sum_{tau >= t} h^2, loss, dL/dEDC -> gr
     double carry = 0.0;
     float acc = 0.f;
     for (int c = nchunks - 1; c >= 0; --c) {
       if (c < nfull)
-        pass1_chunk<G, H_IN_SMEM, VEC, VEC>(p, hdr, tr, gr, sv, c, cf, s_h4, sm, carry, acc);
+        pass1_chunk<G, H_IN_SMEM, VEC, VEC>(rp, sv, c, tn, cf, s_h4, sm, carry, acc);
       else
-        pass1_chunk<G, H_IN_SMEM, VEC, false>(p, hdr, tr, gr, sv, c, cf, s_h4, sm, carry, acc);
+        pass1_chunk<G, H_IN_SMEM, VEC, false>(rp, sv, c, tn, cf, s_h4, sm, carry, acc);
     }
     __syncthreads();  // s_h4 complete; scan buffers of either parity idle
 
@@ -350,11 +365,12 @@ __global__ void __launch_bounds__(kThreads, 1) td_edc_step_kernel(TdParams p) {
 #pragma unroll
     for (int g = 0; g < G; ++g) gsacc[g] = 0.f;
     carry = 0.0;
+    const bool want_gs = p.gs != nullptr;
     for (int c = 0; c < nchunks; ++c) {
       if (c < nfull)
-        pass2_chunk<G, H_IN_SMEM, VEC, VEC>(p, hdr, gr, hdn, trn, sv, c, nchunks, s_h4, sm, carry, gsacc);
+        pass2_chunk<G, H_IN_SMEM, VEC, VEC>(rp, hdn, tdn, sv, c, nchunks, tn, want_gs, s_h4, sm, carry, gsacc);
       else
-        pass2_chunk<G, H_IN_SMEM, VEC, false>(p, hdr, gr, hdn, trn, sv, c, nchunks, s_h4, sm, carry, gsacc);
+        pass2_chunk<G, H_IN_SMEM, VEC, false>(rp, hdn, tdn, sv, c, nchunks, tn, want_gs, s_h4, sm, carry, gsacc);
     }
 
     // ---- block reduction of the row loss and of dL/ds[r, :] (float64, fixed order)
