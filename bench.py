@@ -360,10 +360,23 @@ def main():
 
     if rank == 0:
         hbm, how = peaks()
-        # dominant receiver-scaling kernel: td_edc_step, 8 algorithmic bytes per receiver.sample
-        td = stages["td_edc_step"]
+        # dominant receiver-scaling kernel: 8 algorithmic bytes per receiver.sample
+        if step.use_fused:
+            td_key, rows_per_launch = "td_edc_fused", args.receivers
+            td_name = ("td_fused_kernel<3,2,false> (K3d: cluster of 8 CTAs per receiver row, TMA-staged inputs, mix + EDC + "
+                       "dB loss + whole backward, register-resident ghy accumulators; its finalize launch is inside the "
+                       "timed pair)")
+        else:
+            td_key, rows_per_launch = "td_edc_step", min(args.tile_rows, args.receivers)
+            td_name = "td_edc_step_kernel<3,true> (K3c: mix + EDC + dB loss + backward per receiver row)"
+        td = stages[td_key]
         td_bytes = TD_BYTES_PER_SAMPLE * args.receivers * step.tn  # per step, this rank
         achieved = td_bytes / (td["ms_per_step"] * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")  # dram bytes per launch from `ncu --set full`
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                traffic = json.load(f).get(td_key)
         out = {
             "metric": "DiffGFDN receiver*bin evals/s fwd+bwd", "value": value, "unit": "receiver*bin evals/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
@@ -371,9 +384,8 @@ def main():
             "data": "synthetic", "config": workload_config(args), "loss": loss_val, "clocks": clocks.summary(),
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                         "traffic": None, "peak_source": how,
-                         "kernel": "td_edc_step_kernel<3,true> (mix + EDC + dB loss + backward per receiver row)",
-                         "algorithmic_bytes_per_launch": TD_BYTES_PER_SAMPLE * min(args.tile_rows, args.receivers) * step.tn,
+                         "traffic": traffic, "peak_source": how, "kernel": td_name,
+                         "algorithmic_bytes_per_launch": TD_BYTES_PER_SAMPLE * rows_per_launch * step.tn,
                          "avg_launch_ms": td["ms_per_step"] / td["launches_per_step"],
                          "share_of_step": td["ms_per_step"] / ms,
                          "timing": "CUDA events around every launch of this kernel during %d instrumented eager steps "

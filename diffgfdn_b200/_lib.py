@@ -54,6 +54,10 @@ SIGNATURES = {
     "dgfdn_td_contract_ws_bytes": (c_int64, [c_int, c_int64, c_int64]),
     "dgfdn_td_contract": (c_int, [c_int, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int, c_void_p,
                                   c_void_p]),
+    "dgfdn_td_edc_fused_supported": (c_int, [c_int, c_int64]),
+    "dgfdn_td_edc_fused_ws_bytes": (c_int64, [c_int, c_int64, c_int64]),
+    "dgfdn_td_edc_fused": (c_int, [c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64,
+                                   c_void_p, c_double, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "dgfdn_colorless_fwd": (c_int, [c_int, c_int64, c_void_p, c_int, c_void_p, c_void_p]),
     "dgfdn_colorless_bwd": (c_int, [c_int, c_int64, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "dgfdn_render_groups": (c_int, [c_int, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -1,0 +1,709 @@
+// K3d: the receiver step of K3c (edc_td.cu) with NO per-receiver output: one thread-block cluster owns a receiver row.
+//
+//   h_r[t]  = sum_g s[r,g] hy_g[t] + hd_r[t]                     (model.py:583-619 by linearity of irfft)
+//   EDC_r[t] = sum_{tau >= t} h_r[tau]^2 ;  L += sum_t mask[t] |target_dB[r,t] - 10 log10(EDC_r[t] + eps)|
+//                                                               (losses.py:187-238, utils.py:16-40)
+//   dL/dh_r[t] = 2 h_r[t] sum_{t' <= t} dL/dEDC_r[t']           (adjoint of the reversed cumsum)
+//   gs[r,g]  = <dL/dh_r, hy_g> ;   ghy[g,t] (+)= sum_r s[r,g] dL/dh_r[t]
+//
+// K3c writes dL/dh (4 B per receiver.sample) and a second kernel reads it back for the ghy contraction. Here the
+// time axis of a row is cut into kC = 8 slices, one per CTA of a cluster, and each CTA keeps its slice of the ghy
+// accumulators (G x 4 x segments) in REGISTERS across all rows the cluster processes: dL/dh never exists in memory.
+// HBM traffic is the algorithmic minimum, 8 B per receiver.sample (hd + target dB), moved by 1-D TMA bulk copies
+// (cp.async.bulk + mbarrier) into shared memory one iteration ahead of their use.
+//
+// Per iteration a cluster handles kRows = 2 rows. The two scans (suffix sum of h^2, prefix sum of dL/dEDC) run
+// thread -> warp (shuffles, float32) -> CTA (one warp, float64) -> cluster: every CTA stores its slice total into
+// the other CTAs' shared memory with st.async (DSMEM store that completes tx-bytes on the receiver's mbarrier), so
+// the row loop has no barrier.cluster and no cluster-scope fence. The second exchange is hidden behind the part of the backward that does not need the carry
+// (dL/dh = h (P_local + c) = u + c h, so <u, hy_g> and <h, hy_g> are taken before the wait).
+//
+// Thread t of a CTA owns, in each run u, kRun = 3 consecutive 128-bit segments (12 samples): an odd segment count
+// makes the 48-byte thread stride conflict-free for 128-bit shared-memory accesses. Reduction order is fixed
+// everywhere (deterministic results). Packed fp32x2 FMAs (FFMA2, sm_100) carry the mix / dot / accumulate work.
+#include <type_traits>
+
+#include "common.cuh"
+
+namespace dgfdn {
+namespace {
+
+constexpr int kC = 8;                  // CTAs per cluster = time slices per row
+constexpr int kFT = 256;               // threads per CTA
+constexpr int kFW = kFT / 32;          // warps per CTA
+constexpr int kRun = 3;                // consecutive segments per thread and run
+constexpr int kRunSegs = kFT * kRun;   // 768 segments (3072 samples) per run
+constexpr int kRows = 2;               // rows per iteration
+constexpr int kMaxRuns = 2;
+constexpr int kPos = 16;               // (run, warp) positions per row in the CTA-level scan (kMaxRuns * kFW)
+constexpr float kEpsF = 1.1920928955078125e-07f;   // torch.finfo(float32).eps (reference utils.py:35)
+constexpr float kDbPerLog2 = 3.0102999566398120f;  // 10 / log2(10)
+constexpr double kDbFactor = 4.342944819032518;    // 10 / ln(10)
+static_assert(kMaxRuns * kFW == kPos && kRows * kPos == 32, "CTA-level scan is one warp: rows x positions = 32 lanes");
+
+struct FusedParams {
+  int64_t rows;
+  int tn4;            // tn / 4
+  int slice4;         // segments per CTA slice = ceil(tn4 / kC)
+  const float* s;     // [rows, G]
+  const float* hy;    // [G, tn]
+  const float* hd;    // [rows, ldhd] or null
+  int64_t ldhd;
+  const float* tdb;   // [rows, ldt]
+  int64_t ldt;
+  const float* mask;  // [tn] or null
+  double coef;
+  float* part_ghy;    // [clusters, G, tn]
+  float* part_gs;     // [rows, kC, G]
+  double* part_loss;  // [grid]
+};
+
+// ---- PTX wrappers: cluster, DSMEM, mbarrier, TMA bulk copy ---------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+// 8 bytes into CTA `rank`'s shared memory, completing 8 tx-bytes on that CTA's mbarrier `local_bar`: the data is
+// visible to whoever observes the phase completion -- no cluster-scope fence, no barrier.cluster in the row loop.
+__device__ __forceinline__ void st_async_f64(uint32_t local_addr, uint32_t local_bar, uint32_t rank, double v) {
+  uint32_t raddr, rbar;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(local_addr), "r"(rank));
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbar) : "r"(local_bar), "r"(rank));
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(raddr),
+               "l"(__double_as_longlong(v)), "r"(rbar)
+               : "memory");
+}
+__device__ __forceinline__ float lg2_ftz(float x) {  // x >= eps_f32: no denormal range fix-up needed
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float rcp_ftz(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  for (uint32_t spin = 0; !ok; ++spin) {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (spin > (1u << 22)) __trap();  // a lost copy must abort the launch, never hang the device
+  }
+}
+
+// ---- packed fp32x2 arithmetic on float4 (FFMA2 / FMUL2 / FADD2) ---------------------------------------------
+__device__ __forceinline__ float2 lo(float4 v) { return make_float2(v.x, v.y); }
+__device__ __forceinline__ float2 hi(float4 v) { return make_float2(v.z, v.w); }
+__device__ __forceinline__ float4 cat(float2 a, float2 b) { return make_float4(a.x, a.y, b.x, b.y); }
+__device__ __forceinline__ float4 fma4(float a, float4 y, float4 c) {  // a y + c
+  const float2 a2 = make_float2(a, a);
+  return cat(__ffma2_rn(a2, lo(y), lo(c)), __ffma2_rn(a2, hi(y), hi(c)));
+}
+__device__ __forceinline__ float4 add4(float4 y, float a) {
+  const float2 a2 = make_float2(a, a);
+  return cat(__fadd2_rn(lo(y), a2), __fadd2_rn(hi(y), a2));
+}
+__device__ __forceinline__ float4 mul4(float4 x, float4 y) {
+  return cat(__fmul2_rn(lo(x), lo(y)), __fmul2_rn(hi(x), hi(y)));
+}
+__device__ __forceinline__ void dot4(float2& acc, float4 x, float4 y) {  // acc.x + acc.y accumulates <x, y>
+  acc = __ffma2_rn(lo(x), lo(y), acc);
+  acc = __ffma2_rn(hi(x), hi(y), acc);
+}
+
+struct FusedSmem {                      // static part; the slots follow in dynamic shared memory
+  double wtot[2][kRows][kPos];          // [scan][row][run * kFW + warp] warp totals
+  double cscan[2][kRows][kPos + 1];     // [scan][row][pos] CTA-level inclusive scan (+ a zero sentinel)
+  double xchg[2][2][kRows][kC];         // [scan][parity][row][source CTA]: slice totals stored by the peers (DSMEM)
+  double red[kFW];
+  unsigned long long bar_hd, bar_td;    // mbarriers of the hd / target-dB slots (TMA complete_tx)
+  unsigned long long bar_x[2];          // mbarriers of the two carry exchanges (st.async complete_tx)
+};
+
+// One warp scans the kPos (run, warp) totals of both rows: lane = row * 16 + pos. Returns the inclusive scan.
+template <bool REVERSE>
+__device__ __forceinline__ double cta_scan16(double v, int lane) {
+  const int pos = lane & (kPos - 1);
+#pragma unroll
+  for (int o = 1; o < kPos; o <<= 1) {
+    const double t = REVERSE ? __shfl_down_sync(0xffffffffu, v, o) : __shfl_up_sync(0xffffffffu, v, o);
+    if (REVERSE ? (pos + o < kPos) : (pos >= o)) v += t;
+  }
+  return v;
+}
+
+// G x (tn/4) accumulators of the cluster's slice stay in registers: acc[g][run][k] is a float4 of 4 samples.
+template <int G, int NRUN, bool MASKED>
+__global__ void __launch_bounds__(kFT, 1) td_fused_kernel(FusedParams p) {
+  extern __shared__ __align__(128) unsigned char dyn_smem[];
+  __shared__ FusedSmem sm;
+  constexpr int kSlot = NRUN * kRunSegs;  // padded segments per slot
+  float4* hd_s = reinterpret_cast<float4*>(dyn_smem);  // [kRows][kSlot]
+  float4* td_s = hd_s + kRows * kSlot;                 // [kRows][kSlot]
+  float4* hy_s = td_s + kRows * kSlot;                 // [G][kSlot]
+  float4* mk_s = hy_s + G * kSlot;                     // [kSlot] when MASKED
+  float* red_s = reinterpret_cast<float*>(mk_s + (MASKED ? kSlot : 0));  // [kRows * G][kFT]
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t rank = cluster_ctarank();
+  const int cid = blockIdx.x / kC, ncl = gridDim.x / kC;
+  const int tn4 = p.tn4;
+  const int seg0 = (int)rank * p.slice4;                         // first segment of this CTA's slice
+  const int len4 = max(0, min(p.slice4, tn4 - seg0));            // segments actually present
+  const uint32_t slot_bytes = (uint32_t)len4 * 16u;
+  const bool has_hd = p.hd != nullptr && len4 > 0;
+  const bool has_td = len4 > 0;
+  const float cf2 = (float)(2.0 * p.coef * kDbFactor);           // the factor 2 of d(h^2) rides on dL/dEDC
+
+  // ---- one-time set-up: zero the slots (tails stay zero for ever), stage the hy / mask slices, init barriers
+  for (int i = tid; i < 2 * kRows * kSlot; i += kFT) hd_s[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = tid; i < kSlot; i += kFT) {
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+      hy_s[g * kSlot + i] = i < len4 ? __ldg(reinterpret_cast<const float4*>(p.hy) + (int64_t)g * tn4 + seg0 + i)
+                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (MASKED)
+      mk_s[i] = i < len4 ? __ldg(reinterpret_cast<const float4*>(p.mask) + seg0 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  if (tid < 2 * kRows) {
+    sm.cscan[tid >> 1][tid & 1][kPos] = 0.0;
+  }
+  const uint32_t bar_hd = smem_u32(&sm.bar_hd), bar_td = smem_u32(&sm.bar_td);
+  const uint32_t bar_xa = smem_u32(&sm.bar_x[0]), bar_xb = smem_u32(&sm.bar_x[1]);
+  constexpr uint32_t kXchgBytes = kRows * kC * sizeof(double);  // what one exchange delivers to one CTA
+  if (tid == 0) {
+    mbar_init(bar_hd, 1);
+    mbar_init(bar_td, 1);
+    mbar_init(bar_xa, 1);
+    mbar_init(bar_xb, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic zero-fill before async-proxy (TMA) writes
+  __syncthreads();
+  cluster_arrive();  // every CTA of the cluster is resident and initialised before any DSMEM store
+  cluster_wait();
+
+  // weights of this thread's segments (1 inside the slice, 0 in the padded tail)
+  float wseg[NRUN][kRun];
+#pragma unroll
+  for (int u = 0; u < NRUN; ++u)
+#pragma unroll
+    for (int k = 0; k < kRun; ++k) wseg[u][k] = (u * kRunSegs + tid * kRun + k < len4) ? 1.f : 0.f;
+
+  auto issue = [&](bool is_hd, int64_t it) {  // thread 0: TMA loads of iteration `it` into the hd or td slots
+    const int64_t r0 = it * kRows;
+    const int nvalid = (int)min((int64_t)kRows, p.rows - r0);
+    const uint32_t bar = is_hd ? bar_hd : bar_td;
+    mbar_expect_tx(bar, slot_bytes * (uint32_t)nvalid);
+    for (int q = 0; q < nvalid; ++q) {
+      const float* src = is_hd ? p.hd + (r0 + q) * p.ldhd : p.tdb + (r0 + q) * p.ldt;
+      tma_load_1d(smem_u32((is_hd ? hd_s : td_s) + q * kSlot), src + (int64_t)seg0 * 4, slot_bytes, bar);
+    }
+  };
+
+  float4 acc[G][NRUN][kRun];
+#pragma unroll
+  for (int g = 0; g < G; ++g)
+#pragma unroll
+    for (int u = 0; u < NRUN; ++u)
+#pragma unroll
+      for (int k = 0; k < kRun; ++k) acc[g][u][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  double loss_acc = 0.0;
+
+  const int64_t niter = (p.rows + kRows - 1) / kRows;
+  if (tid == 0 && cid < niter) {
+    if (has_hd) issue(true, cid);
+    if (has_td) issue(false, cid);
+  }
+
+  // reduction of the previous iteration's dL/ds partials (red_s) by warps 1..: value v = row * G + g
+  auto reduce_gs = [&](int64_t it_prev) {
+    for (int v = warp - 1; v < kRows * G; v += kFW - 1) {
+      const int64_t r = it_prev * kRows + v / G;
+      float a = 0.f;
+#pragma unroll
+      for (int i = 0; i < kFT / 32; ++i) a += red_s[v * kFT + lane + 32 * i];
+      const double tot = warp_sum((double)a);
+      if (lane == 0 && r < p.rows) p.part_gs[(r * kC + rank) * G + (v % G)] = (float)tot;
+    }
+  };
+
+  uint32_t parity = 0;
+  int64_t it_prev = -1;
+  for (int64_t it = cid; it < niter; it += ncl, parity ^= 1u) {
+    const int64_t r0 = it * kRows;
+    const bool has_next = it + ncl < niter;
+    if (tid == 0) {  // this iteration's two carry exchanges (their previous phases were waited on by this thread)
+      mbar_expect_tx(bar_xa, kXchgBytes);
+      mbar_expect_tx(bar_xb, kXchgBytes);
+    }
+    float sv[kRows][G], wrow[kRows];
+#pragma unroll
+    for (int q = 0; q < kRows; ++q) {
+      const bool valid = r0 + q < p.rows;
+      wrow[q] = valid ? 1.f : 0.f;
+#pragma unroll
+      for (int g = 0; g < G; ++g) sv[q][g] = valid ? __ldg(p.s + (r0 + q) * G + g) : 0.f;
+    }
+
+    // ================= phase A: h = hd + sum_g s_g hy_g ; suffix sums of h^2 inside the thread's runs ==========
+    if (has_hd) mbar_wait(bar_hd, parity);
+    float4 h[kRows][NRUN][kRun], w[kRows][NRUN][kRun];  // w: suffix sums of h^2, later prefix sums of dL/dEDC, later u
+    float tot[kRows][NRUN];
+#pragma unroll
+    for (int u = 0; u < NRUN; ++u) {
+#pragma unroll
+      for (int k = 0; k < kRun; ++k) {
+        const int idx = u * kRunSegs + tid * kRun + k;
+        float4 y[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) y[g] = hy_s[g * kSlot + idx];
+#pragma unroll
+        for (int q = 0; q < kRows; ++q) {
+          float4 v = hd_s[q * kSlot + idx];
+#pragma unroll
+          for (int g = 0; g < G; ++g) v = fma4(sv[q][g], y[g], v);
+          h[q][u][k] = v;
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < kRows; ++q)
+#pragma unroll
+      for (int u = 0; u < NRUN; ++u) {
+        float run = 0.f;
+#pragma unroll
+        for (int k = kRun - 1; k >= 0; --k) {
+          const float4 v = h[q][u][k];
+          float4 s4;
+          s4.w = fmaf(v.w, v.w, run);
+          s4.z = fmaf(v.z, v.z, s4.w);
+          s4.y = fmaf(v.y, v.y, s4.z);
+          s4.x = fmaf(v.x, v.x, s4.y);
+          w[q][u][k] = s4;
+          run = s4.x;
+        }
+        tot[q][u] = run;
+      }
+    // warp-level inclusive suffix scan of the thread totals (float32)
+    float inc[kRows][NRUN];
+#pragma unroll
+    for (int q = 0; q < kRows; ++q)
+#pragma unroll
+      for (int u = 0; u < NRUN; ++u) inc[q][u] = tot[q][u];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+#pragma unroll
+      for (int q = 0; q < kRows; ++q)
+#pragma unroll
+        for (int u = 0; u < NRUN; ++u) {
+          const float t = __shfl_down_sync(0xffffffffu, inc[q][u], o);
+          if (lane + o < 32) inc[q][u] += t;
+        }
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int q = 0; q < kRows; ++q)
+#pragma unroll
+        for (int u = 0; u < kMaxRuns; ++u) sm.wtot[0][q][u * kFW + warp] = u < NRUN ? (double)inc[q][u < NRUN ? u : 0] : 0.0;
+    }
+#pragma unroll
+    for (int q = 0; q < kRows; ++q)
+#pragma unroll
+      for (int u = 0; u < NRUN; ++u) {  // exclusive: the later lanes of this warp (no inc - tot cancellation)
+        const float t = __shfl_down_sync(0xffffffffu, inc[q][u], 1);
+        inc[q][u] = lane < 31 ? t : 0.f;
+      }
+    __syncthreads();  // B1: every thread has consumed the hd slots
+    if (tid == 0 && has_next && has_hd) issue(true, it + ncl);
+    if (warp == 0) {
+      const int q = lane >> 4, pos = lane & (kPos - 1);
+      const double v = cta_scan16<true>(sm.wtot[0][q][pos], lane);
+      sm.cscan[0][q][pos] = v;
+      const double total = __shfl_sync(0xffffffffu, v, ((lane >> 3) & 1) * kPos);  // lanes 0-7: row 0, 8-15: row 1
+      if (lane < kRows * kC)
+        st_async_f64(smem_u32(&sm.xchg[0][parity][lane >> 3][rank]), bar_xa, (uint32_t)(lane & (kC - 1)), total);
+    } else if (it_prev >= 0) {
+      reduce_gs(it_prev);
+    }
+    __syncthreads();  // B2
+    double offl[kRows][NRUN];  // CTA-local exclusive offsets: later (run, warp) positions of this slice
+#pragma unroll
+    for (int q = 0; q < kRows; ++q)
+#pragma unroll
+      for (int u = 0; u < NRUN; ++u) offl[q][u] = sm.cscan[0][q][u * kFW + warp + 1];
+    if (has_td) mbar_wait(bar_td, parity);
+    mbar_wait(bar_xa, parity);
+
+    // ================= phase B: EDC -> dB -> |target - .| ; dL/dEDC ; prefix sums inside the runs ==============
+    float lacc = 0.f;
+#pragma unroll
+    for (int q = 0; q < kRows; ++q) {
+      double carry = 0.0;  // slices later than this one
+#pragma unroll
+      for (int i = kC - 1; i >= 1; --i)
+        if (i > (int)rank) carry += sm.xchg[0][parity][q][i];
+#pragma unroll
+      for (int u = 0; u < NRUN; ++u) {
+        const float offe = (float)(carry + offl[q][u]) + inc[q][u] + kEpsF;
+        float run = 0.f;
+#pragma unroll
+        for (int k = 0; k < kRun; ++k) {
+          const int idx = u * kRunSegs + tid * kRun + k;
+          const float4 td = td_s[q * kSlot + idx];
+          const float4 e = w[q][u][k];
+          float4 mk;
+          float wcf;  // weight x 2 coef 10/ln10 of an unmasked segment
+          if (MASKED) {
+            mk = mk_s[idx];
+            mk.x *= wrow[q], mk.y *= wrow[q], mk.z *= wrow[q], mk.w *= wrow[q];
+            wcf = 0.f;
+          } else {
+            const float wt = wseg[u][k] * wrow[q];
+            mk.x = mk.y = mk.z = mk.w = wt;
+            wcf = wt * cf2;
+          }
+          float4 ge;
+#define DGFDN_DB_ONE(C)                                                                          \
+  {                                                                                              \
+    const float x = e.C + offe;                                                                  \
+    const float diff = fmaf(-kDbPerLog2, lg2_ftz(x), td.C);                                      \
+    lacc = fmaf(mk.C, fabsf(diff), lacc);                                                        \
+    const float g = (MASKED ? mk.C * cf2 : wcf) * rcp_ftz(x);                                    \
+    const float sg = __int_as_float(__float_as_int(g) ^ (~__float_as_int(diff) & 0x80000000));   \
+    ge.C = diff == 0.f ? 0.f : sg;                                                               \
+  }
+          DGFDN_DB_ONE(x) DGFDN_DB_ONE(y) DGFDN_DB_ONE(z) DGFDN_DB_ONE(w)
+#undef DGFDN_DB_ONE
+          float4 pre;
+          pre.x = run + ge.x;
+          pre.y = pre.x + ge.y;
+          pre.z = pre.y + ge.z;
+          pre.w = pre.z + ge.w;
+          run = pre.w;
+          w[q][u][k] = pre;
+        }
+        tot[q][u] = run;
+      }
+    }
+    loss_acc += (double)lacc;
+#pragma unroll
+    for (int q = 0; q < kRows; ++q)
+#pragma unroll
+      for (int u = 0; u < NRUN; ++u) inc[q][u] = tot[q][u];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+#pragma unroll
+      for (int q = 0; q < kRows; ++q)
+#pragma unroll
+        for (int u = 0; u < NRUN; ++u) {
+          const float t = __shfl_up_sync(0xffffffffu, inc[q][u], o);
+          if (lane >= o) inc[q][u] += t;
+        }
+    }
+    if (lane == 31) {
+#pragma unroll
+      for (int q = 0; q < kRows; ++q)
+#pragma unroll
+        for (int u = 0; u < kMaxRuns; ++u) sm.wtot[1][q][u * kFW + warp] = u < NRUN ? (double)inc[q][u < NRUN ? u : 0] : 0.0;
+    }
+#pragma unroll
+    for (int q = 0; q < kRows; ++q)
+#pragma unroll
+      for (int u = 0; u < NRUN; ++u) {  // exclusive: the earlier lanes of this warp
+        const float t = __shfl_up_sync(0xffffffffu, inc[q][u], 1);
+        inc[q][u] = lane > 0 ? t : 0.f;
+      }
+    __syncthreads();  // B3: every thread has consumed the target-dB slots
+    if (tid == 0 && has_next && has_td) issue(false, it + ncl);
+    if (warp == 0) {
+      const int q = lane >> 4, pos = lane & (kPos - 1);
+      const double v = cta_scan16<false>(sm.wtot[1][q][pos], lane);
+      sm.cscan[1][q][pos] = v;
+      const double total = __shfl_sync(0xffffffffu, v, ((lane >> 3) & 1) * kPos + kPos - 1);
+      if (lane < kRows * kC)
+        st_async_f64(smem_u32(&sm.xchg[1][parity][lane >> 3][rank]), bar_xb, (uint32_t)(lane & (kC - 1)), total);
+    }
+    __syncthreads();  // B4
+
+    // ---- before the carries arrive: u = h P_local, <u, hy_g>, <h, hy_g>
+    float2 du[kRows][G], dv[kRows][G];
+#pragma unroll
+    for (int q = 0; q < kRows; ++q)
+#pragma unroll
+      for (int g = 0; g < G; ++g) du[q][g] = dv[q][g] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int u = 0; u < NRUN; ++u) {
+      float offp[kRows];
+#pragma unroll
+      for (int q = 0; q < kRows; ++q) {
+        const int pos = u * kFW + warp;
+        const double before = pos > 0 ? sm.cscan[1][q][pos - 1] : 0.0;
+        offp[q] = (float)before + inc[q][u];
+      }
+#pragma unroll
+      for (int k = 0; k < kRun; ++k) {
+        const int idx = u * kRunSegs + tid * kRun + k;
+        float4 y[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) y[g] = hy_s[g * kSlot + idx];
+#pragma unroll
+        for (int q = 0; q < kRows; ++q) {
+          const float4 uu = mul4(h[q][u][k], add4(w[q][u][k], offp[q]));
+          w[q][u][k] = uu;
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+            dot4(du[q][g], uu, y[g]);
+            dot4(dv[q][g], h[q][u][k], y[g]);
+          }
+        }
+      }
+    }
+    mbar_wait(bar_xb, parity);
+
+    // ================= phase C: dL/dh = u + c h ; ghy accumulators ; dL/ds partials ============================
+#pragma unroll
+    for (int q = 0; q < kRows; ++q) {
+      double carry = 0.0;  // slices earlier than this one
+#pragma unroll
+      for (int i = 0; i < kC - 1; ++i)
+        if (i < (int)rank) carry += sm.xchg[1][parity][q][i];
+      const float c = (float)carry;
+#pragma unroll
+      for (int u = 0; u < NRUN; ++u)
+#pragma unroll
+        for (int k = 0; k < kRun; ++k) {
+          const float4 gh = fma4(c, h[q][u][k], w[q][u][k]);
+#pragma unroll
+          for (int g = 0; g < G; ++g) acc[g][u][k] = fma4(sv[q][g], gh, acc[g][u][k]);
+        }
+#pragma unroll
+      for (int g = 0; g < G; ++g)
+        red_s[(q * G + g) * kFT + tid] = (du[q][g].x + du[q][g].y) + c * (dv[q][g].x + dv[q][g].y);
+    }
+    it_prev = it;
+  }
+
+  // ---- epilogue: last dL/ds partials, the ghy slice of this cluster, the loss partial
+  __syncthreads();
+  if (it_prev >= 0 && warp > 0) reduce_gs(it_prev);
+  if (cid < niter) {
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+#pragma unroll
+      for (int u = 0; u < NRUN; ++u)
+#pragma unroll
+        for (int k = 0; k < kRun; ++k) {
+          const int idx = u * kRunSegs + tid * kRun + k;
+          if (idx < len4)
+            reinterpret_cast<float4*>(p.part_ghy)[((int64_t)cid * G + g) * tn4 + seg0 + idx] = acc[g][u][k];
+        }
+  }
+  {
+    const double v = warp_sum(loss_acc);
+    if (lane == 0) sm.red[warp] = v;
+    __syncthreads();
+    if (tid == 0) {
+      double t = 0.0;
+      for (int i = 0; i < kFW; ++i) t += sm.red[i];
+      p.part_loss[blockIdx.x] = t;
+    }
+  }
+  cluster_arrive();  // no CTA may exit while a peer can still store into its shared memory
+  cluster_wait();
+}
+
+// ghy[i] (+)= sum_cl part_ghy[cl][i] ; gs[r,g] = sum_k part_gs[r,k,g] ; loss (+)= sum_b part_loss[b] (fixed order)
+__global__ void td_fused_finalize_kernel(int64_t n_ghy, int ncl, const float* __restrict__ part_ghy, float* __restrict__ ghy,
+                                         int64_t rows, int g, const float* __restrict__ part_gs, float* __restrict__ gs,
+                                         int nblocks, const double* __restrict__ part_loss, double* __restrict__ loss,
+                                         int accumulate) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_ghy) {
+    float v = accumulate ? ghy[i] : 0.f;
+    for (int c = 0; c < ncl; ++c) v += part_ghy[(int64_t)c * n_ghy + i];
+    ghy[i] = v;
+    return;
+  }
+  const int64_t j = i - n_ghy;
+  if (j < rows * g) {
+    if (gs == nullptr) return;
+    const int64_t r = j / g;
+    const int gg = (int)(j % g);
+    float v = 0.f;
+    for (int k = 0; k < kC; ++k) v += part_gs[(r * kC + k) * g + gg];
+    gs[j] = v;
+    return;
+  }
+  if (j == rows * g && loss != nullptr) {
+    double v = accumulate ? loss[0] : 0.0;
+    for (int b = 0; b < nblocks; ++b) v += part_loss[b];
+    loss[0] = v;
+  }
+}
+
+constexpr int kMaxClusters = 32;  // workspace is sized for this many resident clusters (a B200 holds <= 18 of 8 CTAs)
+
+struct FusedShape {
+  int nrun;
+  int slice4;
+};
+// The fused kernel needs tn % 4 == 0 and a slice of at most kMaxRuns runs per CTA (tn <= 8 * 2 * 3072 = 49152).
+bool fused_shape(int g, int64_t tn, FusedShape* out) {
+  if (g < 1 || g > 4 || tn < 4 || tn % 4 != 0) return false;
+  const int64_t tn4 = tn / 4;
+  const int64_t slice4 = (tn4 + kC - 1) / kC;
+  const int64_t nrun = (slice4 + kRunSegs - 1) / kRunSegs;
+  if (nrun > kMaxRuns) return false;
+  if (out) {
+    out->nrun = (int)nrun;
+    out->slice4 = (int)slice4;
+  }
+  return true;
+}
+
+inline bool aligned16(const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+size_t fused_dyn_smem(int g, int nrun, bool masked) {
+  const size_t slot = (size_t)nrun * kRunSegs * sizeof(float4);
+  return slot * (2 * kRows + g + (masked ? 1 : 0)) + (size_t)kRows * g * kFT * sizeof(float);
+}
+
+struct WsLayout {
+  size_t off_gs, off_loss, total;
+};
+WsLayout ws_layout(int g, int64_t rows, int64_t tn) {
+  WsLayout w;
+  size_t o = (size_t)kMaxClusters * g * tn * sizeof(float);
+  o = (o + 255) & ~(size_t)255;
+  w.off_gs = o;
+  o += (size_t)rows * kC * g * sizeof(float);
+  o = (o + 255) & ~(size_t)255;
+  w.off_loss = o;
+  o += (size_t)kMaxClusters * kC * sizeof(double);
+  w.total = o;
+  return w;
+}
+
+template <int G, int NRUN, bool MASKED>
+int launch_fused(const FusedParams& p, int64_t rows, size_t smem, cudaStream_t st, int* ncl_out) {
+  auto kern = td_fused_kernel<G, NRUN, MASKED>;
+  static int max_clusters[64] = {0};  // per device
+  int dev = 0;
+  DGFDN_CUDA(cudaGetDevice(&dev));
+  DGFDN_CHECK(dev >= 0 && dev < 64, "td_edc_fused: device index out of range");
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kC;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.blockDim = dim3(kFT);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (max_clusters[dev] == 0) {
+    DGFDN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cfg.gridDim = dim3(kC * kMaxClusters);
+    int n = 0;
+    DGFDN_CUDA(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
+    DGFDN_CHECK(n >= 1, "td_edc_fused: no cluster of %d CTAs fits on this device", kC);
+    max_clusters[dev] = n > kMaxClusters ? kMaxClusters : n;
+  }
+  const int64_t niter = (rows + kRows - 1) / kRows;
+  const int ncl = (int)(niter < max_clusters[dev] ? niter : max_clusters[dev]);
+  cfg.gridDim = dim3((unsigned)(kC * ncl));
+  *ncl_out = ncl;
+  FusedParams pp = p;
+  DGFDN_CUDA(cudaLaunchKernelEx(&cfg, kern, pp));
+  return 0;
+}
+
+}  // namespace
+}  // namespace dgfdn
+
+using namespace dgfdn;
+
+extern "C" int dgfdn_td_edc_fused_supported(int g, int64_t tn) { return fused_shape(g, tn, nullptr) ? 1 : 0; }
+
+extern "C" int64_t dgfdn_td_edc_fused_ws_bytes(int g, int64_t rows, int64_t tn) {
+  if (g < 1 || rows < 1 || tn < 1) return 0;
+  return (int64_t)ws_layout(g, rows, tn).total;
+}
+
+extern "C" int dgfdn_td_edc_fused(int g, int64_t rows, int64_t tn, const float* s, const float* hy, const float* hd,
+                                  int64_t ldhd, const float* target_db, int64_t ldt, const float* mask, double coef,
+                                  double* loss_sum, float* gs, float* ghy, int accumulate, void* ws, void* stream) {
+  DGFDN_CHECK(rows >= 0 && tn >= 1 && s && hy && target_db && ghy && ws, "td_edc_fused: bad arguments");
+  FusedShape shp;
+  DGFDN_CHECK(fused_shape(g, tn, &shp), "td_edc_fused: unsupported shape (g=%d in [1,4], tn=%lld multiple of 4 and <= %d)", g,
+              (long long)tn, kC * kMaxRuns * kRunSegs * 4);
+  DGFDN_CHECK(ldt >= tn && (hd == nullptr || ldhd >= tn), "td_edc_fused: row stride smaller than tn");
+  DGFDN_CHECK(aligned16(hy) && aligned16(hd) && aligned16(target_db) && aligned16(mask) && ldt % 4 == 0 &&
+                  (hd == nullptr || ldhd % 4 == 0),
+              "td_edc_fused: rows must be 16-byte aligned (pointers and strides)");
+  if (rows == 0) return 0;
+  const WsLayout lay = ws_layout(g, rows, tn);
+  unsigned char* base = static_cast<unsigned char*>(ws);
+  FusedParams p{};
+  p.rows = rows;
+  p.tn4 = (int)(tn / 4);
+  p.slice4 = shp.slice4;
+  p.s = s;
+  p.hy = hy;
+  p.hd = hd;
+  p.ldhd = ldhd;
+  p.tdb = target_db;
+  p.ldt = ldt;
+  p.mask = mask;
+  p.coef = coef;
+  p.part_ghy = reinterpret_cast<float*>(base);
+  p.part_gs = reinterpret_cast<float*>(base + lay.off_gs);
+  p.part_loss = reinterpret_cast<double*>(base + lay.off_loss);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool masked = mask != nullptr;
+  const size_t smem = fused_dyn_smem(g, shp.nrun, masked);
+  int ncl = 0, rc = 1;
+  auto go = [&](auto gc, auto rc_) {
+    constexpr int G = decltype(gc)::value;
+    constexpr int NRUN = decltype(rc_)::value;
+    rc = masked ? launch_fused<G, NRUN, true>(p, rows, smem, st, &ncl) : launch_fused<G, NRUN, false>(p, rows, smem, st, &ncl);
+  };
+  auto by_run = [&](auto gc) {
+    if (shp.nrun == 1) go(gc, std::integral_constant<int, 1>{});
+    else go(gc, std::integral_constant<int, 2>{});
+  };
+  switch (g) {
+    case 1: by_run(std::integral_constant<int, 1>{}); break;
+    case 2: by_run(std::integral_constant<int, 2>{}); break;
+    case 3: by_run(std::integral_constant<int, 3>{}); break;
+    default: by_run(std::integral_constant<int, 4>{}); break;
+  }
+  if (rc) return rc;
+  const int64_t n_ghy = (int64_t)g * tn;
+  const int64_t total = n_ghy + rows * g + 1;
+  td_fused_finalize_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(n_ghy, ncl, p.part_ghy, ghy, rows, g, p.part_gs, gs,
+                                                                             ncl * kC, p.part_loss, loss_sum, accumulate);
+  DGFDN_LAUNCH_CHECK();
+  return 0;
+}

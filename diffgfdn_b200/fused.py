@@ -30,6 +30,7 @@ reference's layout -- (B, K) complex64 frequency-domain arrays in pinned host me
 are moved host -> device tile by tile on a copy stream (only bins 0..K/2, the ones irfft(X, n=K) reads), transformed
 with the chirp-z kernels and fed to the same time-domain kernels."""
 import ctypes
+import os
 from typing import Dict, Optional
 
 import torch
@@ -91,9 +92,15 @@ class ShardedEDCStep:
         r = max(1, min(self.tile_rows, self.rows))
         g = self.net.num_groups
         dev = self.dev
-        self._bufs = dict(gh=torch.empty(r, self.tn, dtype=torch.float32, device=dev),
-                          ws=ops.td_contract_workspace(g, r, self.tn, dev),
-                          row_sum=torch.empty(self.rows, dtype=torch.float64, device=dev))
+        # K3d (cluster-fused kernel, no dL/dh in memory) when the shape allows it; DGFDN_TD_FUSED=0 forces K3c
+        self.use_fused = ops.td_fused_supported(g, self.tn) and os.environ.get("DGFDN_TD_FUSED", "1") != "0"
+        if self.use_fused:
+            self._bufs = dict(fws=ops.td_fused_workspace(g, self.rows, self.tn, dev),
+                              loss_sum=torch.zeros(1, dtype=torch.float64, device=dev))
+        else:
+            self._bufs = dict(gh=torch.empty(r, self.tn, dtype=torch.float32, device=dev),
+                              ws=ops.td_contract_workspace(g, r, self.tn, dev),
+                              row_sum=torch.empty(self.rows, dtype=torch.float64, device=dev))
 
     def _window_rows(self, resp: torch.Tensor, to_db: bool) -> torch.Tensor:
         out = torch.empty(resp.shape[0], self.tn, dtype=torch.float32, device=self.dev)
@@ -153,16 +160,19 @@ class ShardedEDCStep:
             if self.target_db is None:
                 raise RuntimeError("step: attach() a target_db (and early_window) first, or pass host buffers")
             b = self._bufs
-            r = b["gh"].shape[0]
-            for i, r0 in enumerate(range(0, self.rows, r)):
-                r1 = min(self.rows, r0 + r)
-                self._td_tile(r0, r1, s_d, hy_d, None if self.hd is None else self.hd[r0:r1], self.target_db[r0:r1],
-                              b["gh"], b["ws"], ghy, gs, coef, stream, i > 0)
+            if self.use_fused:  # the whole shard in one launch: nothing per receiver is written, so no tiling
+                self._td_tile(0, self.rows, s_d, hy_d, self.hd, self.target_db, None, None, ghy, gs, coef, stream, False)
+            else:
+                r = b["gh"].shape[0]
+                for i, r0 in enumerate(range(0, self.rows, r)):
+                    r1 = min(self.rows, r0 + r)
+                    self._td_tile(r0, r1, s_d, hy_d, None if self.hd is None else self.hd[r0:r1],
+                                  self.target_db[r0:r1], b["gh"], b["ws"], ghy, gs, coef, stream, i > 0)
         else:
             self._stream_tiles(host_d, host_target, s_d, hy_d, ghy, gs, coef, stream)
         if sec:
             sec[2].record()
-        edc = self._bufs["row_sum"].sum() * coef
+        edc = (self._bufs["loss_sum"][0] if self.use_fused else self._bufs["row_sum"].sum()) * coef
         aux = (spectral + sparsity.to(spectral.dtype)) / self.world_size
         torch.autograd.backward([hy, s, aux], [ghy, gs, torch.ones_like(aux)])
         self.kernel_launches += 3 + 2 * 2 + 1  # chirp-z adjoint, two adjoint solves (+ reduce each), colorless bwd
@@ -219,6 +229,15 @@ class ShardedEDCStep:
         if ev is not None:
             marks = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
             marks[0].record()
+        if self.use_fused:
+            _lib.call("dgfdn_td_edc_fused", g, rows, tn, _p(s_d[r0:r1]), _p(hy_d), _p(hd_tile), tn, _p(tdb_tile), tn,
+                      _p(self.mask), ctypes.c_double(coef), _p(self._bufs["loss_sum"]), _p(gs[r0:r1]), _p(ghy),
+                      1 if accumulate else 0, _p(self._bufs["fws"]), stream)
+            if ev is not None:
+                marks[1].record()
+                ev.setdefault("td_edc_fused", []).append((marks[0], marks[1]))
+            self.kernel_launches += 2  # td_fused, td_fused_finalize
+            return
         _lib.call("dgfdn_td_edc_step", g, rows, tn, _p(s_d[r0:r1]), _p(hy_d), _p(hd_tile), tn, _p(tdb_tile), tn,
                   _p(self.mask), ctypes.c_double(coef), _p(self._bufs["row_sum"][r0:r1]), _p(gs[r0:r1]), _p(gh), tn,
                   stream)
@@ -254,8 +273,8 @@ class ShardedEDCStep:
                                      hd=torch.empty(r, tn, dtype=torch.float32, device=dev),
                                      ht=torch.empty(r, tn, dtype=torch.float32, device=dev),
                                      tdb=torch.empty(r, tn, dtype=torch.float32, device=dev),
-                                     gh=torch.empty(r, tn, dtype=torch.float32, device=dev),
-                                     ws=ops.td_contract_workspace(g, r, tn, dev))
+                                     gh=None if self.use_fused else torch.empty(r, tn, dtype=torch.float32, device=dev),
+                                     ws=None if self.use_fused else ops.td_contract_workspace(g, r, tn, dev))
         stage = self._bufs["stage"]
         e = self._bufs["e2e"]
         copy_stream = self._bufs["copy_stream"]

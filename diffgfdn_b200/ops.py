@@ -528,6 +528,56 @@ def td_edc_abs_db_sum(s: torch.Tensor, hy: torch.Tensor, hd: Optional[torch.Tens
     return _TDEDCLoss.apply(s, hy, hd, target_db, mask, tile_rows)
 
 
+def td_fused_supported(num_groups: int, tn: int) -> bool:
+    """True when the cluster-fused receiver kernel (K3d, dgfdn_td_edc_fused) handles this shape."""
+    return bool(_lib.load().dgfdn_td_edc_fused_supported(int(num_groups), int(tn)))
+
+
+def td_fused_workspace(num_groups: int, rows: int, tn: int, device) -> torch.Tensor:
+    nbytes = int(_lib.load().dgfdn_td_edc_fused_ws_bytes(num_groups, rows, tn))
+    return torch.empty(max(nbytes // 4, 1), dtype=torch.float32, device=device)
+
+
+class _TDEDCLossFused(torch.autograd.Function):
+    """Same value and gradients as _TDEDCLoss through dgfdn_td_edc_fused: one launch over all rows, dL/dh never
+    stored (clusters of 8 CTAs per row, TMA-staged inputs, register-resident ghy accumulators)."""
+
+    @staticmethod
+    def forward(ctx, s, hy, hd, target_db, mask):
+        s_ = _cuda("s", s, torch.float32)
+        hy_ = _cuda("hy", hy, torch.float32)
+        hd_ = _cuda("hd", hd, torch.float32, optional=True)
+        t_ = _cuda("target_db", target_db, torch.float32)
+        m_ = _cuda("mask", mask, torch.float32, optional=True)
+        rows, g = s_.shape
+        tn = hy_.shape[-1]
+        if hy_.shape[0] != g or tuple(t_.shape) != (rows, tn) or (hd_ is not None and tuple(hd_.shape) != (rows, tn)) \
+                or (m_ is not None and m_.numel() != tn):
+            raise RuntimeError("td_edc_loss_fused: inconsistent shapes")
+        dev = s_.device
+        loss = torch.zeros(1, dtype=torch.float64, device=dev)
+        gs = torch.empty(rows, g, dtype=torch.float32, device=dev)
+        ghy = torch.empty(g, tn, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            ws = td_fused_workspace(g, rows, tn, dev)
+            _lib.call("dgfdn_td_edc_fused", g, rows, tn, _ptr(s_), _ptr(hy_), _ptr(hd_), tn, _ptr(t_), tn, _ptr(m_), 1.0,
+                      _ptr(loss), _ptr(gs), _ptr(ghy), 0, _ptr(ws), _stream())
+        ctx.save_for_backward(gs, ghy)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        gs, ghy = ctx.saved_tensors
+        gf = g.to(torch.float32)
+        return (gs * gf if ctx.needs_input_grad[0] else None, ghy * gf if ctx.needs_input_grad[1] else None, None, None,
+                None)
+
+
+def td_edc_abs_db_sum_fused(s: torch.Tensor, hy: torch.Tensor, hd: Optional[torch.Tensor], target_db: torch.Tensor,
+                            mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+    return _TDEDCLossFused.apply(s, hy, hd, target_db, mask)
+
+
 # ----------------------------------------------------------------------------------------------------------
 # colorless loss
 # ----------------------------------------------------------------------------------------------------------

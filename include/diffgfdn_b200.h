@@ -184,6 +184,23 @@ DGFDN_API int64_t dgfdn_td_contract_ws_bytes(int g, int64_t rows, int64_t tn);
 DGFDN_API int dgfdn_td_contract(int g, int64_t rows, int64_t tn, const float* s, const float* gh, int64_t ldg, float* ghy,
                       int accumulate, void* ws, void* stream);
 
+/* K3d: the same receiver step with NO per-receiver output (replaces dgfdn_td_edc_step + dgfdn_td_contract, i.e. per
+ * receiver model.py:583-619 + losses.py:207-238 + their autograd backward, when only the parameter-side gradients
+ * are wanted). A cluster of 8 CTAs owns a row (one time slice each, scan carries over distributed shared memory),
+ * inputs arrive by TMA bulk copies, and the ghy accumulators stay in registers across rows: dL/dh is never stored.
+ * HBM traffic: hd 4 B + target_db 4 B per receiver.sample.
+ *   loss_sum[0] (+)= sum_{r,t} mask[t] | target_db[r,t] - dB(EDC(h[r,:])[t]) |        float64 (may be NULL)
+ *   gs[r,g]      = coef * d loss_sum / d s[r,g]                                     float32 [rows, G] (may be NULL)
+ *   ghy[g,t]    (+)= coef * d loss_sum / d hy[g,t]                                  float32 [G, tn]
+ * accumulate != 0 adds to loss_sum / ghy instead of overwriting them (receiver tiles). Requirements, reported by
+ * dgfdn_td_edc_fused_supported(g, tn): 1 <= g <= 4, tn % 4 == 0, tn <= 49152; all rows 16-byte aligned.
+ * ws: scratch of dgfdn_td_edc_fused_ws_bytes(g, rows, tn) bytes. */
+DGFDN_API int dgfdn_td_edc_fused_supported(int g, int64_t tn);
+DGFDN_API int64_t dgfdn_td_edc_fused_ws_bytes(int g, int64_t rows, int64_t tn);
+DGFDN_API int dgfdn_td_edc_fused(int g, int64_t rows, int64_t tn, const float* s, const float* hy, const float* hd,
+                       int64_t ldhd, const float* target_db, int64_t ldt, const float* mask, double coef,
+                       double* loss_sum, float* gs, float* ghy, int accumulate, void* ws, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Colorless (spectral flatness) loss of the lossless sub-FDNs, colorless_fdn/losses.py:20-73 with
  * y_true = 1:   loss[g] = mean_k (|H[k,g]| - 1)^p ,  p = 2, or 4 where |H|-1 > 1 when asym != 0.

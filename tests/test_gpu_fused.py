@@ -41,14 +41,18 @@ def module_path(net, t60, z, pos, early, target):
     return float(edc), {k: p.grad.clone() for k, p in net.named_parameters()}
 
 
+@pytest.mark.parametrize("td_fused", ["1", "0"])
 @pytest.mark.parametrize("tile", [4, 11, 64])
-def test_fused_step_equals_module_path(tile):
+def test_fused_step_equals_module_path(tile, td_fused, monkeypatch):
+    """td_fused=1: cluster kernel K3d (dgfdn_td_edc_fused); 0: K3c (dgfdn_td_edc_step + dgfdn_td_contract)."""
     from diffgfdn_b200.fused import ShardedEDCStep
+    monkeypatch.setenv("DGFDN_TD_FUSED", td_fused)
     net, t60, z, pos, early, target = setup()
     edc_ref, g_ref = module_path(net, t60, z, pos, early, target)
     step = ShardedEDCStep(net, max(t60) * 1e3, tile_rows=tile, edc_weight=10.0)
     step.attach(z, pos, None, None)
     step.attach(z, pos, step.precompute_early_window(early), step.precompute_target_db(target))
+    assert step.use_fused == (td_fused == "1")
     out = step.step()
     assert abs(float(out["edc_loss"]) - edc_ref) < 1e-4 * abs(edc_ref)
     for k, p in net.named_parameters():
@@ -127,6 +131,73 @@ def test_time_domain_step_kernel_vs_torch_fp64():
         assert float((hy_c.grad.cpu().double() - hy_r.grad).abs().max() / hy_r.grad.abs().max()) < 1e-3, (rows, g, tn)
         hm = ops.td_mix(s_c.detach(), hy_c.detach(), hd_c)
         assert float((hm.cpu().double() - h.detach()).abs().max() / h.detach().abs().max()) < 1e-6
+
+
+def _td_reference(rows, g, tn, use_hd, use_mask, gen):
+    decay = torch.exp(-torch.arange(tn, dtype=torch.float64) / (0.15 * tn))
+    hy = (torch.randn(g, tn, generator=gen, dtype=torch.float64) * decay).float()
+    hd = (torch.randn(rows, tn, generator=gen, dtype=torch.float64) * decay * 0.3).float() if use_hd else None
+    s = torch.randn(rows, g, generator=gen, dtype=torch.float64).float()
+    tgt = torch.randn(rows, tn, generator=gen, dtype=torch.float64) * decay
+    tdb = (10 * torch.log10(torch.flip(torch.cumsum(torch.flip(tgt**2, [-1]), -1), [-1]) + 1.1920928955078125e-07)).float()
+    mask = (torch.rand(tn, generator=gen) < 0.5).float() if use_mask else None
+    s_r = s.double().requires_grad_(True)
+    hy_r = hy.double().requires_grad_(True)
+    h = s_r @ hy_r + (hd.double() if use_hd else 0.0)
+    edc = torch.flip(torch.cumsum(torch.flip(h**2, [-1]), -1), [-1])
+    db = torch.clamp(10 * torch.log10(edc + 1.1920928955078125e-07), min=-200.0)
+    diff = (tdb.double() - db).abs()
+    ref = (diff * mask.double()).sum() if use_mask else diff.sum()
+    ref.backward()
+    return s, hy, hd, tdb, mask, float(ref), s_r.grad, hy_r.grad
+
+
+@pytest.mark.parametrize("rows,g,tn,use_hd,use_mask", [
+    (5, 3, 9000, True, True),       # one run per CTA, odd row count (last iteration half empty), ragged last slice
+    (3, 2, 16384, False, False),    # no early response
+    (7, 3, 776, True, False),       # slices shorter than a warp's span
+    (1, 4, 8, True, False),         # 2 segments: six of the eight CTAs own nothing
+    (2, 1, 4, True, True),          # a single segment
+    (37, 3, 47360, True, False),    # BASELINE window (T60 1.5 s at 32 kHz): two runs per CTA, more iterations than clusters
+    (4, 4, 49152, True, True),      # largest supported window
+])
+def test_cluster_fused_receiver_kernel_vs_torch_fp64(rows, g, tn, use_hd, use_mask):
+    """dgfdn_td_edc_fused (K3d: cluster of 8 CTAs per row, DSMEM scan carries, TMA-staged inputs, register-resident
+    ghy accumulators) against the float64 torch restatement of reference losses.py:187-238 / utils.py:16-40 and its
+    autograd, and against K3c on the same inputs."""
+    from diffgfdn_b200 import ops
+    assert ops.td_fused_supported(g, tn)
+    gen = torch.Generator().manual_seed(11)
+    s, hy, hd, tdb, mask, ref, gs_ref, ghy_ref = _td_reference(rows, g, tn, use_hd, use_mask, gen)
+    cu = lambda t: None if t is None else t.cuda()  # noqa: E731
+    s_c, hy_c = s.cuda().requires_grad_(True), hy.cuda().requires_grad_(True)
+    out = ops.td_edc_abs_db_sum_fused(s_c, hy_c, cu(hd), cu(tdb), cu(mask))
+    out.backward()
+    assert abs(float(out) - ref) < 2e-5 * abs(ref) + 1e-3
+    assert float((s_c.grad.cpu().double() - gs_ref).abs().max() / gs_ref.abs().max()) < 1e-3
+    assert float((hy_c.grad.cpu().double() - ghy_ref).abs().max() / ghy_ref.abs().max()) < 1e-3
+    s_o, hy_o = s.cuda().requires_grad_(True), hy.cuda().requires_grad_(True)
+    old = ops.td_edc_abs_db_sum(s_o, hy_o, cu(hd), cu(tdb), cu(mask), tile_rows=3)
+    old.backward()
+    assert abs(float(out) - float(old)) < 1e-5 * abs(float(old)) + 1e-3
+    assert float((s_c.grad - s_o.grad).abs().max() / s_o.grad.abs().max()) < 1e-4
+    assert float((hy_c.grad - hy_o.grad).abs().max() / hy_o.grad.abs().max()) < 1e-4
+    # deterministic: a second launch reproduces the first bit for bit
+    s_2, hy_2 = s.cuda().requires_grad_(True), hy.cuda().requires_grad_(True)
+    out2 = ops.td_edc_abs_db_sum_fused(s_2, hy_2, cu(hd), cu(tdb), cu(mask))
+    out2.backward()
+    assert float(out2) == float(out) and torch.equal(s_2.grad, s_c.grad) and torch.equal(hy_2.grad, hy_c.grad)
+
+
+def test_cluster_fused_kernel_rejects_unsupported_shapes():
+    from diffgfdn_b200 import _lib, ops
+    assert not ops.td_fused_supported(3, 777)      # not a multiple of 4
+    assert not ops.td_fused_supported(3, 49156)    # longer than 8 slices x 2 runs
+    assert not ops.td_fused_supported(5, 4096)     # too many groups for the register-resident accumulators
+    t = torch.zeros(4, 780, device='cuda')
+    with pytest.raises(RuntimeError, match="unsupported shape"):
+        _lib.call("dgfdn_td_edc_fused", 3, 1, 777, t.data_ptr(), t.data_ptr(), None, 780, t.data_ptr(), 780, None, 1.0,
+                  None, None, t.data_ptr(), 0, t.data_ptr(), None)
 
 
 def test_full_size_invariants():
