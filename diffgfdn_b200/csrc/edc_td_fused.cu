@@ -13,7 +13,7 @@
 // (cp.async.bulk + mbarrier) into shared memory one iteration ahead of their use.
 //
 // Per iteration a cluster handles kRows = 2 rows. The two scans (suffix sum of h^2, prefix sum of dL/dEDC) run
-// thread -> warp (shuffles, float32) -> CTA (one warp, float64) -> cluster: every CTA stores its slice total into
+// thread -> warp (shuffles) -> CTA (every warp scans the 16 warp totals) -> cluster: every CTA stores its slice total into
 // the other CTAs' shared memory with st.async (DSMEM store that completes tx-bytes on the receiver's mbarrier), so
 // the row loop has no barrier.cluster and no cluster-scope fence. The second exchange is hidden behind the part of the backward that does not need the carry
 // (dL/dh = h (P_local + c) = u + c h, so <u, hy_g> and <h, hy_g> are taken before the wait).
@@ -67,14 +67,14 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 }
 __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
-// 8 bytes into CTA `rank`'s shared memory, completing 8 tx-bytes on that CTA's mbarrier `local_bar`: the data is
+// 4 bytes into CTA `rank`'s shared memory, completing 4 tx-bytes on that CTA's mbarrier `local_bar`: the data is
 // visible to whoever observes the phase completion -- no cluster-scope fence, no barrier.cluster in the row loop.
-__device__ __forceinline__ void st_async_f64(uint32_t local_addr, uint32_t local_bar, uint32_t rank, double v) {
+__device__ __forceinline__ void st_async_f32(uint32_t local_addr, uint32_t local_bar, uint32_t rank, float v) {
   uint32_t raddr, rbar;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(local_addr), "r"(rank));
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbar) : "r"(local_bar), "r"(rank));
-  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(raddr),
-               "l"(__double_as_longlong(v)), "r"(rbar)
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(raddr),
+               "r"(__float_as_uint(v)), "r"(rbar)
                : "memory");
 }
 __device__ __forceinline__ float lg2_ftz(float x) {  // x >= eps_f32: no denormal range fix-up needed
@@ -131,21 +131,22 @@ __device__ __forceinline__ void dot4(float2& acc, float4 x, float4 y) {  // acc.
 }
 
 struct FusedSmem {                      // static part; the slots follow in dynamic shared memory
-  double wtot[2][kRows][kPos];          // [scan][row][run * kFW + warp] warp totals
-  double cscan[2][kRows][kPos + 1];     // [scan][row][pos] CTA-level inclusive scan (+ a zero sentinel)
-  double xchg[2][2][kRows][kC];         // [scan][parity][row][source CTA]: slice totals stored by the peers (DSMEM)
+  float wtot[2][kRows][kPos];           // [scan][row][run * kFW + warp] warp totals
+  float xchg[2][2][kRows][kC];          // [scan][parity][row][source CTA]: slice totals stored by the peers (DSMEM)
   double red[kFW];
   unsigned long long bar_hd, bar_td;    // mbarriers of the hd / target-dB slots (TMA complete_tx)
   unsigned long long bar_x[2];          // mbarriers of the two carry exchanges (st.async complete_tx)
 };
 
-// One warp scans the kPos (run, warp) totals of both rows: lane = row * 16 + pos. Returns the inclusive scan.
+// CTA level of a scan, done redundantly by every warp (one barrier per scan instead of two): lane = row * 16 + pos
+// scans the kPos (run, warp) totals of its row. The sums have at most 16 (here) + 8 (cluster) terms on top of the
+// 384-sample warp level, so float32 is used throughout; only the loss is accumulated in float64.
 template <bool REVERSE>
-__device__ __forceinline__ double cta_scan16(double v, int lane) {
+__device__ __forceinline__ float cta_scan16(float v, int lane) {
   const int pos = lane & (kPos - 1);
 #pragma unroll
   for (int o = 1; o < kPos; o <<= 1) {
-    const double t = REVERSE ? __shfl_down_sync(0xffffffffu, v, o) : __shfl_up_sync(0xffffffffu, v, o);
+    const float t = REVERSE ? __shfl_down_sync(0xffffffffu, v, o) : __shfl_up_sync(0xffffffffu, v, o);
     if (REVERSE ? (pos + o < kPos) : (pos >= o)) v += t;
   }
   return v;
@@ -184,12 +185,9 @@ __global__ void __launch_bounds__(kFT, 1) td_fused_kernel(FusedParams p) {
     if (MASKED)
       mk_s[i] = i < len4 ? __ldg(reinterpret_cast<const float4*>(p.mask) + seg0 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  if (tid < 2 * kRows) {
-    sm.cscan[tid >> 1][tid & 1][kPos] = 0.0;
-  }
   const uint32_t bar_hd = smem_u32(&sm.bar_hd), bar_td = smem_u32(&sm.bar_td);
   const uint32_t bar_xa = smem_u32(&sm.bar_x[0]), bar_xb = smem_u32(&sm.bar_x[1]);
-  constexpr uint32_t kXchgBytes = kRows * kC * sizeof(double);  // what one exchange delivers to one CTA
+  constexpr uint32_t kXchgBytes = kRows * kC * sizeof(float);  // what one exchange delivers to one CTA
   if (tid == 0) {
     mbar_init(bar_hd, 1);
     mbar_init(bar_td, 1);
@@ -324,7 +322,7 @@ __global__ void __launch_bounds__(kFT, 1) td_fused_kernel(FusedParams p) {
 #pragma unroll
       for (int q = 0; q < kRows; ++q)
 #pragma unroll
-        for (int u = 0; u < kMaxRuns; ++u) sm.wtot[0][q][u * kFW + warp] = u < NRUN ? (double)inc[q][u < NRUN ? u : 0] : 0.0;
+        for (int u = 0; u < kMaxRuns; ++u) sm.wtot[0][q][u * kFW + warp] = u < NRUN ? inc[q][u < NRUN ? u : 0] : 0.f;
     }
 #pragma unroll
     for (int q = 0; q < kRows; ++q)
@@ -333,24 +331,28 @@ __global__ void __launch_bounds__(kFT, 1) td_fused_kernel(FusedParams p) {
         const float t = __shfl_down_sync(0xffffffffu, inc[q][u], 1);
         inc[q][u] = lane < 31 ? t : 0.f;
       }
-    __syncthreads();  // B1: every thread has consumed the hd slots
+    __syncthreads();  // B1: every thread has consumed the hd slots; warp totals published
     if (tid == 0 && has_next && has_hd) issue(true, it + ncl);
-    if (warp == 0) {
-      const int q = lane >> 4, pos = lane & (kPos - 1);
-      const double v = cta_scan16<true>(sm.wtot[0][q][pos], lane);
-      sm.cscan[0][q][pos] = v;
-      const double total = __shfl_sync(0xffffffffu, v, ((lane >> 3) & 1) * kPos);  // lanes 0-7: row 0, 8-15: row 1
-      if (lane < kRows * kC)
-        st_async_f64(smem_u32(&sm.xchg[0][parity][lane >> 3][rank]), bar_xa, (uint32_t)(lane & (kC - 1)), total);
-    } else if (it_prev >= 0) {
-      reduce_gs(it_prev);
+    float offl[kRows][NRUN];  // CTA-local exclusive offsets: later (run, warp) positions of this slice
+    {
+      const float v = cta_scan16<true>(sm.wtot[0][lane >> 4][lane & (kPos - 1)], lane);
+#pragma unroll
+      for (int q = 0; q < kRows; ++q)
+#pragma unroll
+        for (int u = 0; u < NRUN; ++u) {
+          const int pos = u * kFW + warp + 1;
+          const float t = __shfl_sync(0xffffffffu, v, q * kPos + (pos & (kPos - 1)));
+          offl[q][u] = pos < kPos ? t : 0.f;
+        }
+      if (warp == 0) {  // lanes 0-7: row 0, 8-15: row 1; receiver `peer` sums the slices later than its own
+        const float total = __shfl_sync(0xffffffffu, v, ((lane >> 3) & 1) * kPos);
+        const uint32_t peer = (uint32_t)(lane & (kC - 1));
+        if (lane < kRows * kC)
+          st_async_f32(smem_u32(&sm.xchg[0][parity][lane >> 3][rank]), bar_xa, peer, rank > peer ? total : 0.f);
+      } else if (it_prev >= 0) {
+        reduce_gs(it_prev);
+      }
     }
-    __syncthreads();  // B2
-    double offl[kRows][NRUN];  // CTA-local exclusive offsets: later (run, warp) positions of this slice
-#pragma unroll
-    for (int q = 0; q < kRows; ++q)
-#pragma unroll
-      for (int u = 0; u < NRUN; ++u) offl[q][u] = sm.cscan[0][q][u * kFW + warp + 1];
     if (has_td) mbar_wait(bar_td, parity);
     mbar_wait(bar_xa, parity);
 
@@ -358,13 +360,12 @@ __global__ void __launch_bounds__(kFT, 1) td_fused_kernel(FusedParams p) {
     float lacc = 0.f;
 #pragma unroll
     for (int q = 0; q < kRows; ++q) {
-      double carry = 0.0;  // slices later than this one
+      float carry = 0.f;  // slices later than this one (the senders masked their totals)
 #pragma unroll
-      for (int i = kC - 1; i >= 1; --i)
-        if (i > (int)rank) carry += sm.xchg[0][parity][q][i];
+      for (int i = kC - 1; i >= 0; --i) carry += sm.xchg[0][parity][q][i];
 #pragma unroll
       for (int u = 0; u < NRUN; ++u) {
-        const float offe = (float)(carry + offl[q][u]) + inc[q][u] + kEpsF;
+        const float offe = (carry + offl[q][u]) + inc[q][u] + kEpsF;
         float run = 0.f;
 #pragma unroll
         for (int k = 0; k < kRun; ++k) {
@@ -424,7 +425,7 @@ __global__ void __launch_bounds__(kFT, 1) td_fused_kernel(FusedParams p) {
 #pragma unroll
       for (int q = 0; q < kRows; ++q)
 #pragma unroll
-        for (int u = 0; u < kMaxRuns; ++u) sm.wtot[1][q][u * kFW + warp] = u < NRUN ? (double)inc[q][u < NRUN ? u : 0] : 0.0;
+        for (int u = 0; u < kMaxRuns; ++u) sm.wtot[1][q][u * kFW + warp] = u < NRUN ? inc[q][u < NRUN ? u : 0] : 0.f;
     }
 #pragma unroll
     for (int q = 0; q < kRows; ++q)
@@ -433,17 +434,26 @@ __global__ void __launch_bounds__(kFT, 1) td_fused_kernel(FusedParams p) {
         const float t = __shfl_up_sync(0xffffffffu, inc[q][u], 1);
         inc[q][u] = lane > 0 ? t : 0.f;
       }
-    __syncthreads();  // B3: every thread has consumed the target-dB slots
+    __syncthreads();  // B2: every thread has consumed the target-dB slots; warp totals published
     if (tid == 0 && has_next && has_td) issue(false, it + ncl);
-    if (warp == 0) {
-      const int q = lane >> 4, pos = lane & (kPos - 1);
-      const double v = cta_scan16<false>(sm.wtot[1][q][pos], lane);
-      sm.cscan[1][q][pos] = v;
-      const double total = __shfl_sync(0xffffffffu, v, ((lane >> 3) & 1) * kPos + kPos - 1);
-      if (lane < kRows * kC)
-        st_async_f64(smem_u32(&sm.xchg[1][parity][lane >> 3][rank]), bar_xb, (uint32_t)(lane & (kC - 1)), total);
+    float offp[kRows][NRUN];  // exclusive offsets inside the CTA: earlier (run, warp) positions + earlier lanes
+    {
+      const float v = cta_scan16<false>(sm.wtot[1][lane >> 4][lane & (kPos - 1)], lane);
+#pragma unroll
+      for (int q = 0; q < kRows; ++q)
+#pragma unroll
+        for (int u = 0; u < NRUN; ++u) {
+          const int pos = u * kFW + warp - 1;
+          const float t = __shfl_sync(0xffffffffu, v, q * kPos + (pos & (kPos - 1)));
+          offp[q][u] = (pos >= 0 ? t : 0.f) + inc[q][u];
+        }
+      if (warp == 0) {  // receiver `peer` sums the slices earlier than its own
+        const float total = __shfl_sync(0xffffffffu, v, ((lane >> 3) & 1) * kPos + kPos - 1);
+        const uint32_t peer = (uint32_t)(lane & (kC - 1));
+        if (lane < kRows * kC)
+          st_async_f32(smem_u32(&sm.xchg[1][parity][lane >> 3][rank]), bar_xb, peer, rank < peer ? total : 0.f);
+      }
     }
-    __syncthreads();  // B4
 
     // ---- before the carries arrive: u = h P_local, <u, hy_g>, <h, hy_g>
     float2 du[kRows][G], dv[kRows][G];
@@ -453,13 +463,6 @@ __global__ void __launch_bounds__(kFT, 1) td_fused_kernel(FusedParams p) {
       for (int g = 0; g < G; ++g) du[q][g] = dv[q][g] = make_float2(0.f, 0.f);
 #pragma unroll
     for (int u = 0; u < NRUN; ++u) {
-      float offp[kRows];
-#pragma unroll
-      for (int q = 0; q < kRows; ++q) {
-        const int pos = u * kFW + warp;
-        const double before = pos > 0 ? sm.cscan[1][q][pos - 1] : 0.0;
-        offp[q] = (float)before + inc[q][u];
-      }
 #pragma unroll
       for (int k = 0; k < kRun; ++k) {
         const int idx = u * kRunSegs + tid * kRun + k;
@@ -468,7 +471,7 @@ __global__ void __launch_bounds__(kFT, 1) td_fused_kernel(FusedParams p) {
         for (int g = 0; g < G; ++g) y[g] = hy_s[g * kSlot + idx];
 #pragma unroll
         for (int q = 0; q < kRows; ++q) {
-          const float4 uu = mul4(h[q][u][k], add4(w[q][u][k], offp[q]));
+          const float4 uu = mul4(h[q][u][k], add4(w[q][u][k], offp[q][u]));
           w[q][u][k] = uu;
 #pragma unroll
           for (int g = 0; g < G; ++g) {
@@ -483,11 +486,9 @@ __global__ void __launch_bounds__(kFT, 1) td_fused_kernel(FusedParams p) {
     // ================= phase C: dL/dh = u + c h ; ghy accumulators ; dL/ds partials ============================
 #pragma unroll
     for (int q = 0; q < kRows; ++q) {
-      double carry = 0.0;  // slices earlier than this one
+      float c = 0.f;  // slices earlier than this one (the senders masked their totals)
 #pragma unroll
-      for (int i = 0; i < kC - 1; ++i)
-        if (i < (int)rank) carry += sm.xchg[1][parity][q][i];
-      const float c = (float)carry;
+      for (int i = 0; i < kC; ++i) c += sm.xchg[1][parity][q][i];
 #pragma unroll
       for (int u = 0; u < NRUN; ++u)
 #pragma unroll
