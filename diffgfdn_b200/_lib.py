@@ -3,7 +3,7 @@
 There is no CPU fallback: if the library cannot be loaded, or a kernel reports an error, a RuntimeError is raised."""
 import ctypes
 import os
-from ctypes import c_char_p, c_double, c_int, c_int64, c_void_p, POINTER
+from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_void_p, POINTER
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libdiffgfdn_b200.so")
@@ -58,6 +58,14 @@ SIGNATURES = {
     "dgfdn_td_edc_fused_ws_bytes": (c_int64, [c_int, c_int64, c_int64]),
     "dgfdn_td_edc_fused": (c_int, [c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64,
                                    c_void_p, c_double, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "dgfdn_mlp_supported": (c_int, [c_int, c_int, c_int, c_int, c_int]),
+    "dgfdn_mlp_num_params": (c_int64, [c_int, c_int, c_int, c_int]),
+    "dgfdn_mlp_bwd_ws_bytes": (c_int64, [c_int64, c_int, c_int, c_int, c_int]),
+    "dgfdn_mlp_fwd": (c_int, [c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_int, c_void_p,
+                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "dgfdn_mlp_bwd": (c_int, [c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_int, c_void_p,
+                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                              c_void_p]),
     "dgfdn_colorless_fwd": (c_int, [c_int, c_int64, c_void_p, c_int, c_void_p, c_void_p]),
     "dgfdn_colorless_bwd": (c_int, [c_int, c_int64, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "dgfdn_render_groups": (c_int, [c_int, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

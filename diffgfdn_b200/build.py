@@ -14,7 +14,8 @@ CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(ROOT, "include")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libdiffgfdn_b200.so")
-SOURCES = ["common.cu", "expm.cu", "solve.cu", "project.cu", "czt.cu", "edc.cu", "edc_td.cu", "edc_td_fused.cu", "colorless.cu", "render.cu"]
+SOURCES = ["common.cu", "expm.cu", "solve.cu", "project.cu", "czt.cu", "edc.cu", "edc_td.cu", "edc_td_fused.cu", "colorless.cu", "render.cu",
+           "mlp.cu"]
 
 
 def _nvcc():
@@ -24,30 +25,51 @@ def _nvcc():
     return cand
 
 
-def _stale():
-    if not os.path.exists(LIB_PATH):
+def _obj_stale(src: str, obj: str) -> bool:
+    if not os.path.exists(obj):
         return True
-    t = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(INCLUDE, "diffgfdn_b200.h")]
+    t = os.path.getmtime(obj)
+    deps = [src, os.path.join(INCLUDE, "diffgfdn_b200.h")] + [os.path.join(CSRC, f) for f in os.listdir(CSRC)
+                                                               if f.endswith((".cuh", ".h"))]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not _stale():
-        return LIB_PATH
+    """One object per .cu (compiled in parallel, only when its source or a header changed), then one link."""
+    from concurrent.futures import ThreadPoolExecutor
     os.makedirs(LIB_DIR, exist_ok=True)
+    obj_dir = os.path.join(LIB_DIR, "obj")
+    os.makedirs(obj_dir, exist_ok=True)
     cuda_lib = os.path.join(os.path.dirname(os.path.dirname(_nvcc())), "lib64")
-    cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--shared",
-           "-Xcompiler", "-fPIC,-fvisibility=hidden", "-I", INCLUDE, "-I", CSRC]
+    base = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler",
+            "-fPIC,-fvisibility=hidden", "-I", INCLUDE, "-I", CSRC]
     if verbose:
-        cmd += ["-Xptxas", "-v"]
-    cmd += [os.path.join(CSRC, s) for s in SOURCES]
-    cmd += ["-o", LIB_PATH, "-L", cuda_lib, "-lcufft", "-lcudart", "-Xlinker", f"-rpath,{cuda_lib}"]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    if verbose:
-        print(res.stdout + res.stderr)
+        base += ["-Xptxas", "-v"]
+    jobs = []
+    for s in SOURCES:
+        src, obj = os.path.join(CSRC, s), os.path.join(obj_dir, s[:-3] + ".o")
+        if force or _obj_stale(src, obj):
+            jobs.append((s, base + ["-c", src, "-o", obj]))
+
+    def run(job):
+        name, cmd = job
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {name}:\n" + res.stdout + res.stderr)
+        return name, res.stdout + res.stderr
+
+    if jobs:
+        with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as pool:
+            for name, log in pool.map(run, jobs):
+                if verbose:
+                    print(f"== {name}\n{log}")
+    objs = [os.path.join(obj_dir, s[:-3] + ".o") for s in SOURCES]
+    if jobs or not os.path.exists(LIB_PATH) or any(os.path.getmtime(o) > os.path.getmtime(LIB_PATH) for o in objs):
+        cmd = [_nvcc(), "--shared", "-o", LIB_PATH] + objs + ["-L", cuda_lib, "-lcufft", "-lcudart", "-Xlinker",
+                                                             f"-rpath,{cuda_lib}"]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("link failed:\n" + res.stdout + res.stderr)
     return LIB_PATH
 
 

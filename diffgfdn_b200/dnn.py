@@ -1,10 +1,16 @@
-"""Position -> gain networks (reference diff_gfdn/dnn.py). These stay stock PyTorch (cuBLAS): they are
-O(receivers x MLP) and feed the kernels with a (receivers, groups) gain table; module and parameter names match
-the reference so that its checkpoints load (`...mlp.model.{0,1,3,4,...}` and the skip-connection layout)."""
+"""Position -> gain networks (reference diff_gfdn/dnn.py). Module and parameter names match the reference so that
+its checkpoints load (`...mlp.model.{0,1,3,4,...}` and the skip-connection layout). On CUDA the whole chain
+encoding -> MLP -> final activation runs in the K7 kernels (`fused_position_mlp`, csrc/mlp.cu); the nn.Module
+`forward`s below are the same arithmetic in stock PyTorch, kept for shapes K7 does not cover (neurons not in
+{64, 128}) and as the float32 reference of the kernel tests."""
+from typing import Optional
+
 import numpy as np
 import torch
 from torch import nn
 from torch.nn import init
+
+from . import ops
 
 
 class Sigmoid(nn.Module):
@@ -34,10 +40,16 @@ class SinusoidalEncoding(nn.Module):
         super().__init__()
         self.num_fourier_features = num_fourier_features
 
+    def frequencies(self, device, dtype) -> torch.Tensor:
+        """f_i pi in the position dtype (float32 table, then cast -- like the reference's broadcast)."""
+        key = (str(device), dtype)
+        if getattr(self, "_freq_key", None) != key:
+            f = torch.exp(torch.linspace(np.log(1.0), np.log(32.0), self.num_fourier_features, device=device))
+            self._freq, self._freq_key = (f * np.pi).to(dtype), key
+        return self._freq
+
     def forward(self, pos_coords: torch.Tensor) -> torch.Tensor:
-        f = torch.exp(torch.linspace(np.log(1.0), np.log(32.0), self.num_fourier_features,
-                                     device=pos_coords.device))
-        arg = (f * np.pi).to(pos_coords.dtype).view(1, -1, 1) * pos_coords.unsqueeze(1)  # (P, F, 3)
+        arg = self.frequencies(pos_coords.device, pos_coords.dtype).view(1, -1, 1) * pos_coords.unsqueeze(1)  # (P, F, 3)
         enc = torch.cat((torch.sin(arg), torch.cos(arg)), dim=-1)  # (P, F, 6): [sin xyz, cos xyz] per feature
         return enc.reshape(pos_coords.shape[0], -1).to(torch.float32)
 
@@ -103,3 +115,33 @@ class MLP_SkipConnections(nn.Module):
         for layer in self.hidden_layers:
             x = layer(x)
         return self.output_layer(x).view(b, self.num_groups, self.num_biquads, self.num_params)
+
+
+def fused_position_mlp(encoder: SinusoidalEncoding, mlp: nn.Module, position: torch.Tensor, final_act: int = 0,
+                       lo: float = 0.0, hi: float = 1.0) -> Optional[torch.Tensor]:
+    """final_act(mlp(encoder(position))) as (P, out_dim) float32 through the K7 kernels, or None when the shape is
+    outside their range (the caller then uses the nn.Module path)."""
+    if not position.is_cuda or position.dtype not in (torch.float32, torch.float64):
+        return None
+    if isinstance(mlp, MLP):
+        mods = list(mlp.model)
+        lins = [m for m in mods if isinstance(m, nn.Linear)]
+        norms = [m for m in mods if isinstance(m, nn.LayerNorm)]
+        residual = False
+    elif isinstance(mlp, MLP_SkipConnections):
+        lins = [mlp.input_layer[0]] + [blk.linear for blk in mlp.hidden_layers] + [mlp.output_layer]
+        norms = [mlp.input_layer[1]] + [blk.norm for blk in mlp.hidden_layers]
+        residual = True
+    else:
+        return None
+    neurons, in_dim = lins[0].weight.shape
+    if not ops.mlp_supported(in_dim, encoder.num_fourier_features, neurons, len(norms), lins[-1].weight.shape[0]):
+        return None
+    if any(abs(n.eps - 1e-5) > 0 for n in norms):
+        return None
+    params = []
+    for lin, norm in zip(lins[:-1], norms):
+        params += [lin.weight, lin.bias, norm.weight, norm.bias]
+    params += [lins[-1].weight, lins[-1].bias]
+    return ops.position_mlp(position.contiguous(), encoder.frequencies(position.device, position.dtype), params,
+                            residual=residual, final_act=final_act, lo=lo, hi=hi)

@@ -137,7 +137,10 @@ class ShardedEDCStep:
         if sec:
             sec[0].record()
         s = net.output_scalars.gains({'norm_listener_position': self.positions})
-        _, y = net.feedback_loop.solve(self.z, net.input_gains.reshape(-1), net.output_gains.reshape(-1))
+        # irfft(X, n=K) reads bins 0..K/2 only (reference losses.py:207-213, quirk Q3), so the coupled system is
+        # solved on those kx bins; the other bins of H reach no loss term (the colorless loss has its own solve)
+        z_edc = self.z if net.feedback_loop.delay_line_gain_response is not None else self.z[:self.kx]
+        _, y = net.feedback_loop.solve(z_edc, net.input_gains.reshape(-1), net.output_gains.reshape(-1))
         hy = ops.irfft_window(y.transpose(0, 1), self.n_fft, self.t0, self.tn)  # (G, tn)
         keep = net.return_per_delay_outputs
         net.return_per_delay_outputs = False

@@ -10,7 +10,7 @@ import torch
 from torch import nn
 
 from .config.config import FeatureEncodingType
-from .dnn import MLP, ScaledSigmoid, SinusoidalEncoding
+from .dnn import MLP, ScaledSigmoid, SinusoidalEncoding, fused_position_mlp
 
 
 class Gains_from_MLP(nn.Module):
@@ -46,8 +46,11 @@ class Gains_from_MLP(nn.Module):
         param = next(self.mlp.parameters())
         position = position.to(param.device)
         self.batch_size = position.shape[0]
-        out = self.mlp(self.encoder(position))
-        gains = self.scaled_sigmoid(out.view(-1)).view(self.batch_size, self.num_groups)
+        gains = fused_position_mlp(self.encoder, self.mlp, position, final_act=1, lo=self.scaled_sigmoid.lower_limit,
+                                   hi=self.scaled_sigmoid.upper_limit)  # K7: one kernel forward, two backward
+        if gains is None:
+            out = self.mlp(self.encoder(position))
+            gains = self.scaled_sigmoid(out.view(-1)).view(self.batch_size, self.num_groups)
         self.gains_ = gains.detach()  # for get_parameters(); detached so no autograd graph outlives the step
         return gains
 

@@ -579,6 +579,78 @@ def td_edc_abs_db_sum_fused(s: torch.Tensor, hy: torch.Tensor, hd: Optional[torc
 
 
 # ----------------------------------------------------------------------------------------------------------
+# K7: position -> gain network (encoding + MLP + final activation), one launch forward, two backward
+# ----------------------------------------------------------------------------------------------------------
+def mlp_supported(in_dim: int, nfeat: int, neurons: int, num_ln_layers: int, out_dim: int) -> bool:
+    return bool(_lib.load().dgfdn_mlp_supported(int(in_dim), int(nfeat), int(neurons), int(num_ln_layers), int(out_dim)))
+
+
+class _PositionMLP(torch.autograd.Function):
+    """out = final_act(MLP(enc(pos))) for the reference's MLP / MLP_SkipConnections (dnn.py:284-400) with the
+    sinusoidal encoding (dnn.py:89-126) and the scaled sigmoid (dnn.py:21-36). params = (W_l, b_l, ln_w_l, ln_b_l)
+    per LayerNorm layer, then (W_out, b_out). Differentiable w.r.t. the parameters (positions are data)."""
+
+    @staticmethod
+    def forward(ctx, pos, freq, residual, final_act, lo, hi, *params):
+        nl = (len(params) - 2) // 4
+        pos_ = _cuda("pos", pos)
+        if pos_.dtype not in (torch.float32, torch.float64):
+            pos_ = pos_.to(torch.float32)
+        freq_ = _cuda("freq", freq, pos_.dtype)
+        ps = [_cuda("param", q, torch.float32) for q in params]
+        rows = pos_.shape[0]
+        neurons, in_dim = ps[0].shape
+        out_dim = ps[-2].shape[0]
+        nfeat = freq_.numel()
+        dev = pos_.device
+        ptrs = (ctypes.c_void_p * len(ps))(*[q.data_ptr() for q in ps])
+        out = torch.empty(rows, out_dim, dtype=torch.float32, device=dev)
+        xhat = torch.empty(nl, rows, neurons, dtype=torch.float32, device=dev)
+        rstd = torch.empty(nl, rows, dtype=torch.float32, device=dev)
+        asave = torch.empty(nl, rows, neurons, dtype=torch.float32, device=dev) if residual else None
+        meta = (rows, in_dim, nfeat, neurons, nl, out_dim, int(residual), int(final_act), float(lo), float(hi),
+                int(pos_.dtype == torch.float64))
+        with torch.cuda.device(dev):
+            _lib.call("dgfdn_mlp_fwd", *meta, _ptr(pos_), _ptr(freq_), ptrs, _ptr(out), _ptr(xhat), _ptr(rstd),
+                      _ptr(asave), _stream())
+        ctx.meta = meta
+        ctx.shapes = [q.shape for q in params]
+        ctx.save_for_backward(pos_, freq_, out, xhat, rstd, *( [asave] if residual else []), *ps)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        saved = ctx.saved_tensors
+        rows, in_dim, nfeat, neurons, nl, out_dim, residual = ctx.meta[:7]
+        pos_, freq_, out, xhat, rstd = saved[:5]
+        asave = saved[5] if residual else None
+        ps = saved[6 if residual else 5:]
+        gout_ = _cuda("gout", gout, torch.float32)
+        dev = pos_.device
+        lib = _lib.load()
+        nparams = int(lib.dgfdn_mlp_num_params(in_dim, neurons, nl, out_dim))
+        grad = torch.empty(nparams, dtype=torch.float32, device=dev)
+        ptrs = (ctypes.c_void_p * len(ps))(*[q.data_ptr() for q in ps])
+        with torch.cuda.device(dev):
+            ws = torch.empty(max(1, int(lib.dgfdn_mlp_bwd_ws_bytes(rows, in_dim, neurons, nl, out_dim)) // 4),
+                             dtype=torch.float32, device=dev)
+            _lib.call("dgfdn_mlp_bwd", *ctx.meta, _ptr(pos_), _ptr(freq_), ptrs, _ptr(out), _ptr(xhat), _ptr(rstd),
+                      _ptr(asave), _ptr(gout_), _ptr(grad), _ptr(ws), _stream())
+        grads, off = [], 0
+        for i, shp in enumerate(ctx.shapes):
+            n = math.prod(shp)
+            grads.append(grad[off:off + n].view(shp) if ctx.needs_input_grad[6 + i] else None)
+            off += n
+        return (None, None, None, None, None, None, *grads)
+
+
+def position_mlp(pos: torch.Tensor, freq: torch.Tensor, params, residual: bool = False, final_act: int = 0,
+                 lo: float = 0.0, hi: float = 1.0) -> torch.Tensor:
+    """(rows, out_dim) float32. params: flat list [W_0, b_0, ln_w_0, ln_b_0, ..., W_out, b_out]."""
+    return _PositionMLP.apply(pos, freq, bool(residual), int(final_act), float(lo), float(hi), *params)
+
+
+# ----------------------------------------------------------------------------------------------------------
 # colorless loss
 # ----------------------------------------------------------------------------------------------------------
 class _Colorless(torch.autograd.Function):

@@ -10,7 +10,7 @@ import torch
 from torch import nn
 
 from .config.config import BeamformerType
-from .dnn import MLP, MLP_SkipConnections, Sigmoid, SinusoidalEncoding
+from .dnn import MLP, MLP_SkipConnections, Sigmoid, SinusoidalEncoding, fused_position_mlp
 
 
 def design_analysis_matrix(ambi_order: int, desired_directions: np.ndarray,
@@ -75,7 +75,10 @@ class Directional_Beamforming_Weights_from_MLP(nn.Module):
         """(B, G, (N_sp+1)^2) weights (reference spatial_sampling/model.py:169-190)."""
         position = x['norm_listener_position'].to(next(self.mlp.parameters()).device)
         self.batch_size = position.shape[0]
-        w = self.mlp(self.encoder(position)).reshape(self.batch_size, self.num_groups, self.num_out_features)
+        w = fused_position_mlp(self.encoder, self.mlp, position)  # K7 kernels
+        if w is None:
+            w = self.mlp(self.encoder(position))
+        w = w.reshape(self.batch_size, self.num_groups, self.num_out_features)
         if normalise_weights:
             w = self.normalise_weights(w)
         self.weights = w

@@ -202,6 +202,30 @@ DGFDN_API int dgfdn_td_edc_fused(int g, int64_t rows, int64_t tn, const float* s
                        double* loss_sum, float* gs, float* ghy, int accumulate, void* ws, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * K7: position -> gain network of a receiver shard.  Replaces SinusoidalEncoding + MLP / MLP_SkipConnections
+ * + ScaledSigmoid (dnn.py:21-36, 89-126, 284-400) as called by Gains_from_MLP.forward (gain_filters.py:497-536)
+ * and Directional_Beamforming_Weights_from_MLP.forward (spatial_sampling/model.py:169-190):
+ *   a_0 = [sin(f_i pi p), cos(f_i pi p)]_i ;  a_l = relu(LayerNorm_l(W_l a_{l-1} + b_l)) (+ a_{l-1}, residual, l >= 1)
+ *   out = W_out a_last + b_out ;  final_act = 1: out <- lo + (hi - lo) / (1 + exp(-out)).
+ * pos [rows,3] and freq [nfeat] (= f_i pi) are float32 (pos_is_double = 0) or float64; in_dim = 6 nfeat.
+ * params_host: HOST array of 4 nl + 2 DEVICE pointers {W_l [neurons,in_l], b_l, ln_gamma_l, ln_beta_l}_l, W_out
+ * [out_dim,neurons], b_out (the torch parameter layouts), 16-byte aligned. neurons in {64,128}, nl <= 8, out_dim <= 32.
+ * fwd: out [rows,out_dim]; saved for the backward: xhat [nl,rows,neurons], rstd [nl,rows], asave [nl,rows,neurons]
+ * (residual variant only, else NULL).
+ * bwd: gout [rows,out_dim] -> grad: flat float32 [dgfdn_mlp_num_params] in the order of params_host; ws: scratch of
+ * dgfdn_mlp_bwd_ws_bytes. Deterministic (fixed-order two-stage reduction). */
+DGFDN_API int dgfdn_mlp_supported(int in_dim, int nfeat, int neurons, int nl, int out_dim);
+DGFDN_API int64_t dgfdn_mlp_num_params(int in_dim, int neurons, int nl, int out_dim);
+DGFDN_API int64_t dgfdn_mlp_bwd_ws_bytes(int64_t rows, int in_dim, int neurons, int nl, int out_dim);
+DGFDN_API int dgfdn_mlp_fwd(int64_t rows, int in_dim, int nfeat, int neurons, int nl, int out_dim, int residual,
+                  int final_act, float lo, float hi, int pos_is_double, const void* pos, const void* freq,
+                  const float* const* params_host, float* out, float* xhat, float* rstd, float* asave, void* stream);
+DGFDN_API int dgfdn_mlp_bwd(int64_t rows, int in_dim, int nfeat, int neurons, int nl, int out_dim, int residual,
+                  int final_act, float lo, float hi, int pos_is_double, const void* pos, const void* freq,
+                  const float* const* params_host, const float* out, const float* xhat, const float* rstd,
+                  const float* asave, const float* gout, float* grad, void* ws, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Colorless (spectral flatness) loss of the lossless sub-FDNs, colorless_fdn/losses.py:20-73 with
  * y_true = 1:   loss[g] = mean_k (|H[k,g]| - 1)^p ,  p = 2, or 4 where |H|-1 > 1 when asym != 0.
  * h_sub [K,G] c64; loss [G] float64 out. bwd: gh[k,g] = coef[g] * dloss[g]/dH[k,g]  (c64 out). */
