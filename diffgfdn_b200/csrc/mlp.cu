@@ -51,6 +51,7 @@ struct MlpParams {
   const float* gout;    // [rows, out_dim]
   float* part;          // [grid, nparams] partial gradients of this CTA
   int64_t nparams;
+  int64_t part_stride;  // nparams rounded up to a multiple of 4 floats (128-bit stores into a CTA's slice)
 };
 
 __device__ __forceinline__ float2 ffma2(float a, float2 w, float2 c) { return __ffma2_rn(make_float2(a, a), w, c); }
@@ -236,7 +237,7 @@ __global__ void __launch_bounds__(kMT, 1) mlp_bwd_kernel(MlpParams p) {
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
   const int64_t row0 = (int64_t)blockIdx.x * kRowsPerCta;
   const int nvalid = (int)min((int64_t)kRowsPerCta, p.rows - row0);
-  float* part = p.part + (int64_t)blockIdx.x * p.nparams;
+  float* part = p.part + (int64_t)blockIdx.x * p.part_stride;
   const int64_t off_out = layer_offset(p.nl, p.in_dim, H);
 
   // activation entering layer l (l = nl: the output layer) into ap
@@ -460,11 +461,12 @@ __global__ void __launch_bounds__(kMT, 1) mlp_bwd_kernel(MlpParams p) {
 }
 
 // grad[i] = sum_c part[c][i] in CTA order, float64 accumulation
-__global__ void mlp_reduce_kernel(const float* __restrict__ part, int ncta, int64_t nparams, float* __restrict__ grad) {
+__global__ void mlp_reduce_kernel(const float* __restrict__ part, int ncta, int64_t stride, int64_t nparams,
+                                  float* __restrict__ grad) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nparams) return;
   double s = 0.0;
-  for (int c = 0; c < ncta; ++c) s += (double)part[(int64_t)c * nparams + i];
+  for (int c = 0; c < ncta; ++c) s += (double)part[(int64_t)c * stride + i];
   grad[i] = (float)s;
 }
 
@@ -530,7 +532,7 @@ extern "C" int64_t dgfdn_mlp_num_params(int in_dim, int neurons, int nl, int out
 
 extern "C" int64_t dgfdn_mlp_bwd_ws_bytes(int64_t rows, int in_dim, int neurons, int nl, int out_dim) {
   const int64_t ncta = (rows + kRowsPerCta - 1) / kRowsPerCta;
-  return ncta * nparams_of(in_dim, neurons, nl, out_dim) * (int64_t)sizeof(float);
+  return ncta * ((nparams_of(in_dim, neurons, nl, out_dim) + 3) / 4 * 4) * (int64_t)sizeof(float);
 }
 
 extern "C" int dgfdn_mlp_fwd(int64_t rows, int in_dim, int nfeat, int neurons, int nl, int out_dim, int residual,
@@ -571,6 +573,7 @@ extern "C" int dgfdn_mlp_bwd(int64_t rows, int in_dim, int nfeat, int neurons, i
     return 1;
   DGFDN_CHECK(out && xhat && rstd && gout && grad && ws && (!residual || asave), "mlp_bwd: missing buffers");
   p.nparams = nparams_of(in_dim, neurons, nl, out_dim);
+  p.part_stride = (p.nparams + 3) / 4 * 4;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (rows == 0) {
     DGFDN_CUDA(cudaMemsetAsync(grad, 0, (size_t)p.nparams * sizeof(float), st));
@@ -592,7 +595,7 @@ extern "C" int dgfdn_mlp_bwd(int64_t rows, int in_dim, int nfeat, int neurons, i
     mlp_bwd_kernel<64><<<grid, kMT, smem, st>>>(p);
   }
   DGFDN_LAUNCH_CHECK();
-  mlp_reduce_kernel<<<(unsigned)((p.nparams + 255) / 256), 256, 0, st>>>(p.part, (int)grid, p.nparams, grad);
+  mlp_reduce_kernel<<<(unsigned)((p.nparams + 255) / 256), 256, 0, st>>>(p.part, (int)grid, p.part_stride, p.nparams, grad);
   DGFDN_LAUNCH_CHECK();
   return 0;
 }

@@ -43,7 +43,9 @@ def test_gains_from_mlp_matches_torch_and_oracle(rows, nfeat, hidden, neurons, s
     else:
         mod = Gains_from_MLP(groups, 4, nfeat, hidden, neurons, device=dev).to(dev)
     _randomise(mod, 5)
-    pos = torch.rand(rows, 3, dtype=pdtype, generator=torch.Generator().manual_seed(1)).to(dev)
+    # seed 11: with seed 1 a float32 position puts one ReLU input of the 97-row case within rounding of zero, and the
+    # float32 formulation itself (stock torch included) then differs from the float64 oracle by a flipped unit
+    pos = torch.rand(rows, 3, dtype=pdtype, generator=torch.Generator().manual_seed(11)).to(dev)
     x = {"norm_listener_position": pos}
     wgt = torch.randn(rows, groups * (9 if skip else 1), generator=torch.Generator().manual_seed(2)).to(dev)
 
