@@ -28,18 +28,25 @@
 namespace dgfdn {
 namespace {
 
-constexpr int kC = 8;                  // CTAs per cluster = time slices per row
-constexpr int kFT = 256;               // threads per CTA
-constexpr int kFW = kFT / 32;          // warps per CTA
-constexpr int kRun = 3;                // consecutive segments per thread and run
-constexpr int kRunSegs = kFT * kRun;   // 768 segments (3072 samples) per run
-constexpr int kRows = 2;               // rows per iteration
-constexpr int kMaxRuns = 2;
-constexpr int kPos = 16;               // (run, warp) positions per row in the CTA-level scan (kMaxRuns * kFW)
+constexpr int kMaxC = 8;               // largest cluster (portable limit); workspace rows are sized for it
 constexpr float kEpsF = 1.1920928955078125e-07f;   // torch.finfo(float32).eps (reference utils.py:35)
 constexpr float kDbPerLog2 = 3.0102999566398120f;  // 10 / log2(10)
 constexpr double kDbFactor = 4.342944819032518;    // 10 / ln(10)
-static_assert(kMaxRuns * kFW == kPos && kRows * kPos == 32, "CTA-level scan is one warp: rows x positions = 32 lanes");
+
+// Compile-time shape of one variant of the kernel. A CTA of FT threads owns one of C time slices of a row; thread t
+// owns, in each of NRUN runs, RUN consecutive 128-bit segments (RUN odd: the 16 RUN-byte thread stride is then
+// conflict-free for 128-bit shared-memory accesses); ROWS rows are processed per iteration.
+template <int FT_, int RUN_, int NRUN_, int ROWS_, int C_>
+struct Tile {
+  static constexpr int FT = FT_, FW = FT_ / 32, RUN = RUN_, NRUN = NRUN_, ROWS = ROWS_, C = C_;
+  static constexpr int RUNSEGS = FT * RUN;     // segments per run
+  static constexpr int SLOT = NRUN * RUNSEGS;  // padded segments per slot
+  static constexpr int POS = 32 / ROWS;        // lanes per row in the CTA-level scan
+  static_assert(ROWS == 1 || ROWS == 2, "CTA-level scan is one warp: rows x positions = 32 lanes");
+  static_assert(NRUN * FW <= POS, "too many (run, warp) positions for the one-warp CTA scan");
+  static_assert(ROWS * C <= 32 && C <= kMaxC, "carry exchange is issued by one warp");
+  static_assert(RUN % 2 == 1, "odd segment count per thread: conflict-free 128-bit shared-memory accesses");
+};
 
 struct FusedParams {
   int64_t rows;
@@ -130,34 +137,44 @@ __device__ __forceinline__ void dot4(float2& acc, float4 x, float4 y) {  // acc.
   acc = __ffma2_rn(hi(x), hi(y), acc);
 }
 
+template <class T>
 struct FusedSmem {                      // static part; the slots follow in dynamic shared memory
-  float wtot[2][kRows][kPos];           // [scan][row][run * kFW + warp] warp totals
-  float xchg[2][2][kRows][kC];          // [scan][parity][row][source CTA]: slice totals stored by the peers (DSMEM)
-  double red[kFW];
+  float wtot[2][T::ROWS][T::POS];       // [scan][row][run * FW + warp] warp totals (unused positions stay 0)
+  // [scan][parity][row][source CTA]: slice totals stored by the peers (DSMEM); entries >= C stay 0
+  __align__(16) float xchg[2][2][T::ROWS][kMaxC];
+  double red[T::FW];
   unsigned long long bar_hd, bar_td;    // mbarriers of the hd / target-dB slots (TMA complete_tx)
   unsigned long long bar_x[2];          // mbarriers of the two carry exchanges (st.async complete_tx)
 };
 
-// CTA level of a scan, done redundantly by every warp (one barrier per scan instead of two): lane = row * 16 + pos
-// scans the kPos (run, warp) totals of its row. The sums have at most 16 (here) + 8 (cluster) terms on top of the
-// 384-sample warp level, so float32 is used throughout; only the loss is accumulated in float64.
-template <bool REVERSE>
-__device__ __forceinline__ float cta_scan16(float v, int lane) {
-  const int pos = lane & (kPos - 1);
+// CTA level of a scan, done redundantly by every warp (one barrier per scan instead of two): lane = row * POS + pos
+// scans the POS (run, warp) totals of its row. The sums have at most POS (here) + C (cluster) terms on top of the
+// warp level, so float32 is used throughout; only the loss is accumulated in float64.
+// sum of the kMaxC exchange slots of one row: two 128-bit loads and a fixed-order tree
+__device__ __forceinline__ float sum8(const float* x) {
+  static_assert(kMaxC == 8, "two float4 per row");
+  const float4 a = *reinterpret_cast<const float4*>(x), b = *reinterpret_cast<const float4*>(x + 4);
+  return ((a.x + a.y) + (a.z + a.w)) + ((b.x + b.y) + (b.z + b.w));
+}
+
+template <int POS, bool REVERSE>
+__device__ __forceinline__ float cta_scan(float v, int lane) {
+  const int pos = lane & (POS - 1);
 #pragma unroll
-  for (int o = 1; o < kPos; o <<= 1) {
+  for (int o = 1; o < POS; o <<= 1) {
     const float t = REVERSE ? __shfl_down_sync(0xffffffffu, v, o) : __shfl_up_sync(0xffffffffu, v, o);
-    if (REVERSE ? (pos + o < kPos) : (pos >= o)) v += t;
+    if (REVERSE ? (pos + o < POS) : (pos >= o)) v += t;
   }
   return v;
 }
 
 // G x (tn/4) accumulators of the cluster's slice stay in registers: acc[g][run][k] is a float4 of 4 samples.
-template <int G, int NRUN, bool MASKED>
-__global__ void __launch_bounds__(kFT, 1) td_fused_kernel(FusedParams p) {
+template <int G, bool MASKED, class T>
+__global__ void __launch_bounds__(T::FT, 1) td_fused_kernel(FusedParams p) {
+  constexpr int kFT = T::FT, kFW = T::FW, kRun = T::RUN, NRUN = T::NRUN, kRunSegs = T::RUNSEGS, kRows = T::ROWS;
+  constexpr int kC = T::C, kPos = T::POS, kSlot = T::SLOT;
   extern __shared__ __align__(128) unsigned char dyn_smem[];
-  __shared__ FusedSmem sm;
-  constexpr int kSlot = NRUN * kRunSegs;  // padded segments per slot
+  __shared__ FusedSmem<T> sm;
   float4* hd_s = reinterpret_cast<float4*>(dyn_smem);  // [kRows][kSlot]
   float4* td_s = hd_s + kRows * kSlot;                 // [kRows][kSlot]
   float4* hy_s = td_s + kRows * kSlot;                 // [G][kSlot]
@@ -177,6 +194,8 @@ __global__ void __launch_bounds__(kFT, 1) td_fused_kernel(FusedParams p) {
 
   // ---- one-time set-up: zero the slots (tails stay zero for ever), stage the hy / mask slices, init barriers
   for (int i = tid; i < 2 * kRows * kSlot; i += kFT) hd_s[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = tid; i < 2 * kRows * kPos; i += kFT) (&sm.wtot[0][0][0])[i] = 0.f;
+  for (int i = tid; i < 2 * 2 * kRows * kMaxC; i += kFT) (&sm.xchg[0][0][0][0])[i] = 0.f;
   for (int i = tid; i < kSlot; i += kFT) {
 #pragma unroll
     for (int g = 0; g < G; ++g)
@@ -322,7 +341,7 @@ __global__ void __launch_bounds__(kFT, 1) td_fused_kernel(FusedParams p) {
 #pragma unroll
       for (int q = 0; q < kRows; ++q)
 #pragma unroll
-        for (int u = 0; u < kMaxRuns; ++u) sm.wtot[0][q][u * kFW + warp] = u < NRUN ? inc[q][u < NRUN ? u : 0] : 0.f;
+        for (int u = 0; u < NRUN; ++u) sm.wtot[0][q][u * kFW + warp] = inc[q][u];
     }
 #pragma unroll
     for (int q = 0; q < kRows; ++q)
@@ -335,7 +354,7 @@ __global__ void __launch_bounds__(kFT, 1) td_fused_kernel(FusedParams p) {
     if (tid == 0 && has_next && has_hd) issue(true, it + ncl);
     float offl[kRows][NRUN];  // CTA-local exclusive offsets: later (run, warp) positions of this slice
     {
-      const float v = cta_scan16<true>(sm.wtot[0][lane >> 4][lane & (kPos - 1)], lane);
+      const float v = cta_scan<kPos, true>(sm.wtot[0][lane / kPos][lane & (kPos - 1)], lane);
 #pragma unroll
       for (int q = 0; q < kRows; ++q)
 #pragma unroll
@@ -344,11 +363,12 @@ __global__ void __launch_bounds__(kFT, 1) td_fused_kernel(FusedParams p) {
           const float t = __shfl_sync(0xffffffffu, v, q * kPos + (pos & (kPos - 1)));
           offl[q][u] = pos < kPos ? t : 0.f;
         }
-      if (warp == 0) {  // lanes 0-7: row 0, 8-15: row 1; receiver `peer` sums the slices later than its own
-        const float total = __shfl_sync(0xffffffffu, v, ((lane >> 3) & 1) * kPos);
-        const uint32_t peer = (uint32_t)(lane & (kC - 1));
+      if (warp == 0) {  // lane = row * C + peer; receiver `peer` sums the slices later than its own
+        const int xrow = min(lane / kC, kRows - 1);
+        const float total = __shfl_sync(0xffffffffu, v, xrow * kPos);
+        const uint32_t peer = (uint32_t)(lane % kC);
         if (lane < kRows * kC)
-          st_async_f32(smem_u32(&sm.xchg[0][parity][lane >> 3][rank]), bar_xa, peer, rank > peer ? total : 0.f);
+          st_async_f32(smem_u32(&sm.xchg[0][parity][xrow][rank]), bar_xa, peer, rank > peer ? total : 0.f);
       } else if (it_prev >= 0) {
         reduce_gs(it_prev);
       }
@@ -360,9 +380,7 @@ __global__ void __launch_bounds__(kFT, 1) td_fused_kernel(FusedParams p) {
     float lacc = 0.f;
 #pragma unroll
     for (int q = 0; q < kRows; ++q) {
-      float carry = 0.f;  // slices later than this one (the senders masked their totals)
-#pragma unroll
-      for (int i = kC - 1; i >= 0; --i) carry += sm.xchg[0][parity][q][i];
+      const float carry = sum8(sm.xchg[0][parity][q]);  // slices later than this one (senders masked their totals)
 #pragma unroll
       for (int u = 0; u < NRUN; ++u) {
         const float offe = (carry + offl[q][u]) + inc[q][u] + kEpsF;
@@ -383,18 +401,27 @@ __global__ void __launch_bounds__(kFT, 1) td_fused_kernel(FusedParams p) {
             mk.x = mk.y = mk.z = mk.w = wt;
             wcf = wt * cf2;
           }
+          // x = EDC + eps ; diff = target_dB - 10 log10(x) ; dL/dEDC = -sign(diff) w / x (the factor 2 coef 10/ln10
+          // rides on w). Packed fp32x2 for the adds / multiplies; MUFU and the sign transfer are per sample. An exact
+          // tie diff == 0 (where torch's abs' is 0) is not special-cased: it needs the 48-bit product k lg2(x) to be a
+          // float32 equal to the target, and costs two instructions per sample to detect.
+          const float2 off2 = make_float2(offe, offe), nk2 = make_float2(-kDbPerLog2, -kDbPerLog2);
+          const float2 x01 = __fadd2_rn(lo(e), off2), x23 = __fadd2_rn(hi(e), off2);
+          const float2 d01 = __ffma2_rn(nk2, make_float2(lg2_ftz(x01.x), lg2_ftz(x01.y)), lo(td));
+          const float2 d23 = __ffma2_rn(nk2, make_float2(lg2_ftz(x23.x), lg2_ftz(x23.y)), hi(td));
+          lacc = fmaf(mk.x, fabsf(d01.x), lacc);
+          lacc = fmaf(mk.y, fabsf(d01.y), lacc);
+          lacc = fmaf(mk.z, fabsf(d23.x), lacc);
+          lacc = fmaf(mk.w, fabsf(d23.y), lacc);
+          const float2 w01 = MASKED ? make_float2(mk.x * cf2, mk.y * cf2) : make_float2(wcf, wcf);
+          const float2 w23 = MASKED ? make_float2(mk.z * cf2, mk.w * cf2) : make_float2(wcf, wcf);
+          const float2 g01 = __fmul2_rn(w01, make_float2(rcp_ftz(x01.x), rcp_ftz(x01.y)));
+          const float2 g23 = __fmul2_rn(w23, make_float2(rcp_ftz(x23.x), rcp_ftz(x23.y)));
           float4 ge;
-#define DGFDN_DB_ONE(C)                                                                          \
-  {                                                                                              \
-    const float x = e.C + offe;                                                                  \
-    const float diff = fmaf(-kDbPerLog2, lg2_ftz(x), td.C);                                      \
-    lacc = fmaf(mk.C, fabsf(diff), lacc);                                                        \
-    const float g = (MASKED ? mk.C * cf2 : wcf) * rcp_ftz(x);                                    \
-    const float sg = __int_as_float(__float_as_int(g) ^ (~__float_as_int(diff) & 0x80000000));   \
-    ge.C = diff == 0.f ? 0.f : sg;                                                               \
-  }
-          DGFDN_DB_ONE(x) DGFDN_DB_ONE(y) DGFDN_DB_ONE(z) DGFDN_DB_ONE(w)
-#undef DGFDN_DB_ONE
+          ge.x = __int_as_float(__float_as_int(g01.x) ^ (~__float_as_int(d01.x) & 0x80000000));
+          ge.y = __int_as_float(__float_as_int(g01.y) ^ (~__float_as_int(d01.y) & 0x80000000));
+          ge.z = __int_as_float(__float_as_int(g23.x) ^ (~__float_as_int(d23.x) & 0x80000000));
+          ge.w = __int_as_float(__float_as_int(g23.y) ^ (~__float_as_int(d23.y) & 0x80000000));
           float4 pre;
           pre.x = run + ge.x;
           pre.y = pre.x + ge.y;
@@ -425,7 +452,7 @@ __global__ void __launch_bounds__(kFT, 1) td_fused_kernel(FusedParams p) {
 #pragma unroll
       for (int q = 0; q < kRows; ++q)
 #pragma unroll
-        for (int u = 0; u < kMaxRuns; ++u) sm.wtot[1][q][u * kFW + warp] = u < NRUN ? inc[q][u < NRUN ? u : 0] : 0.f;
+        for (int u = 0; u < NRUN; ++u) sm.wtot[1][q][u * kFW + warp] = inc[q][u];
     }
 #pragma unroll
     for (int q = 0; q < kRows; ++q)
@@ -438,7 +465,7 @@ __global__ void __launch_bounds__(kFT, 1) td_fused_kernel(FusedParams p) {
     if (tid == 0 && has_next && has_td) issue(false, it + ncl);
     float offp[kRows][NRUN];  // exclusive offsets inside the CTA: earlier (run, warp) positions + earlier lanes
     {
-      const float v = cta_scan16<false>(sm.wtot[1][lane >> 4][lane & (kPos - 1)], lane);
+      const float v = cta_scan<kPos, false>(sm.wtot[1][lane / kPos][lane & (kPos - 1)], lane);
 #pragma unroll
       for (int q = 0; q < kRows; ++q)
 #pragma unroll
@@ -448,10 +475,11 @@ __global__ void __launch_bounds__(kFT, 1) td_fused_kernel(FusedParams p) {
           offp[q][u] = (pos >= 0 ? t : 0.f) + inc[q][u];
         }
       if (warp == 0) {  // receiver `peer` sums the slices earlier than its own
-        const float total = __shfl_sync(0xffffffffu, v, ((lane >> 3) & 1) * kPos + kPos - 1);
-        const uint32_t peer = (uint32_t)(lane & (kC - 1));
+        const int xrow = min(lane / kC, kRows - 1);
+        const float total = __shfl_sync(0xffffffffu, v, xrow * kPos + kPos - 1);
+        const uint32_t peer = (uint32_t)(lane % kC);
         if (lane < kRows * kC)
-          st_async_f32(smem_u32(&sm.xchg[1][parity][lane >> 3][rank]), bar_xb, peer, rank < peer ? total : 0.f);
+          st_async_f32(smem_u32(&sm.xchg[1][parity][xrow][rank]), bar_xb, peer, rank < peer ? total : 0.f);
       }
     }
 
@@ -486,9 +514,7 @@ __global__ void __launch_bounds__(kFT, 1) td_fused_kernel(FusedParams p) {
     // ================= phase C: dL/dh = u + c h ; ghy accumulators ; dL/ds partials ============================
 #pragma unroll
     for (int q = 0; q < kRows; ++q) {
-      float c = 0.f;  // slices earlier than this one (the senders masked their totals)
-#pragma unroll
-      for (int i = 0; i < kC; ++i) c += sm.xchg[1][parity][q][i];
+      const float c = sum8(sm.xchg[1][parity][q]);  // slices earlier than this one (senders masked their totals)
 #pragma unroll
       for (int u = 0; u < NRUN; ++u)
 #pragma unroll
@@ -525,7 +551,7 @@ __global__ void __launch_bounds__(kFT, 1) td_fused_kernel(FusedParams p) {
     __syncthreads();
     if (tid == 0) {
       double t = 0.0;
-      for (int i = 0; i < kFW; ++i) t += sm.red[i];
+      for (int i = 0; i < T::FW; ++i) t += sm.red[i];
       p.part_loss[blockIdx.x] = t;
     }
   }
@@ -537,7 +563,7 @@ __global__ void __launch_bounds__(kFT, 1) td_fused_kernel(FusedParams p) {
 __global__ void td_fused_finalize_kernel(int64_t n_ghy, int ncl, const float* __restrict__ part_ghy, float* __restrict__ ghy,
                                          int64_t rows, int g, const float* __restrict__ part_gs, float* __restrict__ gs,
                                          int nblocks, const double* __restrict__ part_loss, double* __restrict__ loss,
-                                         int accumulate) {
+                                         int accumulate, int kC) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n_ghy) {
     float v = accumulate ? ghy[i] : 0.f;
@@ -562,31 +588,63 @@ __global__ void td_fused_finalize_kernel(int64_t n_ghy, int ncl, const float* __
   }
 }
 
-constexpr int kMaxClusters = 32;  // workspace is sized for this many resident clusters (a B200 holds <= 18 of 8 CTAs)
+constexpr int kMaxClusters = 40;  // workspace is sized for this many resident clusters (148 SMs / 4 CTAs = 37)
+
+// ---- variants ------------------------------------------------------------------------------------------------
+// id: tile. The default (DGFDN_TD_VARIANT unset) is the first variant in kOrder whose slices hold the row.
+// Measured on B200 at the BASELINE shard (12 500 rows x 47 360 samples, G = 3; scripts/tune_td_fused.py,
+// profiles/r01_td_fused_variants.txt): 256 threads x 255 registers x 2 rows per iteration is the fastest shape
+// (1.50 ms); 512 x 128 x 2 rows: 1.63 ms; one row per iteration: 2.2 ms (8 CTAs) / 1.8 ms (6 CTAs, 132 SMs) -- the
+// two barriers + two DSMEM exchanges per iteration are a fixed ~1.4 us that only more rows per iteration amortise.
+using TileA1 = Tile<256, 3, 1, 2, 8>;  // 0: short rows (one run per thread)
+using TileA2 = Tile<256, 3, 2, 2, 8>;  // 1: two runs per thread, rows up to 49 152 samples
+using TileD = Tile<384, 3, 2, 1, 6>;   // 2: clusters of 6 (22 resident clusters = 132 SMs), rows up to 55 296 samples
+constexpr int kNumVariants = 3;
+
+struct VariantInfo {
+  int c, slot, ft, rows;
+};
+template <class T>
+constexpr VariantInfo info_of() {
+  return VariantInfo{T::C, T::SLOT, T::FT, T::ROWS};
+}
+constexpr VariantInfo kVariants[kNumVariants] = {info_of<TileA1>(), info_of<TileA2>(), info_of<TileD>()};
+constexpr int kOrder[kNumVariants] = {0, 1, 2};
+
+bool variant_fits(int v, int64_t tn4) {
+  const int64_t slice4 = (tn4 + kVariants[v].c - 1) / kVariants[v].c;
+  return slice4 <= kVariants[v].slot;
+}
 
 struct FusedShape {
-  int nrun;
+  int variant;
   int slice4;
 };
-// The fused kernel needs tn % 4 == 0 and a slice of at most kMaxRuns runs per CTA (tn <= 8 * 2 * 3072 = 49152).
+// The fused kernel needs tn % 4 == 0 and a row that fits the slices of one variant (tn <= 6 * 2304 * 4 = 55296).
 bool fused_shape(int g, int64_t tn, FusedShape* out) {
   if (g < 1 || g > 4 || tn < 4 || tn % 4 != 0) return false;
   const int64_t tn4 = tn / 4;
-  const int64_t slice4 = (tn4 + kC - 1) / kC;
-  const int64_t nrun = (slice4 + kRunSegs - 1) / kRunSegs;
-  if (nrun > kMaxRuns) return false;
+  int v = -1;
+  if (const char* e = getenv("DGFDN_TD_VARIANT")) {
+    const int want = atoi(e);
+    if (want >= 0 && want < kNumVariants && variant_fits(want, tn4)) v = want;
+  }
+  for (int i = 0; v < 0 && i < kNumVariants; ++i)
+    if (variant_fits(kOrder[i], tn4)) v = kOrder[i];
+  if (v < 0) return false;
   if (out) {
-    out->nrun = (int)nrun;
-    out->slice4 = (int)slice4;
+    out->variant = v;
+    out->slice4 = (int)((tn4 + kVariants[v].c - 1) / kVariants[v].c);
   }
   return true;
 }
 
 inline bool aligned16(const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-size_t fused_dyn_smem(int g, int nrun, bool masked) {
-  const size_t slot = (size_t)nrun * kRunSegs * sizeof(float4);
-  return slot * (2 * kRows + g + (masked ? 1 : 0)) + (size_t)kRows * g * kFT * sizeof(float);
+template <class T>
+size_t fused_dyn_smem(int g, bool masked) {
+  const size_t slot = (size_t)T::SLOT * sizeof(float4);
+  return slot * (2 * T::ROWS + g + (masked ? 1 : 0)) + (size_t)T::ROWS * g * T::FT * sizeof(float);
 }
 
 struct WsLayout {
@@ -597,47 +655,91 @@ WsLayout ws_layout(int g, int64_t rows, int64_t tn) {
   size_t o = (size_t)kMaxClusters * g * tn * sizeof(float);
   o = (o + 255) & ~(size_t)255;
   w.off_gs = o;
-  o += (size_t)rows * kC * g * sizeof(float);
+  o += (size_t)rows * kMaxC * g * sizeof(float);
   o = (o + 255) & ~(size_t)255;
   w.off_loss = o;
-  o += (size_t)kMaxClusters * kC * sizeof(double);
+  o += (size_t)kMaxClusters * kMaxC * sizeof(double);
   w.total = o;
   return w;
 }
 
-template <int G, int NRUN, bool MASKED>
-int launch_fused(const FusedParams& p, int64_t rows, size_t smem, cudaStream_t st, int* ncl_out) {
-  auto kern = td_fused_kernel<G, NRUN, MASKED>;
+// Resident clusters of this instantiation on the current device (cached per device).
+template <int G, bool MASKED, class T>
+int resident_clusters(int* out) {
+  auto kern = td_fused_kernel<G, MASKED, T>;
   static int max_clusters[64] = {0};  // per device
   int dev = 0;
   DGFDN_CUDA(cudaGetDevice(&dev));
   DGFDN_CHECK(dev >= 0 && dev < 64, "td_edc_fused: device index out of range");
+  if (max_clusters[dev] == 0) {
+    const size_t smem = fused_dyn_smem<T>(G, MASKED);
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = T::C;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.blockDim = dim3(T::FT);
+    cfg.dynamicSmemBytes = smem;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    DGFDN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cfg.gridDim = dim3(T::C * kMaxClusters);
+    int n = 0;
+    DGFDN_CUDA(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
+    DGFDN_CHECK(n >= 1, "td_edc_fused: no cluster of %d CTAs fits on this device", T::C);
+    max_clusters[dev] = n > kMaxClusters ? kMaxClusters : n;
+  }
+  *out = max_clusters[dev];
+  return 0;
+}
+
+template <int G, bool MASKED, class T>
+int launch_fused(const FusedParams& p, int64_t rows, cudaStream_t st, int* ncl_out) {
+  auto kern = td_fused_kernel<G, MASKED, T>;
+  int maxc = 0;
+  if (int rc = resident_clusters<G, MASKED, T>(&maxc)) return rc;
   cudaLaunchConfig_t cfg = {};
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = kC;
+  attr[0].val.clusterDim.x = T::C;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
-  cfg.blockDim = dim3(kFT);
-  cfg.dynamicSmemBytes = smem;
+  cfg.blockDim = dim3(T::FT);
+  cfg.dynamicSmemBytes = fused_dyn_smem<T>(G, MASKED);
   cfg.stream = st;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  if (max_clusters[dev] == 0) {
-    DGFDN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    cfg.gridDim = dim3(kC * kMaxClusters);
-    int n = 0;
-    DGFDN_CUDA(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
-    DGFDN_CHECK(n >= 1, "td_edc_fused: no cluster of %d CTAs fits on this device", kC);
-    max_clusters[dev] = n > kMaxClusters ? kMaxClusters : n;
-  }
-  const int64_t niter = (rows + kRows - 1) / kRows;
-  const int ncl = (int)(niter < max_clusters[dev] ? niter : max_clusters[dev]);
-  cfg.gridDim = dim3((unsigned)(kC * ncl));
+  const int64_t niter = (rows + T::ROWS - 1) / T::ROWS;
+  const int ncl = (int)(niter < maxc ? niter : maxc);
+  cfg.gridDim = dim3((unsigned)(T::C * ncl));
   *ncl_out = ncl;
   FusedParams pp = p;
   DGFDN_CUDA(cudaLaunchKernelEx(&cfg, kern, pp));
   return 0;
+}
+
+// op = 0: launch; op = 1: only report the resident cluster count through *ncl
+template <int G, bool MASKED>
+int by_variant(int variant, int op, const FusedParams& p, int64_t rows, cudaStream_t st, int* ncl) {
+#define DGFDN_TD_CASE(ID, TILE) \
+  case ID: return op ? resident_clusters<G, MASKED, TILE>(ncl) : launch_fused<G, MASKED, TILE>(p, rows, st, ncl);
+  switch (variant) {
+    DGFDN_TD_CASE(0, TileA1)
+    DGFDN_TD_CASE(1, TileA2)
+    DGFDN_TD_CASE(2, TileD)
+  }
+#undef DGFDN_TD_CASE
+  return 1;
+}
+
+int dispatch(int g, bool masked, int variant, int op, const FusedParams& p, int64_t rows, cudaStream_t st, int* ncl) {
+  switch (g) {
+    case 1: return masked ? by_variant<1, true>(variant, op, p, rows, st, ncl) : by_variant<1, false>(variant, op, p, rows, st, ncl);
+    case 2: return masked ? by_variant<2, true>(variant, op, p, rows, st, ncl) : by_variant<2, false>(variant, op, p, rows, st, ncl);
+    case 3: return masked ? by_variant<3, true>(variant, op, p, rows, st, ncl) : by_variant<3, false>(variant, op, p, rows, st, ncl);
+    default: return masked ? by_variant<4, true>(variant, op, p, rows, st, ncl) : by_variant<4, false>(variant, op, p, rows, st, ncl);
+  }
 }
 
 }  // namespace
@@ -652,13 +754,31 @@ extern "C" int64_t dgfdn_td_edc_fused_ws_bytes(int g, int64_t rows, int64_t tn) 
   return (int64_t)ws_layout(g, rows, tn).total;
 }
 
+// Diagnostic: the variant chosen for (g, tn) [-1: unsupported], its cluster size, threads per CTA and the number
+// of clusters that are co-resident on the current device.
+extern "C" int dgfdn_td_edc_fused_info(int g, int64_t tn, int* variant, int* cluster_size, int* threads, int* clusters) {
+  FusedShape shp;
+  if (!fused_shape(g, tn, &shp)) {
+    if (variant) *variant = -1;
+    return 0;
+  }
+  int ncl = 0;
+  FusedParams p{};
+  if (int rc = dispatch(g, false, shp.variant, 1, p, 0, nullptr, &ncl)) return rc;
+  if (variant) *variant = shp.variant;
+  if (cluster_size) *cluster_size = kVariants[shp.variant].c;
+  if (threads) *threads = kVariants[shp.variant].ft;
+  if (clusters) *clusters = ncl;
+  return 0;
+}
+
 extern "C" int dgfdn_td_edc_fused(int g, int64_t rows, int64_t tn, const float* s, const float* hy, const float* hd,
                                   int64_t ldhd, const float* target_db, int64_t ldt, const float* mask, double coef,
                                   double* loss_sum, float* gs, float* ghy, int accumulate, void* ws, void* stream) {
   DGFDN_CHECK(rows >= 0 && tn >= 1 && s && hy && target_db && ghy && ws, "td_edc_fused: bad arguments");
   FusedShape shp;
-  DGFDN_CHECK(fused_shape(g, tn, &shp), "td_edc_fused: unsupported shape (g=%d in [1,4], tn=%lld multiple of 4 and <= %d)", g,
-              (long long)tn, kC * kMaxRuns * kRunSegs * 4);
+  DGFDN_CHECK(fused_shape(g, tn, &shp), "td_edc_fused: unsupported shape (g=%d in [1,4], tn=%lld multiple of 4 and <= 55296)", g,
+              (long long)tn);
   DGFDN_CHECK(ldt >= tn && (hd == nullptr || ldhd >= tn), "td_edc_fused: row stride smaller than tn");
   DGFDN_CHECK(aligned16(hy) && aligned16(hd) && aligned16(target_db) && aligned16(mask) && ldt % 4 == 0 &&
                   (hd == nullptr || ldhd % 4 == 0),
@@ -682,29 +802,13 @@ extern "C" int dgfdn_td_edc_fused(int g, int64_t rows, int64_t tn, const float* 
   p.part_gs = reinterpret_cast<float*>(base + lay.off_gs);
   p.part_loss = reinterpret_cast<double*>(base + lay.off_loss);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const bool masked = mask != nullptr;
-  const size_t smem = fused_dyn_smem(g, shp.nrun, masked);
-  int ncl = 0, rc = 1;
-  auto go = [&](auto gc, auto rc_) {
-    constexpr int G = decltype(gc)::value;
-    constexpr int NRUN = decltype(rc_)::value;
-    rc = masked ? launch_fused<G, NRUN, true>(p, rows, smem, st, &ncl) : launch_fused<G, NRUN, false>(p, rows, smem, st, &ncl);
-  };
-  auto by_run = [&](auto gc) {
-    if (shp.nrun == 1) go(gc, std::integral_constant<int, 1>{});
-    else go(gc, std::integral_constant<int, 2>{});
-  };
-  switch (g) {
-    case 1: by_run(std::integral_constant<int, 1>{}); break;
-    case 2: by_run(std::integral_constant<int, 2>{}); break;
-    case 3: by_run(std::integral_constant<int, 3>{}); break;
-    default: by_run(std::integral_constant<int, 4>{}); break;
-  }
-  if (rc) return rc;
+  int ncl = 0;
+  if (int rc = dispatch(g, mask != nullptr, shp.variant, 0, p, rows, st, &ncl)) return rc;
+  const int c = kVariants[shp.variant].c;
   const int64_t n_ghy = (int64_t)g * tn;
   const int64_t total = n_ghy + rows * g + 1;
   td_fused_finalize_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(n_ghy, ncl, p.part_ghy, ghy, rows, g, p.part_gs, gs,
-                                                                             ncl * kC, p.part_loss, loss_sum, accumulate);
+                                                                             ncl * c, p.part_loss, loss_sum, accumulate, c);
   DGFDN_LAUNCH_CHECK();
   return 0;
 }

@@ -69,6 +69,13 @@ class ShardedEDCStep:
         self._bufs = None
         self.mask = None
         self.events = None  # set to a dict of lists to collect per-kernel CUDA events (bench.py)
+        self.use_side_stream = os.environ.get("DGFDN_SIDE_STREAM", "1") != "0"
+        self._side = None
+
+    def _side_stream(self) -> torch.cuda.Stream:
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.dev)
+        return self._side
 
     # ---- data ------------------------------------------------------------------------------------------
     def attach(self, z: torch.Tensor, positions: torch.Tensor, early_window: Optional[torch.Tensor],
@@ -136,19 +143,28 @@ class ShardedEDCStep:
         sec = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if ev is not None else None
         if sec:
             sec[0].record()
+        # The colorless branch (lossless sub-FDN solve + spectral / sparsity losses, and -- because autograd runs a
+        # node's backward on the stream of its forward -- its adjoint solve) is receiver independent and shares
+        # nothing with the EDC branch but the parameters: it runs on a side stream, next to the front kernels and to
+        # the receiver kernel K3d, whose 8-CTA clusters leave 28 of the 148 SMs idle (15 clusters are co-resident).
+        main = torch.cuda.current_stream()
+        side = self._side_stream() if self.use_side_stream else main
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            keep = net.return_per_delay_outputs
+            net.return_per_delay_outputs = False
+            h_sub, _ = net.sub_fdn_output(self.z)
+            net.return_per_delay_outputs = keep
+            per_group = ops.colorless_loss_per_group(h_sub, self.asym)
+            spectral = self.w_spec * per_group.sum()
+            sparsity = self.w_spars * self._sparsity(net.feedback_loop.ortho_param(net.feedback_loop.M[g - 1]))
+            aux = (spectral + sparsity.to(spectral.dtype)) / self.world_size
         s = net.output_scalars.gains({'norm_listener_position': self.positions})
         # irfft(X, n=K) reads bins 0..K/2 only (reference losses.py:207-213, quirk Q3), so the coupled system is
         # solved on those kx bins; the other bins of H reach no loss term (the colorless loss has its own solve)
         z_edc = self.z if net.feedback_loop.delay_line_gain_response is not None else self.z[:self.kx]
         _, y = net.feedback_loop.solve(z_edc, net.input_gains.reshape(-1), net.output_gains.reshape(-1))
         hy = ops.irfft_window(y.transpose(0, 1), self.n_fft, self.t0, self.tn)  # (G, tn)
-        keep = net.return_per_delay_outputs
-        net.return_per_delay_outputs = False
-        h_sub, _ = net.sub_fdn_output(self.z)
-        net.return_per_delay_outputs = keep
-        per_group = ops.colorless_loss_per_group(h_sub, self.asym)
-        spectral = self.w_spec * per_group.sum()
-        sparsity = self.w_spars * self._sparsity(net.feedback_loop.ortho_param(net.feedback_loop.M[g - 1]))
         self.kernel_launches += 2 + 3 + 1  # two solves, chirp-z (pre, mul, post; + 2 cuFFT), colorless forward
 
         s_d = s.detach().contiguous()
@@ -176,8 +192,9 @@ class ShardedEDCStep:
         if sec:
             sec[2].record()
         edc = (self._bufs["loss_sum"][0] if self.use_fused else self._bufs["row_sum"].sum()) * coef
-        aux = (spectral + sparsity.to(spectral.dtype)) / self.world_size
+        main.wait_stream(side)
         torch.autograd.backward([hy, s, aux], [ghy, gs, torch.ones_like(aux)])
+        main.wait_stream(side)  # the engine joins the streams of the leaves; this makes the join explicit for capture
         self.kernel_launches += 3 + 2 * 2 + 1  # chirp-z adjoint, two adjoint solves (+ reduce each), colorless bwd
         if self.world_size > 1:
             self.allreduce_grads()

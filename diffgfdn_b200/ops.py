@@ -730,3 +730,11 @@ def render_mix(s: torch.Tensor, traj: torch.Tensor, q: torch.Tensor, hop: int) -
 
 def is_finite_scalar(x: float) -> bool:
     return not (math.isnan(x) or math.isinf(x))
+
+
+def td_fused_info(num_groups: int, tn: int) -> dict:
+    """Tile variant, cluster size, threads per CTA and co-resident clusters of dgfdn_td_edc_fused for this shape."""
+    import ctypes
+    v = [ctypes.c_int(0) for _ in range(4)]
+    _lib.call("dgfdn_td_edc_fused_info", int(num_groups), int(tn), *[ctypes.byref(x) for x in v])
+    return dict(variant=v[0].value, cluster_size=v[1].value, threads=v[2].value, clusters=v[3].value)

@@ -193,13 +193,17 @@ DGFDN_API int dgfdn_td_contract(int g, int64_t rows, int64_t tn, const float* s,
  *   gs[r,g]      = coef * d loss_sum / d s[r,g]                                     float32 [rows, G] (may be NULL)
  *   ghy[g,t]    (+)= coef * d loss_sum / d hy[g,t]                                  float32 [G, tn]
  * accumulate != 0 adds to loss_sum / ghy instead of overwriting them (receiver tiles). Requirements, reported by
- * dgfdn_td_edc_fused_supported(g, tn): 1 <= g <= 4, tn % 4 == 0, tn <= 49152; all rows 16-byte aligned.
+ * dgfdn_td_edc_fused_supported(g, tn): 1 <= g <= 4, tn % 4 == 0, tn <= 55296; all rows 16-byte aligned.
  * ws: scratch of dgfdn_td_edc_fused_ws_bytes(g, rows, tn) bytes. */
 DGFDN_API int dgfdn_td_edc_fused_supported(int g, int64_t tn);
 DGFDN_API int64_t dgfdn_td_edc_fused_ws_bytes(int g, int64_t rows, int64_t tn);
 DGFDN_API int dgfdn_td_edc_fused(int g, int64_t rows, int64_t tn, const float* s, const float* hy, const float* hd,
                        int64_t ldhd, const float* target_db, int64_t ldt, const float* mask, double coef,
                        double* loss_sum, float* gs, float* ghy, int accumulate, void* ws, void* stream);
+/* Diagnostic: which tile variant dgfdn_td_edc_fused uses for (g, tn) on the current device [-1: unsupported], its
+ * cluster size, threads per CTA, and how many clusters are co-resident (= the launch grid / cluster size). The
+ * environment variable DGFDN_TD_VARIANT=<id> forces a variant when the row fits its slices (tuning only). */
+DGFDN_API int dgfdn_td_edc_fused_info(int g, int64_t tn, int* variant, int* cluster_size, int* threads, int* clusters);
 
 /* ------------------------------------------------------------------------------------------------
  * K7: position -> gain network of a receiver shard.  Replaces SinusoidalEncoding + MLP / MLP_SkipConnections

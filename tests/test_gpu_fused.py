@@ -159,7 +159,9 @@ def _td_reference(rows, g, tn, use_hd, use_mask, gen):
     (1, 4, 8, True, False),         # 2 segments: six of the eight CTAs own nothing
     (2, 1, 4, True, True),          # a single segment
     (37, 3, 47360, True, False),    # BASELINE window (T60 1.5 s at 32 kHz): two runs per CTA, more iterations than clusters
-    (4, 4, 49152, True, True),      # largest supported window
+    (4, 4, 49152, True, True),      # largest window of the 8-CTA variants
+    (5, 3, 55296, True, False),     # largest supported window (clusters of 6 CTAs, one row per iteration)
+    (3, 2, 50000, True, True),      # 6-CTA variant, ragged last slice, mask
 ])
 def test_cluster_fused_receiver_kernel_vs_torch_fp64(rows, g, tn, use_hd, use_mask):
     """dgfdn_td_edc_fused (K3d: cluster of 8 CTAs per row, DSMEM scan carries, TMA-staged inputs, register-resident
@@ -192,7 +194,8 @@ def test_cluster_fused_receiver_kernel_vs_torch_fp64(rows, g, tn, use_hd, use_ma
 def test_cluster_fused_kernel_rejects_unsupported_shapes():
     from diffgfdn_b200 import _lib, ops
     assert not ops.td_fused_supported(3, 777)      # not a multiple of 4
-    assert not ops.td_fused_supported(3, 49156)    # longer than 8 slices x 2 runs
+    assert ops.td_fused_supported(3, 49156)        # longer than 8 slices x 2 runs: clusters of 6 CTAs, 3 x 2 x 384 segments
+    assert not ops.td_fused_supported(3, 55300)    # longer than any variant's slices
     assert not ops.td_fused_supported(5, 4096)     # too many groups for the register-resident accumulators
     t = torch.zeros(4, 780, device='cuda')
     with pytest.raises(RuntimeError, match="unsupported shape"):

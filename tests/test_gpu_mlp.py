@@ -43,9 +43,10 @@ def test_gains_from_mlp_matches_torch_and_oracle(rows, nfeat, hidden, neurons, s
     else:
         mod = Gains_from_MLP(groups, 4, nfeat, hidden, neurons, device=dev).to(dev)
     _randomise(mod, 5)
-    # seed 11: with seed 1 a float32 position puts one ReLU input of the 97-row case within rounding of zero, and the
-    # float32 formulation itself (stock torch included) then differs from the float64 oracle by a flipped unit
-    pos = torch.rand(rows, 3, dtype=pdtype, generator=torch.Generator().manual_seed(11)).to(dev)
+    # seed 13: seeds 1 and 11 put one ReLU input of a float32-position case (97 / 193 rows) within rounding of zero,
+    # and the float32 formulation itself (stock torch on the CPU included: 6e-3) then differs from the float64
+    # oracle by a flipped unit; seed 13 keeps every case 1e3 x clear of that (checked with float32 torch on the CPU)
+    pos = torch.rand(rows, 3, dtype=pdtype, generator=torch.Generator().manual_seed(13)).to(dev)
     x = {"norm_listener_position": pos}
     wgt = torch.randn(rows, groups * (9 if skip else 1), generator=torch.Generator().manual_seed(2)).to(dev)
 
@@ -85,6 +86,8 @@ def test_gains_from_mlp_matches_torch_and_oracle(rows, nfeat, hidden, neurons, s
         den = float(go.abs().max()) + 1e-30
         ek = float((g_k[n].cpu().to(torch.float64) - go).abs().max()) / den
         et = float((g_t[n].cpu().to(torch.float64) - go).abs().max()) / den
+        ekt = float((g_k[n] - g_t[n]).abs().max()) / den
+        assert ekt < 2e-5, f"grad {n}: kernel vs float32 torch {ekt}"
         assert ek < 1e-3, f"grad {n}: kernel vs oracle {ek}"  # north_star: gradients within 1e-3 relative
         assert ek < 8 * et + 2e-5, f"grad {n}: kernel {ek} vs float32 torch {et}"
 
