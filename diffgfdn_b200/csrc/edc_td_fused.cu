@@ -28,7 +28,7 @@
 namespace dgfdn {
 namespace {
 
-constexpr int kMaxC = 8;               // largest cluster (portable limit); workspace rows are sized for it
+constexpr int kMaxC = 16;              // largest cluster (non-portable limit); workspace rows are sized for it
 constexpr float kEpsF = 1.1920928955078125e-07f;   // torch.finfo(float32).eps (reference utils.py:35)
 constexpr float kDbPerLog2 = 3.0102999566398120f;  // 10 / log2(10)
 constexpr double kDbFactor = 4.342944819032518;    // 10 / ln(10)
@@ -36,9 +36,10 @@ constexpr double kDbFactor = 4.342944819032518;    // 10 / ln(10)
 // Compile-time shape of one variant of the kernel. A CTA of FT threads owns one of C time slices of a row; thread t
 // owns, in each of NRUN runs, RUN consecutive 128-bit segments (RUN odd: the 16 RUN-byte thread stride is then
 // conflict-free for 128-bit shared-memory accesses); ROWS rows are processed per iteration.
-template <int FT_, int RUN_, int NRUN_, int ROWS_, int C_>
+template <int FT_, int RUN_, int NRUN_, int ROWS_, int C_, int MINB_ = 1>
 struct Tile {
-  static constexpr int FT = FT_, FW = FT_ / 32, RUN = RUN_, NRUN = NRUN_, ROWS = ROWS_, C = C_;
+  static constexpr int FT = FT_, FW = FT_ / 32, RUN = RUN_, NRUN = NRUN_, ROWS = ROWS_, C = C_, MINB = MINB_;
+  static constexpr int CPAD = C_ <= 8 ? 8 : 16;  // exchange slots per row (entries >= C stay 0)
   static constexpr int RUNSEGS = FT * RUN;     // segments per run
   static constexpr int SLOT = NRUN * RUNSEGS;  // padded segments per slot
   static constexpr int POS = 32 / ROWS;        // lanes per row in the CTA-level scan
@@ -141,7 +142,7 @@ template <class T>
 struct FusedSmem {                      // static part; the slots follow in dynamic shared memory
   float wtot[2][T::ROWS][T::POS];       // [scan][row][run * FW + warp] warp totals (unused positions stay 0)
   // [scan][parity][row][source CTA]: slice totals stored by the peers (DSMEM); entries >= C stay 0
-  __align__(16) float xchg[2][2][T::ROWS][kMaxC];
+  __align__(16) float xchg[2][2][T::ROWS][T::CPAD];
   double red[T::FW];
   unsigned long long bar_hd, bar_td;    // mbarriers of the hd / target-dB slots (TMA complete_tx)
   unsigned long long bar_x[2];          // mbarriers of the two carry exchanges (st.async complete_tx)
@@ -150,11 +151,17 @@ struct FusedSmem {                      // static part; the slots follow in dyna
 // CTA level of a scan, done redundantly by every warp (one barrier per scan instead of two): lane = row * POS + pos
 // scans the POS (run, warp) totals of its row. The sums have at most POS (here) + C (cluster) terms on top of the
 // warp level, so float32 is used throughout; only the loss is accumulated in float64.
-// sum of the kMaxC exchange slots of one row: two 128-bit loads and a fixed-order tree
-__device__ __forceinline__ float sum8(const float* x) {
-  static_assert(kMaxC == 8, "two float4 per row");
+// sum of the CPAD exchange slots of one row: 128-bit loads and a fixed-order tree
+template <int CPAD>
+__device__ __forceinline__ float sum_slots(const float* x) {
+  static_assert(CPAD == 8 || CPAD == 16, "two or four float4 per row");
   const float4 a = *reinterpret_cast<const float4*>(x), b = *reinterpret_cast<const float4*>(x + 4);
-  return ((a.x + a.y) + (a.z + a.w)) + ((b.x + b.y) + (b.z + b.w));
+  float r = ((a.x + a.y) + (a.z + a.w)) + ((b.x + b.y) + (b.z + b.w));
+  if (CPAD == 16) {
+    const float4 c = *reinterpret_cast<const float4*>(x + 8), d = *reinterpret_cast<const float4*>(x + 12);
+    r += ((c.x + c.y) + (c.z + c.w)) + ((d.x + d.y) + (d.z + d.w));
+  }
+  return r;
 }
 
 template <int POS, bool REVERSE>
@@ -170,7 +177,7 @@ __device__ __forceinline__ float cta_scan(float v, int lane) {
 
 // G x (tn/4) accumulators of the cluster's slice stay in registers: acc[g][run][k] is a float4 of 4 samples.
 template <int G, bool MASKED, class T>
-__global__ void __launch_bounds__(T::FT, 1) td_fused_kernel(FusedParams p) {
+__global__ void __launch_bounds__(T::FT, T::MINB) td_fused_kernel(FusedParams p) {
   constexpr int kFT = T::FT, kFW = T::FW, kRun = T::RUN, NRUN = T::NRUN, kRunSegs = T::RUNSEGS, kRows = T::ROWS;
   constexpr int kC = T::C, kPos = T::POS, kSlot = T::SLOT;
   extern __shared__ __align__(128) unsigned char dyn_smem[];
@@ -195,7 +202,7 @@ __global__ void __launch_bounds__(T::FT, 1) td_fused_kernel(FusedParams p) {
   // ---- one-time set-up: zero the slots (tails stay zero for ever), stage the hy / mask slices, init barriers
   for (int i = tid; i < 2 * kRows * kSlot; i += kFT) hd_s[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int i = tid; i < 2 * kRows * kPos; i += kFT) (&sm.wtot[0][0][0])[i] = 0.f;
-  for (int i = tid; i < 2 * 2 * kRows * kMaxC; i += kFT) (&sm.xchg[0][0][0][0])[i] = 0.f;
+  for (int i = tid; i < 2 * 2 * kRows * T::CPAD; i += kFT) (&sm.xchg[0][0][0][0])[i] = 0.f;
   for (int i = tid; i < kSlot; i += kFT) {
 #pragma unroll
     for (int g = 0; g < G; ++g)
@@ -380,7 +387,7 @@ __global__ void __launch_bounds__(T::FT, 1) td_fused_kernel(FusedParams p) {
     float lacc = 0.f;
 #pragma unroll
     for (int q = 0; q < kRows; ++q) {
-      const float carry = sum8(sm.xchg[0][parity][q]);  // slices later than this one (senders masked their totals)
+      const float carry = sum_slots<T::CPAD>(sm.xchg[0][parity][q]);  // slices later than this one (senders masked their totals)
 #pragma unroll
       for (int u = 0; u < NRUN; ++u) {
         const float offe = (carry + offl[q][u]) + inc[q][u] + kEpsF;
@@ -514,7 +521,7 @@ __global__ void __launch_bounds__(T::FT, 1) td_fused_kernel(FusedParams p) {
     // ================= phase C: dL/dh = u + c h ; ghy accumulators ; dL/ds partials ============================
 #pragma unroll
     for (int q = 0; q < kRows; ++q) {
-      const float c = sum8(sm.xchg[1][parity][q]);  // slices earlier than this one (senders masked their totals)
+      const float c = sum_slots<T::CPAD>(sm.xchg[1][parity][q]);  // slices earlier than this one (senders masked their totals)
 #pragma unroll
       for (int u = 0; u < NRUN; ++u)
 #pragma unroll
@@ -577,7 +584,7 @@ __global__ void td_fused_finalize_kernel(int64_t n_ghy, int ncl, const float* __
     const int64_t r = j / g;
     const int gg = (int)(j % g);
     float v = 0.f;
-    for (int k = 0; k < kC; ++k) v += part_gs[(r * kC + k) * g + gg];
+    for (int k = 0; k < kC; ++k) v += part_gs[(r * kC + k) * g + gg];  // kC: cluster size of the launch
     gs[j] = v;
     return;
   }
@@ -599,6 +606,8 @@ constexpr int kMaxClusters = 40;  // workspace is sized for this many resident c
 using TileA1 = Tile<256, 3, 1, 2, 8>;  // 0: short rows (one run per thread)
 using TileA2 = Tile<256, 3, 2, 2, 8>;  // 1: two runs per thread, rows up to 49 152 samples
 using TileD = Tile<384, 3, 2, 1, 6>;   // 2: clusters of 6 (22 resident clusters = 132 SMs), rows up to 55 296 samples
+// Also tried (same file, same run): clusters of 16 with two 128-register CTAs per SM (Tile<256,3,1,2,16,2>: 14 resident
+// clusters, 1.71 ms) and clusters of 8 with one row per iteration at 128 registers (2.70 ms).
 constexpr int kNumVariants = 3;
 
 struct VariantInfo {
@@ -684,6 +693,7 @@ int resident_clusters(int* out) {
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     DGFDN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (T::C > 8) DGFDN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     cfg.gridDim = dim3(T::C * kMaxClusters);
     int n = 0;
     DGFDN_CUDA(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
