@@ -448,11 +448,29 @@ __global__ void solve_bwd_reduce_kernel(const double* ws, int64_t ngroups, int n
 
 constexpr int lanes_for(int np) { return np <= 4 ? 4 : (np <= 8 ? 8 : (np <= 16 ? 16 : 32)); }
 
-int grid_blocks(int64_t systems, int w) {
+constexpr int kMaxBlocksPerSm = 4;  // the backward workspace is sized for this many resident blocks per SM
+
+// One resident wave: `per_sm` is the occupancy of the instantiation being launched (a grid of 4 blocks per SM with
+// only 3 resident leaves a 148-block second wave that runs at a third of the SM's throughput).
+int grid_blocks(int64_t systems, int w, int per_sm) {
   const int per_block = kWarps * (32 / w);
   int64_t want = (systems + per_block - 1) / per_block;
-  int64_t cap = (int64_t)sm_count() * 4;
+  int64_t cap = (int64_t)sm_count() * (per_sm < 1 ? 1 : (per_sm > kMaxBlocksPerSm ? kMaxBlocksPerSm : per_sm));
   return (int)(want < cap ? (want < 1 ? 1 : want) : cap);
+}
+
+// Resident blocks per SM of a kernel at its dynamic shared-memory size (queried once per instantiation and size).
+template <class K>
+int blocks_per_sm(K kern, size_t smem) {
+  static size_t cached_smem = (size_t)-1;
+  static int cached = 0;
+  if (cached_smem != smem) {
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, kWarps * 32, smem) != cudaSuccess) n = 1;
+    cached = n < 1 ? 1 : n;
+    cached_smem = smem;
+  }
+  return cached;
 }
 
 int check_common(int n, int nsys, int g, int64_t k) {
@@ -479,16 +497,19 @@ int launch_fwd(const SolveParams& p, cudaStream_t st) {
   constexpr int W = lanes_for(NP);
   const size_t smem = smem_bytes<NP>(p, false);
   DGFDN_CUDA(cudaFuncSetAttribute(solve_fwd_kernel<NP, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  solve_fwd_kernel<NP, W><<<grid_blocks(p.k * p.nsys, W), kWarps * 32, smem, st>>>(p);
+  const int blocks = grid_blocks(p.k * p.nsys, W, blocks_per_sm(solve_fwd_kernel<NP, W>, smem));
+  solve_fwd_kernel<NP, W><<<blocks, kWarps * 32, smem, st>>>(p);
   DGFDN_LAUNCH_CHECK();
   return 0;
 }
 
 template <int NP>
-int launch_bwd(const SolveParams& p, int blocks, cudaStream_t st) {
+int launch_bwd(const SolveParams& p, int* blocks_out, cudaStream_t st) {
   constexpr int W = lanes_for(NP);
   const size_t smem = smem_bytes<NP>(p, true);
   DGFDN_CUDA(cudaFuncSetAttribute(solve_bwd_kernel<NP, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int blocks = grid_blocks(p.k * p.nsys, W, blocks_per_sm(solve_bwd_kernel<NP, W>, smem));
+  *blocks_out = blocks;
   solve_bwd_kernel<NP, W><<<blocks, kWarps * 32, smem, st>>>(p);
   DGFDN_LAUNCH_CHECK();
   return 0;
@@ -515,7 +536,7 @@ int dispatch_fwd(const SolveParams& p, cudaStream_t st) {
 #undef CALL_FWD
 }
 
-int dispatch_bwd(const SolveParams& p, int blocks, cudaStream_t st) {
+int dispatch_bwd(const SolveParams& p, int* blocks, cudaStream_t st) {
 #define CALL_BWD(NP) launch_bwd<NP>(p, blocks, st)
   DGFDN_DISPATCH_NP(p.n, CALL_BWD);
 #undef CALL_BWD
@@ -540,11 +561,6 @@ int fill_params(SolveParams& p, int n, int nsys, int g, int64_t k, const void* z
   p.b = b;
   p.c = c;
   return 0;
-}
-
-int64_t bwd_groups(int n, int nsys, int64_t k) {
-  const int w = lanes_runtime(n);
-  return (int64_t)grid_blocks(k * nsys, w) * kWarps * (32 / w);
 }
 
 }  // namespace
@@ -580,12 +596,13 @@ static int solve_bwd_impl(int n, int nsys, int g, int64_t k, const void* z, cons
   p.gx = static_cast<const float2*>(gx);
   p.ws = static_cast<double*>(ws);
   const int w = lanes_runtime(n);
-  const int blocks = grid_blocks(k * nsys, w);
+  int blocks = 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (dispatch_bwd(p, blocks, st)) return 1;
+  if (dispatch_bwd(p, &blocks, st)) return 1;
   const int per = (n * n + 3 * n) * nsys;
-  solve_bwd_reduce_kernel<<<(per * 32 + 255) / 256, 256, 0, st>>>(p.ws, bwd_groups(n, nsys, k), n, nsys, transpose_a, ga,
-                                                                 gb, gc, ginvgamma);
+  const int64_t groups = (int64_t)blocks * kWarps * (32 / w);  // lane groups of the grid that was launched
+  solve_bwd_reduce_kernel<<<(per * 32 + 255) / 256, 256, 0, st>>>(p.ws, groups, n, nsys, transpose_a, ga, gb, gc,
+                                                                 ginvgamma);
   DGFDN_LAUNCH_CHECK();
   return 0;
 }
@@ -599,7 +616,7 @@ extern "C" int dgfdn_solve_fwd(int n, int g, int64_t k, const void* z, const int
 // one row of (n^2 + 3n) doubles per lane group of the largest grid the backward kernel launches
 static int64_t bwd_ws_bytes(int n) {
   if (n < 1 || n > DGFDN_MAX_LINES) return 0;
-  const int64_t groups = (int64_t)sm_count() * 4 * kWarps * (32 / lanes_runtime(n));
+  const int64_t groups = (int64_t)sm_count() * kMaxBlocksPerSm * kWarps * (32 / lanes_runtime(n));
   return groups * ((int64_t)n * n + 3 * (int64_t)n) * (int64_t)sizeof(double);
 }
 
