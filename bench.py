@@ -401,9 +401,16 @@ def main():
         }
         if not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(args.nfft, args.cpu_sample_receivers)
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Leave without tearing the NCCL communicator down: destroy_process_group() after a CUDA-graph capture that
+        # holds an all-reduce node hung for the full gpurun limit at N=2 (the JSON line was already out). Every rank
+        # waits for the others first, so no peer is still inside a collective when a process disappears.
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":
