@@ -71,14 +71,15 @@ def make_trainer(cls, net, **kw):
 
 
 def case_omni(name, n_lines, nfft, bsz, t60, seed, hidden, neurons, feats, radius=1.0, subband=False, steps=2,
-              early_scale=1.0):
+              early_scale=1.0, svf=False, pole_factor=1.0):
     cfg = DiffGFDNConfig(seed=235265, num_delay_lines=n_lines)
     delays = cfg.delay_length_samps
     torch.manual_seed(seed)
     np.random.seed(seed)
     net = DiffGFDNVarReceiverPos(FS, 3, delays, 'cpu', FeedbackLoopConfig(use_zero_coupling=False),
-                                 OutputFilterConfig(use_svfs=False, num_hidden_layers=hidden,
-                                                    num_neurons_per_layer=neurons, num_fourier_features=feats),
+                                 OutputFilterConfig(use_svfs=svf, num_hidden_layers=hidden,
+                                                    num_neurons_per_layer=neurons, num_fourier_features=feats,
+                                                    compress_pole_factor=pole_factor),
                                  use_absorption_filters=False, common_decay_times=np.array([t60]),
                                  use_colorless_loss=True)
     # early_scale < 1 brings the direct path d down towards the level of the late (GFDN) part: with the short T60s
@@ -116,7 +117,14 @@ def case_omni(name, n_lines, nfft, bsz, t60, seed, hidden, neurons, feats, radiu
     out["out/H_sub_per_del_s16"] = Hsd.detach().numpy()[:, ::16, :]
     out["out/A"] = net.feedback_loop.get_coupled_feedback_matrix().detach().numpy()
     out["out/phi"] = net.feedback_loop.phi.detach().numpy()
-    out["out/s"] = net.output_scalars.gains.detach().numpy()
+    if svf:  # SVF output filters (gain_filters.py:334-402): constrained (resonance, gain dB) and the biquads
+        out["out/svf_params"] = net.output_filters.svf_params.detach().numpy()
+        out["out/biquads"] = np.stack([np.stack([np.concatenate([c.num_coeffs.detach().numpy(),
+                                                                 c.den_coeffs.detach().numpy()], axis=-1)
+                                                 for c in row]) for row in net.output_filters.biquad_cascade])
+        out["meta/pole_factor"] = pole_factor
+    else:
+        out["out/s"] = net.output_scalars.gains.detach().numpy()
     out["out/gamma"] = net.feedback_loop.delay_line_gains.detach().numpy()
     for kk, v in losses.items():
         out[f"loss/{kk}"] = float(v.detach())
@@ -212,5 +220,6 @@ if __name__ == "__main__":
     case_omni("omni_n12_subband_r", 12, 8192, 3, [0.04, 0.09, 0.11], 12, 2, 16, 4, radius=1.00002, subband=True,
               early_scale=1e-3)
     case_omni("omni_n24", 24, 4096, 3, [0.03, 0.05, 0.06], 13, 1, 16, 4, steps=1)
+    case_omni("omni_n12_svf", 12, 8192, 3, [0.05, 0.08, 0.12], 14, 1, 32, 6, svf=True, pole_factor=0.998)
     case_directional("directional_n27", 8192, 2, [0.05, 0.08, 0.1], 21, 1, 16, 4, skip=False)
     case_directional("directional_n27_skip", 4096, 2, [0.03, 0.04, 0.05], 22, 2, 16, 4, skip=True)

@@ -259,6 +259,80 @@ def gains_from_mlp(norm_pos, weights, num_fourier_features, num_groups,
     return scaled_sigmoid(out, -1.0, 1.0)
 
 
+# --------------------------------------------------------------------------------------
+# SVF output filters (a-7b)
+# --------------------------------------------------------------------------------------
+def svf_cutoffs(fs: float) -> torch.Tensor:
+    """gain_filters.py:369-374 with filters/geq.py:9-56 (eq_freqs / octave_bands, defaults 31.25 Hz .. 16 kHz):
+    pi * [f_1/sqrt(2), f_1 .. f_9, f_9 sqrt(2)] / fs with f_i = 62.5 * 2^(i-1) -- used as the SVF 'g' directly
+    (no tan pre-warping)."""
+    centre = []
+    c = 31.25
+    while c < 16000:
+        c = c * 2.0
+        centre.append(c)
+    freqs = [centre[0] / math.sqrt(2.0)] + centre + [centre[-1] * math.sqrt(2.0)]
+    return math.pi * torch.tensor(freqs, dtype=F64) / fs
+
+
+def svf_params_from_mlp(pos, weights, num_fourier_features, num_groups, num_biquads=11,
+                        prefix='output_filters.mlp.model.') -> torch.Tensor:
+    """gain_filters.py:376-382,403-421: MLP(enc(listener_position)) -> (B, G, S, 2); [...,0] resonance through
+    ScaledSigmoid(1e-6, 1), [...,1] gain in dB through ScaledSigmoid(-6, 6)."""
+    enc = sinusoidal_encoding(pos, num_fourier_features)
+    out = mlp_forward(enc, weights, prefix).reshape(pos.shape[0], num_groups, num_biquads, 2)
+    return torch.stack([scaled_sigmoid(out[..., 0], 1e-6, 1.0), scaled_sigmoid(out[..., 1], -6.0, 6.0)], dim=-1)
+
+
+def svf_to_biquads(svf_params: torch.Tensor, cutoffs: torch.Tensor, pole_factor: float = 1.0) -> torch.Tensor:
+    """gain_filters.py:20-102 (SVF mixing coefficients: section 0 low shelf, last high shelf, others peaking) and
+    :116-151 (BiquadCascade.from_svf_coeffs). svf_params (..., S, 2) -> (..., S, 6) = [b0 b1 b2 a0 a1 a2]."""
+    res, gdb = svf_params[..., 0].to(F64), svf_params[..., 1].to(F64)
+    gain = torch.pow(torch.tensor(10.0, dtype=F64), gdb * 0.05)
+    f = cutoffs.to(F64)
+    ns = f.numel()
+    one = torch.ones_like(gain)
+    kind = torch.zeros(ns, dtype=torch.long)
+    kind[0], kind[-1] = 1, 2  # 0 peaking, 1 low shelf, 2 high shelf
+    m_lp = torch.where(kind == 1, gain, one)
+    m_hp = torch.where(kind == 2, gain, one)
+    m_bp = torch.where(kind == 0, 2.0 * res * gain, 2.0 * res * torch.sqrt(gain))
+    r = pole_factor
+    b0 = f * f * m_lp + f * m_bp + m_hp
+    b1 = (2.0 * f * f * m_lp - 2.0 * m_hp) * r
+    b2 = (f * f * m_lp - f * m_bp + m_hp) * r * r
+    a0 = f * f + 2.0 * res * f + 1.0
+    a1 = (2.0 * f * f - 2.0) * r * one
+    a2 = (f * f - 2.0 * res * f + 1.0) * r * r
+    return torch.stack([b0, b1, b2, a0, a1, a2], dim=-1)
+
+
+def sos_response(z: torch.Tensor, coef: torch.Tensor) -> torch.Tensor:
+    """gain_filters.py:221-241 (SOSFilter.forward): prod_s (b0 + b1 z^-1 + b2 z^-2) / (a0 + a1 z^-1 + a2 z^-2).
+    coef (..., S, 6) -> (..., K) complex128."""
+    zi = (1.0 / z.to(C128))
+    zi2 = zi * zi
+    c = coef.to(C128).unsqueeze(-1)  # (..., S, 6, 1)
+    num = c[..., 0, :] + c[..., 1, :] * zi + c[..., 2, :] * zi2
+    den = c[..., 3, :] + c[..., 4, :] * zi + c[..., 5, :] * zi2
+    return torch.prod(num / den, dim=-2)
+
+
+def omni_response_svf(z, delays, gamma, a, b, c, coef, d=None) -> torch.Tensor:
+    """model.py:583-619 with use_svf_in_output: C[r,n,k] = F[r,g(n),k] c_n (gain_filters.py:388-401, every delay
+    line of a group shares the group's filter); coef is (B, G, S, 6)."""
+    p = feedback_loop_inverse(z, delays, gamma, a)
+    n = delays.numel()
+    g = coef.shape[1]
+    filt = sos_response(z, coef)  # (B, G, K)
+    cfull = filt.repeat_interleave(n // g, dim=1) * c.to(C128).reshape(1, n, 1)  # (B, N, K)
+    htemp = torch.einsum('bnk,knm->bmk', cfull, p)
+    h = torch.einsum('bmk,m->bk', htemp, b.to(C128))
+    if d is not None:
+        h = h + d.to(C128)
+    return h
+
+
 def sh_gains_from_mlp(norm_pos, weights, num_fourier_features, num_groups, num_sh,
                       prefix='sh_output_scalars.mlp.', skip=False, normalise=True) -> torch.Tensor:
     """spatial_sampling/model.py:169-190 with normalise_weights (:78-80): w / (||w||_2 + 1e-6) over l."""

@@ -8,6 +8,7 @@ from oracle import gfdn_oracle as O
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 OMNI_CASES = ["omni_n12", "omni_n12_subband_r", "omni_n24"]
+SVF_CASES = ["omni_n12_svf"]
 DIR_CASES = ["directional_n27", "directional_n27_skip"]
 
 
@@ -28,8 +29,9 @@ def params_of(g, prefix="param/", requires_grad=False):
     return p
 
 
-def oracle_omni(g, p):
-    """Forward + trainer loss composition of an omni golden case through the oracle. Returns dict of tensors."""
+def oracle_omni(g, p, coef_override=None):
+    """Forward + trainer loss composition of an omni golden case through the oracle. Returns dict of tensors.
+    coef_override: biquad coefficients (B, G, S, 6) to use instead of the ones derived from the MLP (SVF cases)."""
     nfft = int(g["meta/nfft"])
     fs = float(g["meta/fs"])
     z = O.z_grid(nfft, float(g["meta/radius"]))
@@ -39,9 +41,15 @@ def oracle_omni(g, p):
     A = O.coupled_feedback_matrix(p["feedback_loop.M"], p["feedback_loop.alpha"])
     b = p["input_gains"].reshape(-1)
     c = p["output_gains"].reshape(-1)
-    s = O.gains_from_mlp(torch.tensor(g["data/norm_listener_position"]), p, int(g["meta/feats"]), G)
     d = torch.tensor(g["data/target_early_response"])
-    H = O.omni_response(z, delays, gamma, A, b, c, s, d)
+    svf = coef = s = None
+    if "out/svf_params" in g:  # SVF output filters instead of scalar receiver gains
+        svf = O.svf_params_from_mlp(torch.tensor(g["data/listener_position"]), p, int(g["meta/feats"]), G)
+        coef = O.svf_to_biquads(svf, O.svf_cutoffs(fs), float(g["meta/pole_factor"]))
+        H = O.omni_response_svf(z, delays, gamma, A, b, c, coef if coef_override is None else coef_override, d)
+    else:
+        s = O.gains_from_mlp(torch.tensor(g["data/norm_listener_position"]), p, int(g["meta/feats"]), G)
+        H = O.omni_response(z, delays, gamma, A, b, c, s, d)
     Hs, Hsd = O.sub_fdn_output(z, delays, p["feedback_loop.M"], b, c)
     Huse = H * torch.tensor(g["data/subband_filter"]) if "data/subband_filter" in g else H
     tgt = torch.tensor(g["data/target_rir_response"])
@@ -49,7 +57,7 @@ def oracle_omni(g, p):
     edr = O.edr_loss(tgt, Huse)
     spec, spars = O.colorless_losses(Hs, p["feedback_loop.M"], 1.0, 1.0, asym=True)
     total = float(g["meta/edc_w"]) * edc + float(g["meta/edr_w"]) * edr + spec + spars
-    return dict(H=H, Huse=Huse, H_sub=Hs, H_sub_per_del=Hsd, A=A, s=s, gamma=gamma, edc=edc, edr=edr, spec=spec,
+    return dict(H=H, Huse=Huse, H_sub=Hs, H_sub_per_del=Hsd, A=A, s=s, svf=svf, coef=coef, gamma=gamma, edc=edc, edr=edr, spec=spec,
                 spars=spars, total=total, z=z, delays=delays, b=b, c=c, d=d, tgt=tgt)
 
 
