@@ -34,6 +34,11 @@ SIGNATURES = {
                                   c_void_p]),
     "dgfdn_project_bwd": (c_int, [c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int,
                                   c_void_p, c_void_p]),
+    "dgfdn_project_svf_fwd": (c_int, [c_int, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
+                                      c_void_p, c_int64, c_void_p]),
+    "dgfdn_project_svf_bwd_ws_bytes": (c_int64, [c_int, c_int, c_int64, c_int64]),
+    "dgfdn_project_svf_bwd": (c_int, [c_int, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
+                                      c_void_p, c_void_p, c_void_p, c_void_p]),
     "dgfdn_project_sh_fwd": (c_int, [c_int, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dgfdn_project_sh_bwd": (c_int, [c_int, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                      c_void_p, c_void_p]),

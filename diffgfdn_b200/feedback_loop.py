@@ -169,21 +169,29 @@ class FeedbackLoop(nn.Module):
             self.delay_line_gain_response = fn(self.delay_line_gain_response)
         return self
 
-    def construct_block_mixing_matrix(self) -> torch.Tensor:
+    def construct_block_mixing_matrix(self, dtype: Optional[torch.dtype] = None) -> torch.Tensor:
         """block_M[i,j] = U_i U_j with U = expm(skew(M)); diagonal blocks are U_i^2 (reference :393-404, Q4)."""
         U = self.ortho_param(self.M)  # (G, L, L)
+        if dtype is not None:
+            U = U.to(dtype)
         G, L, _ = U.shape
         blocks = torch.einsum('iab,jbc->iajc', U, U)  # (G, L, G, L)
         return blocks.reshape(G * L, G * L)
 
-    def construct_coupling_matrix(self) -> torch.Tensor:
+    def construct_coupling_matrix(self, dtype: Optional[torch.dtype] = None) -> torch.Tensor:
         alpha = self.alpha.clamp(min=-np.pi, max=np.pi)
+        if dtype is not None:
+            alpha = alpha.to(dtype)
         return self.nd_unitary(alpha, self.num_groups)
 
-    def coupled_feedback_matrix_real(self) -> torch.Tensor:
-        """A = block_M o (Phi (x) 1_{LxL}), real (N, N) float32 (reference :424-455 before to_complex)."""
-        block_M = self.construct_block_mixing_matrix()
-        phi = self.construct_coupling_matrix()
+    def coupled_feedback_matrix_real(self, dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+        """A = block_M o (Phi (x) 1_{LxL}), real (N, N) float32 (reference :424-455 before to_complex).
+
+        dtype=torch.float64 runs the small product / Givens graph in float64: dL/dalpha is a sum of O(1) terms of
+        dL/dA that cancels to ~1e-4 of their size, which a float32 graph resolves to 1e-3 only (the K1 adjoint hands
+        dL/dA over in float64; the forward value is rounded to float32 by K1 either way)."""
+        block_M = self.construct_block_mixing_matrix(dtype)
+        phi = self.construct_coupling_matrix(dtype)
         self.phi = phi.detach()  # kept for get_parameters()/get_param_dict(); detached (no graph outlives the step)
         L = self.num_delay_lines_per_group
         return block_M * torch.kron(phi, torch.ones(L, L, dtype=block_M.dtype, device=block_M.device))
@@ -194,8 +202,8 @@ class FeedbackLoop(nn.Module):
 
     def solve(self, z: torch.Tensor, b: torch.Tensor, c: torch.Tensor, transpose: bool = False):
         """x_k = (D(z_k) Gamma^-1 - A)^-1 b and y[k,g] = sum_{n in g} c_n x_k[n] on the GPU (one warp per bin)."""
-        a = self.coupled_feedback_matrix_real()
-        self.coupled_feedback_matrix = a.detach()
+        a = self.coupled_feedback_matrix_real(torch.float64)
+        self.coupled_feedback_matrix = a.detach().to(torch.float32)
         gamma = None if self.delay_line_gain_response is not None else self.delay_line_gains
         return ops.gfdn_solve(z, self.delays.to(torch.int32), a, gamma, b, c, self.num_groups, transpose_a=transpose,
                               gamma_z=self.delay_line_gain_response)

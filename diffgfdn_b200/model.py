@@ -21,7 +21,7 @@ from . import ops
 from .absorption_filters import decay_times_to_gain_per_sample
 from .config.config import CouplingMatrixType, FeedbackLoopConfig, OutputFilterConfig
 from .feedback_loop import FeedbackLoop
-from .gain_filters import Gains_from_MLP
+from .gain_filters import Gains_from_MLP, SVF_from_MLP
 from .sh_gains import Directional_Beamforming_Weights_from_MLP
 
 
@@ -176,13 +176,19 @@ class DiffGFDNVarReceiverPos(DiffGFDN):
         self.use_svf_in_output = output_filter_config.use_svfs
         self.input_scalars = torch.ones(self.num_groups, 1)
         if self.use_svf_in_output:
-            raise NotImplementedError("SVF output filters (use_svfs=True) are the next row of the scope table "
-                                      "(SURVEY.md section 8f rank 3); use scalar receiver gains (use_svfs: False)")
-        self.output_scalars = Gains_from_MLP(self.num_groups, self.num_delay_lines_per_group,
-                                             output_filter_config.num_fourier_features,
-                                             output_filter_config.num_hidden_layers,
-                                             output_filter_config.num_neurons_per_layer,
-                                             output_filter_config.encoding_type, device=self.device).to(self.device)
+            self.output_filters = SVF_from_MLP(self.sample_rate, self.num_groups, self.num_delay_lines_per_group,
+                                               output_filter_config.num_fourier_features,
+                                               output_filter_config.num_hidden_layers,
+                                               output_filter_config.num_neurons_per_layer,
+                                               output_filter_config.encoding_type,
+                                               output_filter_config.compress_pole_factor,
+                                               device=self.device).to(self.device)
+        else:
+            self.output_scalars = Gains_from_MLP(self.num_groups, self.num_delay_lines_per_group,
+                                                 output_filter_config.num_fourier_features,
+                                                 output_filter_config.num_hidden_layers,
+                                                 output_filter_config.num_neurons_per_layer,
+                                                 output_filter_config.encoding_type, device=self.device).to(self.device)
 
     def forward(self, x: Dict, output_scalars: Optional[torch.Tensor] = None):
         """H(z) = c^T (D Gamma^-1 - A)^-1 b + d for every receiver of the batch and every bin.
@@ -191,7 +197,10 @@ class DiffGFDNVarReceiverPos(DiffGFDN):
            'target_early_response' (B,K) complex.  Returns H (B,K) complex64, or (H, (H_sub, H_sub_per_del))."""
         z = self._on_device(x['z_values'], torch.complex128)
         self.batch_size = x['listener_position'].shape[0]
-        if output_scalars is None:
+        coef = s = None
+        if self.use_svf_in_output:  # the provided-scalars override only exists on the gains branch (model.py:589-605)
+            coef = self.output_filters.coefficients(x)
+        elif output_scalars is None:
             s = self.output_scalars.gains(x)
         else:
             assert output_scalars.shape == (self.batch_size, self.num_groups)
@@ -199,13 +208,23 @@ class DiffGFDNVarReceiverPos(DiffGFDN):
         _, y = self.feedback_loop.solve(z, self._gains_vec(self.input_gains), self._gains_vec(self.output_gains))
         d = x.get('target_early_response')
         d = None if d is None else self._on_device(d, torch.complex64)
-        H = ops.receiver_project(s, y, d)
+        H = ops.svf_project(coef, z, y, d) if coef is not None else ops.receiver_project(s, y, d)
         if self.use_colorless_loss:
             return H, self.sub_fdn_output(z)
         return H
 
+    def get_parameters(self) -> Tuple:
+        """reference model.py:627-636 (only defined for the SVF variant there)."""
+        fl = self.feedback_loop
+        svf_params, biquad_coeffs = self.output_filters.get_parameters()
+        return (self.delays, fl.delay_line_gains, self.input_gains, fl.M, fl.nd_unitary(fl.alpha, self.num_groups),
+                fl.get_coupled_feedback_matrix(), svf_params, biquad_coeffs)
+
     @torch.no_grad()
     def get_param_dict_inference(self, data: Dict) -> Dict:
+        if self.use_svf_in_output:
+            out = self.output_filters.get_param_dict(data)
+            return {'output_svf_params': out['svf_params'], 'output_biquad_coeffs': out['biquad_coeffs']}
         return {'output_scalars': self.output_scalars.get_param_dict(data)['gains']}
 
     @torch.no_grad()

@@ -105,6 +105,7 @@ class _GFDNSolve(torch.autograd.Function):
                       _ptr(gamma_), _ptr(gamma_z_), _ptr(b_), _ptr(c_), _ptr(x), _ptr(y), _stream())
         ctx.save_for_backward(z, delays, a_, gamma_, gamma_z_, c_, x)
         ctx.meta = (n, num_groups, k, int(transpose_a), b.shape, c.shape)
+        ctx.a_dtype = a.dtype  # float64 callers (FeedbackLoop.solve) get dL/dA back in float64
         return x, y
 
     @staticmethod
@@ -123,7 +124,7 @@ class _GFDNSolve(torch.autograd.Function):
             _lib.call("dgfdn_solve_bwd", n, g, k, _ptr(z), _ptr(delays), _ptr(a_), tr, _ptr(gamma_), _ptr(gamma_z_),
                       _ptr(c_), _ptr(x), _ptr(gy_), _ptr(gx_), _ptr(ga), _ptr(gb), _ptr(gc), _ptr(gig), _ptr(ws),
                       _stream())
-        g_a = ga.reshape(n, n).to(torch.float32) if ctx.needs_input_grad[2] else None
+        g_a = ga.reshape(n, n).to(ctx.a_dtype) if ctx.needs_input_grad[2] else None
         g_gamma = None
         if gamma_ is not None and ctx.needs_input_grad[3]:
             g_gamma = (-gig / gamma_.to(torch.float64)**2).to(torch.float32)
@@ -237,6 +238,54 @@ class _ReceiverProject(torch.autograd.Function):
 
 def receiver_project(s: torch.Tensor, y: torch.Tensor, d: Optional[torch.Tensor] = None) -> torch.Tensor:
     return _ReceiverProject.apply(s, y, d)
+
+
+class _SVFProject(torch.autograd.Function):
+    """H[r,k] = sum_g F[r,g,k] y[k,g] + d[r,k], F the biquad-cascade response of coef[r,g] (reference
+    gain_filters.py:221-241, 383-401; model.py:583-619 with use_svf_in_output)."""
+
+    @staticmethod
+    def forward(ctx, coef, z, y, d):
+        coef_ = _cuda("coef", coef, torch.float32)
+        z_ = _cuda("z", z, torch.complex128)
+        y_ = _cuda("y", y, C64)
+        d_ = _cuda("d", d, C64, optional=True)
+        if coef_.dim() != 4 or coef_.shape[3] != 6:
+            raise RuntimeError("svf_project: coef must be (rows, groups, sections, 6)")
+        rows, g, nsec, _ = coef_.shape
+        k = y_.shape[0]
+        if y_.shape[1] != g or z_.numel() != k or (d_ is not None and tuple(d_.shape) != (rows, k)):
+            raise RuntimeError("svf_project: inconsistent shapes")
+        h = torch.empty(rows, k, dtype=C64, device=coef_.device)
+        with torch.cuda.device(coef_.device):
+            _lib.call("dgfdn_project_svf_fwd", g, nsec, rows, k, _ptr(coef_), _ptr(z_), _ptr(y_), _ptr(d_), k, _ptr(h), k,
+                      _stream())
+        ctx.save_for_backward(coef_, z_, y_)
+        ctx.d_dtype = None if d is None else d.dtype
+        return h
+
+    @staticmethod
+    def backward(ctx, gh):
+        coef_, z_, y_ = ctx.saved_tensors
+        rows, g, nsec, _ = coef_.shape
+        k = y_.shape[0]
+        gh_ = _cuda("gh", gh, C64)
+        gcoef = torch.empty_like(coef_) if ctx.needs_input_grad[0] else None
+        gy = torch.empty_like(y_) if ctx.needs_input_grad[2] else None
+        with torch.cuda.device(coef_.device):
+            ws = None
+            if gcoef is not None:
+                nbytes = _lib.load().dgfdn_project_svf_bwd_ws_bytes(g, nsec, rows, k)
+                ws = torch.empty(max(1, nbytes // 8), dtype=torch.float64, device=coef_.device)
+            _lib.call("dgfdn_project_svf_bwd", g, nsec, rows, k, _ptr(coef_), _ptr(z_), _ptr(y_), _ptr(gh_), k,
+                      _ptr(gcoef), _ptr(gy), _ptr(ws), _stream())
+        gd = gh_.to(ctx.d_dtype) if (ctx.d_dtype is not None and ctx.needs_input_grad[3]) else None
+        return gcoef, None, gy, gd
+
+
+def svf_project(coef: torch.Tensor, z: torch.Tensor, y: torch.Tensor, d: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """coef (R,G,S,6) float32 biquad coefficients, z (K,) complex128, y (K,G) complex64, d (R,K) complex64 or None."""
+    return _SVFProject.apply(coef, z, y, d)
 
 
 class _SHProject(torch.autograd.Function):

@@ -220,6 +220,7 @@ if __name__ == "__main__":
     case_omni("omni_n12_subband_r", 12, 8192, 3, [0.04, 0.09, 0.11], 12, 2, 16, 4, radius=1.00002, subband=True,
               early_scale=1e-3)
     case_omni("omni_n24", 24, 4096, 3, [0.03, 0.05, 0.06], 13, 1, 16, 4, steps=1)
-    case_omni("omni_n12_svf", 12, 8192, 3, [0.05, 0.08, 0.12], 14, 1, 32, 6, svf=True, pole_factor=0.998)
+    case_omni("omni_n12_svf", 12, 8192, 3, [0.05, 0.08, 0.12], 14, 1, 32, 6, svf=True, pole_factor=0.998,
+              early_scale=1e-3)
     case_directional("directional_n27", 8192, 2, [0.05, 0.08, 0.1], 21, 1, 16, 4, skip=False)
     case_directional("directional_n27_skip", 4096, 2, [0.03, 0.04, 0.05], 22, 2, 16, 4, skip=True)

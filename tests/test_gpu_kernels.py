@@ -2,6 +2,8 @@
 
 Tolerances are the ones BASELINE.json states: |H| 1e-4 relative, EDC 0.01 dB, gradients 1e-3 relative,
 rendered samples 1e-5 of peak. All calls go through the C ABI (ctypes) via diffgfdn_b200.ops."""
+import math
+
 import numpy as np
 import pytest
 import torch
@@ -179,6 +181,34 @@ def test_receiver_projection_forward_backward(rows, k, g, with_d):
     (h.to(torch.complex128) * dev(w).conj()).real.sum().backward()
     assert rel(h.cpu().to(torch.complex128), ho) < 1e-5
     assert rel(sd.grad, so.grad) < 1e-4
+    assert rel(yd.grad.cpu().to(torch.complex128), yo.grad) < 1e-4
+
+
+@pytest.mark.parametrize("rows,k,g,nsec,with_d,radius", [(5, 1025, 3, 11, True, 1.0), (2, 4097, 2, 3, False, 1.0003),
+                                                         (9, 300, 4, 16, True, 1.0), (1, 1, 1, 1, False, 1.0)])
+def test_svf_projection_forward_backward(rows, k, g, nsec, with_d, radius):
+    """K2s against the oracle's SOS response (gain_filters.py:221-241) on random stable cascades."""
+    from diffgfdn_b200 import ops
+    torch.manual_seed(rows * 31 + k)
+    svf = torch.stack([torch.rand(rows, g, nsec) * 0.9 + 0.05, torch.rand(rows, g, nsec) * 12 - 6], dim=-1)
+    cut = math.pi * torch.logspace(math.log10(40.0), math.log10(15000.0), nsec, dtype=F64) / 32000.0
+    coef = O.svf_to_biquads(svf, cut, 0.999).to(torch.float32)
+    z = O.z_grid(2 * (k - 1), radius) if k > 1 else torch.ones(1, dtype=torch.complex128)
+    y = torch.randn(k, g, dtype=torch.complex64)
+    d = torch.randn(rows, k, dtype=torch.complex64) if with_d else None
+    w = torch.randn(rows, k, dtype=torch.complex128)
+    co = coef.to(F64).requires_grad_(True)
+    yo = y.to(torch.complex128).requires_grad_(True)
+    ho = torch.einsum('rgk,kg->rk', O.sos_response(z, co), yo)
+    if d is not None:
+        ho = ho + d.to(torch.complex128)
+    (ho * w.conj()).real.sum().backward()
+    cd = coef.cuda().requires_grad_(True)
+    yd = y.cuda().requires_grad_(True)
+    h = ops.svf_project(cd, z.cuda(), yd, None if d is None else d.cuda())
+    (h.to(torch.complex128) * w.cuda().conj()).real.sum().backward()
+    assert rel(h.cpu().to(torch.complex128), ho.detach()) < 1e-5
+    assert rel(cd.grad, co.grad) < 1e-4
     assert rel(yd.grad.cpu().to(torch.complex128), yo.grad) < 1e-4
 
 

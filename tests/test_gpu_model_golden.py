@@ -14,6 +14,7 @@ OMNI = {  # name: (hidden, neurons, fourier features, steps)
     "omni_n12": (1, 32, 6, 2),
     "omni_n12_subband_r": (2, 16, 4, 2),
     "omni_n24": (1, 16, 4, 1),
+    "omni_n12_svf": (1, 32, 6, 2),  # SVF output filters (use_svfs: True), compress_pole_factor 0.998
 }
 DIRECTIONAL = {"directional_n27": (1, 16, 4, False), "directional_n27_skip": (2, 16, 4, True)}
 
@@ -29,8 +30,9 @@ def build_omni(g, hidden, neurons, feats):
     from diffgfdn_b200.model import DiffGFDNVarReceiverPos
     net = DiffGFDNVarReceiverPos(float(g["meta/fs"]), 3, [int(v) for v in g["meta/delays"]], 'cuda',
                                  FeedbackLoopConfig(use_zero_coupling=False),
-                                 OutputFilterConfig(use_svfs=False, num_hidden_layers=hidden,
-                                                    num_neurons_per_layer=neurons, num_fourier_features=feats),
+                                 OutputFilterConfig(use_svfs="out/svf_params" in g, num_hidden_layers=hidden,
+                                                    num_neurons_per_layer=neurons, num_fourier_features=feats,
+                                                    compress_pole_factor=float(g.get("meta/pole_factor", 1.0))),
                                  use_absorption_filters=False, common_decay_times=np.array([g["meta/t60"]]),
                                  use_colorless_loss=True)
     state = {k[len("param/"):]: torch.tensor(v) for k, v in g.items() if k.startswith("param/")}
@@ -71,8 +73,14 @@ def test_omni_forward_losses_grads_match_reference(name, tmp_path):
     # d input is complex128, quirk Q6)
     with torch.no_grad():
         H_late, _ = net({k: v for k, v in data.items() if k != "target_early_response"})
-    assert rel(H_late.cpu().to(torch.complex128).numpy(), g["out/H"] - d) < 1e-4
-    assert rel(np.abs(H.detach().cpu().numpy()), np.abs(g["out/H"])) < 1e-4
+    # SVF case: the biquad coefficients are float32 on both sides and a0 + a1 z^-1 + a2 z^-2 cancels to ~4 f_c^2 near
+    # DC, so one ulp of difference between the CPU and the GPU pow/sqrt shows up as ~1e-3 there (see
+    # tests/test_oracle_golden.py); the kernel itself is checked to 1e-5 against the oracle in test_gpu_kernels.py
+    assert rel(H_late.cpu().to(torch.complex128).numpy(), g["out/H"] - d) < (5e-3 if net.use_svf_in_output else 1e-4)
+    if net.use_svf_in_output:
+        assert rel(net.output_filters.svf_params, g["out/svf_params"]) < 1e-5
+        assert rel(net.output_filters.biquad_coeffs_, g["out/biquads"]) < 1e-5
+    assert rel(np.abs(H.detach().cpu().numpy()), np.abs(g["out/H"])) < (5e-3 if net.use_svf_in_output else 1e-4)
     assert rel(Hs, g["out/H_sub"]) < 1e-4
     assert rel(Hsd.detach().cpu().numpy()[:, ::16, :], g["out/H_sub_per_del_s16"]) < 1e-4
     assert rel(net.feedback_loop.coupled_feedback_matrix_real(), np.real(g["out/A"])) < 1e-4
