@@ -27,8 +27,10 @@ from diff_gfdn.colorless_fdn.losses import amse_loss, mse_loss, sparsity_loss  #
 from diff_gfdn.config.config import (DiffGFDNConfig, FeedbackLoopConfig, OutputFilterConfig,  # noqa: E402
                                      TrainerConfig)
 from diff_gfdn.losses import directional_edc_loss, edc_loss, edr_loss  # noqa: E402
-from diff_gfdn.model import DiffDirectionalFDNVarReceiverPos, DiffGFDNVarReceiverPos  # noqa: E402
-from diff_gfdn.trainer import DirectionalFDNVarReceiverPosTrainer, VarReceiverPosTrainer  # noqa: E402
+from diff_gfdn.model import (DiffDirectionalFDNVarReceiverPos, DiffGFDNSinglePos, DiffGFDNVarReceiverPos,  # noqa: E402
+                             DiffGFDNVarSourceReceiverPos)
+from diff_gfdn.trainer import (DirectionalFDNVarReceiverPosTrainer, SinglePosTrainer,  # noqa: E402
+                               VarReceiverPosTrainer)
 from diff_gfdn.utils import get_response  # noqa: E402
 import spaudiopy  # noqa: E402  (stub)
 
@@ -163,6 +165,89 @@ def case_omni(name, n_lines, nfft, bsz, t60, seed, hidden, neurons, feats, radiu
     print(name, "total", out["loss/total"], {k: v for k, v in out.items() if k.startswith("loss/")}, step_losses)
 
 
+def _finish_variant(name, net, trainer, data, out, t60, nfft):
+    """forward + trainer losses + backward of a model variant; common tail of the a-8c cases"""
+    out.update(np_state(net))
+    net.zero_grad()
+    if getattr(net, "use_svf_in_output", False) and isinstance(net, DiffGFDNSinglePos):
+        # the reference deep-copies its non-leaf biquad tensors (model.py:903-906), which raises under autograd with
+        # this torch: the SVF branch of DiffGFDNSinglePos only runs without a graph -- forward values only
+        with torch.no_grad():
+            H, (Hs, Hsd) = net(data)
+            losses = trainer.calculate_losses(data, H, (Hs, Hsd))
+            total = sum(losses.values())
+        for tag, casc in (("in", net.input_biquad_cascade), ("out", net.output_biquad_cascade)):
+            out[f"out/biquads_{tag}"] = np.stack([np.concatenate([c.num_coeffs.numpy(), c.den_coeffs.numpy()], axis=-1)
+                                                  for c in casc])
+    else:
+        H, (Hs, Hsd) = net(data)
+        losses = trainer.calculate_losses(data, H, (Hs, Hsd))
+        total = sum(losses.values())
+        total.backward()
+    out["out/H"] = H.detach().numpy()
+    out["out/H_sub"] = Hs.detach().numpy()
+    out["out/A"] = net.feedback_loop.get_coupled_feedback_matrix().detach().numpy()
+    for kk, v in losses.items():
+        out[f"loss/{kk}"] = float(v.detach())
+    out["loss/total"] = float(total.detach())
+    out.update(grads_of(net))
+    np.savez_compressed(os.path.join(OUT, f"{name}.npz"), **out)
+    print(name, {k: v for k, v in out.items() if k.startswith("loss/")})
+
+
+def case_src_rx(name, n_lines, nfft, bsz, t60, seed, hidden, neurons, feats):
+    """DiffGFDNVarSourceReceiverPos (model.py:303-452): MLP-driven gains on the source AND the receiver side."""
+    cfg = DiffGFDNConfig(seed=235265, num_delay_lines=n_lines)
+    delays = cfg.delay_length_samps
+    torch.manual_seed(seed)
+    np.random.seed(seed)
+    ofc = OutputFilterConfig(use_svfs=False, num_hidden_layers=hidden, num_neurons_per_layer=neurons,
+                             num_fourier_features=feats)
+    net = DiffGFDNVarSourceReceiverPos(FS, 3, delays, 'cpu', FeedbackLoopConfig(use_zero_coupling=False), ofc, ofc,
+                                       use_absorption_filters=False, learn_common_decay_times=False,
+                                       common_decay_times=np.array([t60]), use_colorless_loss=True)
+    data = synth_batch(nfft, bsz, seed + 1, early_scale=1e-3)
+    rng = np.random.default_rng(seed + 5)
+    data['source_position'] = torch.tensor(rng.uniform(0, 1, (bsz, 3)))
+    trainer = make_trainer(VarReceiverPosTrainer, net, use_colorless_loss=True, use_asym_spectral_loss=True,
+                           edc_loss_weight=10.0, num_freq_bins=nfft)
+    out = {"meta/delays": np.array(delays), "meta/nfft": nfft, "meta/fs": FS, "meta/t60": np.array(t60),
+           "meta/radius": 1.0, "meta/feats": feats, "meta/edc_w": 10.0, "meta/edr_w": 1.0,
+           "meta/max_ir_len_ms": float(np.max(t60) * 1e3)}
+    for key in ("listener_position", "norm_listener_position", "source_position", "target_early_response",
+                "target_rir_response"):
+        out[f"data/{key}"] = data[key].numpy()
+    _finish_variant(name, net, trainer, data, out, t60, nfft)
+
+
+def case_single(name, n_lines, nfft, t60, seed, svf_in, svf_out, pole_factor=0.998):
+    """DiffGFDNSinglePos (model.py:667-960): one source-receiver pair, learnable per-group scalars or SVF cascades."""
+    cfg = DiffGFDNConfig(seed=235265, num_delay_lines=n_lines)
+    delays = cfg.delay_length_samps
+    torch.manual_seed(seed)
+    np.random.seed(seed)
+    net = DiffGFDNSinglePos(FS, 3, delays, 'cpu', FeedbackLoopConfig(use_zero_coupling=False),
+                            OutputFilterConfig(use_svfs=svf_out, compress_pole_factor=pole_factor),
+                            use_absorption_filters=False, common_decay_times=np.array([t60]), use_colorless_loss=True,
+                            input_filter_config=OutputFilterConfig(use_svfs=svf_in, compress_pole_factor=pole_factor))
+    with torch.no_grad():  # move the SVF gains off their 0 dB initialisation so every coefficient path is exercised
+        for nm, prm in net.named_parameters():
+            if 'svf_params' in nm:
+                prm[..., 1] = torch.randn_like(prm[..., 1])
+            if nm in ('input_scalars', 'output_scalars'):
+                prm.mul_(1.0 + 0.3 * torch.randn_like(prm))
+    batch = synth_batch(nfft, 1, seed + 1, early_scale=1e-3)
+    data = {k: (v[0] if k in ("target_early_response", "target_rir_response") else v) for k, v in batch.items()}
+    trainer = make_trainer(lambda n, c: SinglePosTrainer(n, c, "golden"), net, use_colorless_loss=True,
+                           use_asym_spectral_loss=True, edc_loss_weight=10.0, num_freq_bins=nfft)
+    out = {"meta/delays": np.array(delays), "meta/nfft": nfft, "meta/fs": FS, "meta/t60": np.array(t60),
+           "meta/radius": 1.0, "meta/edc_w": 10.0, "meta/edr_w": 1.0, "meta/max_ir_len_ms": float(np.max(t60) * 1e3),
+           "meta/svf_in": svf_in, "meta/svf_out": svf_out, "meta/pole_factor": pole_factor}
+    for key in ("target_early_response", "target_rir_response"):
+        out[f"data/{key}"] = data[key].numpy()
+    _finish_variant(name, net, trainer, data, out, t60, nfft)
+
+
 def case_directional(name, nfft, bsz, t60, seed, hidden, neurons, feats, skip):
     ambi = 2
     lsh = (ambi + 1)**2
@@ -222,5 +307,8 @@ if __name__ == "__main__":
     case_omni("omni_n24", 24, 4096, 3, [0.03, 0.05, 0.06], 13, 1, 16, 4, steps=1)
     case_omni("omni_n12_svf", 12, 8192, 3, [0.05, 0.08, 0.12], 14, 1, 32, 6, svf=True, pole_factor=0.998,
               early_scale=1e-3)
+    case_src_rx("src_rx_n12", 12, 8192, 3, [0.05, 0.08, 0.12], 15, 1, 16, 4)
+    case_single("single_n12", 12, 8192, [0.05, 0.08, 0.12], 16, False, False)
+    case_single("single_n12_svf", 12, 8192, [0.05, 0.08, 0.12], 17, True, True)
     case_directional("directional_n27", 8192, 2, [0.05, 0.08, 0.1], 21, 1, 16, 4, skip=False)
     case_directional("directional_n27_skip", 4096, 2, [0.03, 0.04, 0.05], 22, 2, 16, 4, skip=True)

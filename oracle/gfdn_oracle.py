@@ -333,6 +333,43 @@ def omni_response_svf(z, delays, gamma, a, b, c, coef, d=None) -> torch.Tensor:
     return h
 
 
+def source_receiver_response(z, delays, gamma, a, b, c, s_rx, s_src, d=None) -> torch.Tensor:
+    """model.py:402-452 (DiffGFDNVarSourceReceiverPos.forward, gains on both sides):
+    H[r,k] = sum_{n,m} (s_rx[r,g(n)] c_n) P_k[n,m] (s_src[r,g(m)] b_m) + d[r,k]."""
+    p = feedback_loop_inverse(z, delays, gamma, a)
+    n = delays.numel()
+    g = s_rx.shape[1]
+    cfull = (s_rx.to(F64).repeat_interleave(n // g, dim=1) * c.to(F64).unsqueeze(0)).to(C128)
+    bfull = (s_src.to(F64).repeat_interleave(n // g, dim=1) * b.to(F64).unsqueeze(0)).to(C128)
+    htemp = torch.einsum('bn,knm->bmk', cfull, p)
+    h = torch.einsum('bmk,bm->bk', htemp, bfull)
+    if d is not None:
+        h = h + d.to(C128)
+    return h
+
+
+def single_position_response(z, delays, gamma, a, b, c, f_out, f_in, d=None) -> torch.Tensor:
+    """model.py:779-836 (DiffGFDNSinglePos.forward): one source-receiver pair. f_out / f_in are the per-group
+    receiver / source factors: (G,) learnable scalars or (G, K) filter responses (get_filter, :838-908).
+    H[k] = sum_{n,m} f_out[g(n),k] c_n P_k[n,m] f_in[g(m),k] b_m + d[k]."""
+    p = feedback_loop_inverse(z, delays, gamma, a)
+    n = delays.numel()
+    k = z.numel()
+
+    def expand(f):
+        f = f.to(C128)
+        if f.dim() == 1:
+            f = f.unsqueeze(-1).expand(-1, k)
+        return f.repeat_interleave(n // f.shape[0], dim=0)  # (N, K)
+
+    cz = expand(f_out) * c.to(C128).unsqueeze(-1)
+    bz = expand(f_in) * b.to(C128).unsqueeze(-1)
+    h = torch.einsum('nk,knm,mk->k', cz, p, bz)
+    if d is not None:
+        h = h + d.to(C128)
+    return h
+
+
 def sh_gains_from_mlp(norm_pos, weights, num_fourier_features, num_groups, num_sh,
                       prefix='sh_output_scalars.mlp.', skip=False, normalise=True) -> torch.Tensor:
     """spatial_sampling/model.py:169-190 with normalise_weights (:78-80): w / (||w||_2 + 1e-6) over l."""

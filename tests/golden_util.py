@@ -10,6 +10,7 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 OMNI_CASES = ["omni_n12", "omni_n12_subband_r", "omni_n24"]
 SVF_CASES = ["omni_n12_svf"]
 DIR_CASES = ["directional_n27", "directional_n27_skip"]
+VARIANT_CASES = ["src_rx_n12", "single_n12", "single_n12_svf"]  # a-8c: source+receiver gains, single position
 
 
 def load(name):
@@ -59,6 +60,47 @@ def oracle_omni(g, p, coef_override=None):
     total = float(g["meta/edc_w"]) * edc + float(g["meta/edr_w"]) * edr + spec + spars
     return dict(H=H, Huse=Huse, H_sub=Hs, H_sub_per_del=Hsd, A=A, s=s, svf=svf, coef=coef, gamma=gamma, edc=edc, edr=edr, spec=spec,
                 spars=spars, total=total, z=z, delays=delays, b=b, c=c, d=d, tgt=tgt)
+
+
+def oracle_variant(g, p, biquads_from_golden=False):
+    """DiffGFDNVarSourceReceiverPos / DiffGFDNSinglePos golden cases (SURVEY a-8c) through the oracle."""
+    nfft = int(g["meta/nfft"])
+    fs = float(g["meta/fs"])
+    z = O.z_grid(nfft, float(g["meta/radius"]))
+    delays = torch.tensor(g["meta/delays"], dtype=torch.float64)
+    G = p["feedback_loop.M"].shape[0]
+    gamma = O.decay_times_to_gain_per_sample(g["meta/t60"], g["meta/delays"], fs, G)
+    A = O.coupled_feedback_matrix(p["feedback_loop.M"], p["feedback_loop.alpha"])
+    b = p["input_gains"].reshape(-1)
+    c = p["output_gains"].reshape(-1)
+    d = torch.tensor(g["data/target_early_response"])
+    if "data/source_position" in g:
+        feats = int(g["meta/feats"])
+        s_rx = O.gains_from_mlp(torch.tensor(g["data/norm_listener_position"]), p, feats, G,
+                                prefix='output_scalars.mlp.model.')
+        s_src = O.gains_from_mlp(torch.tensor(g["data/source_position"]), p, feats, G,
+                                 prefix='input_scalars.mlp.model.')
+        H = O.source_receiver_response(z, delays, gamma, A, b, c, s_rx, s_src, d)
+    else:
+        def factor(tag, svf):
+            if not svf:
+                return p[f"{tag}_scalars"].reshape(-1)
+            if biquads_from_golden:
+                coef = torch.tensor(g[f"out/biquads_{'in' if tag == 'input' else 'out'}"])
+            else:
+                raw = p[f"{tag}_svf_params"]
+                svfp = torch.stack([O.scaled_sigmoid(raw[..., 0], 1e-6, 1.0), O.scaled_sigmoid(raw[..., 1], -6.0, 6.0)], -1)
+                coef = O.svf_to_biquads(svfp, O.svf_cutoffs(fs), float(g["meta/pole_factor"]))
+            return O.sos_response(z, coef)
+        H = O.single_position_response(z, delays, gamma, A, b, c, factor("output", bool(g["meta/svf_out"])),
+                                       factor("input", bool(g["meta/svf_in"])), d)
+    Hs, Hsd = O.sub_fdn_output(z, delays, p["feedback_loop.M"], b, c)
+    tgt = torch.tensor(g["data/target_rir_response"])
+    edc = O.edc_loss(tgt, H, float(g["meta/max_ir_len_ms"]), fs)
+    edr = O.edr_loss(tgt, H)
+    spec, spars = O.colorless_losses(Hs, p["feedback_loop.M"], 1.0, 1.0, asym=True)
+    total = float(g["meta/edc_w"]) * edc + float(g["meta/edr_w"]) * edr + spec + spars
+    return dict(H=H, H_sub=Hs, A=A, edc=edc, edr=edr, spec=spec, spars=spars, total=total, d=d)
 
 
 def oracle_directional(g, p):
