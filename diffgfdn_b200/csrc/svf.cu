@@ -8,8 +8,9 @@
 // einsums of model.py:583-619: every delay line of a group shares the group's filter, so the filter multiplies
 // the group-folded state y[k,g] = sum_{n in g} c_n x_k[n] and no (B,N,K) tensor exists.
 //
-// The response is evaluated in float64 like the reference (its z grid is complex128, gain_filters.py:233-239):
-// a0 + a1 z^-1 + a2 z^-2 cancels to ~4 f_c^2 (7e-5 for the 44 Hz shelf) near DC, which float32 cannot resolve.
+// The response is evaluated in float64 like the reference (its z grid is complex128, gain_filters.py:233-239), and
+// the coefficients are float64 too: a0 + a1 z^-1 + a2 z^-2 cancels to ~4 f_c^2 (7e-5 for the 44 Hz shelf) near DC,
+// so coefficients rounded to float32 (what the reference holds) already cost 1e-3 of the response there.
 // Numerators and denominators are multiplied up separately and divided once per group.
 //
 // Backward (torch convention g = dL/dRe + i dL/dIm, real parameters take the real part):
@@ -35,12 +36,12 @@ __device__ __forceinline__ double2 cmul_d(double2 a, double2 b) {
   return make_double2(fma(a.x, b.x, -a.y * b.y), fma(a.x, b.y, a.y * b.x));
 }
 // c0 + c1 zi + c2 zi2 with real c
-__device__ __forceinline__ double2 quad(const float* c, double2 zi, double2 zi2) {
+__device__ __forceinline__ double2 quad(const double* c, double2 zi, double2 zi2) {
   const double c0 = c[0], c1 = c[1], c2 = c[2];
   return make_double2(fma(c2, zi2.x, fma(c1, zi.x, c0)), fma(c2, zi2.y, c1 * zi.y));
 }
 // cascade response of one (row, group): coefficients in shared memory
-__device__ __forceinline__ double2 cascade(const float* coef, int nsec, double2 zi, double2 zi2) {
+__device__ __forceinline__ double2 cascade(const double* coef, int nsec, double2 zi, double2 zi2) {
   double2 pn = make_double2(1.0, 0.0), pd = make_double2(1.0, 0.0);
   for (int s = 0; s < nsec; ++s) {
     pn = cmul_d(pn, quad(coef + 6 * s, zi, zi2));
@@ -50,12 +51,12 @@ __device__ __forceinline__ double2 cascade(const float* coef, int nsec, double2 
 }
 
 __global__ void __launch_bounds__(kThreads) svf_project_fwd_kernel(int g, int nsec, int64_t rows, int64_t k,
-                                                                   const float* __restrict__ coef,
+                                                                   const double* __restrict__ coef,
                                                                    const double2* __restrict__ z,
                                                                    const float2* __restrict__ y,
                                                                    const float2* __restrict__ d, int64_t ldd,
                                                                    float2* __restrict__ h, int64_t ldh) {
-  extern __shared__ float s_coef[];  // [kRowsPerBlock][g][nsec][6]
+  extern __shared__ double s_coef[];  // [kRowsPerBlock][g][nsec][6]
   const int per_row = g * nsec * 6;
   const int64_t r0 = (int64_t)blockIdx.y * kRowsPerBlock;
   const int nr = (int)min((int64_t)kRowsPerBlock, rows - r0);
@@ -84,11 +85,11 @@ __global__ void __launch_bounds__(kThreads) svf_project_fwd_kernel(int g, int ns
 
 // gy[k,g] = sum_r conj(F[r,g,k]) gh[r,k]: one thread per bin walks over every row (fixed order).
 __global__ void __launch_bounds__(kThreads) svf_project_bwd_gy_kernel(int g, int nsec, int64_t rows, int64_t k,
-                                                                      const float* __restrict__ coef,
+                                                                      const double* __restrict__ coef,
                                                                       const double2* __restrict__ z,
                                                                       const float2* __restrict__ gh, int64_t ldh,
                                                                       float2* __restrict__ gy) {
-  extern __shared__ float s_coef[];  // [kRowsPerBlock][g][nsec][6]
+  extern __shared__ double s_coef[];  // [kRowsPerBlock][g][nsec][6]
   const int per_row = g * nsec * 6;
   const int64_t bin = (int64_t)blockIdx.x * kThreads + threadIdx.x;
   const bool active = bin < k;
@@ -128,17 +129,17 @@ __global__ void __launch_bounds__(kThreads) svf_project_bwd_gy_kernel(int g, int
 // Partial coefficient gradients of one (row, group, chunk of bins): part[((row*g + gi)*chunks + chunk)*nsec*6 + s*6 + j]
 template <int NSEC>
 __global__ void __launch_bounds__(kThreads) svf_project_bwd_coef_kernel(int g, int64_t k, int chunks,
-                                                                        const float* __restrict__ coef,
+                                                                        const double* __restrict__ coef,
                                                                         const double2* __restrict__ z,
                                                                         const float2* __restrict__ y,
                                                                         const float2* __restrict__ gh, int64_t ldh,
                                                                         double* __restrict__ part) {
-  __shared__ float s_coef[NSEC * 6];
+  __shared__ double s_coef[NSEC * 6];
   __shared__ double s_red[kThreads / 32][NSEC * 6];
   const int chunk = blockIdx.x;
   const int gi = blockIdx.y;
   const int64_t row = blockIdx.z;
-  const float* cg = coef + (row * g + gi) * NSEC * 6;
+  const double* cg = coef + (row * g + gi) * NSEC * 6;
   for (int i = threadIdx.x; i < NSEC * 6; i += kThreads) s_coef[i] = cg[i];
   __syncthreads();
   double acc[NSEC][6];
@@ -195,14 +196,14 @@ __global__ void __launch_bounds__(kThreads) svf_project_bwd_coef_kernel(int g, i
 }
 
 __global__ void svf_coef_reduce_kernel(int64_t n_out, int per, int chunks, const double* __restrict__ part,
-                                       float* __restrict__ gcoef) {
+                                       double* __restrict__ gcoef) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_out) return;
   const int64_t rg = i / per;
   const int j = (int)(i % per);
   double v = 0.0;
   for (int c = 0; c < chunks; ++c) v += part[(rg * chunks + c) * per + j];
-  gcoef[i] = (float)v;
+  gcoef[i] = v;
 }
 
 int check(int g, int nsec, int64_t rows, int64_t k) {
@@ -220,14 +221,14 @@ int chunks_of(int64_t k) { return (int)((k + kChunkBins - 1) / kChunkBins); }
 
 using namespace dgfdn;
 
-extern "C" int dgfdn_project_svf_fwd(int g, int nsec, int64_t rows, int64_t k, const float* coef, const void* z,
+extern "C" int dgfdn_project_svf_fwd(int g, int nsec, int64_t rows, int64_t k, const double* coef, const void* z,
                                      const void* y, const void* d, int64_t ldd, void* h, int64_t ldh, void* stream) {
   if (check(g, nsec, rows, k)) return 1;
   DGFDN_CHECK(coef && z && y && h, "project_svf_fwd: null pointer");
   DGFDN_CHECK(ldh >= k && (d == nullptr || ldd >= k), "project_svf_fwd: row stride smaller than k");
   if (rows == 0) return 0;
   const dim3 grid((unsigned)((k + kThreads - 1) / kThreads), (unsigned)((rows + kRowsPerBlock - 1) / kRowsPerBlock));
-  const size_t smem = (size_t)kRowsPerBlock * g * nsec * 6 * sizeof(float);
+  const size_t smem = (size_t)kRowsPerBlock * g * nsec * 6 * sizeof(double);
   svf_project_fwd_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(
       g, nsec, rows, k, coef, static_cast<const double2*>(z), static_cast<const float2*>(y),
       static_cast<const float2*>(d), ldd, static_cast<float2*>(h), ldh);
@@ -240,8 +241,8 @@ extern "C" int64_t dgfdn_project_svf_bwd_ws_bytes(int g, int nsec, int64_t rows,
   return rows * g * (int64_t)chunks_of(k) * nsec * 6 * (int64_t)sizeof(double);
 }
 
-extern "C" int dgfdn_project_svf_bwd(int g, int nsec, int64_t rows, int64_t k, const float* coef, const void* z,
-                                     const void* y, const void* gh, int64_t ldh, float* gcoef, void* gy, void* ws,
+extern "C" int dgfdn_project_svf_bwd(int g, int nsec, int64_t rows, int64_t k, const double* coef, const void* z,
+                                     const void* y, const void* gh, int64_t ldh, double* gcoef, void* gy, void* ws,
                                      void* stream) {
   if (check(g, nsec, rows, k)) return 1;
   DGFDN_CHECK(coef && z && y && gh, "project_svf_bwd: null pointer");
@@ -252,7 +253,7 @@ extern "C" int dgfdn_project_svf_bwd(int g, int nsec, int64_t rows, int64_t k, c
     if (rows == 0) {
       DGFDN_CUDA(cudaMemsetAsync(gy, 0, (size_t)k * g * sizeof(float2), st));
     } else {
-      const size_t smem = (size_t)kRowsPerBlock * g * nsec * 6 * sizeof(float);
+      const size_t smem = (size_t)kRowsPerBlock * g * nsec * 6 * sizeof(double);
       svf_project_bwd_gy_kernel<<<(unsigned)((k + kThreads - 1) / kThreads), kThreads, smem, st>>>(
           g, nsec, rows, k, coef, static_cast<const double2*>(z), static_cast<const float2*>(gh), ldh,
           static_cast<float2*>(gy));

@@ -208,6 +208,25 @@ class FeedbackLoop(nn.Module):
         return ops.gfdn_solve(z, self.delays.to(torch.int32), a, gamma, b, c, self.num_groups, transpose_a=transpose,
                               gamma_z=self.delay_line_gain_response)
 
+    def transfer_matrix(self, z: torch.Tensor, b: torch.Tensor, c: torch.Tensor) -> List[torch.Tensor]:
+        """Group-to-group transfer functions T[g'][k,g] = sum_{n in g, m in g'} c_n P_k[n,m] b_m: one K1 solve per
+        source group g' (b masked to that group), A assembled once. The model variants with source-side gains or
+        filters (reference model.py:402-452, 779-836) are bilinear in the per-group factors of both sides, so these
+        G x G functions per bin are all they need of the feedback loop."""
+        a = self.coupled_feedback_matrix_real(torch.float64)
+        self.coupled_feedback_matrix = a.detach().to(torch.float32)
+        gamma = None if self.delay_line_gain_response is not None else self.delay_line_gains
+        delays = self.delays.to(torch.int32)
+        L = self.num_delay_lines_per_group
+        b = b.reshape(-1)
+        out = []
+        for gp in range(self.num_groups):
+            mask = torch.zeros_like(b)
+            mask[gp * L:(gp + 1) * L] = 1.0
+            out.append(ops.gfdn_solve(z, delays, a, gamma, b * mask, c, self.num_groups,
+                                      gamma_z=self.delay_line_gain_response)[1])
+        return out
+
     def forward(self, z: torch.Tensor) -> torch.Tensor:
         """Dense P[k] = (D Gamma^-1 - A)^-1, (K, N, N) complex64 -- API compatibility with reference :326-391.
         The models never call this (they solve against b directly); it runs N single-RHS solves."""

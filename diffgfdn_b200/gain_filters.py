@@ -18,21 +18,24 @@ from .dnn import MLP, ScaledSigmoid, SinusoidalEncoding, fused_position_mlp
 
 def svf_cutoff_frequencies(sample_rate: float) -> torch.Tensor:
     """pi f_c / fs for the low shelf, the nine octave-band peaking sections (62.5 Hz .. 16 kHz) and the high shelf
-    (reference gain_filters.py:369-374 with filters/geq.py:9-56 at its defaults). float32 like the reference."""
+    (reference gain_filters.py:369-374 with filters/geq.py:9-56 at its defaults)."""
     centre = []
     c = 31.25
     while c < 16000:
         c = c * 2.0
         centre.append(c)
     freqs = [centre[0] / math.sqrt(2.0)] + centre + [centre[-1] * math.sqrt(2.0)]
-    return math.pi * torch.tensor(freqs, dtype=torch.float32) / sample_rate
+    return math.pi * torch.tensor(freqs, dtype=torch.float64) / sample_rate
 
 
 def svf_to_biquads(svf_params: torch.Tensor, cutoffs: torch.Tensor, compress_pole_factor: float = 1.0) -> torch.Tensor:
     """(..., S, 2) constrained (resonance, gain dB) -> (..., S, 6) biquad coefficients (b0 b1 b2 a0 a1 a2), all
     receivers / groups / sections at once and differentiable. Section 0 is a low shelf, the last a high shelf, the
     others peaking (reference gain_filters.py:405-414); mixing coefficients of SVF.__post_init__ (:59-102) and the
-    bilinear form of BiquadCascade.from_svf_coeffs (:116-151), in the reference's float32 and operation order."""
+    bilinear form of BiquadCascade.from_svf_coeffs (:116-151). Computed and returned in float64: the denominator
+    a0 + a1 z^-1 + a2 z^-2 cancels to ~4 f_c^2 near DC, so coefficients held in float32 (the reference's) already
+    perturb the response by 1e-3 there."""
+    svf_params = svf_params.to(torch.float64)
     res, gain_db = svf_params[..., 0], svf_params[..., 1]
     gain = torch.pow(10.0, gain_db * 0.05)
     f = cutoffs.to(device=svf_params.device, dtype=svf_params.dtype)

@@ -21,7 +21,9 @@ from . import ops
 from .absorption_filters import decay_times_to_gain_per_sample
 from .config.config import CouplingMatrixType, FeedbackLoopConfig, OutputFilterConfig
 from .feedback_loop import FeedbackLoop
-from .gain_filters import Gains_from_MLP, SVF_from_MLP
+from .dnn import ScaledSigmoid
+from .gain_filters import (Gains_from_MLP, SOSFilter, SVF_from_MLP, cascade_response, svf_cutoff_frequencies,
+                           svf_to_biquads)
 from .sh_gains import Directional_Beamforming_Weights_from_MLP
 
 
@@ -234,6 +236,178 @@ class DiffGFDNVarReceiverPos(DiffGFDN):
         return d
 
 
+class DiffGFDNVarSourceReceiverPos(DiffGFDN):
+    """GFDN for a grid of source AND receiver positions: MLP-driven factors on both sides (reference model.py:303-500).
+
+    H[r,k] = sum_{g,g'} C_g(r,k) T[k,g,g'] B_g'(r,k) + d[r,k] with T the group-to-group transfer functions
+    (FeedbackLoop.transfer_matrix): the receiver-side projection kernel runs once per source group with the row
+    gains (or the first biquad numerator) scaled by that group's source gain, chaining through its additive input."""
+
+    def __init__(self,
+                 sample_rate: int,
+                 num_groups: int,
+                 delays: List[int],
+                 device: torch.device,
+                 feedback_loop_config: FeedbackLoopConfig,
+                 output_filter_config: OutputFilterConfig,
+                 input_filter_config: OutputFilterConfig,
+                 use_absorption_filters: bool,
+                 learn_common_decay_times: bool = False,
+                 common_decay_times: Optional[List] = None,
+                 band_centre_hz: Optional[List] = None,
+                 colorless_fdn_params: Optional[List] = None,
+                 use_colorless_loss: bool = False):
+        super().__init__(sample_rate, num_groups, delays, device, feedback_loop_config, use_absorption_filters,
+                         learn_common_decay_times, common_decay_times, band_centre_hz, colorless_fdn_params,
+                         use_colorless_loss)
+        self.use_svf_in_output = output_filter_config.use_svfs
+        self.use_svf_in_input = input_filter_config.use_svfs
+        if self.use_svf_in_input:
+            raise NotImplementedError("SVF cascades on the SOURCE side of DiffGFDNVarSourceReceiverPos: no shipped "
+                                      "config enables them (the multi-source YAML uses gains on both sides)")
+        if self.use_svf_in_output:
+            self.output_filters = SVF_from_MLP(self.sample_rate, self.num_groups, self.num_delay_lines_per_group,
+                                               output_filter_config.num_fourier_features,
+                                               output_filter_config.num_hidden_layers,
+                                               output_filter_config.num_neurons_per_layer,
+                                               output_filter_config.encoding_type,
+                                               output_filter_config.compress_pole_factor,
+                                               position_type="output_gains", device=self.device).to(self.device)
+        else:
+            self.output_scalars = Gains_from_MLP(self.num_groups, self.num_delay_lines_per_group,
+                                                 output_filter_config.num_fourier_features,
+                                                 output_filter_config.num_hidden_layers,
+                                                 output_filter_config.num_neurons_per_layer,
+                                                 output_filter_config.encoding_type, position_type="output_gains",
+                                                 device=self.device).to(self.device)
+        self.input_scalars = Gains_from_MLP(self.num_groups, self.num_delay_lines_per_group,
+                                            input_filter_config.num_fourier_features,
+                                            input_filter_config.num_hidden_layers,
+                                            input_filter_config.num_neurons_per_layer,
+                                            input_filter_config.encoding_type, position_type="input_gains",
+                                            device=self.device).to(self.device)
+
+    def forward(self, x: Dict):
+        z = self._on_device(x['z_values'], torch.complex128)
+        self.batch_size = x['listener_position'].shape[0]
+        s_src = self.input_scalars.gains(x)  # (B, G) from x['source_position']
+        coef = self.output_filters.coefficients(x) if self.use_svf_in_output else None
+        s_rx = None if self.use_svf_in_output else self.output_scalars.gains(x)
+        T = self.feedback_loop.transfer_matrix(z, self._gains_vec(self.input_gains), self._gains_vec(self.output_gains))
+        d = x.get('target_early_response')
+        H = None if d is None else self._on_device(d, torch.complex64)
+        for gp in range(self.num_groups):
+            w = s_src[:, gp]
+            if coef is not None:  # scale the cascade by the source gain through its first numerator
+                scale = torch.ones_like(coef)
+                scale[:, :, 0, :3] = w.reshape(-1, 1, 1)
+                H = ops.svf_project(coef * scale, z, T[gp], H)
+            else:
+                H = ops.receiver_project(s_rx * w.unsqueeze(-1), T[gp], H)
+        if self.use_colorless_loss:
+            return H, self.sub_fdn_output(z)
+        return H
+
+    @torch.no_grad()
+    def get_param_dict_inference(self, data: Dict) -> Dict:
+        out = {'input_scalars': self.input_scalars.get_param_dict(data)['gains']}
+        if self.use_svf_in_output:
+            o = self.output_filters.get_param_dict(data)
+            out.update({'output_svf_params': o['svf_params'], 'output_biquad_coeffs': o['biquad_coeffs']})
+        else:
+            out['output_scalars'] = self.output_scalars.get_param_dict(data)['gains']
+        return out
+
+
+class DiffGFDNSinglePos(DiffGFDN):
+    """GFDN for ONE source-receiver pair: learnable per-group scalars or SVF cascades on either side (reference
+    model.py:667-960). H[k] = sum_{g,g'} C_g(z_k) T[k,g,g'] B_g'(z_k) + d[k]."""
+
+    def __init__(self,
+                 sample_rate: int,
+                 num_groups: int,
+                 delays: List[int],
+                 device: torch.device,
+                 feedback_loop_config: FeedbackLoopConfig,
+                 output_filter_config: OutputFilterConfig,
+                 use_absorption_filters: bool,
+                 learn_common_decay_times: Optional[bool] = False,
+                 common_decay_times: Optional[List] = None,
+                 band_centre_hz: Optional[List] = None,
+                 colorless_fdn_params: Optional[List] = None,
+                 use_colorless_loss: bool = False,
+                 input_filter_config: Optional[OutputFilterConfig] = None):
+        super().__init__(sample_rate, num_groups, delays, device, feedback_loop_config, use_absorption_filters,
+                         learn_common_decay_times, common_decay_times, band_centre_hz, colorless_fdn_params,
+                         use_colorless_loss)
+        self.use_svf_in_input = input_filter_config.use_svfs if input_filter_config is not None else False
+        self.use_svf_in_output = output_filter_config.use_svfs
+        if self.use_svf_in_output or self.use_svf_in_input:
+            self.svf_cutoff_freqs = svf_cutoff_frequencies(self.sample_rate).to(self.device)
+            self.num_biquads = self.svf_cutoff_freqs.numel()
+            self.compress_pole_factor = output_filter_config.compress_pole_factor
+        for side, svf in (("input", self.use_svf_in_input), ("output", self.use_svf_in_output)):
+            if svf:  # random resonance, 0 dB gains (reference :744-776)
+                init = torch.randn(self.num_groups, self.num_biquads, 2)
+                init[..., 1] = 0.0
+                setattr(self, f"{side}_svf_params", nn.Parameter(init.to(self.device)))
+                setattr(self, f"{side}_filters", SOSFilter(self.num_biquads, device=self.device))
+                setattr(self, f"{side}_scaled_res", ScaledSigmoid(lower_limit=1e-6, upper_limit=1.0))
+                setattr(self, f"{side}_scaled_gains", ScaledSigmoid(lower_limit=-6.0, upper_limit=6.0))
+            else:
+                setattr(self, f"{side}_scalars",
+                        nn.Parameter((torch.ones(self.num_groups, 1) / np.sqrt(self.num_groups)).to(self.device)))
+
+    def biquad_coefficients(self, filt_type: str = 'output') -> torch.Tensor:
+        """(G, S, 6) biquads of the learnable cascades of one side (reference get_filter :838-893)."""
+        side = 'output' if filt_type == 'output' else 'input'
+        raw = getattr(self, f"{side}_svf_params")
+        svf = torch.stack([getattr(self, f"{side}_scaled_res")(raw[..., 0]),
+                           getattr(self, f"{side}_scaled_gains")(raw[..., 1])], dim=-1)
+        coef = svf_to_biquads(svf, self.svf_cutoff_freqs, self.compress_pole_factor)
+        setattr(self, f"{side}_biquad_coeffs_", coef.detach())
+        return coef
+
+    def get_filter(self, z_values: torch.Tensor, filt_type: str = 'output') -> torch.Tensor:
+        """(N, K) complex64 filter responses, every delay line of a group sharing the group's filter."""
+        f = cascade_response(self.biquad_coefficients(filt_type).unsqueeze(0), self._on_device(z_values, torch.complex128))
+        return f[0].repeat_interleave(self.num_delay_lines_per_group, dim=0)
+
+    def forward(self, x: Dict):
+        z = self._on_device(x['z_values'], torch.complex128)
+        T = self.feedback_loop.transfer_matrix(z, self._gains_vec(self.input_gains), self._gains_vec(self.output_gains))
+        if self.use_svf_in_input:
+            f_in = cascade_response(self.biquad_coefficients('input').unsqueeze(0), z)[0]  # (G, K) complex64
+            y = sum(T[gp] * f_in[gp].unsqueeze(-1) for gp in range(self.num_groups))
+        else:
+            y = sum(T[gp] * self.input_scalars[gp, 0] for gp in range(self.num_groups))
+        d = x.get('target_early_response')
+        d = None if d is None else self._on_device(d, torch.complex64).reshape(1, -1)
+        if self.use_svf_in_output:
+            H = ops.svf_project(self.biquad_coefficients('output').unsqueeze(0), z, y, d)[0]
+        else:
+            H = ops.receiver_project(self.output_scalars.reshape(1, -1), y, d)[0]
+        if self.use_colorless_loss:
+            return H, self.sub_fdn_output(z)
+        return H
+
+    @torch.no_grad()
+    def get_param_dict(self) -> Dict:
+        d = super().get_param_dict()
+        d['absorption_coeffs'] = self.feedback_loop.delay_line_gains
+        for side, svf in (("input", self.use_svf_in_input), ("output", self.use_svf_in_output)):
+            if svf:
+                coef = self.biquad_coefficients(side)
+                raw = getattr(self, f"{side}_svf_params")
+                d[f'{side}_svf_params'] = torch.stack([getattr(self, f"{side}_scaled_res")(raw[..., 0]),
+                                                       getattr(self, f"{side}_scaled_gains")(raw[..., 1])],
+                                                      dim=-1).squeeze().cpu().numpy()
+                d[f'{side}_biquad_coeffs'] = [coef[g].cpu().numpy() for g in range(self.num_groups)]
+            else:
+                d[f'{side}_scalars'] = getattr(self, f"{side}_scalars").squeeze().cpu().numpy()
+        return d
+
+
 class DiffDirectionalFDNVarReceiverPos(DiffGFDN):
     """Directional FDN: one delay line per (group, SH channel), MLP-driven SH gains (reference model.py:975-1126)."""
 
@@ -296,4 +470,5 @@ class DiffDirectionalFDNVarReceiverPos(DiffGFDN):
         return d
 
 
-__all__ = ["DiffGFDN", "DiffGFDNVarReceiverPos", "DiffDirectionalFDNVarReceiverPos", "CouplingMatrixType"]
+__all__ = ["DiffGFDN", "DiffGFDNVarReceiverPos", "DiffGFDNVarSourceReceiverPos", "DiffGFDNSinglePos",
+           "DiffDirectionalFDNVarReceiverPos", "CouplingMatrixType"]

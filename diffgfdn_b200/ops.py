@@ -246,7 +246,7 @@ class _SVFProject(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, coef, z, y, d):
-        coef_ = _cuda("coef", coef, torch.float32)
+        coef_ = _cuda("coef", coef, torch.float64)
         z_ = _cuda("z", z, torch.complex128)
         y_ = _cuda("y", y, C64)
         d_ = _cuda("d", d, C64, optional=True)
@@ -262,6 +262,7 @@ class _SVFProject(torch.autograd.Function):
                       _stream())
         ctx.save_for_backward(coef_, z_, y_)
         ctx.d_dtype = None if d is None else d.dtype
+        ctx.coef_dtype = coef.dtype
         return h
 
     @staticmethod
@@ -280,11 +281,12 @@ class _SVFProject(torch.autograd.Function):
             _lib.call("dgfdn_project_svf_bwd", g, nsec, rows, k, _ptr(coef_), _ptr(z_), _ptr(y_), _ptr(gh_), k,
                       _ptr(gcoef), _ptr(gy), _ptr(ws), _stream())
         gd = gh_.to(ctx.d_dtype) if (ctx.d_dtype is not None and ctx.needs_input_grad[3]) else None
-        return gcoef, None, gy, gd
+        return (None if gcoef is None else gcoef.to(ctx.coef_dtype)), None, gy, gd
 
 
 def svf_project(coef: torch.Tensor, z: torch.Tensor, y: torch.Tensor, d: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """coef (R,G,S,6) float32 biquad coefficients, z (K,) complex128, y (K,G) complex64, d (R,K) complex64 or None."""
+    """coef (R,G,S,6) biquad coefficients (evaluated in float64), z (K,) complex128, y (K,G) complex64, d (R,K) complex64
+    or None."""
     return _SVFProject.apply(coef, z, y, d)
 
 

@@ -222,5 +222,48 @@ class VarReceiverPosTrainer(Trainer):
     """Omni GFDN over a grid of receivers (reference trainer.py:338-564)."""
 
 
+class SinglePosTrainer(Trainer):
+    """One measured RIR, one source-receiver pair (reference trainer.py:570-688): no batching, no validation split,
+    energy-matched initial gains."""
+
+    def __init__(self, net, trainer_config: TrainerConfig, filename: str = "ir"):
+        super().__init__(net, trainer_config)
+        self.filename = filename
+
+    @torch.no_grad()
+    def normalize(self, data: Dict):
+        """Sub-FDN normalisation, then scale the per-group scalars so that the mean energy of H matches the target
+        (reference :633-648; there `H` is only defined when the colorless loss is off -- a NameError otherwise --
+        here the response is evaluated in both cases)."""
+        super().normalize(data)
+        out = self.net(data)
+        H = out[0] if self.use_colorless_loss else out
+        target = data['target_rir_response'].to(self.device)
+        ratio = torch.mean(torch.abs(H)**2) / torch.mean(torch.abs(target)**2)
+        for name, prm in self.net.named_parameters():
+            if name in ('input_scalars', 'output_scalars'):
+                prm.data /= torch.pow(ratio, 0.25).to(prm.dtype)
+
+    def train(self, train_dataset, valid_dataset=None):
+        data = next(iter(train_dataset))
+        self.normalize(data)
+        self.train_loss, self.individual_train_loss = [], []
+        st = time.time()
+        for epoch in range(self.max_epochs):
+            et = time.time()
+            for data in train_dataset:
+                epoch_loss, parts = self.train_step(data)
+            self.scheduler.step()
+            self.train_loss.append(epoch_loss)
+            self.individual_train_loss.append(parts)
+            self.save_model(epoch)
+            print(f"epoch {epoch:3d}, train_loss {epoch_loss:.4f}, time {time.time() - et:.3f}s")
+            if epoch >= 1:
+                self.early_stop = self.early_stop + 1 if abs(self.train_loss[-2] - self.train_loss[-1]) <= 1e-4 else 0
+            if self.early_stop == self.patience:
+                break
+        print(f"Training time: {time.time() - st:.3f}s")
+
+
 class DirectionalFDNVarReceiverPosTrainer(Trainer):
     """Directional FDN over a grid of receivers (reference trainer.py:690-921)."""

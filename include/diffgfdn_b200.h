@@ -115,15 +115,16 @@ DGFDN_API int dgfdn_project_bwd(int g, int64_t rows, int64_t k, const float* s, 
  * (receiver, group, section) with its (B,N,K) complex filter tensor (gain_filters.py:383-401), SOSFilter.forward
  * (gain_filters.py:221-241) and the einsums of model.py:583-619:
  *   F[r,g,k] = prod_s (b0 + b1 z_k^-1 + b2 z_k^-2) / (a0 + a1 z_k^-1 + a2 z_k^-2) ;  H[r,k] = sum_g F[r,g,k] y[k,g] + d[r,k]
- * coef [R,G,S,6] float32 = (b0 b1 b2 a0 a1 a2) per section (S <= 16), z [K] c128, y [K,G] c64, d [R,K] c64 or NULL,
- * h [R,K] c64 out. The response is evaluated in float64 (the reference evaluates it on its complex128 z grid). */
-DGFDN_API int dgfdn_project_svf_fwd(int g, int nsec, int64_t rows, int64_t k, const float* coef, const void* z, const void* y,
+ * coef [R,G,S,6] float64 = (b0 b1 b2 a0 a1 a2) per section (S <= 16), z [K] c128, y [K,G] c64, d [R,K] c64 or NULL,
+ * h [R,K] c64 out. Coefficients and response are float64 (the reference evaluates on its complex128 z grid; the
+ * denominators cancel to ~4 f_c^2 near DC, which float32 coefficients resolve to 1e-3 only). */
+DGFDN_API int dgfdn_project_svf_fwd(int g, int nsec, int64_t rows, int64_t k, const double* coef, const void* z, const void* y,
                           const void* d, int64_t ldd, void* h, int64_t ldh, void* stream);
 /* Adjoint: gy[k,g] = sum_r conj(F[r,g,k]) gh[r,k] ;  gcoef[r,g,s,:] = Re sum_k conj(gh[r,k]) dH[r,k]/dcoef (deterministic
  * two-stage reduction over bins; ws of dgfdn_project_svf_bwd_ws_bytes bytes). gy / gcoef may be NULL. rows <= 65535. */
 DGFDN_API int64_t dgfdn_project_svf_bwd_ws_bytes(int g, int nsec, int64_t rows, int64_t k);
-DGFDN_API int dgfdn_project_svf_bwd(int g, int nsec, int64_t rows, int64_t k, const float* coef, const void* z, const void* y,
-                          const void* gh, int64_t ldh, float* gcoef, void* gy, void* ws, void* stream);
+DGFDN_API int dgfdn_project_svf_bwd(int g, int nsec, int64_t rows, int64_t k, const double* coef, const void* z, const void* y,
+                          const void* gh, int64_t ldh, double* gcoef, void* gy, void* ws, void* stream);
 
 /* Directional (SH) projection, model.py:1056-1088:
  *   H_sh[r,l,k] = sum_g cw[r,g,l] x[k, g L + l]          cw = w o c  [R,G,L] float32, x [K,N] c64

@@ -138,7 +138,10 @@ def test_omni_normalize_and_adam_steps_match_reference(name, tmp_path):
     assert np.allclose(got, g["steps/loss"], rtol=2e-3)
     for k, v in net.state_dict().items():
         ref = g[f"steps/param/{k}"]
-        assert float(np.abs(v.cpu().numpy() - ref).max()) < 5e-3 * max(1e-3, float(np.abs(ref).max())) + 2e-4, k
+        # Adam's first steps move every entry by ~lr * sign(grad): entries whose gradient is at the level of the
+        # reference's float32 biquad-coefficient noise (SVF case, see above) may differ by a fraction of lr = 0.01
+        slack = 1e-3 if net.use_svf_in_output else 2e-4
+        assert float(np.abs(v.cpu().numpy() - ref).max()) < 5e-3 * max(1e-3, float(np.abs(ref).max())) + slack, k
 
 
 @pytest.mark.parametrize("name", list(DIRECTIONAL))
@@ -179,6 +182,59 @@ def test_directional_forward_losses_grads_match_reference(name, tmp_path):
     # oracle agrees on the same inputs (ties the oracle, the reference fixture and the kernels together)
     o = oracle_directional(g, params_of(g))
     assert rel(H_sh, o["H_sh"]) < 1e-4
+
+
+@pytest.mark.parametrize("name", ["src_rx_n12", "single_n12", "single_n12_svf"])
+def test_source_receiver_and_single_position_variants_match_reference(name, tmp_path):
+    """SURVEY a-8c: DiffGFDNVarSourceReceiverPos (model.py:402-452) and DiffGFDNSinglePos (:779-908) on the K1
+    group-to-group transfer functions + the projection kernels."""
+    from diffgfdn_b200.config import FeedbackLoopConfig, OutputFilterConfig
+    from diffgfdn_b200.model import DiffGFDNSinglePos, DiffGFDNVarSourceReceiverPos
+    from diffgfdn_b200.trainer import SinglePosTrainer, VarReceiverPosTrainer
+    from diffgfdn_b200.utils import unit_circle_grid
+    from golden_util import oracle_variant
+    g = load(name)
+    delays = [int(v) for v in g["meta/delays"]]
+    common = dict(use_absorption_filters=False, common_decay_times=np.array([g["meta/t60"]]), use_colorless_loss=True)
+    if name.startswith("src_rx"):
+        ofc = OutputFilterConfig(use_svfs=False, num_hidden_layers=1, num_neurons_per_layer=16, num_fourier_features=4)
+        net = DiffGFDNVarSourceReceiverPos(float(g["meta/fs"]), 3, delays, 'cuda', FeedbackLoopConfig(use_zero_coupling=False),
+                                           ofc, ofc, learn_common_decay_times=False, **common)
+        tcls = VarReceiverPosTrainer
+    else:
+        pf = float(g["meta/pole_factor"])
+        net = DiffGFDNSinglePos(float(g["meta/fs"]), 3, delays, 'cuda', FeedbackLoopConfig(use_zero_coupling=False),
+                                OutputFilterConfig(use_svfs=bool(g["meta/svf_out"]), compress_pole_factor=pf),
+                                input_filter_config=OutputFilterConfig(use_svfs=bool(g["meta/svf_in"]),
+                                                                       compress_pole_factor=pf), **common)
+        tcls = SinglePosTrainer
+    net.load_state_dict({k[len("param/"):]: torch.tensor(v) for k, v in g.items() if k.startswith("param/")},
+                        strict=True)
+    data = {k[len("data/"):]: torch.tensor(v) for k, v in g.items() if k.startswith("data/")}
+    data["z_values"] = unit_circle_grid(int(g["meta/nfft"]))
+    data["target_rir_response"] = data["target_rir_response"].cuda()
+    trainer = make_trainer(tcls, net, tmp_path, use_colorless_loss=True, use_asym_spectral_loss=True,
+                           edc_loss_weight=10.0, num_freq_bins=int(g["meta/nfft"]))
+    net.zero_grad()
+    H, (Hs, Hsd) = net(data)
+    d = g["data/target_early_response"]
+    svf = name.endswith("_svf")
+    assert tuple(H.shape) == d.shape and H.dtype == torch.complex64
+    assert rel(H.detach().cpu().to(torch.complex128).numpy() - d, g["out/H"] - d) < (5e-3 if svf else 1e-4)
+    assert rel(Hs, g["out/H_sub"]) < 1e-4
+    po = params_of(g, requires_grad=True)
+    o = oracle_variant(g, po)
+    assert rel(H.detach().cpu().to(torch.complex128).numpy() - d, o["H"].detach().numpy() - d) < 1e-4  # float64 oracle
+    losses = trainer.calculate_losses(data, H, (Hs, Hsd))
+    total = sum(losses.values())
+    total.backward()
+    assert abs(float(losses["edc_loss"]) - g["loss/edc_loss"]) < 0.01 * float(g["meta/edc_w"])
+    assert abs(float(total) - g["loss/total"]) < 2e-3 * g["loss/total"]
+    if svf:  # the reference cannot differentiate this branch (oracle/gen_golden.py): gradients against the oracle
+        o["total"].backward()
+    for k, p in net.named_parameters():
+        ref = po[k].grad if svf else g[f"grad/{k}"]
+        assert rel(p.grad, ref) < 1e-3, k
 
 
 def test_feedback_loop_dense_inverse_api():
