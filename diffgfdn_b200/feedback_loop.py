@@ -132,17 +132,56 @@ class FeedbackLoop(nn.Module):
                 decay_times_to_gain_per_sample(self.common_decay_times[i], self.delays[i * per:(i + 1) * per],
                                                torch.tensor(self.sample_rate)) for i in range(self.num_groups)
             ]).detach().to(self.device)
+        elif self.use_absorption_filters:
+            # Frequency-dependent absorption (reference :236-255): `gains` holds the filter coefficients, designed at
+            # init time on the host (GEQ: (N, S, 3, 2) biquads [.., 0] numerators / [.., 1] denominators; Prony:
+            # (N, order, 2)). Their responses Gamma_i(z_k) are evaluated on the z grid of the first solve and cached.
+            g = torch.as_tensor(gains, device=self.device)
+            if g.ndim not in (3, 4):
+                raise RuntimeError("absorption filters: expected (N, S, 3, 2) biquads or (N, order, 2) IIR coefficients")
+            self.absorption_coeffs = g
+            self.delay_line_gains = g
+            self._gamma_cache = None
         else:
-            if self.use_absorption_filters:
-                raise NotImplementedError(
-                    "frequency-dependent absorption: pass the per-bin responses Gamma_i(z_k) with "
-                    "set_absorption_response((N, K) complex); SOS/GEQ design is init-time host code outside the "
-                    "hot path (SURVEY.md section 8f rank 3)")
             self.delay_line_gains = torch.as_tensor(gains, dtype=torch.float32, device=self.device)
 
     def set_absorption_response(self, gamma_z: torch.Tensor):
         """Use per-bin complex delay-line gains Gamma_i(z_k), shape (N, K) (reference feedback_loop.py:333-344)."""
         self.delay_line_gain_response = gamma_z.to(torch.complex64)
+
+    @torch.no_grad()
+    def absorption_response(self, z: torch.Tensor) -> Optional[torch.Tensor]:
+        """Gamma_i(z_k) (N, K) complex64 of the absorption filters on this z grid, or None for scalar gains.
+        GEQ biquads go through the cascade kernel (K2s, float64 inside; reference :334-340 multiplies the sections
+        in complex64); Prony filters are sum_k b_k z^-k / (sum_k a_k z^-k + 1e-9) (reference gain_filters.py:176-203).
+        Constant over training: cached per (grid, coefficient version)."""
+        if self.delay_line_gain_response is not None:
+            if self.delay_line_gain_response.shape[-1] != z.numel():
+                raise RuntimeError("absorption response was set for a different number of bins")
+            return self.delay_line_gain_response
+        coeffs = getattr(self, "absorption_coeffs", None)
+        if coeffs is None:
+            return None
+        key = (z.data_ptr(), z.numel(), coeffs.data_ptr(), coeffs._version)
+        if self._gamma_cache is not None and self._gamma_cache[0] == key:
+            return self._gamma_cache[1]
+        if not bool(coeffs.abs().sum() > 0):
+            raise RuntimeError("absorption filters are all zero: the GEQ design runs on the host at init time and is "
+                               "outside this package -- load a reference checkpoint (buffer 'delay_filters') or call "
+                               "DiffGFDN.set_absorption_filters(coefficients)")
+        from .gain_filters import cascade_response
+        zc = z.to(device=coeffs.device, dtype=torch.complex128)
+        if coeffs.ndim == 4:
+            coef = torch.cat([coeffs[..., 0], coeffs[..., 1]], dim=-1).to(torch.float64).unsqueeze(1)  # (N, 1, S, 6)
+            gamma = cascade_response(coef, zc)[:, 0]
+        else:
+            k = torch.arange(coeffs.shape[1], device=coeffs.device, dtype=torch.float64)
+            zp = zc.unsqueeze(0)**(-k.unsqueeze(-1))  # (order, K)
+            num = coeffs[..., 0].to(torch.complex128) @ zp
+            den = coeffs[..., 1].to(torch.complex128) @ zp
+            gamma = (num / (den + 1e-9)).to(torch.complex64)
+        self._gamma_cache = (key, gamma)
+        return gamma
 
     # ---- feedback matrix (reference feedback_loop.py:260-324) --------------------------------------------
     def _init_feedback_matrix(self, colorless_feedback_matrix):
@@ -167,6 +206,9 @@ class FeedbackLoop(nn.Module):
             self.M = fn(self.M)
         if self.delay_line_gain_response is not None:
             self.delay_line_gain_response = fn(self.delay_line_gain_response)
+        if getattr(self, "absorption_coeffs", None) is not None:
+            self.absorption_coeffs = self.delay_line_gains  # same tensor (moved above)
+            self._gamma_cache = None
         return self
 
     def construct_block_mixing_matrix(self, dtype: Optional[torch.dtype] = None) -> torch.Tensor:
@@ -204,9 +246,10 @@ class FeedbackLoop(nn.Module):
         """x_k = (D(z_k) Gamma^-1 - A)^-1 b and y[k,g] = sum_{n in g} c_n x_k[n] on the GPU (one warp per bin)."""
         a = self.coupled_feedback_matrix_real(torch.float64)
         self.coupled_feedback_matrix = a.detach().to(torch.float32)
-        gamma = None if self.delay_line_gain_response is not None else self.delay_line_gains
+        gamma_z = self.absorption_response(z)
+        gamma = None if gamma_z is not None else self.delay_line_gains
         return ops.gfdn_solve(z, self.delays.to(torch.int32), a, gamma, b, c, self.num_groups, transpose_a=transpose,
-                              gamma_z=self.delay_line_gain_response)
+                              gamma_z=gamma_z)
 
     def transfer_matrix(self, z: torch.Tensor, b: torch.Tensor, c: torch.Tensor) -> List[torch.Tensor]:
         """Group-to-group transfer functions T[g'][k,g] = sum_{n in g, m in g'} c_n P_k[n,m] b_m: one K1 solve per
@@ -215,7 +258,8 @@ class FeedbackLoop(nn.Module):
         G x G functions per bin are all they need of the feedback loop."""
         a = self.coupled_feedback_matrix_real(torch.float64)
         self.coupled_feedback_matrix = a.detach().to(torch.float32)
-        gamma = None if self.delay_line_gain_response is not None else self.delay_line_gains
+        gamma_z = self.absorption_response(z)
+        gamma = None if gamma_z is not None else self.delay_line_gains
         delays = self.delays.to(torch.int32)
         L = self.num_delay_lines_per_group
         b = b.reshape(-1)
@@ -223,8 +267,7 @@ class FeedbackLoop(nn.Module):
         for gp in range(self.num_groups):
             mask = torch.zeros_like(b)
             mask[gp * L:(gp + 1) * L] = 1.0
-            out.append(ops.gfdn_solve(z, delays, a, gamma, b * mask, c, self.num_groups,
-                                      gamma_z=self.delay_line_gain_response)[1])
+            out.append(ops.gfdn_solve(z, delays, a, gamma, b * mask, c, self.num_groups, gamma_z=gamma_z)[1])
         return out
 
     def forward(self, z: torch.Tensor) -> torch.Tensor:

@@ -76,6 +76,11 @@ class DiffGFDN(nn.Module):
         per = self.num_delay_lines_per_group
         self.delays_by_group = [self.delays[i:i + per] for i in range(0, self.num_delay_lines, per)]
         self.device = self.delay_buffer.device
+        fl = getattr(self, "feedback_loop", None)
+        if fl is not None and getattr(fl, "absorption_coeffs", None) is not None:
+            # the feedback loop reads the SAME tensor as the 'delay_filters' buffer (load_state_dict copies in place)
+            fl.absorption_coeffs = fl.delay_line_gains = self.delay_filters
+            fl._gamma_cache = None
         return self
 
     def _init_io_gains(self, colorless_fdn_params=None):
@@ -97,9 +102,16 @@ class DiffGFDN(nn.Module):
             self.gain_per_sample = None
             return
         if self.use_absorption_filters:
-            raise NotImplementedError("GEQ absorption-filter design is outside the hot path; construct with "
-                                      "use_absorption_filters=False and call "
-                                      "feedback_loop.set_absorption_response(Gamma (N, K)) with the filter responses")
+            # The reference designs one graphic equaliser per delay line here (absorption_filters.py:108-155 ->
+            # filters/geq.py, an LBFGS fit per line, ~50 s): init-time host code outside the hot path. The buffer keeps
+            # the reference's name and (N, bands + 3, 3, 2) layout so its checkpoints load unchanged; fill it with
+            # load_state_dict() or set_absorption_filters(). The per-bin responses are evaluated on the GPU.
+            if band_centre_hz is None:
+                raise RuntimeError("use_absorption_filters=True needs band_centre_hz (one T60 per band and group)")
+            self.gain_per_sample = torch.zeros(self.num_delay_lines, len(band_centre_hz) + 3, 3, 2, device=self.device)
+            self.filter_order = 3
+            self.register_buffer('delay_filters', self.gain_per_sample)
+            return
         t60 = np.squeeze(np.asarray(self.common_decay_times))
         gains = [decay_times_to_gain_per_sample(float(t60[i]), self.delays_by_group[i].cpu().numpy(),
                                                 self.sample_rate).tolist() for i in range(self.num_groups)]
@@ -118,6 +130,12 @@ class DiffGFDN(nn.Module):
                 [torch.from_numpy(colorless_fdn_params[i].opt_feedback_matrix) for i in range(self.num_groups)], dim=0)
         self.feedback_loop = FeedbackLoop(self.sample_rate, self.num_groups, self.num_delay_lines_per_group,
                                           self.delays, self.use_absorption_filters, **kw)
+
+    @torch.no_grad()
+    def set_absorption_filters(self, coeffs: torch.Tensor):
+        """Absorption-filter coefficients from an external design (decay_times_to_gain_filters_geq of the reference,
+        (N, S, 3, 2)), copied into the 'delay_filters' buffer."""
+        self.delay_filters.copy_(torch.as_tensor(coeffs).to(self.delay_filters))
 
     # ---- helpers ---------------------------------------------------------------------------------------
     def _on_device(self, t: torch.Tensor, dtype=None) -> torch.Tensor:

@@ -73,7 +73,7 @@ def make_trainer(cls, net, **kw):
 
 
 def case_omni(name, n_lines, nfft, bsz, t60, seed, hidden, neurons, feats, radius=1.0, subband=False, steps=2,
-              early_scale=1.0, svf=False, pole_factor=1.0):
+              early_scale=1.0, svf=False, pole_factor=1.0, geq_bands=None):
     cfg = DiffGFDNConfig(seed=235265, num_delay_lines=n_lines)
     delays = cfg.delay_length_samps
     torch.manual_seed(seed)
@@ -82,8 +82,9 @@ def case_omni(name, n_lines, nfft, bsz, t60, seed, hidden, neurons, feats, radiu
                                  OutputFilterConfig(use_svfs=svf, num_hidden_layers=hidden,
                                                     num_neurons_per_layer=neurons, num_fourier_features=feats,
                                                     compress_pole_factor=pole_factor),
-                                 use_absorption_filters=False, common_decay_times=np.array([t60]),
-                                 use_colorless_loss=True)
+                                 use_absorption_filters=geq_bands is not None,
+                                 common_decay_times=np.array([t60]) if geq_bands is None else np.asarray(t60),
+                                 band_centre_hz=geq_bands, use_colorless_loss=True)
     # early_scale < 1 brings the direct path d down towards the level of the late (GFDN) part: with the short T60s
     # that fit these small fixtures a random initialisation leaves the late part ~1e4 below |d|, which no float32
     # FFT can resolve to 1e-3 (the reference runs this path in float64)
@@ -127,7 +128,12 @@ def case_omni(name, n_lines, nfft, bsz, t60, seed, hidden, neurons, feats, radiu
         out["meta/pole_factor"] = pole_factor
     else:
         out["out/s"] = net.output_scalars.gains.detach().numpy()
-    out["out/gamma"] = net.feedback_loop.delay_line_gains.detach().numpy()
+    if geq_bands is None:
+        out["out/gamma"] = net.feedback_loop.delay_line_gains.detach().numpy()
+    else:  # GEQ absorption filters (absorption_filters.py:108-155): responses on a decimated grid
+        out["meta/band_centre_hz"] = np.asarray(geq_bands, dtype=np.float64)
+        out["out/gamma_z_s8"] = np.stack([f(data['z_values'][::8]).detach().numpy()
+                                          for f in net.feedback_loop.delay_line_gains])
     for kk, v in losses.items():
         out[f"loss/{kk}"] = float(v.detach())
     out["loss/total"] = float(total.detach())
@@ -307,6 +313,10 @@ if __name__ == "__main__":
     case_omni("omni_n24", 24, 4096, 3, [0.03, 0.05, 0.06], 13, 1, 16, 4, steps=1)
     case_omni("omni_n12_svf", 12, 8192, 3, [0.05, 0.08, 0.12], 14, 1, 32, 6, svf=True, pole_factor=0.998,
               early_scale=1e-3)
+    bands = [63.0, 125.0, 250.0, 500.0, 1000.0, 2000.0, 4000.0, 8000.0]
+    t60_bands = np.stack([np.linspace(0.12, 0.05, 8), np.linspace(0.09, 0.06, 8), np.linspace(0.06, 0.04, 8)], axis=1)
+    case_omni("omni_n12_geq_svf", 12, 8192, 2, t60_bands, 18, 1, 16, 4, svf=True, pole_factor=0.998, early_scale=1e-3,
+              geq_bands=bands, steps=1)
     case_src_rx("src_rx_n12", 12, 8192, 3, [0.05, 0.08, 0.12], 15, 1, 16, 4)
     case_single("single_n12", 12, 8192, [0.05, 0.08, 0.12], 16, False, False)
     case_single("single_n12_svf", 12, 8192, [0.05, 0.08, 0.12], 17, True, True)

@@ -318,6 +318,14 @@ def sos_response(z: torch.Tensor, coef: torch.Tensor) -> torch.Tensor:
     return torch.prod(num / den, dim=-2)
 
 
+def absorption_filter_response(z: torch.Tensor, delay_filters: torch.Tensor) -> torch.Tensor:
+    """feedback_loop.py:236-255, 333-340: Gamma_i(z_k) of the GEQ absorption filters. delay_filters is the
+    reference's buffer (N, S, 3, 2): [..., 0] numerators, [..., 1] denominators of S biquads per delay line
+    (model.py:131-147). -> (N, K) complex128 (the reference multiplies the sections in complex64)."""
+    coef = torch.cat([delay_filters[..., 0], delay_filters[..., 1]], dim=-1)  # (N, S, 6)
+    return sos_response(z, coef)
+
+
 def omni_response_svf(z, delays, gamma, a, b, c, coef, d=None) -> torch.Tensor:
     """model.py:583-619 with use_svf_in_output: C[r,n,k] = F[r,g(n),k] c_n (gain_filters.py:388-401, every delay
     line of a group shares the group's filter); coef is (B, G, S, 6)."""

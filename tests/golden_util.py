@@ -8,7 +8,7 @@ from oracle import gfdn_oracle as O
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 OMNI_CASES = ["omni_n12", "omni_n12_subband_r", "omni_n24"]
-SVF_CASES = ["omni_n12_svf"]
+SVF_CASES = ["omni_n12_svf", "omni_n12_geq_svf"]  # the second adds GEQ absorption filters (the full-band YAML)
 DIR_CASES = ["directional_n27", "directional_n27_skip"]
 VARIANT_CASES = ["src_rx_n12", "single_n12", "single_n12_svf"]  # a-8c: source+receiver gains, single position
 
@@ -38,7 +38,10 @@ def oracle_omni(g, p, coef_override=None):
     z = O.z_grid(nfft, float(g["meta/radius"]))
     delays = torch.tensor(g["meta/delays"], dtype=torch.float64)
     G = p["feedback_loop.M"].shape[0]
-    gamma = O.decay_times_to_gain_per_sample(g["meta/t60"], g["meta/delays"], fs, G)
+    if g["param/delay_filters"].ndim == 4:  # GEQ absorption filters: per-bin complex delay-line gains
+        gamma = O.absorption_filter_response(z, torch.tensor(g["param/delay_filters"], dtype=torch.float64))
+    else:
+        gamma = O.decay_times_to_gain_per_sample(g["meta/t60"], g["meta/delays"], fs, G)
     A = O.coupled_feedback_matrix(p["feedback_loop.M"], p["feedback_loop.alpha"])
     b = p["input_gains"].reshape(-1)
     c = p["output_gains"].reshape(-1)

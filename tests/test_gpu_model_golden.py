@@ -15,6 +15,7 @@ OMNI = {  # name: (hidden, neurons, fourier features, steps)
     "omni_n12_subband_r": (2, 16, 4, 2),
     "omni_n24": (1, 16, 4, 1),
     "omni_n12_svf": (1, 32, 6, 2),  # SVF output filters (use_svfs: True), compress_pole_factor 0.998
+    "omni_n12_geq_svf": (1, 16, 4, 1),  # + GEQ absorption filters (use_absorption_filters: True): the full-band YAML
 }
 DIRECTIONAL = {"directional_n27": (1, 16, 4, False), "directional_n27_skip": (2, 16, 4, True)}
 
@@ -28,12 +29,15 @@ def rel(a, b):
 def build_omni(g, hidden, neurons, feats):
     from diffgfdn_b200.config import FeedbackLoopConfig, OutputFilterConfig
     from diffgfdn_b200.model import DiffGFDNVarReceiverPos
+    geq = "meta/band_centre_hz" in g
     net = DiffGFDNVarReceiverPos(float(g["meta/fs"]), 3, [int(v) for v in g["meta/delays"]], 'cuda',
                                  FeedbackLoopConfig(use_zero_coupling=False),
                                  OutputFilterConfig(use_svfs="out/svf_params" in g, num_hidden_layers=hidden,
                                                     num_neurons_per_layer=neurons, num_fourier_features=feats,
                                                     compress_pole_factor=float(g.get("meta/pole_factor", 1.0))),
-                                 use_absorption_filters=False, common_decay_times=np.array([g["meta/t60"]]),
+                                 use_absorption_filters=geq,
+                                 common_decay_times=g["meta/t60"] if geq else np.array([g["meta/t60"]]),
+                                 band_centre_hz=list(g["meta/band_centre_hz"]) if geq else None,
                                  use_colorless_loss=True)
     state = {k[len("param/"):]: torch.tensor(v) for k, v in g.items() if k.startswith("param/")}
     net.load_state_dict(state, strict=True)  # reference checkpoint layout must load unchanged
