@@ -52,6 +52,10 @@ SIGNATURES = {
     "dgfdn_edc_db": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
     "dgfdn_edc_loss_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
     "dgfdn_edc_loss_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_double, c_void_p, c_void_p]),
+    "dgfdn_edr_db": (c_int, [c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
+    "dgfdn_edr_ws_bytes": (c_int64, [c_int64, c_int64]),
+    "dgfdn_edr_loss_fwd": (c_int, [c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "dgfdn_edr_loss_bwd": (c_int, [c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dgfdn_td_edc_step": (c_int, [c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64,
                                   c_void_p, c_double, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "dgfdn_td_mix": (c_int, [c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64,

@@ -145,9 +145,9 @@ class edr_loss(nn.Module):
     """Energy-decay-relief loss (reference losses.py:377-495): irfft(n=K) -> STFT (hann 4096 / hop 2048,
     center=False) -> EDR[f,m] = sum_{m'>=m} |S|^2 -> dB; sum_b sum|dEDR| / sum|EDR_target|.
 
-    The odd-length inverse DFT runs on the chirp-z kernel; the STFT + frame scan is batched cuFFT / torch ops on the
-    device in this round (ERB grouping and frequency weighting of the reference are not ported: no shipped config
-    on the hot path enables them)."""
+    The odd-length inverse DFT runs on the chirp-z kernel (K3a), the STFT of the framed response on cuFFT, and the
+    frame scan + dB + normalised L1 and its whole adjoint in the K3e kernels (ERB grouping and frequency weighting
+    of the reference are not ported: no shipped config on the hot path enables them)."""
 
     def __init__(self, sample_rate: float, win_size: int = 2**12, hop_size: int = 2**11,
                  reduced_pole_radius: Optional[float] = None, use_erb_grouping: bool = False, time_axis: int = -1,
@@ -162,32 +162,31 @@ class edr_loss(nn.Module):
         self.reduced_pole_radius = reduced_pole_radius
         self._target_cache = {}
 
-    def _edr_db(self, rir: torch.Tensor) -> torch.Tensor:
+    def _stft(self, rir: torch.Tensor) -> torch.Tensor:
+        """(R, T_f, F) complex64: zero-pad to a hop multiple, hann(win), center=False (reference :501-553). The
+        batched R2C transform of the frames is cuFFT; everything after it is the K3e kernel."""
         t = rir.shape[-1]
         if t % self.hop_size != 0:
             rir = nn.functional.pad(rir, (0, self.hop_size * int(np.ceil(t / self.hop_size)) - t))
         window = torch.hann_window(self.win_size, device=rir.device, dtype=rir.dtype)
-        frames = rir.unfold(-1, self.win_size, self.hop_size) * window  # (B, T_f, win)
-        power = torch.fft.rfft(frames, dim=-1).abs().pow(2).transpose(-1, -2)  # (B, F, T_f)
-        edr = torch.flip(torch.cumsum(torch.flip(power, dims=[-1]), dim=-1), dims=[-1])
-        return db(edr, is_squared=True)
+        frames = rir.reshape(-1, rir.shape[-1]).unfold(-1, self.win_size, self.hop_size) * window  # (R, T_f, win)
+        return torch.fft.rfft(frames, dim=-1)
 
     def forward(self, target_response: torch.Tensor, achieved_response: torch.Tensor) -> torch.Tensor:
         assert target_response.shape == achieved_response.shape
         k = target_response.shape[-1]
         key = (target_response.data_ptr(), tuple(target_response.shape), target_response._version)
-        tgt = self._target_cache.get(key)
-        if tgt is None:
+        hit = self._target_cache.get(key)
+        if hit is None:
             with torch.no_grad():
-                tgt = self._edr_db(ops.irfft_window(target_response.to(torch.complex64), k, 0, k))
+                tgt = ops.edr_db(self._stft(ops.irfft_window(target_response.to(torch.complex64), k, 0, k)))
+                hit = (tgt, tgt.abs().sum(dim=(-1, -2), dtype=torch.float64))
             if len(self._target_cache) > 64:
                 self._target_cache.clear()
-            self._target_cache[key] = tgt
+            self._target_cache[key] = hit
+        tgt, den = hit
         rir = ops.irfft_window(achieved_response, k, 0, k)
         if self.reduced_pole_radius is not None:
             rir = rir * torch.pow(torch.tensor(1.0 / self.reduced_pole_radius, device=rir.device),
                                   torch.arange(k, device=rir.device))
-        ach = self._edr_db(rir)
-        num = torch.abs(tgt - ach).sum(dim=(-1, -2))
-        den = torch.abs(tgt).sum(dim=(-1, -2))
-        return (num / den).sum().to(torch.float64)
+        return ops.edr_l1_normalised(self._stft(rir), tgt, den)

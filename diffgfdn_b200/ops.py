@@ -506,6 +506,52 @@ def edc_abs_db_sum(h: torch.Tensor, target_db: torch.Tensor, mask: Optional[torc
 # ----------------------------------------------------------------------------------------------------------
 # K3c: receiver step in the time domain (mix + EDC + dB loss + backward in one kernel)
 # ----------------------------------------------------------------------------------------------------------
+# ----------------------------------------------------------------------------------------------------------
+# K3e: energy decay relief on an STFT
+# ----------------------------------------------------------------------------------------------------------
+def edr_db(s: torch.Tensor) -> torch.Tensor:
+    """10 log10(sum_{m' >= m} |S[..., m', f]|^2 + eps) of an STFT S (R, T_f, F) complex64 -> (R, T_f, F) float32."""
+    s_ = _cuda("S", s, C64)
+    rows, tf, f = s_.shape
+    out = torch.empty(rows, tf, f, dtype=torch.float32, device=s_.device)
+    with torch.cuda.device(s_.device):
+        _lib.call("dgfdn_edr_db", rows, tf, f, _ptr(s_), _ptr(out), _stream())
+    return out
+
+
+class _EDRLoss(torch.autograd.Function):
+    """sum_b sum_{f,m} |T_dB - EDR_dB(S_b)| / den[b]  (reference losses.py:447-495)."""
+
+    @staticmethod
+    def forward(ctx, s, target_db, den):
+        s_ = _cuda("S", s, C64)
+        t_ = _cuda("target_db", target_db, torch.float32)
+        den_ = _cuda("den", den, torch.float64)
+        rows, tf, f = s_.shape
+        if tuple(t_.shape) != (rows, tf, f) or den_.numel() != rows:
+            raise RuntimeError("edr_loss: inconsistent shapes")
+        loss = torch.empty(1, dtype=torch.float64, device=s_.device)
+        with torch.cuda.device(s_.device):
+            ws = torch.empty(max(1, _lib.load().dgfdn_edr_ws_bytes(rows, f) // 8), dtype=torch.float64, device=s_.device)
+            _lib.call("dgfdn_edr_loss_fwd", rows, tf, f, _ptr(s_), _ptr(t_), _ptr(den_), _ptr(loss), _ptr(ws), _stream())
+        ctx.save_for_backward(s_, t_, den_)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, gloss):
+        s_, t_, den_ = ctx.saved_tensors
+        rows, tf, f = s_.shape
+        g_ = _cuda("gloss", gloss.reshape(1), torch.float64)
+        gs = torch.empty_like(s_)
+        with torch.cuda.device(s_.device):
+            _lib.call("dgfdn_edr_loss_bwd", rows, tf, f, _ptr(s_), _ptr(t_), _ptr(den_), _ptr(g_), _ptr(gs), _stream())
+        return gs, None, None
+
+
+def edr_l1_normalised(s: torch.Tensor, target_db: torch.Tensor, den: torch.Tensor) -> torch.Tensor:
+    return _EDRLoss.apply(s, target_db, den)
+
+
 def td_contract_workspace(num_groups: int, rows: int, tn: int, device) -> torch.Tensor:
     nbytes = int(_lib.load().dgfdn_td_contract_ws_bytes(num_groups, rows, tn))
     return torch.empty(max(nbytes // 4, 1), dtype=torch.float32, device=device)

@@ -175,6 +175,20 @@ DGFDN_API int dgfdn_edc_loss_bwd(const float* h, const float* target_db, const f
                        double coef, float* gh, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * K3e: energy-decay-relief loss on an STFT.  Replaces get_edr_from_stft + db + the normalised L1 reduction of
+ * edr_loss.forward (losses.py:447-495, 556-575; utils.py:16-40) and their autograd:
+ *   EDR[f,m] = sum_{m' >= m} |S[f,m']|^2 ;  loss = sum_b ( sum_{f,m} |T_dB[b,m,f] - 10 log10(EDR_b[f,m] + eps)| ) / den[b]
+ * s [R, T_f, F] c64 (torch.fft.rfft of the hann-windowed frames [R, T_f, win]: the STFT stays cuFFT), target_db and
+ * out_db [R, T_f, F] float32 in the same layout, den [R] float64 (= sum |T_dB|), loss [1] float64 out, ws of
+ * dgfdn_edr_ws_bytes bytes. bwd: gs [R, T_f, F] c64 = gloss[0] * dloss/dS (torch convention). R <= 65535. */
+DGFDN_API int dgfdn_edr_db(int64_t rows, int64_t tf, int64_t f, const void* s, float* out_db, void* stream);
+DGFDN_API int64_t dgfdn_edr_ws_bytes(int64_t rows, int64_t f);
+DGFDN_API int dgfdn_edr_loss_fwd(int64_t rows, int64_t tf, int64_t f, const void* s, const float* target_db, const double* den,
+                       double* loss, void* ws, void* stream);
+DGFDN_API int dgfdn_edr_loss_bwd(int64_t rows, int64_t tf, int64_t f, const void* s, const float* target_db, const double* den,
+                       const double* gloss, void* gs, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * K3c: receiver step in the time domain.  irfft is linear and a receiver enters H_r = sum_g s[r,g] y_g + d_r
  * (model.py:583-619) only through its G real gains, so irfft(H_r)[window] = sum_g s[r,g] hy[g,:] + hd[r,:] with
  * hy = irfft(y_g)[window] (G rows per step, dgfdn_irfft_window_fwd) and hd[r,:] = irfft(d_r)[window] a constant of

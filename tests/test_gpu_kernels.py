@@ -294,6 +294,30 @@ def test_edc_loss_forward_backward(rows, tn, masked):
     assert rel(hd.grad, ho.grad) < 1e-3
 
 
+@pytest.mark.parametrize("rows,k,win", [(3, 4097, 512), (1, 8193, 4096), (5, 1500, 256)])
+def test_edr_loss_forward_backward(rows, k, win):
+    """K3e (+ chirp-z + cuFFT STFT) against the oracle's edr_loss (losses.py:430-495, 501-575)."""
+    from diffgfdn_b200.losses import edr_loss
+    torch.manual_seed(rows + k)
+    t = torch.arange(k, dtype=F64)
+    def resp(scale):
+        h = torch.randn(rows, k, dtype=F64) * torch.exp(-t / (0.1 * k * scale))
+        return torch.fft.rfft(h, n=2 * (k - 1))  # (rows, k)
+    tgt, ach = resp(1.0), resp(0.7)
+    ao = ach.clone().requires_grad_(True)
+    lo = O.edr_loss(tgt, ao, win=win, hop=win // 2)
+    lo.backward()
+    ad = ach.to(torch.complex64).cuda().requires_grad_(True)
+    crit = edr_loss(32000.0, win_size=win, hop_size=win // 2)
+    lk = crit(tgt.to(torch.complex64).cuda(), ad)
+    lk.backward()
+    assert abs(float(lk) - float(lo)) < 2e-4 * abs(float(lo))
+    assert rel(ad.grad.cpu().to(torch.complex128), ao.grad) < 1e-3
+    # 1-D responses (DiffGFDNSinglePos) take the same path
+    l1 = crit(tgt[0].to(torch.complex64).cuda(), ach[0].to(torch.complex64).cuda())
+    assert abs(float(l1) - float(O.edr_loss(tgt[:1], ach[:1], win=win, hop=win // 2))) < 2e-4 * abs(float(l1))
+
+
 @pytest.mark.parametrize("asym", [False, True])
 def test_colorless_loss(asym):
     from diffgfdn_b200 import ops
