@@ -295,7 +295,7 @@ def main():
     hd = hd_pool.repeat(reps, 1)[:args.receivers].contiguous()
     target_db = tdb_pool.repeat(reps, 1)[:args.receivers].contiguous()
     step.attach(z, positions, hd, target_db)
-    opt = torch.optim.Adam(net.parameters(), lr=1e-3, capturable=True)
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3, capturable=True, fused=True)  # one multi-tensor kernel per step
 
     def eager_step():
         losses = step.step()

@@ -51,19 +51,22 @@ class ND_Unitary(nn.Module):
         self._consts = {}
 
     def _constants(self, n, like):
+        """c0[i] + cos(a_i) c1[i] + sin(a_i) c2[i] is the rotation of the (i, n-1) plane; `corner` completes the
+        embedding of U_{n-1} into n dimensions."""
         key = (n, like.device, like.dtype)
         c = self._consts.get(key)
         if c is None:
             eye = torch.eye(n)
-            diag, up, lo = torch.zeros(n - 1, n, n), torch.zeros(n - 1, n, n), torch.zeros(n - 1, n, n)
+            c0, c1, c2 = torch.zeros(n - 1, n, n), torch.zeros(n - 1, n, n), torch.zeros(n - 1, n, n)
             for i in range(n - 1):
-                diag[i, i, i] = 1.0
-                diag[i, n - 1, n - 1] = 1.0
-                up[i, i, n - 1] = 1.0
-                lo[i, n - 1, i] = 1.0
+                c1[i, i, i] = 1.0
+                c1[i, n - 1, n - 1] = 1.0
+                c0[i] = eye - c1[i]
+                c2[i, n - 1, i] = 1.0
+                c2[i, i, n - 1] = -1.0
             corner = torch.zeros(n, n)
             corner[n - 1, n - 1] = 1.0
-            c = tuple(t.to(device=like.device, dtype=like.dtype) for t in (eye, diag, up, lo, corner))
+            c = tuple(t.to(device=like.device, dtype=like.dtype) for t in (c0, c1, c2, corner))
             self._consts[key] = c
         return c
 
@@ -73,12 +76,12 @@ class ND_Unitary(nn.Module):
             return torch.ones(1, 1, dtype=alpha.dtype, device=alpha.device)
         start = (N - 1) * (N - 2) // 2
         cur = alpha[start:]
-        eye, diag, up, lo, corner = self._constants(N, alpha)
-        cs, sn = torch.cos(cur), torch.sin(cur)
-        rot = eye
-        for i in range(N - 1):
-            r = eye - diag[i] + cs[i] * diag[i] - sn[i] * up[i] + sn[i] * lo[i]
-            rot = r @ rot
+        c0, c1, c2, corner = self._constants(N, alpha)
+        # every rotation of this level in four launches (the reference writes them entry by entry, :60-87)
+        rots = c0 + torch.cos(cur).view(-1, 1, 1) * c1 + torch.sin(cur).view(-1, 1, 1) * c2
+        rot = rots[0]
+        for i in range(1, N - 1):
+            rot = rots[i] @ rot
         big = nn.functional.pad(self.forward(alpha[:start], N - 1), (0, 1, 0, 1)) + corner
         return rot @ big
 
@@ -235,8 +238,9 @@ class FeedbackLoop(nn.Module):
         block_M = self.construct_block_mixing_matrix(dtype)
         phi = self.construct_coupling_matrix(dtype)
         self.phi = phi.detach()  # kept for get_parameters()/get_param_dict(); detached (no graph outlives the step)
-        L = self.num_delay_lines_per_group
-        return block_M * torch.kron(phi, torch.ones(L, L, dtype=block_M.dtype, device=block_M.device))
+        G, L = self.num_groups, self.num_delay_lines_per_group
+        # block_M o (Phi (x) 1_{LxL}) as one broadcast multiply over the (G, L, G, L) view
+        return (block_M.view(G, L, G, L) * phi.view(G, 1, G, 1)).reshape(G * L, G * L)
 
     def get_coupled_feedback_matrix(self) -> torch.Tensor:
         a = self.coupled_feedback_matrix_real()
