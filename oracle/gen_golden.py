@@ -305,6 +305,52 @@ def case_directional(name, nfft, bsz, t60, seed, hidden, neurons, feats, skip):
     print(name, {k: v for k, v in out.items() if k.startswith("loss/")})
 
 
+def case_dataloader(name):
+    """Data boundary (dataloader.py:185-325, 515-600, 674-745): a small two-room grid through the reference classes."""
+    from diff_gfdn.dataloader import (MultiRIRDataset, RIRData, RoomDataset, SingleRIRDataset, create_fixed_test_split,
+                                      custom_collate)
+    rng = np.random.default_rng(77)
+    fs, nrec, tlen, nfft = 8000.0, 7, 1500, 2048
+    rirs = rng.standard_normal((nrec, tlen)) * np.exp(-np.arange(tlen) / 300.0)
+    rec = rng.uniform(0.0, 5.0, (nrec, 3))
+    src = np.array([1.0, 2.0, 1.5])
+    kw = dict(num_rooms=2, sample_rate=fs, source_position=src, receiver_position=rec,
+              common_decay_times=np.array([[0.2, 0.4]]), room_dims=[[3.0, 2.0, 2.5], [2.0, 2.0, 2.5]],
+              room_start_coord=[[0.0, 0.0, 0.0], [3.0, 0.0, 0.0]], mixing_time_ms=20.0, nfft=nfft)
+    out = {"in/rirs": rirs.copy(), "in/receiver_position": rec.copy(), "in/source_position": src.copy(),
+           "meta/fs": fs, "meta/nfft": nfft, "meta/radius": 1.0005}
+    room = RoomDataset(rirs=rirs.copy(), **kw)
+    ds = MultiRIRDataset('cpu', room, new_sampling_radius=1.0005)
+    out["out/rir_mag_response"] = np.asarray(room.rir_mag_response)
+    out["out/early_rir_mag_response"] = np.asarray(room.early_rir_mag_response)
+    out["out/late_rir_mag_response"] = np.asarray(room.late_rir_mag_response)
+    out["out/norm_receiver_position"] = room.norm_receiver_position
+    out["out/z_values"] = ds.z_values.numpy()
+    test_set, rest = create_fixed_test_split(ds, test_ratio=0.3, seed=4314)
+    out["out/test_indices"] = np.asarray(test_set.indices)
+    out["out/rest_indices"] = np.asarray(rest.indices)
+    batch = custom_collate([ds[int(i)] for i in rest.indices[:3]])
+    for k, v in batch.items():
+        out[f"batch/{k}"] = v.numpy()
+    # multi-source layout (index pairs) and the single-RIR classes
+    src2 = np.stack([src, src + 0.5])
+    rirs2 = rng.standard_normal((2, nrec, tlen)) * np.exp(-np.arange(tlen) / 250.0)
+    out["in/rirs2"] = rirs2.copy()
+    out["in/source_position2"] = src2.copy()
+    room2 = RoomDataset(rirs=rirs2.copy(), **{**kw, "source_position": src2})
+    ds2 = MultiRIRDataset('cpu', room2)
+    batch2 = custom_collate([ds2[i] for i in (1, 9, 13)])
+    for k, v in batch2.items():
+        out[f"batch2/{k}"] = v.numpy()
+    rd = RIRData(np.array([[0.2, 0.4]]), None, mixing_time_ms=20.0, nfft=nfft, rir=rirs[0].copy(), sample_rate=fs)
+    sd = SingleRIRDataset('cpu', rd)
+    out["single/rir_mag_response"] = sd.rir_mag_response.numpy()
+    out["single/early_rir_mag_response"] = sd.early_rir_mag_response.numpy()
+    out["single/late_rir_mag_response"] = sd.late_rir_mag_response.numpy()
+    np.savez_compressed(os.path.join(OUT, f"{name}.npz"), **out)
+    print(name, {k: np.asarray(v).shape for k, v in out.items() if k.startswith(("out/", "batch"))})
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     case_omni("omni_n12", 12, 8192, 4, [0.05, 0.08, 0.12], 11, 1, 32, 6)
@@ -320,5 +366,6 @@ if __name__ == "__main__":
     case_src_rx("src_rx_n12", 12, 8192, 3, [0.05, 0.08, 0.12], 15, 1, 16, 4)
     case_single("single_n12", 12, 8192, [0.05, 0.08, 0.12], 16, False, False)
     case_single("single_n12_svf", 12, 8192, [0.05, 0.08, 0.12], 17, True, True)
+    case_dataloader("dataloader_small")
     case_directional("directional_n27", 8192, 2, [0.05, 0.08, 0.1], 21, 1, 16, 4, skip=False)
     case_directional("directional_n27_skip", 4096, 2, [0.03, 0.04, 0.05], 22, 2, 16, 4, skip=True)

@@ -32,7 +32,7 @@ def main():
     hd = step.precompute_early_window(early).repeat(reps, 1)[:a.receivers].contiguous()
     tdb = step.precompute_target_db(tgt).repeat(reps, 1)[:a.receivers].contiguous()
     step.attach(z, pos, hd, tdb)
-    opt = torch.optim.Adam(net.parameters(), lr=1e-3)
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3, fused=True)
     for _ in range(3):
         step.step()
         opt.step()

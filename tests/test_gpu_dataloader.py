@@ -1,0 +1,87 @@
+"""GPU parity of the data boundary (diffgfdn_b200/dataloader.py) against a fixture produced by the reference's own
+RoomDataset / MultiRIRDataset / RIRData / SingleRIRDataset / create_fixed_test_split / custom_collate
+(tests/golden/dataloader_small.npz, oracle/gen_golden.py:case_dataloader)."""
+import numpy as np
+import pytest
+import torch
+
+from golden_util import load
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a = np.asarray(a.detach().cpu() if torch.is_tensor(a) else a)
+    b = np.asarray(b)
+    return float(np.abs(a - b).max() / max(1e-30, np.abs(b).max()))
+
+
+KW = dict(num_rooms=2, common_decay_times=np.array([[0.2, 0.4]]), room_dims=[[3.0, 2.0, 2.5], [2.0, 2.0, 2.5]],
+          room_start_coord=[[0.0, 0.0, 0.0], [3.0, 0.0, 0.0]], mixing_time_ms=20.0)
+
+
+def test_room_dataset_split_and_batches_match_reference():
+    from diffgfdn_b200.dataloader import (GPUBatchLoader, MultiRIRDataset, RoomDataset, create_fixed_test_split,
+                                          custom_collate, load_dataset)
+    g = load("dataloader_small")
+    room = RoomDataset(sample_rate=float(g["meta/fs"]), source_position=g["in/source_position"],
+                       receiver_position=g["in/receiver_position"], rirs=g["in/rirs"], nfft=int(g["meta/nfft"]),
+                       device="cuda", **KW)
+    for key in ("rir_mag_response", "early_rir_mag_response", "late_rir_mag_response"):
+        got = getattr(room, key)
+        assert got.is_cuda and got.dtype == torch.complex64
+        assert rel(got, g[f"out/{key}"]) < 2e-7, key  # complex64 storage of the reference's complex128 arrays
+    assert rel(room.norm_receiver_position, g["out/norm_receiver_position"]) < 1e-15
+    ds = MultiRIRDataset("cuda", room, new_sampling_radius=float(g["meta/radius"]))
+    assert rel(ds.z_values, g["out/z_values"]) < 1e-15 and ds.z_values.dtype == torch.complex128
+    test_set, rest = create_fixed_test_split(ds, test_ratio=0.3, seed=4314)
+    assert list(np.asarray(test_set.indices)) == list(g["out/test_indices"])  # the reference's held-out receivers
+    assert list(np.asarray(rest.indices)) == list(g["out/rest_indices"])
+    batch = ds.batch(torch.as_tensor(g["out/rest_indices"][:3]))
+    item_batch = custom_collate([ds[int(i)] for i in g["out/rest_indices"][:3]])
+    for k in ("z_values", "source_position", "listener_position", "norm_listener_position", "target_early_response",
+              "target_late_response", "target_rir_response"):
+        assert batch[k].is_cuda
+        assert rel(batch[k], g[f"batch/{k}"]) < 2e-7, k
+        assert torch.equal(batch[k], item_batch[k]), k
+    # loaders: every receiver of the split exactly once per epoch, ragged last batch kept unless drop_last
+    loader = GPUBatchLoader(rest, batch_size=2, shuffle=True, drop_last=False)
+    assert len(loader) == 3
+    seen = torch.cat([b["listener_position"] for b in loader])
+    want = ds.listener_positions[torch.as_tensor(g["out/rest_indices"]).cuda()]
+    assert sorted(map(tuple, seen.cpu().tolist())) == sorted(map(tuple, want.cpu().tolist()))
+    assert len(GPUBatchLoader(rest, batch_size=2, shuffle=False, drop_last=True)) == 2
+    train, valid, test = load_dataset(room, "cuda", train_valid_split_ratio=0.8, batch_size=2, hold_out_test_set=True,
+                                      test_set_ratio=0.3, test_set_seed=4314)
+    assert sum(b["target_rir_response"].shape[0] for b in test) == 2
+    assert sum(b["target_rir_response"].shape[0] for b in train) + sum(b["target_rir_response"].shape[0] for b in valid) == 5
+
+
+def test_multi_source_and_single_rir_datasets_match_reference():
+    from diffgfdn_b200.dataloader import MultiRIRDataset, RIRData, RoomDataset, SingleRIRDataset, load_dataset
+    g = load("dataloader_small")
+    room2 = RoomDataset(sample_rate=float(g["meta/fs"]), source_position=g["in/source_position2"],
+                        receiver_position=g["in/receiver_position"], rirs=g["in/rirs2"], nfft=int(g["meta/nfft"]),
+                        device="cuda", **KW)
+    ds2 = MultiRIRDataset("cuda", room2)
+    assert len(ds2) == 14
+    batch = ds2.batch(torch.tensor([1, 9, 13]))
+    for k in ("source_position", "listener_position", "norm_listener_position", "target_early_response",
+              "target_late_response", "target_rir_response"):
+        assert rel(batch[k], g[f"batch2/{k}"]) < 2e-7, k
+    rd = RIRData(np.array([[0.2, 0.4]]), None, mixing_time_ms=20.0, nfft=int(g["meta/nfft"]), rir=g["in/rirs"][0],
+                 sample_rate=float(g["meta/fs"]), device="cuda")
+    sd = SingleRIRDataset("cuda", rd)
+    for key in ("rir_mag_response", "early_rir_mag_response", "late_rir_mag_response"):
+        assert rel(getattr(sd, key), g[f"single/{key}"]) < 2e-7, key
+    loader = load_dataset(rd, "cuda", batch_size=len(sd), shuffle=False)
+    (only, ) = list(loader)
+    assert only["target_rir_response"].shape[0] == int(g["meta/nfft"]) // 2 + 1
+
+
+def test_dataloader_has_no_cpu_path():
+    from diffgfdn_b200.dataloader import RoomDataset
+    g = load("dataloader_small")
+    with pytest.raises(RuntimeError, match="GPU resident"):
+        RoomDataset(sample_rate=8000.0, source_position=g["in/source_position"], receiver_position=g["in/receiver_position"],
+                    rirs=g["in/rirs"], nfft=2048, device="cpu", **KW)
