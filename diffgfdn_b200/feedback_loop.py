@@ -183,7 +183,7 @@ class FeedbackLoop(nn.Module):
             num = coeffs[..., 0].to(torch.complex128) @ zp
             den = coeffs[..., 1].to(torch.complex128) @ zp
             gamma = (num / (den + 1e-9)).to(torch.complex64)
-        self._gamma_cache = (key, gamma)
+        self._gamma_cache = (key, gamma, z)  # z is kept alive: its address cannot be handed to another grid
         return gamma
 
     # ---- feedback matrix (reference feedback_loop.py:260-324) --------------------------------------------

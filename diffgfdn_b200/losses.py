@@ -15,7 +15,7 @@ import torch
 from torch import nn
 
 from . import ops
-from .utils import db, ms_to_samps
+from .utils import TensorKeyedCache, db, ms_to_samps
 
 
 def _bernoulli_mask(tn: int, device) -> torch.Tensor:
@@ -47,7 +47,7 @@ class edc_loss(nn.Module):
         self.band_centre_hz = band_centre_hz
         self.mixing_time_samps = ms_to_samps(mixing_time_ms, sample_rate)
         self.use_mask = use_mask
-        self._target_cache = {}
+        self._target_cache = TensorKeyedCache()
 
     def window(self, num_bins: int):
         """(n, t0, tn) of the reference's slice irfft(X, n=K)[mix : min(max_len, K)]."""
@@ -58,9 +58,8 @@ class edc_loss(nn.Module):
     def target_edc_db(self, target_response: torch.Tensor, filt: Optional[torch.Tensor] = None) -> torch.Tensor:
         """EDC of the target in dB, (B, tn) float32. Targets are constant over training: the result is cached per
         tensor (identity + in-place version), which removes the target side from every later step."""
-        key = (target_response.data_ptr(), tuple(target_response.shape), target_response._version,
-               str(target_response.device), None if filt is None else filt.data_ptr())
-        hit = self._target_cache.get(key)
+        extra = None if filt is None else (filt.data_ptr(), filt._version)
+        hit = self._target_cache.get(target_response, extra)
         if hit is not None:
             return hit
         n, t0, tn = self.window(target_response.shape[-1])
@@ -69,10 +68,7 @@ class edc_loss(nn.Module):
             raise RuntimeError("edc_loss: target_response must be a CUDA tensor (no CPU fallback)")
         h = ops.irfft_window(t.to(torch.complex64), n, t0, tn, filt)
         out = ops.edc_db(h)
-        if len(self._target_cache) > 64:
-            self._target_cache.clear()
-        self._target_cache[key] = out
-        return out
+        return self._target_cache.put(target_response, out, extra)
 
     def forward(self, target_response: torch.Tensor, achieved_response: torch.Tensor,
                 mask_index: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -160,7 +156,7 @@ class edr_loss(nn.Module):
         self.win_size = win_size
         self.hop_size = hop_size
         self.reduced_pole_radius = reduced_pole_radius
-        self._target_cache = {}
+        self._target_cache = TensorKeyedCache()
 
     def _stft(self, rir: torch.Tensor) -> torch.Tensor:
         """(R, T_f, F) complex64: zero-pad to a hop multiple, hann(win), center=False (reference :501-553). The
@@ -175,15 +171,12 @@ class edr_loss(nn.Module):
     def forward(self, target_response: torch.Tensor, achieved_response: torch.Tensor) -> torch.Tensor:
         assert target_response.shape == achieved_response.shape
         k = target_response.shape[-1]
-        key = (target_response.data_ptr(), tuple(target_response.shape), target_response._version)
-        hit = self._target_cache.get(key)
+        hit = self._target_cache.get(target_response)
         if hit is None:
             with torch.no_grad():
                 tgt = ops.edr_db(self._stft(ops.irfft_window(target_response.to(torch.complex64), k, 0, k)))
                 hit = (tgt, tgt.abs().sum(dim=(-1, -2), dtype=torch.float64))
-            if len(self._target_cache) > 64:
-                self._target_cache.clear()
-            self._target_cache[key] = hit
+            self._target_cache.put(target_response, hit)
         tgt, den = hit
         rir = ops.irfft_window(achieved_response, k, 0, k)
         if self.reduced_pole_radius is not None:

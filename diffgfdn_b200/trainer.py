@@ -18,6 +18,7 @@ from .colorless_fdn.losses import amse_loss, mse_loss, sparsity_loss
 from .config.config import TrainerConfig
 from .losses import directional_edc_loss, edc_loss, edr_loss
 from .model import DiffGFDN
+from .utils import TensorKeyedCache
 
 
 class Trainer:
@@ -128,14 +129,12 @@ class Trainer:
 
     def _as_c64(self, t: torch.Tensor) -> torch.Tensor:
         """complex128 dataset tensors are converted once and remembered (targets are constant over training)."""
-        cache = self.__dict__.setdefault("_c64_cache", {})
-        key = (t.data_ptr(), tuple(t.shape), t._version)
-        out = cache.get(key)
+        cache = self.__dict__.get("_c64_cache")
+        if cache is None:
+            cache = self.__dict__["_c64_cache"] = TensorKeyedCache(max_entries=8)
+        out = cache.get(t)
         if out is None:
-            if len(cache) > 64:
-                cache.clear()
-            out = t.to(torch.complex64)
-            cache[key] = out
+            out = cache.put(t, t.to(torch.complex64))
         return out
 
     @torch.no_grad()

@@ -62,3 +62,33 @@ def get_response(x: Union[Dict, torch.Tensor], net: nn.Module, output_scalars: O
         return H, H_sub, torch.fft.irfft(H, dim=-1)
     H = net(x)
     return H, torch.fft.irfft(H, dim=-1)
+
+
+class TensorKeyedCache:
+    """Small FIFO cache of values derived from constant input tensors (targets, z grids), keyed by storage identity.
+
+    A key made of data_ptr alone is NOT an identity: once a batch tensor is freed the caching allocator hands the same
+    address to the next batch of the same shape, and a stale entry would be returned for different data (a loader
+    that gathers a fresh batch every step hits this within a few steps). Every entry therefore keeps a reference to
+    its source tensor: while the entry lives the address cannot be reused, so pointer + shape + version is exact."""
+
+    def __init__(self, max_entries: int = 16):
+        self.max_entries = max_entries
+        self._entries = {}
+
+    @staticmethod
+    def _key(t: torch.Tensor, extra=None):
+        return (t.data_ptr(), tuple(t.shape), tuple(t.stride()), t.dtype, t._version, str(t.device), extra)
+
+    def get(self, t: torch.Tensor, extra=None):
+        hit = self._entries.get(self._key(t, extra))
+        return None if hit is None else hit[1]
+
+    def put(self, t: torch.Tensor, value, extra=None):
+        while len(self._entries) >= self.max_entries:
+            self._entries.pop(next(iter(self._entries)))
+        self._entries[self._key(t, extra)] = (t, value)
+        return value
+
+    def clear(self):
+        self._entries.clear()

@@ -379,3 +379,25 @@ def test_no_cpu_fallback():
     from diffgfdn_b200 import ops
     with pytest.raises(RuntimeError):
         ops.receiver_project(torch.zeros(2, 3), torch.zeros(8, 3, dtype=torch.complex64), None)
+
+
+def test_target_caches_survive_allocator_address_reuse():
+    """Targets gathered per batch are freed and their address is handed to the next batch by the caching allocator:
+    the loss callables must not serve the previous batch's cached EDC/EDR for it (regression: pointer-keyed caches)."""
+    from diffgfdn_b200.losses import edc_loss, edr_loss
+    torch.manual_seed(0)
+    k, rows = 2049, 4
+    t = torch.arange(k, dtype=F64)
+    pool = torch.fft.rfft(torch.randn(7 * rows, k, dtype=F64) * torch.exp(-t / 150.0), n=2 * (k - 1)).to(torch.complex64).cuda()
+    ach = pool[6 * rows:].clone()
+    crit_c, crit_r = edc_loss(100.0, 16000.0), edr_loss(16000.0, win_size=256, hop_size=128)
+    ptrs = set()
+    for step in range(6):
+        tgt = pool.index_select(0, torch.arange(step * rows, (step + 1) * rows, device="cuda"))  # fresh tensor per step
+        ptrs.add(tgt.data_ptr())
+        want_c = O.edc_loss(tgt.cpu().to(torch.complex128), ach.cpu().to(torch.complex128), 100.0, 16000.0)
+        want_r = O.edr_loss(tgt.cpu().to(torch.complex128), ach.cpu().to(torch.complex128), win=256, hop=128)
+        assert abs(float(crit_c(tgt, ach)) - float(want_c)) < 0.01, step
+        assert abs(float(crit_r(tgt, ach)) - float(want_r)) < 2e-3 * float(want_r) + 1e-6, step
+        del tgt
+    assert len(ptrs) >= 1
