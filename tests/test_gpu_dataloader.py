@@ -127,3 +127,64 @@ def test_end_to_end_training_on_a_synthetic_room(tmp_path):
     ckpt = os.path.join(str(tmp_path / "out"), "checkpoints", f"model_e{len(trainer.train_loss) - 1}.pt")
     state = torch.load(ckpt)
     assert {"input_gains", "output_gains", "delay_buffer", "delay_filters", "feedback_loop.M"} <= set(state)
+
+
+def _synthetic_room(nrec=12, fs=16000.0, nfft=8192, seed=9):
+    from diffgfdn_b200.dataloader import RoomDataset
+    rng = np.random.default_rng(seed)
+    t60 = np.array([[0.08, 0.15]])
+    t = np.arange(nfft // 2)
+    rec = rng.uniform(0.0, 5.0, (nrec, 3))
+    amp = 0.5 + rec[:, :1] / 5.0
+    rirs = rng.standard_normal((nrec, t.size)) * ((1.5 - amp) * np.exp(-6.9 * t / (t60[0, 0] * fs)) +
+                                                   amp * np.exp(-6.9 * t / (t60[0, 1] * fs)))
+    room = RoomDataset(sample_rate=fs, source_position=np.array([1.0, 1.0, 1.5]), receiver_position=rec, rirs=rirs,
+                       nfft=nfft, device="cuda", **{**KW, "common_decay_times": t60})
+    return room, rirs, t60
+
+
+def test_svf_model_trains_through_the_loaders(tmp_path):
+    """use_svfs: True (SVF_from_MLP + K2s) through Trainer.train(): finite, decreasing loss."""
+    from diffgfdn_b200.config import DiffGFDNConfig, FeedbackLoopConfig, OutputFilterConfig, TrainerConfig
+    from diffgfdn_b200.dataloader import load_dataset
+    from diffgfdn_b200.model import DiffGFDNVarReceiverPos
+    from diffgfdn_b200.trainer import VarReceiverPosTrainer
+    torch.manual_seed(11)
+    room, _, t60 = _synthetic_room()
+    train, valid = load_dataset(room, "cuda", train_valid_split_ratio=0.75, batch_size=3)
+    cfg = DiffGFDNConfig(num_delay_lines=8, sample_rate=16000.0, num_groups=2)
+    net = DiffGFDNVarReceiverPos(16000.0, 2, cfg.delay_length_samps, "cuda", FeedbackLoopConfig(),
+                                 OutputFilterConfig(use_svfs=True, num_hidden_layers=1, num_neurons_per_layer=32,
+                                                    num_fourier_features=6, compress_pole_factor=0.999),
+                                 use_absorption_filters=False, common_decay_times=t60, use_colorless_loss=True)
+    trainer = VarReceiverPosTrainer(net, TrainerConfig(train_dir=str(tmp_path / "out"), ir_dir=str(tmp_path / "ir"),
+                                                       max_epochs=6, batch_size=3, num_freq_bins=8192,
+                                                       use_colorless_loss=True, edc_loss_weight=10.0, io_lr=2e-3, lr=2e-3))
+    trainer.train(train, valid)
+    assert np.isfinite(trainer.train_loss).all() and trainer.train_loss[-1] < trainer.train_loss[0]
+    out = net.get_param_dict_inference(next(iter(valid)))
+    assert out['output_svf_params'].shape[-2:] == (11, 2)
+
+
+def test_single_position_trainer_runs(tmp_path):
+    """RIRData -> SingleRIRDataset -> DiffGFDNSinglePos -> SinglePosTrainer.train() (reference trainer.py:570-688)."""
+    from diffgfdn_b200.config import DiffGFDNConfig, FeedbackLoopConfig, OutputFilterConfig, TrainerConfig
+    from diffgfdn_b200.dataloader import RIRData, load_dataset
+    from diffgfdn_b200.model import DiffGFDNSinglePos
+    from diffgfdn_b200.trainer import SinglePosTrainer
+    torch.manual_seed(12)
+    _, rirs, t60 = _synthetic_room()
+    rd = RIRData(t60, None, mixing_time_ms=20.0, nfft=8192, rir=rirs[0], sample_rate=16000.0, device="cuda")
+    loader = load_dataset(rd, "cuda", batch_size=8192 // 2 + 1, shuffle=False)
+    cfg = DiffGFDNConfig(num_delay_lines=8, sample_rate=16000.0, num_groups=2)
+    net = DiffGFDNSinglePos(16000.0, 2, cfg.delay_length_samps, "cuda", FeedbackLoopConfig(),
+                            OutputFilterConfig(use_svfs=True, compress_pole_factor=0.999), use_absorption_filters=False,
+                            common_decay_times=t60, use_colorless_loss=True,
+                            input_filter_config=OutputFilterConfig(use_svfs=False))
+    trainer = SinglePosTrainer(net, TrainerConfig(train_dir=str(tmp_path / "out"), ir_dir=str(tmp_path / "ir"),
+                                                  max_epochs=8, batch_size=4097, num_freq_bins=8192,
+                                                  use_colorless_loss=True, edc_loss_weight=10.0, io_lr=5e-3, lr=5e-3),
+                               "synthetic")
+    trainer.train(loader)
+    assert np.isfinite(trainer.train_loss).all() and trainer.train_loss[-1] < trainer.train_loss[0]
+    assert set(net.get_param_dict()) >= {'output_svf_params', 'output_biquad_coeffs', 'input_scalars'}
