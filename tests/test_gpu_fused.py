@@ -243,3 +243,51 @@ def test_full_size_invariants():
     lhs = float((ha * gvec).sum())
     rhs = float((xin.grad.conj() * h1).real.sum())
     assert abs(lhs - rhs) < 1e-3 * abs(lhs)
+
+
+def test_graph_captured_training_reduces_the_loss_like_the_module_path():
+    """40 replays of the captured step (+ fused Adam): the EDC loss comes down, and the parameters after the run
+    equal those of the same 40 steps taken through the autograd module path (net(x) + edc_loss + Adam)."""
+    import copy
+
+    from diffgfdn_b200 import ops
+    from diffgfdn_b200.fused import ShardedEDCStep
+    from diffgfdn_b200.losses import edc_loss
+    net, t60, z, pos, early, target = setup(rows=16, seed=3)
+    ref = copy.deepcopy(net)
+    steps = 40
+    # module path
+    opt_r = torch.optim.Adam(ref.parameters(), lr=2e-3)
+    crit = edc_loss(max(t60) * 1e3, 32000.0)
+    data = dict(z_values=z, listener_position=pos, norm_listener_position=pos, target_early_response=early)
+    ref_losses = []
+    for _ in range(steps):
+        opt_r.zero_grad()
+        H, (Hs, _) = ref(data)
+        edc = 10.0 * crit(target, H)
+        a = ref.feedback_loop.ortho_param(ref.feedback_loop.M[2])
+        loss = edc + ops.colorless_loss_per_group(Hs, True).sum() - (a.abs().sum() - 4 * 2.0) / (4 * (2.0 - 1))
+        loss.backward()
+        opt_r.step()
+        ref_losses.append(float(edc))
+    # captured fused step
+    step = ShardedEDCStep(net, max(t60) * 1e3, tile_rows=16, edc_weight=10.0)
+    step.attach(z, pos, None, None)
+    step.attach(z, pos, step.precompute_early_window(early), step.precompute_target_db(target))
+    opt = torch.optim.Adam(net.parameters(), lr=2e-3, capturable=True, fused=True)
+    state0 = copy.deepcopy(net.state_dict())
+    step.capture(optimizer=opt, warmup=1)  # the warm-up and the capture itself take optimizer steps: rewind
+    net.load_state_dict(state0)
+    for grp in opt.param_groups:
+        for p in grp["params"]:
+            st = opt.state[p]
+            st["step"].zero_()
+            st["exp_avg"].zero_()
+            st["exp_avg_sq"].zero_()
+    losses = []
+    for _ in range(steps):
+        losses.append(float(step.replay()["edc_loss"]))
+    assert np.isfinite(losses).all() and losses[-1] < losses[0]
+    assert np.allclose(losses, ref_losses, rtol=2e-3)
+    for (k, p), (_, q) in zip(net.named_parameters(), ref.named_parameters()):
+        assert float((p - q).abs().max()) < 2e-3 * max(1e-2, float(q.abs().max())), k
