@@ -51,6 +51,10 @@ struct SolveParams {
   const float2* gy;
   const float2* gx;
   double* ws;
+  // saved elimination (optional): multipliers of every step, and per lane its pivot value / z^m / pivot column
+  float2* fac;   // [bins * nsys][NP][W]
+  float4* rec;   // [bins * nsys][W]   (pivot.x, pivot.y, zm.x, zm.y)
+  int* pcol;     // [bins * nsys][W]   column this lane was pivot for (-1: padding lane)
 };
 
 // Shared memory (in doubles). Block-wide constants per system type q: A_eff row-major [NP*NP] and transposed
@@ -110,7 +114,8 @@ struct GJState {
 // One elimination step per template instance, so that every register-array index is a compile-time constant.
 template <int NP, int W, int K>
 struct GJStep {
-  static __device__ __forceinline__ void run(double2 (&m)[NP], GJState& st, int sl, double2* line0, double2* line1) {
+  static __device__ __forceinline__ void run(double2 (&m)[NP], GJState& st, int sl, double2* line0, double2* line1,
+                                             float2* fac) {
     double2* line = (K & 1) ? line1 : line0;
     unsigned key = 0u;
     if (!st.used) {
@@ -127,8 +132,10 @@ struct GJStep {
       st.diag = m[K];
     }
     __syncwarp();
+    float2 fsave = make_float2(0.f, 0.f);
     if (sl != piv && sl < NP) {
       const double2 f = cmul(m[K], fast_cinv(line[K]));
+      fsave = make_float2((float)f.x, (float)f.y);
       const double nfx = -f.x, nfy = -f.y;
 #pragma unroll
       for (int j = K + 1; j < NP; ++j) {  // m[j] -= f * p[j]: four fused multiply-adds per complex element
@@ -140,8 +147,10 @@ struct GJStep {
       st.rhs.x = fma(f.y, pr.y, fma(nfx, pr.x, st.rhs.x));
       st.rhs.y = fma(nfy, pr.x, fma(nfx, pr.y, st.rhs.y));
     }
+    // the multiplier of this (step, row): what the adjoint replay needs (0 for the pivot row and the padding lanes)
+    if (fac != nullptr) fac[K * W + sl] = fsave;
     // no second barrier: step K+1 writes the other line; step K+2 reuses this one only after the barrier of K+1
-    if constexpr (K + 1 < NP) GJStep<NP, W, K + 1>::run(m, st, sl, line0, line1);
+    if constexpr (K + 1 < NP) GJStep<NP, W, K + 1>::run(m, st, sl, line0, line1, fac);
   }
 };
 
@@ -149,15 +158,16 @@ struct GJStep {
 // sub-lanes < NP; sub-lanes >= NP return col = -1).
 template <int NP, int W>
 __device__ __forceinline__ double2 gauss_jordan(double2 (&m)[NP], double2 rhs, int sl, double2* line0, double2* line1,
-                                                int* col) {
+                                                int* col, float2* fac = nullptr, double2* pivot = nullptr) {
   GJState st;
   st.rhs = rhs;
   st.diag = make_double2(1.0, 0.0);
   st.mycol = -1;
   st.used = sl >= NP;
-  GJStep<NP, W, 0>::run(m, st, sl, line0, line1);
+  GJStep<NP, W, 0>::run(m, st, sl, line0, line1, fac);
   __syncwarp();  // the lines may be rewritten by the caller's next system
   *col = st.mycol;
+  if (pivot != nullptr) *pivot = st.diag;
   return cmul(st.rhs, fast_cinv(st.diag));
 }
 
@@ -270,13 +280,21 @@ __global__ void __launch_bounds__(kWarps * 32, (NP <= 24 ? 3 : 2)) solve_fwd_ker
     int64_t bin = gi.bin0 + it * gi.bin_stride;
     const bool live_bin = bin < p.k;
     if (!live_bin) bin = p.k - 1;
-    double2 zm;
+    double2 zm = make_double2(0.0, 0.0);
     double2 dz = make_double2(0.0, 0.0);
     if (sl < n) dz = diag_entry(p, bin, my_line, my_invg, my_delay, nbits, &zm);
     double2 m[NP];
     build_row<NP>(m, s_a, s_at, n, sl, dz, false);
     int col;
-    const double2 xr = gauss_jordan<NP, W>(m, make_double2(my_b, 0.0), sl, line0, line1, &col);
+    double2 pivot;
+    const bool save = p.fac != nullptr && live_bin;
+    const int64_t slot = bin * p.nsys + q;  // saved-elimination slot of this (bin, system)
+    const double2 xr = gauss_jordan<NP, W>(m, make_double2(my_b, 0.0), sl, line0, line1, &col,
+                                           save ? p.fac + slot * (NP * W) : nullptr, &pivot);
+    if (save) {
+      p.rec[slot * W + sl] = make_float4((float)pivot.x, (float)pivot.y, (float)zm.x, (float)zm.y);
+      p.pcol[slot * W + sl] = col;
+    }
     const bool live = col >= 0 && col < n;
     if (p.x != nullptr && live && live_bin) p.x[bin * p.ntot + q * n + col] = make_float2((float)xr.x, (float)xr.y);
     if (p.y != nullptr) {
@@ -413,6 +431,125 @@ __global__ void __launch_bounds__(kWarps * 32, (NP <= 24 ? 3 : 2)) solve_bwd_ker
   }
 }
 
+template <int W>
+__device__ __forceinline__ double2 group_sum(double2 v) {  // sum over the W lanes of a group, every lane gets it
+#pragma unroll
+  for (int o = W / 2; o > 0; o >>= 1) {
+    v.x += __shfl_xor_sync(0xffffffffu, v.x, o);
+    v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
+  }
+  return v;
+}
+
+// Backward WITHOUT a second factorisation: the forward kernel saved, per (bin, system), the multipliers f[k][i] of
+// its Gauss-Jordan steps T_k = I - f_k e_{p_k}^T (T_N ... T_1 M = E, E[p_k, k] = pivot_k). The adjoint solve
+// lambda = M^-H g = T_1^H ... T_N^H E^-H g is then N rank-one updates: w[p_k] = g_k / conj(pivot_k), and for
+// k = N-1 .. 0 only component p_k changes, w[p_k] -= sum_i conj(f[k][i]) w[i] (one group-wide complex sum per step).
+// ~1/4 of the instructions of a fresh elimination and a handful of registers, so the latency chain is hidden by
+// occupancy. The gradient accumulation (outer products in shared memory, fixed-order two-stage reduction) is the
+// one of solve_bwd_kernel.
+template <int NP, int W>
+__global__ void __launch_bounds__(kWarps * 32) solve_bwd_replay_kernel(SolveParams p) {
+  extern __shared__ double smem[];
+  constexpr int kSpw = 32 / W;
+  const int n = p.n;
+  double* s_c = smem;                                  // [nsys * NP] output gains per line
+  double* s_groups = s_c + (size_t)p.nsys * NP;
+  const GroupIndex<W> gi(p);
+  const int sl = gi.sl, q = gi.q;
+  const int lg = (threadIdx.x >> 5) * kSpw + (threadIdx.x & 31) / W;
+  double* gbase = s_groups + (size_t)lg * (2 * NP + (size_t)NP * NP);
+  double2* xs = reinterpret_cast<double2*>(gbase);
+  double* acc = gbase + 2 * NP;
+  for (int i = threadIdx.x; i < p.nsys * NP; i += blockDim.x) {
+    const int qq = i / NP, r = i % NP;
+    s_c[i] = (r < n && p.c) ? (double)p.c[qq * n + r] : 0.0;
+  }
+  if (sl < NP)
+    for (int j = 0; j < NP; ++j) acc[sl + NP * j] = 0.0;
+  __syncthreads();
+  const int my_line = q * n + sl;
+  const int my_group = p.nsys == 1 ? sl / p.l : q;
+
+  const int64_t iters = (p.k + gi.bin_stride - 1) / gi.bin_stride;
+  int64_t iters_max = iters;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const int64_t other = __shfl_xor_sync(0xffffffffu, iters_max, o);
+    iters_max = other > iters_max ? other : iters_max;
+  }
+  double gb_acc = 0.0, gc_acc = 0.0, gig_acc = 0.0;
+  for (int64_t it = 0; it < iters_max; ++it) {
+    int64_t bin = gi.bin0 + it * gi.bin_stride;
+    const bool live_bin = bin < p.k;
+    if (!live_bin) bin = p.k - 1;
+    const int64_t slot = bin * p.nsys + q;
+    const float4 rec = p.rec[slot * W + sl];
+    const int col = p.pcol[slot * W + sl];
+    double2 xr = make_double2(0.0, 0.0), gyr = make_double2(0.0, 0.0), w = make_double2(0.0, 0.0);
+    if (live_bin) {
+      if (sl < n) {
+        const float2 xv = p.xin[bin * p.ntot + my_line];
+        xr = make_double2((double)xv.x, (double)xv.y);
+        if (p.gy != nullptr) {
+          const float2 gv = p.gy[bin * p.g + my_group];
+          gyr = make_double2((double)gv.x, (double)gv.y);
+        }
+      }
+      if (col >= 0 && col < n) {  // right-hand side of the column this lane was pivot for
+        double2 g = make_double2(0.0, 0.0);
+        if (p.gy != nullptr) {
+          const float2 gv = p.gy[bin * p.g + (p.nsys == 1 ? col / p.l : q)];
+          const double cc = s_c[q * NP + col];
+          g = make_double2(cc * (double)gv.x, cc * (double)gv.y);
+        }
+        if (p.gx != nullptr) {
+          const float2 gv = p.gx[bin * p.ntot + q * n + col];
+          g.x += (double)gv.x;
+          g.y += (double)gv.y;
+        }
+        const double px = (double)rec.x, py = (double)rec.y;
+        const double inv = fast_rcp(px * px + py * py);
+        w = make_double2((g.x * px - g.y * py) * inv, (g.x * py + g.y * px) * inv);  // g / conj(pivot)
+      }
+    }
+    if (sl < NP) xs[sl] = xr;
+    const float2* fac = p.fac + slot * (NP * W) + sl;
+#pragma unroll 4
+    for (int k = NP - 1; k >= 0; --k) {
+      const float2 f = fac[k * W];
+      const double fx = (double)f.x, fy = (double)f.y;
+      const double2 s = group_sum<W>(make_double2(fx * w.x + fy * w.y, fx * w.y - fy * w.x));  // conj(f) w
+      if (col == k) {
+        w.x -= s.x;
+        w.y -= s.y;
+      }
+    }
+    __syncwarp();
+    if (sl < n) {  // a dead bin contributes zeros: its w and x are zero
+      const double2 lr = w;
+#pragma unroll 4
+      for (int j = 0; j < n; ++j) {
+        const double2 o = xs[j];
+        acc[sl + NP * j] += lr.x * o.x + lr.y * o.y;
+      }
+      gb_acc += lr.x;
+      gc_acc += xr.x * gyr.x + xr.y * gyr.y;
+      const double2 t = cmulc(lr, xr);
+      gig_acc -= (double)rec.z * t.x + (double)rec.w * t.y;
+    }
+    __syncwarp();
+  }
+  const size_t per = (size_t)n * n + 3 * (size_t)n;
+  double* out = p.ws + (size_t)gi.sgid * per;
+  if (sl < n) {
+    for (int j = 0; j < n; ++j) out[sl + n * j] = acc[sl + NP * j];
+    out[(size_t)n * n + sl] = gb_acc;
+    out[(size_t)n * n + n + sl] = gc_acc;
+    out[(size_t)n * n + 2 * n + sl] = gig_acc;
+  }
+}
+
 // One warp per output element: lanes stride over the partial rows of the lane groups that served system type q
 // (sgid = q, q + nsys, ...), fixed-order shuffle reduction.
 __global__ void solve_bwd_reduce_kernel(const double* ws, int64_t ngroups, int n, int nsys, int transpose_a, double* ga,
@@ -515,6 +652,19 @@ int launch_bwd(const SolveParams& p, int* blocks_out, cudaStream_t st) {
   return 0;
 }
 
+template <int NP>
+int launch_bwd_replay(const SolveParams& p, int* blocks_out, cudaStream_t st) {
+  constexpr int W = lanes_for(NP);
+  const size_t groups = kWarps * (32 / W);
+  const size_t smem = ((size_t)p.nsys * NP + groups * (2 * NP + (size_t)NP * NP)) * sizeof(double);
+  DGFDN_CUDA(cudaFuncSetAttribute(solve_bwd_replay_kernel<NP, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int blocks = grid_blocks(p.k * p.nsys, W, blocks_per_sm(solve_bwd_replay_kernel<NP, W>, smem));
+  *blocks_out = blocks;
+  solve_bwd_replay_kernel<NP, W><<<blocks, kWarps * 32, smem, st>>>(p);
+  DGFDN_LAUNCH_CHECK();
+  return 0;
+}
+
 #define DGFDN_DISPATCH_NP(n, CALL)  \
   do {                              \
     const int np__ = ((n) + 3) & ~3; \
@@ -540,6 +690,41 @@ int dispatch_bwd(const SolveParams& p, int* blocks, cudaStream_t st) {
 #define CALL_BWD(NP) launch_bwd<NP>(p, blocks, st)
   DGFDN_DISPATCH_NP(p.n, CALL_BWD);
 #undef CALL_BWD
+}
+
+int dispatch_bwd_replay(const SolveParams& p, int* blocks, cudaStream_t st) {
+#define CALL_BWD(NP) launch_bwd_replay<NP>(p, blocks, st)
+  DGFDN_DISPATCH_NP(p.n, CALL_BWD);
+#undef CALL_BWD
+}
+
+// The saved elimination of one forward call: [fac | rec | pcol], W lanes per system
+struct FactorLayout {
+  size_t off_rec, off_pcol, total;
+};
+FactorLayout factor_layout(int n, int nsys, int64_t k) {
+  const int np = (n + 3) & ~3;
+  const int w = lanes_for(np > 32 ? 32 : np);
+  const size_t slots = (size_t)k * nsys;
+  FactorLayout f;
+  size_t o = slots * np * w * sizeof(float2);
+  o = (o + 255) & ~(size_t)255;
+  f.off_rec = o;
+  o += slots * w * sizeof(float4);
+  o = (o + 255) & ~(size_t)255;
+  f.off_pcol = o;
+  o += slots * w * sizeof(int);
+  f.total = o;
+  return f;
+}
+
+void bind_factors(SolveParams& p, void* factors, int n, int nsys, int64_t k) {
+  if (factors == nullptr) return;
+  const FactorLayout f = factor_layout(n, nsys, k);
+  unsigned char* base = static_cast<unsigned char*>(factors);
+  p.fac = reinterpret_cast<float2*>(base);
+  p.rec = reinterpret_cast<float4*>(base + f.off_rec);
+  p.pcol = reinterpret_cast<int*>(base + f.off_pcol);
 }
 
 int lanes_runtime(int n) { return lanes_for((n + 3) & ~3); }
@@ -570,7 +755,7 @@ using namespace dgfdn;
 
 static int solve_fwd_impl(int n, int nsys, int g, int64_t k, const void* z, const int32_t* delays, const float* a,
                           int transpose_a, const float* gamma, const void* gamma_z, const float* b, const float* c,
-                          void* x, void* y, void* stream) {
+                          void* x, void* y, void* factors, void* stream) {
   if (check_common(n, nsys, g, k)) return 1;
   DGFDN_CHECK(z && delays && a && b, "solve_fwd: null input pointer");
   DGFDN_CHECK(y == nullptr || c != nullptr, "solve_fwd: y requested without c");
@@ -578,13 +763,14 @@ static int solve_fwd_impl(int n, int nsys, int g, int64_t k, const void* z, cons
   fill_params(p, n, nsys, g, k, z, delays, a, transpose_a, gamma, gamma_z, b, c);
   p.x = static_cast<float2*>(x);
   p.y = static_cast<float2*>(y);
+  bind_factors(p, factors, n, nsys, k);
   return dispatch_fwd(p, static_cast<cudaStream_t>(stream));
 }
 
 static int solve_bwd_impl(int n, int nsys, int g, int64_t k, const void* z, const int32_t* delays, const float* a,
                           int transpose_a, const float* gamma, const void* gamma_z, const float* c, const void* x,
                           const void* gy, const void* gx, double* ga, double* gb, double* gc, double* ginvgamma,
-                          void* ws, void* stream) {
+                          void* ws, const void* factors, void* stream) {
   if (check_common(n, nsys, g, k)) return 1;
   DGFDN_CHECK(z && delays && a && x && ws, "solve_bwd: null input pointer");
   DGFDN_CHECK(gy || gx, "solve_bwd: need gy or gx");
@@ -598,7 +784,8 @@ static int solve_bwd_impl(int n, int nsys, int g, int64_t k, const void* z, cons
   const int w = lanes_runtime(n);
   int blocks = 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (dispatch_bwd(p, &blocks, st)) return 1;
+  bind_factors(p, const_cast<void*>(factors), n, nsys, k);
+  if (factors != nullptr ? dispatch_bwd_replay(p, &blocks, st) : dispatch_bwd(p, &blocks, st)) return 1;
   const int per = (n * n + 3 * n) * nsys;
   const int64_t groups = (int64_t)blocks * kWarps * (32 / w);  // lane groups of the grid that was launched
   solve_bwd_reduce_kernel<<<(per * 32 + 255) / 256, 256, 0, st>>>(p.ws, groups, n, nsys, transpose_a, ga, gb, gc,
@@ -609,8 +796,17 @@ static int solve_bwd_impl(int n, int nsys, int g, int64_t k, const void* z, cons
 
 extern "C" int dgfdn_solve_fwd(int n, int g, int64_t k, const void* z, const int32_t* delays, const float* a,
                                int transpose_a, const float* gamma, const void* gamma_z, const float* b,
-                               const float* c, void* x, void* y, void* stream) {
-  return solve_fwd_impl(n, 1, g, k, z, delays, a, transpose_a, gamma, gamma_z, b, c, x, y, stream);
+                               const float* c, void* x, void* y, void* factors, void* stream) {
+  return solve_fwd_impl(n, 1, g, k, z, delays, a, transpose_a, gamma, gamma_z, b, c, x, y, factors, stream);
+}
+
+extern "C" int64_t dgfdn_solve_factors_bytes(int n, int64_t k) {
+  if (n < 1 || n > DGFDN_MAX_LINES || k < 1) return 0;
+  return (int64_t)factor_layout(n, 1, k).total;
+}
+extern "C" int64_t dgfdn_solve_groups_factors_bytes(int l, int g, int64_t k) {
+  if (l < 1 || g < 1 || l * g > DGFDN_MAX_LINES || k < 1) return 0;
+  return (int64_t)factor_layout(l, g, k).total;
 }
 
 // one row of (n^2 + 3n) doubles per lane group of the largest grid the backward kernel launches
@@ -626,19 +822,21 @@ extern "C" int64_t dgfdn_solve_groups_bwd_ws_bytes(int l) { return bwd_ws_bytes(
 extern "C" int dgfdn_solve_bwd(int n, int g, int64_t k, const void* z, const int32_t* delays, const float* a,
                                int transpose_a, const float* gamma, const void* gamma_z, const float* c,
                                const void* x, const void* gy, const void* gx, double* ga, double* gb, double* gc,
-                               double* ginvgamma, void* ws, void* stream) {
+                               double* ginvgamma, void* ws, const void* factors, void* stream) {
   return solve_bwd_impl(n, 1, g, k, z, delays, a, transpose_a, gamma, gamma_z, c, x, gy, gx, ga, gb, gc, ginvgamma, ws,
-                        stream);
+                        factors, stream);
 }
 
 extern "C" int dgfdn_solve_groups_fwd(int l, int g, int64_t k, const void* z, const int32_t* delays, const float* m_raw,
                                       const float* gamma, const float* b, const float* c, void* x, void* y,
-                                      void* stream) {
-  return solve_fwd_impl(l, g, g, k, z, delays, m_raw, 0, gamma, nullptr, b, c, x, y, stream);
+                                      void* factors, void* stream) {
+  return solve_fwd_impl(l, g, g, k, z, delays, m_raw, 0, gamma, nullptr, b, c, x, y, factors, stream);
 }
 
 extern "C" int dgfdn_solve_groups_bwd(int l, int g, int64_t k, const void* z, const int32_t* delays, const float* m_raw,
                                       const float* gamma, const float* c, const void* x, const void* gy, const void* gx,
-                                      double* gm, double* gb, double* gc, double* ginvgamma, void* ws, void* stream) {
-  return solve_bwd_impl(l, g, g, k, z, delays, m_raw, 0, gamma, nullptr, c, x, gy, gx, gm, gb, gc, ginvgamma, ws, stream);
+                                      double* gm, double* gb, double* gc, double* ginvgamma, void* ws,
+                                      const void* factors, void* stream) {
+  return solve_bwd_impl(l, g, g, k, z, delays, m_raw, 0, gamma, nullptr, c, x, gy, gx, gm, gb, gc, ginvgamma, ws, factors,
+                        stream);
 }

@@ -4,6 +4,7 @@ Every op takes and returns CUDA tensors, runs on torch's current stream and rais
 CPU or eager fallback. Shapes follow the reference (orchidas/DiffGFDN): K frequency bins, N delay lines, G groups,
 R receivers (rows)."""
 import ctypes
+import os
 import math
 from typing import Optional, Tuple
 
@@ -78,6 +79,15 @@ def skew_expm(m: torch.Tensor) -> torch.Tensor:
 # ----------------------------------------------------------------------------------------------------------
 # K1: per-bin solve
 # ----------------------------------------------------------------------------------------------------------
+def _factor_buffer(wanted: bool, size_fn: str, size_args, device) -> Optional[torch.Tensor]:
+    """Buffer for the saved elimination of a K1 forward call (None when no gradient will be needed, or when
+    DGFDN_SOLVE_REPLAY=0 asks for the fresh adjoint elimination)."""
+    if not wanted or os.environ.get("DGFDN_SOLVE_REPLAY", "1") == "0":
+        return None
+    nbytes = int(getattr(_lib.load(), size_fn)(*size_args))
+    return torch.empty(nbytes, dtype=torch.uint8, device=device)
+
+
 class _GFDNSolve(torch.autograd.Function):
     """x_k = (diag(z_k^m / gamma) - A)^-1 b ;  y[k,g] = sum_{n in g} c_n x_k[n].
 
@@ -101,8 +111,11 @@ class _GFDNSolve(torch.autograd.Function):
         x = torch.empty(k, n, dtype=C64, device=z.device)
         y = torch.empty(k, num_groups, dtype=C64, device=z.device)
         with torch.cuda.device(z.device):
+            # when a gradient will be asked for, keep the elimination: the adjoint solve replays it (no 2nd factorisation)
+            factors = _factor_buffer(any(ctx.needs_input_grad), "dgfdn_solve_factors_bytes", (n, k), z.device)
             _lib.call("dgfdn_solve_fwd", n, num_groups, k, _ptr(z), _ptr(delays), _ptr(a_), int(transpose_a),
-                      _ptr(gamma_), _ptr(gamma_z_), _ptr(b_), _ptr(c_), _ptr(x), _ptr(y), _stream())
+                      _ptr(gamma_), _ptr(gamma_z_), _ptr(b_), _ptr(c_), _ptr(x), _ptr(y), _ptr(factors), _stream())
+        ctx.factors = factors
         ctx.save_for_backward(z, delays, a_, gamma_, gamma_z_, c_, x)
         ctx.meta = (n, num_groups, k, int(transpose_a), b.shape, c.shape)
         ctx.a_dtype = a.dtype  # float64 callers (FeedbackLoop.solve) get dL/dA back in float64
@@ -123,7 +136,7 @@ class _GFDNSolve(torch.autograd.Function):
             ws = torch.empty(_lib.load().dgfdn_solve_bwd_ws_bytes(n) // 8, dtype=torch.float64, device=dev)
             _lib.call("dgfdn_solve_bwd", n, g, k, _ptr(z), _ptr(delays), _ptr(a_), tr, _ptr(gamma_), _ptr(gamma_z_),
                       _ptr(c_), _ptr(x), _ptr(gy_), _ptr(gx_), _ptr(ga), _ptr(gb), _ptr(gc), _ptr(gig), _ptr(ws),
-                      _stream())
+                      _ptr(ctx.factors), _stream())
         g_a = ga.reshape(n, n).to(ctx.a_dtype) if ctx.needs_input_grad[2] else None
         g_gamma = None
         if gamma_ is not None and ctx.needs_input_grad[3]:
@@ -161,8 +174,10 @@ class _GFDNSolveGroups(torch.autograd.Function):
         x = torch.empty(k, n, dtype=C64, device=z.device)
         y = torch.empty(k, g, dtype=C64, device=z.device)
         with torch.cuda.device(z.device):
+            factors = _factor_buffer(any(ctx.needs_input_grad), "dgfdn_solve_groups_factors_bytes", (l, g, k), z.device)
             _lib.call("dgfdn_solve_groups_fwd", l, g, k, _ptr(z), _ptr(delays), _ptr(m_), _ptr(gamma_), _ptr(b_),
-                      _ptr(c_), _ptr(x), _ptr(y), _stream())
+                      _ptr(c_), _ptr(x), _ptr(y), _ptr(factors), _stream())
+        ctx.factors = factors
         ctx.save_for_backward(z, delays, m_, gamma_, c_, x)
         ctx.meta = (g, l, k, b.shape, c.shape)
         return x, y
@@ -183,7 +198,8 @@ class _GFDNSolveGroups(torch.autograd.Function):
         with torch.cuda.device(dev):
             ws = torch.empty(_lib.load().dgfdn_solve_groups_bwd_ws_bytes(l) // 8, dtype=torch.float64, device=dev)
             _lib.call("dgfdn_solve_groups_bwd", l, g, k, _ptr(z), _ptr(delays), _ptr(m_), _ptr(gamma_), _ptr(c_), _ptr(x),
-                      _ptr(gy_), _ptr(gx_), _ptr(gm), _ptr(gb), _ptr(gc), _ptr(gig), _ptr(ws), _stream())
+                      _ptr(gy_), _ptr(gx_), _ptr(gm), _ptr(gb), _ptr(gc), _ptr(gig), _ptr(ws), _ptr(ctx.factors),
+                      _stream())
         g_m = gm.reshape(g, l, l).to(torch.float32) if ctx.needs_input_grad[2] else None
         g_gamma = None
         if gamma_ is not None and ctx.needs_input_grad[3]:

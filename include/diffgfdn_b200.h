@@ -67,10 +67,14 @@ DGFDN_API int dgfdn_skew_expm_bwd(int g, int l, const float* m, const float* gu,
  * gamma   [N]    float32 or NULL (= 1);  gamma_z [N,K] c64 or NULL (per-bin filter response, overrides gamma)
  * b, c    [N]    float32
  * x       [K,N]  c64 out (may be NULL)     y [K,G] c64 out (may be NULL)
+ * factors NULL, or dgfdn_solve_factors_bytes(n, k) bytes that receive the elimination itself (the multipliers of every
+ *         Gauss-Jordan step, the pivots, z^m): handed to dgfdn_solve_bwd, the adjoint solve then replays them as N
+ *         rank-one updates instead of factorising M^H again (the reference's autograd re-solves with the saved LU too).
  */
+DGFDN_API int64_t dgfdn_solve_factors_bytes(int n, int64_t k);
 DGFDN_API int dgfdn_solve_fwd(int n, int g, int64_t k, const void* z, const int32_t* delays, const float* a,
                     int transpose_a, const float* gamma, const void* gamma_z, const float* b, const float* c,
-                    void* x, void* y, void* stream);
+                    void* x, void* y, void* factors, void* stream);
 
 /* Adjoint of dgfdn_solve_fwd (replaces autograd through torch.linalg.inv + einsum, trainer.py:473-474).
  *   lambda_k = M_k^{-H} (c o gy[k, g(.)] + gx[k, .])
@@ -79,25 +83,30 @@ DGFDN_API int dgfdn_solve_fwd(int n, int g, int64_t k, const void* z, const int3
  * x [K,N] c64 is the state saved by the forward call; gy [K,G] c64 and gx [K,N] c64 may be NULL (not both).
  * Outputs are float64: ga [N,N], gb [N], gc [N], ginvgamma [N] (gradient w.r.t. 1/gamma_i; ignored if NULL).
  * ws: scratch of dgfdn_solve_bwd_ws_bytes(n) bytes. Reduction order is fixed (deterministic).
+ * factors: the buffer filled by the forward call with the same (z, a, gamma, ...) or NULL (fresh elimination of M^H).
  */
 DGFDN_API int64_t dgfdn_solve_bwd_ws_bytes(int n);
 DGFDN_API int dgfdn_solve_bwd(int n, int g, int64_t k, const void* z, const int32_t* delays, const float* a,
                     int transpose_a, const float* gamma, const void* gamma_z, const float* c, const void* x,
                     const void* gy, const void* gx, double* ga, double* gb, double* gc, double* ginvgamma,
-                    void* ws, void* stream);
+                    void* ws, const void* factors, void* stream);
 
 /* Group mode of K1: the G independent lossless LxL systems of DiffGFDN.sub_fdn_output (model.py:209-252, quirk Q1:
  * RAW mixing matrices, normally no absorption) solved as G small systems per bin -- four 8x8 systems to a warp --
  * instead of one block-diagonal NxN system.
  *   x[k, g L + i] = ((diag(z_k^{m_g} / gamma_g) - M_g)^{-1} b_g)[i],   y[k,g] = sum_i c[g L + i] x[k, g L + i]
  * m_raw [G,L,L] float32; delays, gamma (or NULL), b, c [G*L]; x [K, G*L] c64 (may be NULL), y [K,G] c64.
- * The adjoint returns gm [G,L,L], gb, gc, ginvgamma [G*L] (float64); ws: dgfdn_solve_groups_bwd_ws_bytes(l) bytes. */
+ * The adjoint returns gm [G,L,L], gb, gc, ginvgamma [G*L] (float64); ws: dgfdn_solve_groups_bwd_ws_bytes(l) bytes.
+ * factors: as for dgfdn_solve_fwd/bwd, dgfdn_solve_groups_factors_bytes(l, g, k) bytes or NULL. */
+DGFDN_API int64_t dgfdn_solve_groups_factors_bytes(int l, int g, int64_t k);
 DGFDN_API int dgfdn_solve_groups_fwd(int l, int g, int64_t k, const void* z, const int32_t* delays, const float* m_raw,
-                           const float* gamma, const float* b, const float* c, void* x, void* y, void* stream);
+                           const float* gamma, const float* b, const float* c, void* x, void* y, void* factors,
+                           void* stream);
 DGFDN_API int64_t dgfdn_solve_groups_bwd_ws_bytes(int l);
 DGFDN_API int dgfdn_solve_groups_bwd(int l, int g, int64_t k, const void* z, const int32_t* delays, const float* m_raw,
                            const float* gamma, const float* c, const void* x, const void* gy, const void* gx,
-                           double* gm, double* gb, double* gc, double* ginvgamma, void* ws, void* stream);
+                           double* gm, double* gb, double* gc, double* ginvgamma, void* ws, const void* factors,
+                           void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K2: receiver projection.  Replaces the (B,N,K) expansion + einsums of model.py:583-619.
