@@ -585,7 +585,7 @@ __global__ void solve_bwd_reduce_kernel(const double* ws, int64_t ngroups, int n
 
 constexpr int lanes_for(int np) { return np <= 4 ? 4 : (np <= 8 ? 8 : (np <= 16 ? 16 : 32)); }
 
-constexpr int kMaxBlocksPerSm = 4;  // the backward workspace is sized for this many resident blocks per SM
+constexpr int kMaxBlocksPerSm = 8;  // the backward workspace is sized for this many resident blocks per SM
 
 // One resident wave: `per_sm` is the occupancy of the instantiation being launched (a grid of 4 blocks per SM with
 // only 3 resident leaves a 148-block second wave that runs at a third of the SM's throughput).
