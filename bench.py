@@ -59,6 +59,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager steps instead of CUDA-graph replays")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-render", action="store_true", help="skip the secondary metric (BASELINE configs[4] renderer)")
     ap.add_argument("--cpu-sample-receivers", type=int, default=4)
     return ap.parse_args()
 
@@ -129,6 +130,57 @@ def build_net(device, seed=1234):
     return DiffGFDNVarReceiverPos(FS, N_GROUPS, delays_for(N_LINES), device, FeedbackLoopConfig(use_zero_coupling=False),
                                   OutputFilterConfig(use_svfs=False), use_absorption_filters=False,
                                   common_decay_times=np.array([T60]), use_colorless_loss=True)
+
+
+def render_metric(device, hbm_peak):
+    """Secondary metric of BASELINE.json (configs[4]): block-recursive time-domain render of 10 s of late tail for 4096
+    moving listeners x 8 octave bands from GFDN parameters (N = 12, G = 3 per band): K6 render_groups (the recursion,
+    min(m) samples per block) + render_mix (per-listener gains switched every 100 ms, bands summed). Output resident in
+    HBM: 4 B written per listener.sample."""
+    from diffgfdn_b200 import ops
+    from diffgfdn_b200.config import FeedbackLoopConfig, OutputFilterConfig
+    from diffgfdn_b200.model import DiffGFDNVarReceiverPos
+    bands, n_lines, listeners, seconds, positions = 8, 12, 4096, 10.0, 838
+    t = int(seconds * FS)
+    hop = int(0.1 * FS)
+    gen = torch.Generator(device=device).manual_seed(77)
+    pos = torch.rand(positions, 3, device=device, generator=gen)
+    a, gam, b, c, s, dl = [], [], [], [], [], []
+    with torch.no_grad():
+        for bd in range(bands):
+            torch.manual_seed(500 + bd)
+            net = DiffGFDNVarReceiverPos(FS, N_GROUPS, delays_for(n_lines), device, FeedbackLoopConfig(use_zero_coupling=False),
+                                         OutputFilterConfig(use_svfs=False), use_absorption_filters=False,
+                                         common_decay_times=np.array([T60]), use_colorless_loss=False)
+            a.append(net.feedback_loop.coupled_feedback_matrix_real().float())
+            gam.append(net.feedback_loop.delay_line_gains.float())
+            b.append(net.input_gains.reshape(-1).float())
+            c.append(net.output_gains.reshape(-1).float())
+            s.append(net.output_scalars.gains({'norm_listener_position': pos}).float())
+            dl.append(net.delays.to(torch.int32))
+    a, gam, b, c, s, dl = (torch.stack(v).contiguous() for v in (a, gam, b, c, s, dl))
+    traj = torch.randint(0, positions, (listeners, (t + hop - 1) // hop), device=device, generator=gen, dtype=torch.int32)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    for it in range(3):  # two warm-up passes, the third is timed
+        ev[0].record()
+        q = ops.render_groups(dl, a, gam, b, c, N_GROUPS, t)
+        ev[1].record()
+        out = ops.render_mix(s, traj, q, hop)
+        ev[2].record()
+        if it < 2:
+            del out
+    torch.cuda.synchronize()
+    ms_groups, ms_mix = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])
+    peak = float(out.abs().max())
+    total = listeners * t
+    return {"metric": "render listener*samples/s (10 s late tail, 4096 moving listeners x 8 octave bands)",
+            "value": total / ((ms_groups + ms_mix) * 1e-3), "unit": "listener*samples/s",
+            "ms": {"render_groups(recursion, 8 bands)": ms_groups, "render_mix(4096 listeners)": ms_mix},
+            "roofline": {"bound": "hbm", "kernel": "render_mix", "achieved": 4.0 * total / (ms_mix * 1e-3) / 1e9,
+                         "peak": hbm_peak, "unit": "GB/s", "frac": 4.0 * total / (ms_mix * 1e-3) / 1e9 / hbm_peak,
+                         "note": "4 B written per listener.sample; the recursion is latency bound (T / min(m) dependent blocks)"},
+            "config": {"workload": "BASELINE configs[4]", "bands": bands, "delay_lines": n_lines, "listeners": listeners,
+                       "samples": t, "hop": hop, "positions": positions}, "finite": bool(np.isfinite(peak))}
 
 
 def synth_responses(rows, nfft, device, seed):
@@ -399,6 +451,8 @@ def main():
             "cuda_graph": not args.no_graph,
             "e2e": e2e,
         }
+        if not args.no_render:
+            out["render"] = render_metric(device, hbm)
         if not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(args.nfft, args.cpu_sample_receivers)
         print(json.dumps(out), flush=True)

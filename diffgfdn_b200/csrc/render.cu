@@ -9,6 +9,8 @@
 // With a block of L = min_i m_i samples every right-hand side refers to earlier blocks, so a block is one
 // dense (N x N) * (N x L) product. render_groups advances one CTA per (octave) band; render_mix streams the
 // listener outputs (4 B written per listener.sample, the only HBM-heavy part).
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace dgfdn {
@@ -99,6 +101,90 @@ __global__ void __launch_bounds__(256) render_mix_kernel(int bands, int g, int64
   }
 }
 
+// Tiled listener mix (hop % 4 == 0): a block owns up to 1024 samples of ONE hop and kMixTile listeners. A thread keeps
+// 4 samples x kMixTile listeners of accumulators in registers, reads the 4 x G group samples of a band with G 128-bit
+// loads (q is [band][t][g], so 4 consecutive samples are 4 G contiguous floats) and reuses them for every listener
+// of the tile; the listeners' gains for this hop sit in shared memory (one broadcast LDS per gain). Per output
+// sample that is the bands x G FMAs the sum needs plus ~1/kMixTile of a load: the kernel streams its 4 B per
+// listener.sample at HBM write speed instead of re-reading q and s from L2 for every listener.
+constexpr int kMixTile = 8;
+
+template <int G>
+__global__ void __launch_bounds__(256) render_mix_tiled_kernel(int bands, int64_t tlen, int64_t listeners,
+                                                               int64_t positions, int64_t hop, int64_t nhops,
+                                                               int blocks_per_hop, const float* __restrict__ s,
+                                                               const int32_t* __restrict__ traj,
+                                                               const float* __restrict__ q, float* __restrict__ out) {
+  extern __shared__ float s_tile[];  // [kMixTile][bands * G]
+  const int bg = bands * G;
+  const int64_t hidx = blockIdx.x / blocks_per_hop;
+  const int sub = blockIdx.x % blocks_per_hop;
+  const int64_t r0 = (int64_t)blockIdx.y * kMixTile;
+  const int nl = (int)min((int64_t)kMixTile, listeners - r0);
+  for (int i = threadIdx.x; i < kMixTile * bg; i += 256) {
+    const int l = i / bg, j = i % bg;
+    float v = 0.f;
+    if (l < nl) {
+      const int64_t pos = traj[(r0 + l) * nhops + hidx];
+      v = s[((size_t)(j / G) * positions + pos) * G + (j % G)];
+    }
+    s_tile[i] = v;
+  }
+  __syncthreads();
+  const int64_t hop_end = min(tlen, (hidx + 1) * hop);
+  const int64_t t0 = hidx * hop + 4 * ((int64_t)sub * 256 + threadIdx.x);
+  if (t0 >= hop_end) return;
+  const bool full = t0 + 3 < hop_end;
+  float acc[kMixTile][4];
+#pragma unroll
+  for (int l = 0; l < kMixTile; ++l)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[l][e] = 0.f;
+  for (int bd = 0; bd < bands; ++bd) {
+    float v[4 * G];
+    const float* qp = q + ((size_t)bd * tlen + t0) * G;
+    if (full && (reinterpret_cast<uintptr_t>(qp) & 15u) == 0) {  // (a band starts 16-byte aligned only if tlen G % 4 == 0)
+#pragma unroll
+      for (int i = 0; i < G; ++i) {
+        const float4 w = __ldg(reinterpret_cast<const float4*>(qp) + i);
+        v[4 * i] = w.x, v[4 * i + 1] = w.y, v[4 * i + 2] = w.z, v[4 * i + 3] = w.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4 * G; ++i) v[i] = (t0 + i / G < hop_end) ? __ldg(qp + i) : 0.f;
+    }
+#pragma unroll
+    for (int l = 0; l < kMixTile; ++l) {
+#pragma unroll
+      for (int gi = 0; gi < G; ++gi) {
+        const float w = s_tile[l * bg + bd * G + gi];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[l][e] = fmaf(w, v[e * G + gi], acc[l][e]);
+      }
+    }
+  }
+  for (int l = 0; l < nl; ++l) {
+    float* o = out + (r0 + l) * tlen + t0;
+    if (full && ((reinterpret_cast<uintptr_t>(o) & 15u) == 0)) {
+      st_stream(reinterpret_cast<float4*>(o), make_float4(acc[l][0], acc[l][1], acc[l][2], acc[l][3]));
+    } else {
+      for (int e = 0; e < 4 && t0 + e < hop_end; ++e) o[e] = acc[l][e];
+    }
+  }
+}
+
+template <int G>
+int launch_mix_tiled(int bands, int64_t t, int64_t listeners, int64_t positions, int64_t hop, int64_t nhops,
+                     const float* s, const int32_t* traj, const float* q, float* out, cudaStream_t st) {
+  const int blocks_per_hop = (int)((std::min(hop, t) + 1023) / 1024);
+  const dim3 grid((unsigned)(nhops * blocks_per_hop), (unsigned)((listeners + kMixTile - 1) / kMixTile));
+  const size_t smem = (size_t)kMixTile * bands * G * sizeof(float);
+  render_mix_tiled_kernel<G><<<grid, 256, smem, st>>>(bands, t, listeners, positions, hop, nhops, blocks_per_hop, s, traj,
+                                                      q, out);
+  DGFDN_LAUNCH_CHECK();
+  return 0;
+}
+
 }  // namespace
 }  // namespace dgfdn
 
@@ -125,9 +211,21 @@ extern "C" int dgfdn_render_mix(int bands, int g, int64_t t, int64_t listeners, 
   DGFDN_CHECK(listeners <= 65535, "render_mix: listeners=%lld exceeds grid.y limit; tile the call",
               (long long)listeners);
   const int64_t nhops = (t + hop - 1) / hop;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // tiled kernel: hops of a multiple of 4 samples (128-bit accesses never straddle a hop), 16-byte aligned q, and a
+  // grid.x that fits; anything else takes the per-sample kernel below
+  const int64_t gx = nhops * ((std::min(hop, t) + 1023) / 1024);
+  if (hop % 4 == 0 && g <= 4 && (reinterpret_cast<uintptr_t>(q) & 15u) == 0 && gx < (int64_t)1 << 31 &&
+      (size_t)kMixTile * bands * g * sizeof(float) <= 48 * 1024) {
+    switch (g) {
+      case 1: return launch_mix_tiled<1>(bands, t, listeners, positions, hop, nhops, s, traj, q, out, st);
+      case 2: return launch_mix_tiled<2>(bands, t, listeners, positions, hop, nhops, s, traj, q, out, st);
+      case 3: return launch_mix_tiled<3>(bands, t, listeners, positions, hop, nhops, s, traj, q, out, st);
+      default: return launch_mix_tiled<4>(bands, t, listeners, positions, hop, nhops, s, traj, q, out, st);
+    }
+  }
   dim3 grid((unsigned)((t + 1023) / 1024), (unsigned)listeners);
-  render_mix_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(bands, g, t, positions, hop, nhops, s, traj,
-                                                                         q, out);
+  render_mix_kernel<<<grid, 256, 0, st>>>(bands, g, t, positions, hop, nhops, s, traj, q, out);
   DGFDN_LAUNCH_CHECK();
   return 0;
 }

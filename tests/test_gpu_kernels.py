@@ -401,3 +401,24 @@ def test_target_caches_survive_allocator_address_reuse():
         assert abs(float(crit_r(tgt, ach)) - float(want_r)) < 2e-3 * float(want_r) + 1e-6, step
         del tgt
     assert len(ptrs) >= 1
+
+
+@pytest.mark.parametrize("bands,g,t,hop,listeners", [(8, 3, 6400, 3200, 19), (2, 3, 1001, 300, 5), (3, 2, 1000, 250, 9),
+                                                     (1, 1, 7, 4, 1), (4, 4, 2048, 4096, 8)])
+def test_render_mix_tiled_and_fallback_paths(bands, g, t, hop, listeners):
+    """render_mix (sound_examples.py:163-226 semantics: gains switched per hop, bands summed) on random group signals:
+    the tiled kernel (hop % 4 == 0), its ragged hop / listener / time tails, and the per-sample fallback."""
+    from diffgfdn_b200 import ops
+    gen = torch.Generator().manual_seed(bands * 100 + t)
+    positions = 11
+    q = torch.randn(bands, t, g, generator=gen)
+    s = torch.rand(bands, positions, g, generator=gen) - 0.5
+    nh = (t + hop - 1) // hop
+    traj = torch.randint(0, positions, (listeners, nh), generator=gen, dtype=torch.int32)
+    out = ops.render_mix(s.cuda(), traj.cuda(), q.cuda(), hop)
+    ref = torch.zeros(listeners, t, dtype=F64)
+    for r in range(listeners):
+        for hb in range(nh):
+            sl = slice(hb * hop, min(t, (hb + 1) * hop))
+            ref[r, sl] = torch.einsum('bg,btg->t', s[:, traj[r, hb]].to(F64), q[:, sl].to(F64))
+    assert float((out.cpu().to(F64) - ref).abs().max() / ref.abs().max()) < 1e-5
