@@ -10,6 +10,7 @@
 // dense (N x N) * (N x L) product. render_groups advances one CTA per (octave) band; render_mix streams the
 // listener outputs (4 B written per listener.sample, the only HBM-heavy part).
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -65,6 +66,76 @@ __global__ void __launch_bounds__(kThreads) render_groups_kernel(int n, int g, i
       const int64_t t = s0 + w / g;
       float acc = 0.f;
       for (int j = 0; j < l; ++j) acc = fmaf(s_c[gi * l + j], hb[t * n + gi * l + j], acc);
+      qb[t * g + gi] = acc;
+    }
+  }
+}
+
+// The same recursion with a thread-block CLUSTER per band: the (sample, line) items of a block of min(m) samples are
+// spread over kRenderCluster CTAs (8 SMs per band instead of 1), the state history lives in global memory (L2) and one
+// barrier.cluster (release / acquire: orders the global writes at cluster scope) separates a block from the next.
+// History reads bypass L1 (ld.global.cg): the lines were written by other SMs.
+constexpr int kRenderCluster = 8;
+
+__global__ void __launch_bounds__(kThreads) render_groups_cluster_kernel(int n, int g, int64_t tlen,
+                                                                         const int32_t* __restrict__ delays,
+                                                                         const float* __restrict__ a,
+                                                                         const float* __restrict__ gamma,
+                                                                         const float* __restrict__ b,
+                                                                         const float* __restrict__ c,
+                                                                         const float* __restrict__ u, float* hist,
+                                                                         float* __restrict__ q) {
+  __shared__ float s_a[DGFDN_MAX_LINES * DGFDN_MAX_LINES];
+  __shared__ float s_gamma[DGFDN_MAX_LINES], s_b[DGFDN_MAX_LINES], s_c[DGFDN_MAX_LINES];
+  __shared__ int s_m[DGFDN_MAX_LINES];
+  const int band = blockIdx.x / kRenderCluster;
+  const int rank = blockIdx.x % kRenderCluster;
+  const int l = n / g;
+  for (int i = threadIdx.x; i < n * n; i += kThreads) s_a[i] = a[(size_t)band * n * n + i];
+  for (int i = threadIdx.x; i < n; i += kThreads) {
+    s_gamma[i] = gamma ? gamma[band * n + i] : 1.f;
+    s_b[i] = b[band * n + i];
+    s_c[i] = c[band * n + i];
+    s_m[i] = delays[band * n + i];
+  }
+  __syncthreads();
+  int blk = s_m[0];
+  for (int i = 1; i < n; ++i) blk = min(blk, s_m[i]);
+  float* hb = hist + (size_t)band * tlen * n;
+  float* qb = q + (size_t)band * tlen * g;
+  const int gtid = rank * kThreads + threadIdx.x;
+  constexpr int kStride = kRenderCluster * kThreads;
+  for (int64_t s0 = 0; s0 < tlen; s0 += blk) {
+    const int len = (int)min((int64_t)blk, tlen - s0);
+    for (int w = gtid; w < len * n; w += kStride) {
+      const int i = w % n;
+      const int64_t t = s0 + w / n;
+      const int64_t src = t - s_m[i];
+      float v = 0.f;
+      if (src >= 0) {
+        const float* xr = hb + src * n;
+        float acc = s_b[i] * (u ? u[src] : (src == 0 ? 1.f : 0.f));
+        if ((n & 3) == 0 && (reinterpret_cast<uintptr_t>(xr) & 15u) == 0) {  // a state vector is n/4 128-bit L2 loads
+          for (int j = 0; j < n; j += 4) {
+            const float4 x4 = __ldcg(reinterpret_cast<const float4*>(xr + j));
+            acc = fmaf(s_a[i * n + j], x4.x, acc);
+            acc = fmaf(s_a[i * n + j + 1], x4.y, acc);
+            acc = fmaf(s_a[i * n + j + 2], x4.z, acc);
+            acc = fmaf(s_a[i * n + j + 3], x4.w, acc);
+          }
+        } else {
+          for (int j = 0; j < n; ++j) acc = fmaf(s_a[i * n + j], __ldcg(xr + j), acc);
+        }
+        v = s_gamma[i] * acc;
+      }
+      hb[t * n + i] = v;
+    }
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    for (int w = gtid; w < len * g; w += kStride) {
+      const int gi = w % g;
+      const int64_t t = s0 + w / g;
+      float acc = 0.f;
+      for (int j = 0; j < l; ++j) acc = fmaf(s_c[gi * l + j], __ldcg(hb + t * n + gi * l + j), acc);
       qb[t * g + gi] = acc;
     }
   }
@@ -196,8 +267,23 @@ extern "C" int dgfdn_render_groups(int bands, int n, int g, int64_t t, const int
   DGFDN_CHECK(bands >= 1 && n >= 1 && n <= DGFDN_MAX_LINES && g >= 1 && n % g == 0 && t >= 1,
               "render_groups: bad sizes");
   DGFDN_CHECK(delays && a && b && c && hist && q, "render_groups: null pointer");
-  render_groups_kernel<<<bands, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(n, g, t, delays, a, gamma, b, c, u,
-                                                                                  hist, q);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (getenv("DGFDN_RENDER_SINGLE_CTA") == nullptr) {  // one cluster of 8 CTAs per band
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kRenderCluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.gridDim = dim3((unsigned)(bands * kRenderCluster));
+    cfg.blockDim = dim3(kThreads);
+    cfg.stream = st;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    DGFDN_CUDA(cudaLaunchKernelEx(&cfg, render_groups_cluster_kernel, n, g, t, delays, a, gamma, b, c, u, hist, q));
+    return 0;
+  }
+  render_groups_kernel<<<bands, kThreads, 0, st>>>(n, g, t, delays, a, gamma, b, c, u, hist, q);
   DGFDN_LAUNCH_CHECK();
   return 0;
 }
