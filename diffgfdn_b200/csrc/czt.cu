@@ -273,6 +273,7 @@ extern "C" int64_t dgfdn_czt_plan_mc(const dgfdn_czt_plan* p) { return p ? p->mc
 
 extern "C" int dgfdn_irfft_window_fwd(dgfdn_czt_plan* p, const void* x, int64_t ldx, int64_t rows, const void* filt,
                                       void* scratch, float* out, void* stream) {
+  if (rows == 0) return 0;  // an empty batch (empty tensors carry null pointers)
   DGFDN_CHECK(p && x && scratch && out, "irfft_window_fwd: null pointer");
   DGFDN_CHECK(ldx >= p->kh + 1, "irfft_window_fwd: rows hold %lld bins, need %lld", (long long)ldx,
               (long long)(p->kh + 1));

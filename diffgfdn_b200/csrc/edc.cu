@@ -175,6 +175,7 @@ __global__ void __launch_bounds__(kThreads) edc_loss_bwd_kernel(const float* __r
 using namespace dgfdn;
 
 extern "C" int dgfdn_edc_db(const float* h, int64_t rows, int64_t tn, float* curve_db, void* stream) {
+  if (rows == 0) return 0;
   DGFDN_CHECK(h && curve_db && rows >= 0 && tn >= 1, "edc_db: bad arguments");
   if (rows == 0) return 0;
   edc_db_kernel<<<(unsigned)rows, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(h, tn, curve_db);

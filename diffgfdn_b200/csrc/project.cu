@@ -336,6 +336,7 @@ using namespace dgfdn;
 
 extern "C" int dgfdn_project_fwd(int g, int64_t rows, int64_t k, const float* s, const void* y, const void* d,
                                  int64_t ldd, void* h, int64_t ldh, void* stream) {
+  if (rows == 0) return 0;  // an empty batch: nothing to write (empty tensors carry null pointers)
   DGFDN_CHECK(rows >= 0 && k >= 1 && s && y && h, "project_fwd: bad arguments");
   if (rows == 0) return 0;
   DGFDN_CHECK(ldh >= k && (d == nullptr || ldd >= k), "project_fwd: row stride smaller than k");

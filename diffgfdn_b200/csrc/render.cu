@@ -292,8 +292,8 @@ extern "C" int dgfdn_render_mix(int bands, int g, int64_t t, int64_t listeners, 
                                 const float* s, const int32_t* traj, const float* q, float* out, void* stream) {
   DGFDN_CHECK(bands >= 1 && g >= 1 && t >= 1 && listeners >= 0 && positions >= 1 && hop >= 1,
               "render_mix: bad sizes");
-  DGFDN_CHECK(s && traj && q && out, "render_mix: null pointer");
   if (listeners == 0) return 0;
+  DGFDN_CHECK(s && traj && q && out, "render_mix: null pointer");
   DGFDN_CHECK(listeners <= 65535, "render_mix: listeners=%lld exceeds grid.y limit; tile the call",
               (long long)listeners);
   const int64_t nhops = (t + hop - 1) / hop;

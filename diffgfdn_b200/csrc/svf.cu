@@ -224,6 +224,7 @@ using namespace dgfdn;
 extern "C" int dgfdn_project_svf_fwd(int g, int nsec, int64_t rows, int64_t k, const double* coef, const void* z,
                                      const void* y, const void* d, int64_t ldd, void* h, int64_t ldh, void* stream) {
   if (check(g, nsec, rows, k)) return 1;
+  if (rows == 0) return 0;
   DGFDN_CHECK(coef && z && y && h, "project_svf_fwd: null pointer");
   DGFDN_CHECK(ldh >= k && (d == nullptr || ldd >= k), "project_svf_fwd: row stride smaller than k");
   if (rows == 0) return 0;

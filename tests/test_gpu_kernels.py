@@ -422,3 +422,37 @@ def test_render_mix_tiled_and_fallback_paths(bands, g, t, hop, listeners):
             sl = slice(hb * hop, min(t, (hb + 1) * hop))
             ref[r, sl] = torch.einsum('bg,btg->t', s[:, traj[r, hb]].to(F64), q[:, sl].to(F64))
     assert float((out.cpu().to(F64) - ref).abs().max() / ref.abs().max()) < 1e-5
+
+
+def test_empty_and_degenerate_inputs():
+    """Zero receivers, one bin, one delay line, argument errors: every entry point either returns empty results or
+    raises a RuntimeError with the C ABI's message -- never a CUDA fault."""
+    from diffgfdn_b200 import ops
+    from diffgfdn_b200.losses import edc_loss
+    k, g = 257, 3
+    y = torch.randn(k, g, dtype=torch.complex64).cuda()
+    z = O.z_grid(2 * (k - 1)).cuda()
+    # zero receivers
+    h0 = ops.receiver_project(torch.zeros(0, g).cuda(), y, None)
+    assert tuple(h0.shape) == (0, k)
+    coef0 = torch.zeros(0, g, 4, 6, dtype=torch.float64).cuda()
+    assert tuple(ops.svf_project(coef0, z, y, None).shape) == (0, k)
+    assert tuple(ops.irfft_window(torch.zeros(0, k, dtype=torch.complex64).cuda(), 2 * (k - 1), 0, 64).shape) == (0, 64)
+    assert tuple(ops.edc_db(torch.zeros(0, 128).cuda()).shape) == (0, 128)
+    out = ops.render_mix(torch.rand(2, 5, g).cuda(), torch.zeros(0, 4, dtype=torch.int32).cuda(),
+                         torch.randn(2, 256, g).cuda(), 64)
+    assert tuple(out.shape) == (0, 256)
+    # one delay line, one group, one bin
+    x, y1 = ops.gfdn_solve(torch.ones(1, dtype=torch.complex128).cuda(), torch.tensor([7], dtype=torch.int32).cuda(),
+                           torch.tensor([[0.5]]).cuda(), torch.tensor([0.9]).cuda(), torch.tensor([2.0]).cuda(),
+                           torch.tensor([3.0]).cuda(), 1)
+    want = 3.0 * 2.0 / (1.0 / 0.9 - 0.5)
+    assert abs(complex(y1[0, 0].cpu()) - want) < 1e-5 * want
+    # argument errors surface as RuntimeError with the library's message
+    with pytest.raises(RuntimeError, match="out of range|exceed"):
+        ops.gfdn_solve(z, torch.ones(33, dtype=torch.int32).cuda(), torch.eye(33).cuda(), torch.ones(33).cuda(),
+                       torch.ones(33).cuda(), torch.ones(33).cuda(), 3)
+    with pytest.raises(RuntimeError):
+        ops.svf_project(torch.zeros(2, g, 17, 6, dtype=torch.float64).cuda(), z, y, None)  # > 16 sections
+    with pytest.raises(RuntimeError, match="empty"):
+        edc_loss(10.0, 32000.0)(y.t().contiguous(), y.t().contiguous())  # window shorter than the mixing time
