@@ -151,6 +151,12 @@ class ShardedEDCStep:
         side = self._side_stream() if self.use_side_stream else main
         side.wait_stream(main)
         with torch.cuda.stream(side):
+            # the position -> gain network only meets the solve chain at the receiver kernel: its forward runs next to
+            # the coupled solve, and (autograd keeps a node's backward on its forward's stream) its backward next to
+            # the adjoint solve
+            s = net.output_scalars.gains({'norm_listener_position': self.positions})
+            s_ready = torch.cuda.Event()
+            s_ready.record(side)
             keep = net.return_per_delay_outputs
             net.return_per_delay_outputs = False
             h_sub, _ = net.sub_fdn_output(self.z)
@@ -159,7 +165,6 @@ class ShardedEDCStep:
             spectral = self.w_spec * per_group.sum()
             sparsity = self.w_spars * self._sparsity(net.feedback_loop.ortho_param(net.feedback_loop.M[g - 1]))
             aux = (spectral + sparsity.to(spectral.dtype)) / self.world_size
-        s = net.output_scalars.gains({'norm_listener_position': self.positions})
         # irfft(X, n=K) reads bins 0..K/2 only (reference losses.py:207-213, quirk Q3), so the coupled system is
         # solved on those kx bins; the other bins of H reach no loss term (the colorless loss has its own solve)
         z_edc = self.z if net.feedback_loop.delay_line_gain_response is not None else self.z[:self.kx]
@@ -167,6 +172,7 @@ class ShardedEDCStep:
         hy = ops.irfft_window(y.transpose(0, 1), self.n_fft, self.t0, self.tn)  # (G, tn)
         self.kernel_launches += 2 + 3 + 1  # two solves, chirp-z (pre, mul, post; + 2 cuFFT), colorless forward
 
+        main.wait_event(s_ready)
         s_d = s.detach().contiguous()
         hy_d = hy.detach().contiguous()
         ghy = torch.empty_like(hy_d)
