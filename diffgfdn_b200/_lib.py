@@ -18,6 +18,8 @@ SIGNATURES = {
     "dgfdn_copy_rows_h2d": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p]),
     "dgfdn_skew_expm_fwd": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "dgfdn_skew_expm_bwd": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "dgfdn_coupled_feedback_fwd": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "dgfdn_coupled_feedback_bwd": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dgfdn_solve_factors_bytes": (c_int64, [c_int, c_int64]),
     "dgfdn_solve_fwd": (c_int, [c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

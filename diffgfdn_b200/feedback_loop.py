@@ -4,6 +4,7 @@ Mirrors reference diff_gfdn/feedback_loop.py (class and parameter names, state_d
 parameter pre-processing (matrix exponential, Givens rotations, Kronecker mask) is O(N^2) and stays in PyTorch on
 the device, differentiable for free; the O(K N^3) part -- the reference's `torch.linalg.inv` over K dense matrices
 (feedback_loop.py:391) -- is the sm_100a kernel behind `ops.gfdn_solve`."""
+import os
 from typing import List, Optional
 
 import numpy as np
@@ -242,14 +243,25 @@ class FeedbackLoop(nn.Module):
         # block_M o (Phi (x) 1_{LxL}) as one broadcast multiply over the (G, L, G, L) view
         return (block_M.view(G, L, G, L) * phi.view(G, 1, G, 1)).reshape(G * L, G * L)
 
+    def _assembled(self) -> torch.Tensor:
+        """A (N, N) float64 for the solves: one fused kernel forward, one backward (ops.coupled_feedback) instead of
+        the ~135 tiny launches of the torch graph in coupled_feedback_matrix_real (which stays the public, float32
+        form). DGFDN_FUSED_ASSEMBLY=0 falls back to the torch graph."""
+        if os.environ.get("DGFDN_FUSED_ASSEMBLY", "1") == "0" or self.num_groups > 8:
+            a = self.coupled_feedback_matrix_real(torch.float64)
+        else:
+            a, phi = ops.coupled_feedback(self.ortho_param(self.M), self.alpha)
+            self.phi = phi
+        self.coupled_feedback_matrix = a.detach()
+        return a
+
     def get_coupled_feedback_matrix(self) -> torch.Tensor:
         a = self.coupled_feedback_matrix_real()
         return torch.complex(a, torch.zeros_like(a))
 
     def solve(self, z: torch.Tensor, b: torch.Tensor, c: torch.Tensor, transpose: bool = False):
         """x_k = (D(z_k) Gamma^-1 - A)^-1 b and y[k,g] = sum_{n in g} c_n x_k[n] on the GPU (one warp per bin)."""
-        a = self.coupled_feedback_matrix_real(torch.float64)
-        self.coupled_feedback_matrix = a.detach().to(torch.float32)
+        a = self._assembled()
         gamma_z = self.absorption_response(z)
         gamma = None if gamma_z is not None else self.delay_line_gains
         return ops.gfdn_solve(z, self.delays.to(torch.int32), a, gamma, b, c, self.num_groups, transpose_a=transpose,
@@ -260,8 +272,7 @@ class FeedbackLoop(nn.Module):
         source group g' (b masked to that group), A assembled once. The model variants with source-side gains or
         filters (reference model.py:402-452, 779-836) are bilinear in the per-group factors of both sides, so these
         G x G functions per bin are all they need of the feedback loop."""
-        a = self.coupled_feedback_matrix_real(torch.float64)
-        self.coupled_feedback_matrix = a.detach().to(torch.float32)
+        a = self._assembled()
         gamma_z = self.absorption_response(z)
         gamma = None if gamma_z is not None else self.delay_line_gains
         delays = self.delays.to(torch.int32)

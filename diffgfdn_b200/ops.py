@@ -79,6 +79,42 @@ def skew_expm(m: torch.Tensor) -> torch.Tensor:
 # ----------------------------------------------------------------------------------------------------------
 # K1: per-bin solve
 # ----------------------------------------------------------------------------------------------------------
+class _CoupledFeedback(torch.autograd.Function):
+    """A = block(U_i U_j) o (ND_Unitary(alpha) (x) 1), float64 (reference feedback_loop.py:39-87, 393-455)."""
+
+    @staticmethod
+    def forward(ctx, u, alpha):
+        u_ = _cuda("U", u, torch.float32)
+        g, l, _ = u_.shape
+        alpha_ = _cuda("alpha", alpha, torch.float32) if g > 1 else None
+        if g > 1 and alpha_.numel() != g * (g - 1) // 2:
+            raise RuntimeError("coupled_feedback: alpha must hold G(G-1)/2 angles")
+        a = torch.empty(g * l, g * l, dtype=torch.float64, device=u_.device)
+        phi = torch.empty(g, g, dtype=torch.float64, device=u_.device)
+        with torch.cuda.device(u_.device):
+            _lib.call("dgfdn_coupled_feedback_fwd", g, l, _ptr(u_), _ptr(alpha_), _ptr(a), _ptr(phi), _stream())
+        ctx.save_for_backward(u_, alpha_)
+        ctx.mark_non_differentiable(phi)
+        return a, phi
+
+    @staticmethod
+    def backward(ctx, ga, _gphi):
+        u_, alpha_ = ctx.saved_tensors
+        g, l, _ = u_.shape
+        ga_ = _cuda("gA", ga, torch.float64)
+        gu = torch.empty_like(u_) if ctx.needs_input_grad[0] else None
+        galpha = torch.empty_like(alpha_) if (alpha_ is not None and ctx.needs_input_grad[1]) else None
+        with torch.cuda.device(u_.device):
+            _lib.call("dgfdn_coupled_feedback_bwd", g, l, _ptr(u_), _ptr(alpha_), _ptr(ga_), _ptr(gu), _ptr(galpha),
+                      _stream())
+        return gu, galpha
+
+
+def coupled_feedback(u: torch.Tensor, alpha: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(A (N,N) float64, Phi (G,G) float64) from the orthogonal mixing matrices U (G,L,L) and the coupling angles."""
+    return _CoupledFeedback.apply(u, alpha)
+
+
 def _factor_buffer(wanted: bool, size_fn: str, size_args, device) -> Optional[torch.Tensor]:
     """Buffer for the saved elimination of a K1 forward call (None when no gradient will be needed, or when
     DGFDN_SOLVE_REPLAY=0 asks for the fresh adjoint elimination)."""

@@ -51,6 +51,14 @@ DGFDN_API int dgfdn_copy_rows_h2d(void* dst, int64_t dst_pitch_bytes, const void
 DGFDN_API int dgfdn_skew_expm_fwd(int g, int l, const float* m, float* u, void* stream);
 DGFDN_API int dgfdn_skew_expm_bwd(int g, int l, const float* m, const float* gu, float* gm, void* stream);
 
+/* Coupled feedback matrix and its adjoint in one launch each (feedback_loop.py:39-87, 393-412, 424-455):
+ *   Phi = ND_Unitary(clamp(alpha, -pi, pi)) [G,G];   A[iL+a, jL+b] = Phi[i,j] (U_i U_j)[a,b]   (diagonal blocks U_i^2)
+ * u [G,L,L] float32 (the orthogonal mixing matrices), alpha [G(G-1)/2] float32 (NULL when G = 1), a [N,N] and phi [G,G]
+ * float64 out. bwd: ga [N,N] float64 -> gu [G,L,L], galpha [G(G-1)/2] float32 (either may be NULL). G <= 8. */
+DGFDN_API int dgfdn_coupled_feedback_fwd(int g, int l, const float* u, const float* alpha, double* a, double* phi, void* stream);
+DGFDN_API int dgfdn_coupled_feedback_bwd(int g, int l, const float* u, const float* alpha, const double* ga, float* gu,
+                               float* galpha, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * K1: per-bin build + solve.   Replaces FeedbackLoop.forward (diff_gfdn/feedback_loop.py:326-391),
  * the two einsums of DiffGFDNVarReceiverPos.forward (model.py:615-619) up to the receiver gains,

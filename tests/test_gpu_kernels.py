@@ -456,3 +456,34 @@ def test_empty_and_degenerate_inputs():
         ops.svf_project(torch.zeros(2, g, 17, 6, dtype=torch.float64).cuda(), z, y, None)  # > 16 sections
     with pytest.raises(RuntimeError, match="empty"):
         edc_loss(10.0, 32000.0)(y.t().contiguous(), y.t().contiguous())  # window shorter than the mixing time
+
+
+@pytest.mark.parametrize("g,l", [(3, 4), (3, 8), (2, 6), (1, 5), (5, 2), (8, 4), (3, 9)])
+def test_fused_coupled_feedback_matrix_matches_the_torch_graph_and_the_oracle(g, l):
+    """ops.coupled_feedback (one kernel forward, one backward) against FeedbackLoop.coupled_feedback_matrix_real (the
+    reference's graph, feedback_loop.py:39-87, 393-455) and the oracle; one angle sits outside [-pi, pi] (clamp)."""
+    from diffgfdn_b200 import ops
+    from diffgfdn_b200.feedback_loop import FeedbackLoop
+    torch.manual_seed(g * 10 + l)
+    fl = FeedbackLoop(32000.0, g, l, torch.arange(100, 100 + g * l), False, use_zero_coupling=False,
+                      common_decay_times=np.ones((1, g)), gains=torch.full((g * l, ), 0.9), device="cuda")
+    if g > 1:
+        with torch.no_grad():
+            fl.alpha.copy_((torch.rand(g * (g - 1) // 2) * 4 - 2).cuda())
+            if g > 2:
+                fl.alpha[0] = 3.5  # beyond pi: clamped, zero gradient
+    w = torch.randn(g * l, g * l, dtype=F64).cuda()
+    a_ref = fl.coupled_feedback_matrix_real(torch.float64)
+    (a_ref * w).sum().backward()
+    g_m, g_alpha = fl.M.grad.clone(), (fl.alpha.grad.clone() if g > 1 else None)
+    fl.zero_grad()
+    a, phi = ops.coupled_feedback(fl.ortho_param(fl.M), fl.alpha)
+    (a * w).sum().backward()
+    assert rel(a, a_ref) < 1e-6
+    ao = O.coupled_feedback_matrix(fl.M.detach().cpu().to(F64), fl.alpha.detach().cpu().to(F64).clamp(-np.pi, np.pi))
+    assert rel(a, ao) < 1e-5  # float32 expm kernel
+    assert rel(fl.M.grad, g_m) < 1e-5
+    if g > 1:
+        assert rel(fl.alpha.grad, g_alpha) < 1e-5
+        assert g == 2 or float(fl.alpha.grad[0]) == 0.0
+        assert rel(phi, fl.construct_coupling_matrix(torch.float64)) < 1e-9
