@@ -190,8 +190,12 @@ class Trainer:
         for epoch in range(self.max_epochs):
             et = time.time()
             tot, parts = 0.0, {}
+            svf = getattr(self.net, "use_svf_in_output", False)
+            if svf:  # full-band (SVF) models normalise b, c once per epoch, the others before every step (:366-377)
+                self.normalize(next(iter(train_dataset)))
             for data in train_dataset:
-                self.normalize(data)
+                if not svf:
+                    self.normalize(data)
                 cur, cur_all = self.train_step(data)
                 tot += cur
                 for k, v in cur_all.items():
