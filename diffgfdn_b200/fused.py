@@ -170,7 +170,9 @@ class ShardedEDCStep:
         z_edc = self.z if net.feedback_loop.delay_line_gain_response is not None else self.z[:self.kx]
         _, y = net.feedback_loop.solve(z_edc, net.input_gains.reshape(-1), net.output_gains.reshape(-1))
         hy = ops.irfft_window(y.transpose(0, 1), self.n_fft, self.t0, self.tn)  # (G, tn)
-        self.kernel_launches += 2 + 3 + 1  # two solves, chirp-z (pre, mul, post; + 2 cuFFT), colorless forward
+        # own kernels of the front: position network, 2 x skew-expm (coupled matrix, sparsity term), matrix assembly,
+        # two solves, chirp-z (pre, mul, post; the 2 cuFFT launches are not counted), colorless forward
+        self.kernel_launches += 1 + 2 + 1 + 2 + 3 + 1
 
         main.wait_event(s_ready)
         s_d = s.detach().contiguous()
@@ -201,7 +203,9 @@ class ShardedEDCStep:
         main.wait_stream(side)
         torch.autograd.backward([hy, s, aux], [ghy, gs, torch.ones_like(aux)])
         main.wait_stream(side)  # the engine joins the streams of the leaves; this makes the join explicit for capture
-        self.kernel_launches += 3 + 2 * 2 + 1  # chirp-z adjoint, two adjoint solves (+ reduce each), colorless bwd
+        # chirp-z adjoint, two adjoint solves (+ reduce each), colorless bwd, assembly bwd, 2 x skew-expm bwd,
+        # position network bwd (+ reduce)
+        self.kernel_launches += 3 + 2 * 2 + 1 + 1 + 2 + 2
         if self.world_size > 1:
             self.allreduce_grads()
         if sec:
