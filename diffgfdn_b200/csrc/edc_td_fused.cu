@@ -721,6 +721,10 @@ int launch_fused(const FusedParams& p, int64_t rows, cudaStream_t st, int* ncl_o
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   const int64_t niter = (rows + T::ROWS - 1) / T::ROWS;
+  if (const char* e = getenv("DGFDN_TD_CLUSTERS")) {  // experiment knob: more clusters than the occupancy query reports
+    const int want = atoi(e);
+    if (want >= 1 && want <= kMaxClusters) maxc = want;
+  }
   const int ncl = (int)(niter < maxc ? niter : maxc);
   cfg.gridDim = dim3((unsigned)(T::C * ncl));
   *ncl_out = ncl;
