@@ -115,7 +115,7 @@ struct GJState {
 template <int NP, int W, int K>
 struct GJStep {
   static __device__ __forceinline__ void run(double2 (&m)[NP], GJState& st, int sl, double2* line0, double2* line1,
-                                             float2* fac) {
+                                             float2* fac, double2* fm) {
     double2* line = (K & 1) ? line1 : line0;
     unsigned key = 0u;
     if (!st.used) {
@@ -133,9 +133,11 @@ struct GJStep {
     }
     __syncwarp();
     float2 fsave = make_float2(0.f, 0.f);
+    if (fm != nullptr) fm[K] = make_double2(0.0, 0.0);  // (constant index after inlining: stays in registers)
     if (sl != piv && sl < NP) {
       const double2 f = cmul(m[K], fast_cinv(line[K]));
       fsave = make_float2((float)f.x, (float)f.y);
+      if (fm != nullptr) fm[K] = f;
       const double nfx = -f.x, nfy = -f.y;
 #pragma unroll
       for (int j = K + 1; j < NP; ++j) {  // m[j] -= f * p[j]: four fused multiply-adds per complex element
@@ -150,7 +152,7 @@ struct GJStep {
     // the multiplier of this (step, row): what the adjoint replay needs (0 for the pivot row and the padding lanes)
     if (fac != nullptr) fac[K * W + sl] = fsave;
     // no second barrier: step K+1 writes the other line; step K+2 reuses this one only after the barrier of K+1
-    if constexpr (K + 1 < NP) GJStep<NP, W, K + 1>::run(m, st, sl, line0, line1, fac);
+    if constexpr (K + 1 < NP) GJStep<NP, W, K + 1>::run(m, st, sl, line0, line1, fac, fm);
   }
 };
 
@@ -158,13 +160,14 @@ struct GJStep {
 // sub-lanes < NP; sub-lanes >= NP return col = -1).
 template <int NP, int W>
 __device__ __forceinline__ double2 gauss_jordan(double2 (&m)[NP], double2 rhs, int sl, double2* line0, double2* line1,
-                                                int* col, float2* fac = nullptr, double2* pivot = nullptr) {
+                                                int* col, float2* fac = nullptr, double2* pivot = nullptr,
+                                                double2* fm = nullptr) {
   GJState st;
   st.rhs = rhs;
   st.diag = make_double2(1.0, 0.0);
   st.mycol = -1;
   st.used = sl >= NP;
-  GJStep<NP, W, 0>::run(m, st, sl, line0, line1, fac);
+  GJStep<NP, W, 0>::run(m, st, sl, line0, line1, fac, fm);
   __syncwarp();  // the lines may be rewritten by the caller's next system
   *col = st.mycol;
   if (pivot != nullptr) *pivot = st.diag;
@@ -550,6 +553,135 @@ __global__ void __launch_bounds__(kWarps * 32) solve_bwd_replay_kernel(SolvePara
   }
 }
 
+// Adjoint replay with the multipliers in registers (compile-time step index).
+template <int NP, int W, int K>
+struct ReplayStep {
+  static __device__ __forceinline__ void run(const double2 (&fm)[NP], double2& w, int col) {
+    const double2 f = fm[K];
+    const double2 s = group_sum<W>(make_double2(f.x * w.x + f.y * w.y, f.x * w.y - f.y * w.x));  // conj(f) w
+    if (col == K) {
+      w.x -= s.x;
+      w.y -= s.y;
+    }
+    if constexpr (K > 0) ReplayStep<NP, W, K - 1>::run(fm, w, col);
+  }
+};
+
+// K1c: the colorless branch in ONE pass per bin. For every lossless LxL sub-FDN system: eliminate, y = c^T x, the
+// spectral-flatness term (|y| - 1)^p (p = 4 where asym and |y| - 1 > 1, else 2; colorless_fdn/losses.py:20-73) and its
+// gradient dL/dy, then the adjoint solve with the elimination still in registers (ReplayStep) and the gradient outer
+// products. Replaces solve_fwd(groups) + colorless_fwd + colorless_bwd + solve_bwd(groups): the second elimination,
+// the H_sub round trip and three launches disappear. loss_part[sgid] holds the group's partial sum of the loss terms.
+template <int NP, int W>
+__global__ void __launch_bounds__(kWarps * 32, 3) solve_colorless_kernel(SolveParams p, int asym, double* loss_part) {
+  extern __shared__ double smem[];
+  constexpr int kSpw = 32 / W;
+  const int n = p.n;
+  double* s_const = smem;
+  double* s_vec = s_const + (size_t)p.nsys * 2 * NP * NP;
+  double* s_groups = s_vec + (size_t)p.nsys * 4 * NP;
+  const GroupIndex<W> gi(p);
+  const int sl = gi.sl, q = gi.q;
+  const int lg = (threadIdx.x >> 5) * kSpw + (threadIdx.x & 31) / W;
+  double* gbase = s_groups + (size_t)lg * Smem<NP>::kGroupBwd;
+  double2* line0 = reinterpret_cast<double2*>(gbase);
+  double2* line1 = line0 + (NP + 1);
+  double2* xs = line1 + (NP + 1) + NP;  // (the lam slot of the backward layout is unused here)
+  double* acc = reinterpret_cast<double*>(xs + NP);
+
+  load_block_constants<NP>(p, s_const, s_vec);
+  if (sl < NP)
+    for (int j = 0; j < NP; ++j) acc[sl + NP * j] = 0.0;
+  __syncthreads();
+  const double* s_a = s_const + (size_t)q * 2 * NP * NP;
+  const double* s_at = s_a + NP * NP;
+  const double* s_c = s_vec + 2 * p.nsys * NP + q * NP;
+  const int li = q * NP + (sl < NP ? sl : 0);
+  const double my_invg = s_vec[li], my_b = s_vec[p.nsys * NP + li];
+  const int my_delay = (int)s_vec[3 * p.nsys * NP + li];
+  const int my_line = q * n + sl;
+  const int nbits = 32 - __clz((int)__reduce_max_sync(0xffffffffu, (unsigned)(sl < n ? my_delay : 0)));
+  const double inv_k = 1.0 / (double)p.k;
+
+  const int64_t iters = (p.k + gi.bin_stride - 1) / gi.bin_stride;
+  int64_t iters_max = iters;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const int64_t other = __shfl_xor_sync(0xffffffffu, iters_max, o);
+    iters_max = other > iters_max ? other : iters_max;
+  }
+  double gb_acc = 0.0, gc_acc = 0.0, loss_acc = 0.0;
+  for (int64_t it = 0; it < iters_max; ++it) {
+    int64_t bin = gi.bin0 + it * gi.bin_stride;
+    const bool live_bin = bin < p.k;
+    if (!live_bin) bin = p.k - 1;
+    double2 zm = make_double2(0.0, 0.0), dz = make_double2(0.0, 0.0);
+    if (sl < n) dz = diag_entry(p, bin, my_line, my_invg, my_delay, nbits, &zm);
+    double2 m[NP], fm[NP];
+    build_row<NP>(m, s_a, s_at, n, sl, dz, false);
+    int col;
+    double2 pivot;
+    const double2 xr = gauss_jordan<NP, W>(m, make_double2(my_b, 0.0), sl, line0, line1, &col, nullptr, &pivot, fm);
+    const bool live = col >= 0 && col < n;
+    if (col >= 0) xs[col] = live ? xr : make_double2(0.0, 0.0);
+    __syncwarp();
+    double2 y = make_double2(0.0, 0.0);
+    for (int j = 0; j < n; ++j) {  // every lane of the group forms the same y (fixed order)
+      const double2 v = xs[j];
+      y.x += s_c[j] * v.x;
+      y.y += s_c[j] * v.y;
+    }
+    const float2 yf = make_float2((float)y.x, (float)y.y);  // the loss sees the complex64 response, like the module path
+    const double a = hypot((double)yf.x, (double)yf.y);
+    const double d = a - 1.0;
+    const double d2 = d * d;
+    const bool quartic = asym && d > 1.0;
+    const double dfd = quartic ? 4.0 * d2 * d : 2.0 * d;
+    const double sc = (a > 0.0 && live_bin) ? dfd * inv_k / a : 0.0;
+    const double2 gy = make_double2(sc * (double)yf.x, sc * (double)yf.y);
+    if (sl == 0 && live_bin) loss_acc += quartic ? d2 * d2 : d2;
+    // adjoint: w[p_k] = g_k / conj(pivot_k), g_k = c_k gy; then the saved steps backwards
+    double2 w = make_double2(0.0, 0.0);
+    if (live) {
+      const double cc = s_c[col];
+      const double inv = fast_rcp(pivot.x * pivot.x + pivot.y * pivot.y);
+      const double gx = cc * gy.x, gyy = cc * gy.y;
+      w = make_double2((gx * pivot.x - gyy * pivot.y) * inv, (gx * pivot.y + gyy * pivot.x) * inv);
+    }
+    ReplayStep<NP, W, NP - 1>::run(fm, w, col);
+    if (sl < n) {
+#pragma unroll 4
+      for (int j = 0; j < n; ++j) {
+        const double2 o = xs[j];
+        acc[sl + NP * j] += w.x * o.x + w.y * o.y;
+      }
+      gb_acc += w.x;
+      const double2 xo = xs[sl];
+      gc_acc += xo.x * gy.x + xo.y * gy.y;
+    }
+    __syncwarp();
+  }
+  const size_t per = (size_t)n * n + 3 * (size_t)n;
+  double* out = p.ws + (size_t)gi.sgid * per;
+  if (sl < n) {
+    for (int j = 0; j < n; ++j) out[sl + n * j] = acc[sl + NP * j];
+    out[(size_t)n * n + sl] = gb_acc;
+    out[(size_t)n * n + n + sl] = gc_acc;
+    out[(size_t)n * n + 2 * n + sl] = 0.0;
+  }
+  if (sl == 0) loss_part[gi.sgid] = loss_acc;
+}
+
+// loss[q] = (1/K) sum over the lane groups that served system type q (fixed order)
+__global__ void colorless_loss_reduce_kernel(const double* part, int64_t ngroups, int nsys, int64_t k, double* loss) {
+  const int q = blockIdx.x;
+  const int lane = threadIdx.x;
+  double s = 0.0;
+  for (int64_t sg = q + (int64_t)lane * nsys; sg < ngroups; sg += 32 * (int64_t)nsys) s += part[sg];
+  s = warp_sum(s);
+  if (lane == 0) loss[q] = s / (double)k;
+}
+
 // One warp per output element: lanes stride over the partial rows of the lane groups that served system type q
 // (sgid = q, q + nsys, ...), fixed-order shuffle reduction.
 __global__ void solve_bwd_reduce_kernel(const double* ws, int64_t ngroups, int n, int nsys, int transpose_a, double* ga,
@@ -814,6 +946,58 @@ static int64_t bwd_ws_bytes(int n) {
   if (n < 1 || n > DGFDN_MAX_LINES) return 0;
   const int64_t groups = (int64_t)sm_count() * kMaxBlocksPerSm * kWarps * (32 / lanes_runtime(n));
   return groups * ((int64_t)n * n + 3 * (int64_t)n) * (int64_t)sizeof(double);
+}
+
+template <int NP>
+int launch_colorless(const SolveParams& p, int asym, double* loss_part, int* blocks_out, cudaStream_t st) {
+  constexpr int W = lanes_for(NP);
+  const size_t smem = smem_bytes<NP>(p, true);
+  DGFDN_CUDA(cudaFuncSetAttribute(solve_colorless_kernel<NP, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int blocks = grid_blocks(p.k * p.nsys, W, blocks_per_sm(solve_colorless_kernel<NP, W>, smem));
+  *blocks_out = blocks;
+  solve_colorless_kernel<NP, W><<<blocks, kWarps * 32, smem, st>>>(p, asym, loss_part);
+  DGFDN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int64_t dgfdn_solve_colorless_ws_bytes(int l) {
+  const int64_t b = bwd_ws_bytes(l);
+  if (b == 0) return 0;
+  const int64_t groups = (int64_t)sm_count() * kMaxBlocksPerSm * kWarps * (32 / lanes_runtime(l));
+  return b + groups * (int64_t)sizeof(double);
+}
+
+extern "C" int dgfdn_solve_colorless(int l, int g, int64_t k, const void* z, const int32_t* delays, const float* m_raw,
+                                     const float* gamma, const float* b, const float* c, int asym, double* loss,
+                                     double* gm, double* gb, double* gc, void* ws, void* stream) {
+  if (check_common(l, g, g, k)) return 1;
+  DGFDN_CHECK(z && delays && m_raw && b && c && loss && gm && gb && gc && ws, "solve_colorless: null pointer");
+  SolveParams p{};
+  fill_params(p, l, g, g, k, z, delays, m_raw, 0, gamma, nullptr, b, c);
+  p.ws = static_cast<double*>(ws);
+  double* loss_part = reinterpret_cast<double*>(static_cast<unsigned char*>(ws) + bwd_ws_bytes(l));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int blocks = 0;
+  const int np = (l + 3) & ~3;
+  int rc = 1;
+  switch (np) {
+    case 4: rc = launch_colorless<4>(p, asym, loss_part, &blocks, st); break;
+    case 8: rc = launch_colorless<8>(p, asym, loss_part, &blocks, st); break;
+    case 12: rc = launch_colorless<12>(p, asym, loss_part, &blocks, st); break;
+    case 16: rc = launch_colorless<16>(p, asym, loss_part, &blocks, st); break;
+    default:
+      set_error("solve_colorless: at most 16 lines per group (got %d)", l);
+      return 1;
+  }
+  if (rc) return rc;
+  const int w = lanes_runtime(l);
+  const int64_t groups = (int64_t)blocks * kWarps * (32 / w);
+  const int per = (l * l + 3 * l) * g;
+  solve_bwd_reduce_kernel<<<(per * 32 + 255) / 256, 256, 0, st>>>(p.ws, groups, l, g, 0, gm, gb, gc, nullptr);
+  DGFDN_LAUNCH_CHECK();
+  colorless_loss_reduce_kernel<<<g, 32, 0, st>>>(loss_part, groups, g, k, loss);
+  DGFDN_LAUNCH_CHECK();
+  return 0;
 }
 
 extern "C" int64_t dgfdn_solve_bwd_ws_bytes(int n) { return bwd_ws_bytes(n); }

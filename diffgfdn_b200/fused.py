@@ -70,6 +70,7 @@ class ShardedEDCStep:
         self.mask = None
         self.events = None  # set to a dict of lists to collect per-kernel CUDA events (bench.py)
         self.use_side_stream = os.environ.get("DGFDN_SIDE_STREAM", "1") != "0"
+        self.use_fused_colorless = os.environ.get("DGFDN_FUSED_COLORLESS", "1") != "0"
         self._side = None
 
     def _side_stream(self) -> torch.cuda.Stream:
@@ -157,11 +158,16 @@ class ShardedEDCStep:
             s = net.output_scalars.gains({'norm_listener_position': self.positions})
             s_ready = torch.cuda.Event()
             s_ready.record(side)
-            keep = net.return_per_delay_outputs
-            net.return_per_delay_outputs = False
-            h_sub, _ = net.sub_fdn_output(self.z)
-            net.return_per_delay_outputs = keep
-            per_group = ops.colorless_loss_per_group(h_sub, self.asym)
+            if self.use_fused_colorless and net.num_delay_lines_per_group <= 16:
+                # K1c: solve, loss, dL/dy and the adjoint in one pass per bin (no H_sub, no second elimination)
+                per_group = ops.colorless_solve_loss(self.z, net.delays.to(torch.int32), net.feedback_loop.M,
+                                                     net.input_gains.reshape(-1), net.output_gains.reshape(-1), self.asym)
+            else:
+                keep = net.return_per_delay_outputs
+                net.return_per_delay_outputs = False
+                h_sub, _ = net.sub_fdn_output(self.z)
+                net.return_per_delay_outputs = keep
+                per_group = ops.colorless_loss_per_group(h_sub, self.asym)
             spectral = self.w_spec * per_group.sum()
             sparsity = self.w_spars * self._sparsity(net.feedback_loop.ortho_param(net.feedback_loop.M[g - 1]))
             aux = (spectral + sparsity.to(spectral.dtype)) / self.world_size
@@ -171,8 +177,9 @@ class ShardedEDCStep:
         _, y = net.feedback_loop.solve(z_edc, net.input_gains.reshape(-1), net.output_gains.reshape(-1))
         hy = ops.irfft_window(y.transpose(0, 1), self.n_fft, self.t0, self.tn)  # (G, tn)
         # own kernels of the front: position network, 2 x skew-expm (coupled matrix, sparsity term), matrix assembly,
-        # two solves, chirp-z (pre, mul, post; the 2 cuFFT launches are not counted), colorless forward
-        self.kernel_launches += 1 + 2 + 1 + 2 + 3 + 1
+        # coupled solve, chirp-z (pre, mul, post; the 2 cuFFT launches are not counted), colorless branch
+        fused_cl = self.use_fused_colorless and net.num_delay_lines_per_group <= 16
+        self.kernel_launches += 1 + 2 + 1 + 1 + 3 + (3 if fused_cl else 2)  # K1c + its two reductions | groups solve + loss
 
         main.wait_event(s_ready)
         s_d = s.detach().contiguous()
@@ -203,9 +210,9 @@ class ShardedEDCStep:
         main.wait_stream(side)
         torch.autograd.backward([hy, s, aux], [ghy, gs, torch.ones_like(aux)])
         main.wait_stream(side)  # the engine joins the streams of the leaves; this makes the join explicit for capture
-        # chirp-z adjoint, two adjoint solves (+ reduce each), colorless bwd, assembly bwd, 2 x skew-expm bwd,
-        # position network bwd (+ reduce)
-        self.kernel_launches += 3 + 2 * 2 + 1 + 1 + 2 + 2
+        # chirp-z adjoint, coupled adjoint solve (+ reduce), assembly bwd, 2 x skew-expm bwd, position network bwd
+        # (+ reduce); the separate colorless path adds its adjoint solve (+ reduce) and the loss backward
+        self.kernel_launches += 3 + 2 + 1 + 2 + 2 + (0 if fused_cl else 3)
         if self.world_size > 1:
             self.allreduce_grads()
         if sec:

@@ -830,6 +830,51 @@ class _Colorless(torch.autograd.Function):
         return gh, None
 
 
+class _ColorlessSolve(torch.autograd.Function):
+    """loss[g] = mean_k (|c_g^T (diag(z_k^{m_g}) - M_g)^-1 b_g| - 1)^p and its parameter gradients in ONE kernel pass
+    (K1c): sub_fdn_output + mse/amse loss + both backward passes of the module path (reference model.py:209-252,
+    colorless_fdn/losses.py:20-73, trainer.py:298-303)."""
+
+    @staticmethod
+    def forward(ctx, z, delays, m, b, c, asym):
+        z = _cuda("z", z, C128)
+        delays = _cuda("delays", delays, torch.int32)
+        m_ = _cuda("M", m, torch.float32)
+        b_ = _cuda("b", b.reshape(-1), torch.float32)
+        c_ = _cuda("c", c.reshape(-1), torch.float32)
+        g, l, _ = m_.shape
+        n, k = g * l, z.shape[0]
+        if delays.numel() != n or b_.numel() != n or c_.numel() != n:
+            raise RuntimeError("colorless_solve_loss: inconsistent shapes")
+        dev = z.device
+        loss = torch.empty(g, dtype=torch.float64, device=dev)
+        out = torch.empty(g * l * l + 2 * n, dtype=torch.float64, device=dev)
+        gm, gb, gc = out[:g * l * l], out[g * l * l:g * l * l + n], out[g * l * l + n:]
+        with torch.cuda.device(dev):
+            ws = torch.empty(_lib.load().dgfdn_solve_colorless_ws_bytes(l) // 8, dtype=torch.float64, device=dev)
+            _lib.call("dgfdn_solve_colorless", l, g, k, _ptr(z), _ptr(delays), _ptr(m_), None, _ptr(b_), _ptr(c_),
+                      int(asym), _ptr(loss), _ptr(gm), _ptr(gb), _ptr(gc), _ptr(ws), _stream())
+        ctx.save_for_backward(gm.reshape(g, l, l), gb.reshape(g, l), gc.reshape(g, l))
+        ctx.shapes = (b.shape, c.shape)
+        return loss
+
+    @staticmethod
+    def backward(ctx, gl):
+        gm, gb, gc = ctx.saved_tensors
+        bshape, cshape = ctx.shapes
+        gl = gl.to(torch.float64)
+        g_m = (gm * gl.view(-1, 1, 1)).to(torch.float32) if ctx.needs_input_grad[2] else None
+        g_b = (gb * gl.view(-1, 1)).to(torch.float32).reshape(bshape) if ctx.needs_input_grad[3] else None
+        g_c = (gc * gl.view(-1, 1)).to(torch.float32).reshape(cshape) if ctx.needs_input_grad[4] else None
+        return None, None, g_m, g_b, g_c, None
+
+
+def colorless_solve_loss(z: torch.Tensor, delays: torch.Tensor, m: torch.Tensor, b: torch.Tensor, c: torch.Tensor,
+                         asym: bool) -> torch.Tensor:
+    """Per-group colorless loss (G,) float64 of the lossless sub-FDNs, differentiable w.r.t. m (G,L,L), b, c."""
+    return _ColorlessSolve.apply(z, delays, m, b, c, bool(asym))
+
+
 def colorless_loss_per_group(h_sub: torch.Tensor, asym: bool) -> torch.Tensor:
     return _Colorless.apply(h_sub, asym)
 

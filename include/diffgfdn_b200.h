@@ -116,6 +116,16 @@ DGFDN_API int dgfdn_solve_groups_bwd(int l, int g, int64_t k, const void* z, con
                            double* gm, double* gb, double* gc, double* ginvgamma, void* ws, const void* factors,
                            void* stream);
 
+/* K1c: the colorless branch of a training step in one pass per bin (trainer.py:298-308 with DiffGFDN.sub_fdn_output,
+ * model.py:209-252, and mse_loss / amse_loss, colorless_fdn/losses.py:20-73):
+ *   loss[g] = mean_k (|y[k,g]| - 1)^p,  y[k,g] = c_g^T (diag(z_k^{m_g} / gamma_g) - M_g)^{-1} b_g,  p = 4 where asym and
+ *   |y| - 1 > 1, else 2 -- together with dloss[g]/dM_g, /db, /dc (float64: gm [G,L,L], gb, gc [G*L]), the adjoint solved with
+ * the elimination still in registers. L <= 16. ws: dgfdn_solve_colorless_ws_bytes(l) bytes. */
+DGFDN_API int64_t dgfdn_solve_colorless_ws_bytes(int l);
+DGFDN_API int dgfdn_solve_colorless(int l, int g, int64_t k, const void* z, const int32_t* delays, const float* m_raw,
+                          const float* gamma, const float* b, const float* c, int asym, double* loss, double* gm,
+                          double* gb, double* gc, void* ws, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * K2: receiver projection.  Replaces the (B,N,K) expansion + einsums of model.py:583-619.
  *   H[r,k] = sum_g s[r,g] y[k,g] + d[r,k]

@@ -487,3 +487,33 @@ def test_fused_coupled_feedback_matrix_matches_the_torch_graph_and_the_oracle(g,
         assert rel(fl.alpha.grad, g_alpha) < 1e-5
         assert g == 2 or float(fl.alpha.grad[0]) == 0.0
         assert rel(phi, fl.construct_coupling_matrix(torch.float64)) < 1e-9
+
+
+@pytest.mark.parametrize("n,g,k_bins,asym", [(12, 3, 1024, True), (24, 3, 2049, True), (8, 2, 513, False), (16, 1, 300, True),
+                                             (5, 5, 64, False), (27, 3, 700, True)])
+def test_fused_colorless_solve_matches_solve_plus_loss_and_the_oracle(n, g, k_bins, asym):
+    """K1c (solve + colorless loss + both adjoints in one pass) against K1 groups -> colorless kernels, and against the
+    oracle's sub_fdn_output + (a)mse_loss (model.py:209-252, colorless_fdn/losses.py:20-73)."""
+    from diffgfdn_b200 import ops
+    sy = make_system(n, g, 2 * (k_bins - 1), seed=n + g)
+    l = n // g
+    gen = torch.Generator().manual_seed(n * 7 + g)
+    m_raw = ((2 * torch.rand(g, l, l, generator=gen) - 1) * (1.6 / np.sqrt(l))).to(torch.float32)  # some |y| - 1 > 1
+    z = dev(sy["z"])
+    upstream = torch.rand(g, dtype=F64, generator=gen) + 0.5
+    leaves = [t.clone().cuda().requires_grad_(True) for t in (m_raw, sy["b"], sy["c"])]
+    loss = ops.colorless_solve_loss(z, dev(sy["delays"]), *leaves, asym)
+    (loss * upstream.cuda()).sum().backward()
+    ref_leaves = [t.clone().cuda().requires_grad_(True) for t in (m_raw, sy["b"], sy["c"])]
+    _, hs = ops.gfdn_solve_groups(z, dev(sy["delays"]), ref_leaves[0], None, ref_leaves[1], ref_leaves[2])
+    loss_ref = ops.colorless_loss_per_group(hs, asym)
+    (loss_ref * upstream.cuda()).sum().backward()
+    assert rel(loss, loss_ref) < 1e-6
+    for a, b in zip(leaves, ref_leaves):
+        assert rel(a.grad, b.grad) < 1e-4
+    mo, bo, co = (t.to(F64).requires_grad_(True) for t in (m_raw, sy["b"], sy["c"]))
+    ho, _ = O.sub_fdn_output(sy["z"], sy["delays"].to(F64), mo, bo, co)
+    lo = torch.stack([(O.amse_loss if asym else O.mse_loss)(ho[:, i]) for i in range(g)])
+    (lo * upstream).sum().backward()
+    assert rel(loss, lo.detach()) < 1e-5
+    assert rel(leaves[0].grad, mo.grad) < 1e-3 and rel(leaves[1].grad, bo.grad) < 1e-3 and rel(leaves[2].grad, co.grad) < 1e-3
