@@ -118,14 +118,21 @@ struct GJStep {
                                              float2* fac, double2* fm) {
     double2* line = (K & 1) ? line1 : line0;
     unsigned key = 0u;
+    const double nrm = cnorm(m[K]);
     if (!st.used) {
-      const unsigned hi = (unsigned)__double2hiint(cnorm(m[K]));  // monotone in |m|^2 for non-negative doubles
+      const unsigned hi = (unsigned)__double2hiint(nrm);  // monotone in |m|^2 for non-negative doubles
       key = 0x80000000u | (hi & ~(unsigned)(W - 1)) | (unsigned)(W - 1 - sl);
     }
+    // Every lane takes the reciprocal of its own candidate while the pivot search is in flight: the winner publishes
+    // 1 / pivot in the slot of the pivot value, so the reciprocal (rcp + 2 Newton steps) leaves the critical path
+    // search -> broadcast -> multiplier. Same instruction count: the other lanes no longer invert what they read.
+    const double rn = fast_rcp(nrm);
+    const double2 myinv = make_double2(m[K].x * rn, -m[K].y * rn);
     const int piv = pivot_sublane<W>(key);
     if (sl == piv) {
+      line[K] = myinv;
 #pragma unroll
-      for (int j = K; j < NP; ++j) line[j] = m[j];
+      for (int j = K + 1; j < NP; ++j) line[j] = m[j];
       line[NP] = st.rhs;
       st.used = true;
       st.mycol = K;
@@ -135,7 +142,7 @@ struct GJStep {
     float2 fsave = make_float2(0.f, 0.f);
     if (fm != nullptr) fm[K] = make_double2(0.0, 0.0);  // (constant index after inlining: stays in registers)
     if (sl != piv && sl < NP) {
-      const double2 f = cmul(m[K], fast_cinv(line[K]));
+      const double2 f = cmul(m[K], line[K]);
       fsave = make_float2((float)f.x, (float)f.y);
       if (fm != nullptr) fm[K] = f;
       const double nfx = -f.x, nfy = -f.y;
