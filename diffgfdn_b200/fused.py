@@ -144,33 +144,10 @@ class ShardedEDCStep:
         sec = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if ev is not None else None
         if sec:
             sec[0].record()
-        # The colorless branch (lossless sub-FDN solve + spectral / sparsity losses, and -- because autograd runs a
-        # node's backward on the stream of its forward -- its adjoint solve) is receiver independent and shares
-        # nothing with the EDC branch but the parameters: it runs on a side stream, next to the front kernels and to
-        # the receiver kernel K3d, whose 8-CTA clusters leave 28 of the 148 SMs idle (15 clusters are co-resident).
         main = torch.cuda.current_stream()
         side = self._side_stream() if self.use_side_stream else main
-        side.wait_stream(main)
-        with torch.cuda.stream(side):
-            # the position -> gain network only meets the solve chain at the receiver kernel: its forward runs next to
-            # the coupled solve, and (autograd keeps a node's backward on its forward's stream) its backward next to
-            # the adjoint solve
-            s = net.output_scalars.gains({'norm_listener_position': self.positions})
-            s_ready = torch.cuda.Event()
-            s_ready.record(side)
-            if self.use_fused_colorless and net.num_delay_lines_per_group <= 16:
-                # K1c: solve, loss, dL/dy and the adjoint in one pass per bin (no H_sub, no second elimination)
-                per_group = ops.colorless_solve_loss(self.z, net.delays.to(torch.int32), net.feedback_loop.M,
-                                                     net.input_gains.reshape(-1), net.output_gains.reshape(-1), self.asym)
-            else:
-                keep = net.return_per_delay_outputs
-                net.return_per_delay_outputs = False
-                h_sub, _ = net.sub_fdn_output(self.z)
-                net.return_per_delay_outputs = keep
-                per_group = ops.colorless_loss_per_group(h_sub, self.asym)
-            spectral = self.w_spec * per_group.sum()
-            sparsity = self.w_spars * self._sparsity(net.feedback_loop.ortho_param(net.feedback_loop.M[g - 1]))
-            aux = (spectral + sparsity.to(spectral.dtype)) / self.world_size
+        start = torch.cuda.Event()
+        start.record(main)
         # irfft(X, n=K) reads bins 0..K/2 only (reference losses.py:207-213, quirk Q3), so the coupled system is
         # solved on those kx bins; the other bins of H reach no loss term (the colorless loss has its own solve)
         z_edc = self.z if net.feedback_loop.delay_line_gain_response is not None else self.z[:self.kx]
@@ -181,6 +158,16 @@ class ShardedEDCStep:
         fused_cl = self.use_fused_colorless and net.num_delay_lines_per_group <= 16
         self.kernel_launches += 1 + 2 + 1 + 1 + 3 + (3 if fused_cl else 2)  # K1c + its two reductions | groups solve + loss
 
+        # Side stream, enqueued AFTER the coupled solve so that the solve chain leads the step: the position -> gain
+        # network only meets that chain at the receiver kernel (and, autograd keeping a node's backward on its
+        # forward's stream, its backward runs next to the adjoint solve); the sparsity term is a handful of tiny
+        # kernels on one mixing matrix.
+        side.wait_event(start)
+        with torch.cuda.stream(side):
+            s = net.output_scalars.gains({'norm_listener_position': self.positions})
+            s_ready = torch.cuda.Event()
+            s_ready.record(side)
+            sparsity = self.w_spars * self._sparsity(net.feedback_loop.ortho_param(net.feedback_loop.M[g - 1]))
         main.wait_event(s_ready)
         s_d = s.detach().contiguous()
         hy_d = hy.detach().contiguous()
@@ -188,6 +175,8 @@ class ShardedEDCStep:
         gs = torch.empty_like(s_d)
         coef = self.w_edc / (self.total_receivers * self.tn)
         stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        pre_rx = torch.cuda.Event()
+        pre_rx.record(main)
         if sec:
             sec[1].record()
         if host_d is None:
@@ -206,9 +195,32 @@ class ShardedEDCStep:
             self._stream_tiles(host_d, host_target, s_d, hy_d, ghy, gs, coef, stream)
         if sec:
             sec[2].record()
+        # The colorless branch is receiver independent and shares nothing with the EDC branch but the parameters. It
+        # is enqueued on the side stream AFTER the receiver kernel, gated only on what precedes that kernel: K3d's
+        # 15 clusters of 8 CTAs take their 120 SMs first and K1c runs on the 28 SMs they cannot use (0.29 ms of work
+        # for the whole chip = 1.5 ms on 28 SMs, the length of K3d), instead of competing with the coupled solve.
+        side.wait_event(pre_rx)
+        with torch.cuda.stream(side):
+            if self.use_fused_colorless and net.num_delay_lines_per_group <= 16:
+                # K1c: solve, loss, dL/dy and the adjoint in one pass per bin (no H_sub, no second elimination)
+                per_group = ops.colorless_solve_loss(self.z, net.delays.to(torch.int32), net.feedback_loop.M,
+                                                     net.input_gains.reshape(-1), net.output_gains.reshape(-1), self.asym)
+            else:
+                keep = net.return_per_delay_outputs
+                net.return_per_delay_outputs = False
+                h_sub, _ = net.sub_fdn_output(self.z)
+                net.return_per_delay_outputs = keep
+                per_group = ops.colorless_loss_per_group(h_sub, self.asym)
+            spectral = self.w_spec * per_group.sum()
+            aux = (spectral + sparsity.to(spectral.dtype)) / self.world_size
         edc = (self._bufs["loss_sum"][0] if self.use_fused else self._bufs["row_sum"].sum()) * coef
-        main.wait_stream(side)
-        torch.autograd.backward([hy, s, aux], [ghy, gs, torch.ones_like(aux)])
+        # no join before the backward: the engine runs each node on its forward's stream and orders producers and
+        # consumers itself, so the adjoint solve of the EDC branch does not wait for the tail of the colorless branch
+        # two calls: the EDC branch first, so that its nodes are enqueued (and captured) ahead of the colorless tail --
+        # the branches share nothing but leaf parameters
+        torch.autograd.backward([hy, s], [ghy, gs])
+        with torch.cuda.stream(side):
+            torch.autograd.backward([aux], [torch.ones_like(aux)])
         main.wait_stream(side)  # the engine joins the streams of the leaves; this makes the join explicit for capture
         # chirp-z adjoint, coupled adjoint solve (+ reduce), assembly bwd, 2 x skew-expm bwd, position network bwd
         # (+ reduce); the separate colorless path adds its adjoint solve (+ reduce) and the loss backward
