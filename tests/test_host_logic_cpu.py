@@ -1,0 +1,73 @@
+"""CPU checks of host-side logic that needs no GPU: the reference-holding tensor cache, the batched Givens product
+against the oracle, the SVF coefficient formulas against the oracle, the config schema of the shipped YAMLs."""
+import numpy as np
+import torch
+
+from oracle import gfdn_oracle as O
+
+
+def test_tensor_keyed_cache_holds_sources_and_evicts_fifo():
+    from diffgfdn_b200.utils import TensorKeyedCache
+    cache = TensorKeyedCache(max_entries=3)
+    keep = []
+    for i in range(3):
+        t = torch.full((4, ), float(i))
+        keep.append(t.data_ptr())
+        cache.put(t, i)
+        del t  # the cache keeps the tensor alive: a new tensor cannot get its address
+    fresh = torch.full((4, ), 9.0)
+    assert fresh.data_ptr() not in keep
+    assert cache.get(fresh) is None
+    a = torch.zeros(4)
+    cache.put(a, "a")  # fourth entry: the first one is evicted
+    assert len(cache._entries) == 3 and cache.get(a) == "a"
+    a.add_(1.0)  # in-place change bumps the version: the stale value is not served
+    assert cache.get(a) is None
+    b = torch.zeros(8)[::2]
+    cache.put(b, "strided", extra=("x", 1))
+    assert cache.get(b, extra=("x", 1)) == "strided" and cache.get(b) is None
+
+
+def test_batched_givens_product_matches_oracle_and_is_orthogonal():
+    from diffgfdn_b200.feedback_loop import ND_Unitary
+    torch.manual_seed(0)
+    for n in (1, 2, 3, 5, 8):
+        alpha = (torch.rand(n * (n - 1) // 2, dtype=torch.float64) * 2 - 1).requires_grad_(True)
+        u = ND_Unitary()(alpha, n)
+        assert float((u - O.nd_unitary(alpha.detach(), n)).abs().max()) < 1e-14
+        assert float((u @ u.t() - torch.eye(n, dtype=torch.float64)).abs().max()) < 1e-13
+        if n > 1:
+            u.sum().backward()
+            assert torch.isfinite(alpha.grad).all()
+
+
+def test_svf_coefficients_match_oracle():
+    from diffgfdn_b200.gain_filters import svf_cutoff_frequencies, svf_to_biquads
+    torch.manual_seed(1)
+    svf = torch.stack([torch.rand(4, 3, 11) * 0.98 + 1e-6, torch.rand(4, 3, 11) * 12 - 6], dim=-1).to(torch.float32)
+    for fs, pf in ((32000.0, 1.0), (48000.0, 0.997)):
+        cut = svf_cutoff_frequencies(fs)
+        assert float((cut - O.svf_cutoffs(fs)).abs().max()) < 1e-15 and cut.numel() == 11
+        got = svf_to_biquads(svf, cut, pf)
+        want = O.svf_to_biquads(svf, O.svf_cutoffs(fs), pf)
+        assert got.dtype == torch.float64 and float((got - want).abs().max()) < 1e-13
+
+
+def test_shipped_yaml_shapes_validate():
+    """The dictionaries run_model.py / run_subband_training_treble.py build must pass the (extra='forbid') schema."""
+    from diffgfdn_b200.config import DiffGFDNConfig
+    cfg = DiffGFDNConfig(**{
+        "sample_rate": 32000.0, "num_delay_lines": 12, "num_groups": 3,
+        "decay_filter_config": {"use_absorption_filters": False},
+        "feedback_loop_config": {"coupling_matrix_type": "scalar_matrix", "use_zero_coupling": False},
+        "output_filter_config": {"use_svfs": True, "num_hidden_layers": 3, "num_neurons_per_layer": 128,
+                                 "num_fourier_features": 20, "compress_pole_factor": 0.998},
+        "trainer_config": {"max_epochs": 5, "batch_size": 32, "use_colorless_loss": True, "num_freq_bins": 131072,
+                           "train_dir": "out/", "ir_dir": "ir/"}})
+    assert len(cfg.delay_length_samps) == 12 and cfg.output_filter_config.use_svfs
+    try:
+        DiffGFDNConfig(not_a_key=1)
+    except Exception:
+        pass
+    else:
+        raise AssertionError("unknown keys must be rejected")
