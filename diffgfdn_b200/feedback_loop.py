@@ -113,9 +113,9 @@ class FeedbackLoop(nn.Module):
         self.device = device
         self.coupling_matrix_type = coupling_matrix_type or CouplingMatrixType.SCALAR
         self.coupling_matrix_order = coupling_matrix_order
-        if self.coupling_matrix_type != CouplingMatrixType.SCALAR:
-            raise NotImplementedError("only the scalar (unitary) coupling matrix is on the B200 hot path; "
-                                      "no shipped config uses filter/random coupling (SURVEY.md a-5)")
+        if self.coupling_matrix_type == CouplingMatrixType.FILTER:
+            raise NotImplementedError("paraunitary FIR coupling A(z) is not built (no shipped config uses it; "
+                                      "SURVEY.md a-5); scalar and random (unstructured orthogonal) coupling are")
         self._init_absorption(gains, common_decay_times)
         self._init_feedback_matrix(colorless_feedback_matrix)
 
@@ -191,6 +191,11 @@ class FeedbackLoop(nn.Module):
     def _init_feedback_matrix(self, colorless_feedback_matrix):
         self.ortho_param = OrthoParam()
         L = self.num_delay_lines_per_group
+        if self.coupling_matrix_type == CouplingMatrixType.RANDOM:
+            # any orthogonal N x N matrix, no group structure (reference :272-277):  A = expm(skew(R))
+            n = self.num_delays
+            self.random_feedback_matrix = nn.Parameter(((2 * torch.rand(n, n) - 1) / np.sqrt(L)).to(self.device))
+            return
         if colorless_feedback_matrix is not None:
             self.M = colorless_feedback_matrix.clone().detach().to(self.device)
         else:
@@ -206,7 +211,7 @@ class FeedbackLoop(nn.Module):
         super()._apply(fn, *args, **kwargs)
         self.delays = fn(self.delays)
         self.delay_line_gains = fn(self.delay_line_gains)
-        if not isinstance(self.M, nn.Parameter):
+        if hasattr(self, "M") and not isinstance(self.M, nn.Parameter):
             self.M = fn(self.M)
         if self.delay_line_gain_response is not None:
             self.delay_line_gain_response = fn(self.delay_line_gain_response)
@@ -231,6 +236,12 @@ class FeedbackLoop(nn.Module):
         return self.nd_unitary(alpha, self.num_groups)
 
     def coupled_feedback_matrix_real(self, dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+        if self.coupling_matrix_type == CouplingMatrixType.RANDOM:
+            a = self.ortho_param(self.random_feedback_matrix)
+            return a if dtype is None else a.to(dtype)
+        return self._structured_feedback_matrix(dtype)
+
+    def _structured_feedback_matrix(self, dtype: Optional[torch.dtype] = None) -> torch.Tensor:
         """A = block_M o (Phi (x) 1_{LxL}), real (N, N) float32 (reference :424-455 before to_complex).
 
         dtype=torch.float64 runs the small product / Givens graph in float64: dL/dalpha is a sum of O(1) terms of
@@ -247,6 +258,10 @@ class FeedbackLoop(nn.Module):
         """A (N, N) float64 for the solves: one fused kernel forward, one backward (ops.coupled_feedback) instead of
         the ~135 tiny launches of the torch graph in coupled_feedback_matrix_real (which stays the public, float32
         form). DGFDN_FUSED_ASSEMBLY=0 falls back to the torch graph."""
+        if self.coupling_matrix_type == CouplingMatrixType.RANDOM:
+            a = self.ortho_param(self.random_feedback_matrix)
+            self.coupled_feedback_matrix = a.detach()
+            return a
         if os.environ.get("DGFDN_FUSED_ASSEMBLY", "1") == "0" or self.num_groups > 8:
             a = self.coupled_feedback_matrix_real(torch.float64)
         else:
@@ -294,6 +309,8 @@ class FeedbackLoop(nn.Module):
         return torch.stack(cols, dim=-1)
 
     def get_parameters(self):
+        if self.coupling_matrix_type == CouplingMatrixType.RANDOM:  # reference :465-466
+            return self.ortho_param(self.random_feedback_matrix)
         M = [self.ortho_param(self.M[i]) for i in range(self.num_groups)]
         coupled = self.get_coupled_feedback_matrix()
         return (M, self.phi, None, None, coupled, self.delay_line_gains)
@@ -301,6 +318,11 @@ class FeedbackLoop(nn.Module):
     @torch.no_grad()
     def get_param_dict(self):
         coupled = self.get_coupled_feedback_matrix()
+        if self.coupling_matrix_type == CouplingMatrixType.RANDOM:  # reference :490-494
+            d = {'delay_line_gains': self.delay_line_gains, 'coupled_feedback_matrix': coupled.squeeze().cpu().numpy()}
+            if hasattr(self, 'common_decay_times'):
+                d['common_decay_times'] = self.common_decay_times
+            return d
         d = {'delay_line_gains': self.delay_line_gains, 'coupling_matrix': self.phi.squeeze().cpu().numpy(),
              'individual_mixing_matrix': self.M.squeeze().cpu().numpy(),
              'coupled_feedback_matrix': coupled.squeeze().cpu().numpy()}

@@ -168,9 +168,10 @@ class DiffGFDN(nn.Module):
              'gains_per_sample': fl.delay_line_gains.squeeze().cpu().numpy(),
              'input_gains': self.input_gains.squeeze().cpu().numpy(),
              'output_gains': self.output_gains.squeeze().cpu().numpy(),
-             'coupled_feedback_matrix': fl.get_coupled_feedback_matrix().squeeze().cpu().numpy(),
-             'individual_mixing_matrix': fl.M.squeeze().cpu().numpy(),
-             'coupling_matrix': fl.nd_unitary(fl.alpha, self.num_groups).squeeze().cpu().numpy()}
+             'coupled_feedback_matrix': fl.get_coupled_feedback_matrix().squeeze().cpu().numpy()}
+        if fl.coupling_matrix_type != CouplingMatrixType.RANDOM:  # the unstructured matrix has no group / coupling parts
+            d['individual_mixing_matrix'] = fl.M.squeeze().cpu().numpy()
+            d['coupling_matrix'] = fl.nd_unitary(fl.alpha, self.num_groups).squeeze().cpu().numpy()
         return d
 
 

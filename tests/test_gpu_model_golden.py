@@ -241,6 +241,39 @@ def test_source_receiver_and_single_position_variants_match_reference(name, tmp_
         assert rel(p.grad, ref) < 1e-3, k
 
 
+def test_random_coupling_matches_reference(tmp_path):
+    """coupling_matrix_type: random_matrix (the single-room sub-band YAML): forward, losses and gradients vs the
+    reference golden; checkpoint key 'feedback_loop.random_feedback_matrix'."""
+    from diffgfdn_b200.config import CouplingMatrixType, FeedbackLoopConfig, OutputFilterConfig
+    from diffgfdn_b200.model import DiffGFDNVarReceiverPos
+    from diffgfdn_b200.trainer import VarReceiverPosTrainer
+    g = load("random_coupling_n8")
+    net = DiffGFDNVarReceiverPos(float(g["meta/fs"]), len(g["meta/t60"]), [int(v) for v in g["meta/delays"]], 'cuda',
+                                 FeedbackLoopConfig(coupling_matrix_type=CouplingMatrixType.RANDOM),
+                                 OutputFilterConfig(use_svfs=False, num_hidden_layers=1, num_neurons_per_layer=16,
+                                                    num_fourier_features=4),
+                                 use_absorption_filters=False, common_decay_times=np.array([g["meta/t60"]]),
+                                 use_colorless_loss=False)
+    net.load_state_dict({k[len("param/"):]: torch.tensor(v) for k, v in g.items() if k.startswith("param/")},
+                        strict=True)
+    data = omni_data({**g, "meta/radius": 1.0})
+    trainer = make_trainer(VarReceiverPosTrainer, net, tmp_path, use_colorless_loss=False, edc_loss_weight=10.0,
+                           num_freq_bins=int(g["meta/nfft"]))
+    net.zero_grad()
+    H = net(data)
+    d = g["data/target_early_response"]
+    assert rel(H.detach().cpu().to(torch.complex128).numpy() - d, g["out/H"] - d) < 1e-4
+    assert rel(net.feedback_loop.coupled_feedback_matrix, g["out/A"]) < 1e-5
+    losses = trainer.calculate_losses(data, H)
+    total = sum(losses.values())
+    total.backward()
+    assert abs(float(losses["edc_loss"]) - g["loss/edc_loss"]) < 0.01 * float(g["meta/edc_w"])
+    assert abs(float(total) - g["loss/total"]) < 2e-3 * g["loss/total"]
+    for k, p in net.named_parameters():
+        assert rel(p.grad, g[f"grad/{k}"]) < 1e-3, k
+    assert set(net.feedback_loop.get_param_dict()) >= {"coupled_feedback_matrix", "delay_line_gains"}
+
+
 def test_feedback_loop_dense_inverse_api():
     """FeedbackLoop.forward(z) keeps the reference's (K, N, N) inverse for API compatibility."""
     from oracle import gfdn_oracle as O
