@@ -18,7 +18,7 @@ import torch
 from torch import nn
 
 from . import ops
-from .absorption_filters import decay_times_to_gain_per_sample
+from .absorption_filters import decay_times_to_gain_filters_geq, decay_times_to_gain_per_sample
 from .config.config import CouplingMatrixType, FeedbackLoopConfig, OutputFilterConfig
 from .feedback_loop import FeedbackLoop
 from .dnn import ScaledSigmoid
@@ -102,13 +102,18 @@ class DiffGFDN(nn.Module):
             self.gain_per_sample = None
             return
         if self.use_absorption_filters:
-            # The reference designs one graphic equaliser per delay line here (absorption_filters.py:108-155 ->
-            # filters/geq.py, an LBFGS fit per line, ~50 s): init-time host code outside the hot path. The buffer keeps
-            # the reference's name and (N, bands + 3, 3, 2) layout so its checkpoints load unchanged; fill it with
-            # load_state_dict() or set_absorption_filters(). The per-bin responses are evaluated on the GPU.
+            # One graphic equaliser per delay line (reference absorption_filters.py:108-155 -> filters/geq.py: an LBFGS
+            # fit per line, ~1 s each; here the exact least-squares minimiser, init-time host code). The buffer keeps
+            # the reference's name and (N, bands + 3, 3, 2) layout so its checkpoints load unchanged (load_state_dict
+            # or set_absorption_filters replace the design). The per-bin responses are evaluated on the GPU.
             if band_centre_hz is None:
                 raise RuntimeError("use_absorption_filters=True needs band_centre_hz (one T60 per band and group)")
-            self.gain_per_sample = torch.zeros(self.num_delay_lines, len(band_centre_hz) + 3, 3, 2, device=self.device)
+            t60 = np.squeeze(np.asarray(self.common_decay_times))  # (bands, G)
+            per_group = [decay_times_to_gain_filters_geq(band_centre_hz, t60[:, i] if t60.ndim > 1 else t60,
+                                                         self.delays_by_group[i].cpu().numpy(), self.sample_rate)
+                         for i in range(self.num_groups)]  # each (bands + 3, L, 3, 2)
+            stacked = torch.stack(per_group).permute(0, 2, 1, 3, 4)  # (G, L, bands + 3, 3, 2), reference :141-147
+            self.gain_per_sample = stacked.reshape(self.num_delay_lines, len(band_centre_hz) + 3, 3, 2).to(self.device)
             self.filter_order = 3
             self.register_buffer('delay_filters', self.gain_per_sample)
             return

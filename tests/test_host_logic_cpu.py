@@ -71,3 +71,29 @@ def test_shipped_yaml_shapes_validate():
         pass
     else:
         raise AssertionError("unknown keys must be rejected")
+
+
+def test_geq_absorption_design_matches_the_reference_cascades():
+    """decay_times_to_gain_filters_geq (absorption_filters.py:108-155 / filters/geq.py) against coefficients produced
+    by the reference's own design (tests/golden/geq_design.npz): same layout, cascade responses within 0.05 dB (the
+    reference's section gains carry its float32 probing / LBFGS noise, see design_geq), and the target attenuation
+    10^(-3 m / (fs T60(f))) is met at the band centres."""
+    import os
+    from diffgfdn_b200.absorption_filters import decay_times_to_gain_filters_geq
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "geq_design.npz"))
+    ref = g["coeffs"]
+    fs = float(g["fs"])
+    got = decay_times_to_gain_filters_geq(list(g["bands"]), g["t60"], list(g["delays"]), fs).numpy()
+    assert got.shape == ref.shape == (len(g["bands"]) + 3, len(g["delays"]), 3, 2)
+
+    def cascade_db(c, w):
+        z = np.exp(-1j * w)
+        num = c[..., 0, 0, None] + c[..., 1, 0, None] * z + c[..., 2, 0, None] * z * z
+        den = c[..., 0, 1, None] + c[..., 1, 1, None] * z + c[..., 2, 1, None] * z * z
+        return 20 * np.log10(np.abs(np.prod(num / den, axis=0)))
+
+    w = np.linspace(0.001, np.pi, 4000)
+    assert np.abs(cascade_db(got, w) - cascade_db(ref, w)).max() < 0.05
+    wb = 2 * np.pi * g["bands"] / fs
+    want = 20 * np.log10((10.0**(-3.0 / fs / g["t60"]))[None, :]**g["delays"][:, None])  # (delays, bands)
+    assert np.abs(cascade_db(got, wb) - want).max() < 0.5  # a graphic equaliser meets its band targets to a fraction of a dB
