@@ -373,14 +373,20 @@ def main():
     step.kernel_launches = 0
     with ClockSampler(local) as clocks:
         ms, losses = timed_steps(one_step, args.steps, barrier)
-    launches = step.kernel_launches
-    t = torch.tensor([ms], device=device, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
+        launches = step.kernel_launches
+        loss_val = float(sum(v for v in losses.values()))  # of the last timed step (the replays below train on)
+        t = torch.tensor([ms], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        # the timed region lasts a few milliseconds, one nvidia-smi poll takes longer: keep the SAME step running
+        # (untimed) for ~1 s so that the clock / throttle samples are taken under this load. The count is derived from
+        # the rank-agreed step time: every rank replays the same number of (all-reducing) steps.
+        for _ in range(min(2000, max(20, int(1000.0 / max(ms, 0.5))))):
+            one_step()
+        torch.cuda.synchronize()
     evals_per_step = float(args.receivers) * world * k
     value = evals_per_step / (ms / 1e3)
-    loss_val = float(sum(v for v in losses.values()))
 
     # end-to-end: inputs from pinned host memory every step, loss read back
     e2e = None
