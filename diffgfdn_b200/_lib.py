@@ -72,6 +72,7 @@ SIGNATURES = {
                                   c_void_p]),
     "dgfdn_td_edc_fused_supported": (c_int, [c_int, c_int64]),
     "dgfdn_td_edc_fused_ws_bytes": (c_int64, [c_int, c_int64, c_int64]),
+    "dgfdn_td_edc_fused_ws_init": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p]),
     "dgfdn_td_edc_fused": (c_int, [c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64,
                                    c_void_p, c_double, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "dgfdn_td_edc_fused_info": (c_int, [c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),

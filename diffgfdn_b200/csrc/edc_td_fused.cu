@@ -24,6 +24,7 @@
 #include <type_traits>
 
 #include "common.cuh"
+#include "edc_td_sliced.cuh"
 
 namespace dgfdn {
 namespace {
@@ -761,16 +762,50 @@ int dispatch(int g, bool masked, int variant, int op, const FusedParams& p, int6
 
 using namespace dgfdn;
 
-extern "C" int dgfdn_td_edc_fused_supported(int g, int64_t tn) { return fused_shape(g, tn, nullptr) ? 1 : 0; }
+// Which kernel takes (g, tn): the cluster kernel K3d wherever its slices hold the row (measured faster: 1.45 ms vs
+// 1.69 ms at the BASELINE shard, profiles/r02_td_sliced_vs_cluster.txt), the time-sliced persistent kernel K3t
+// (edc_td_sliced.cu) for the longer windows K3d cannot hold (55 296 < tn <= 94 720). DGFDN_TD_KERNEL=cluster|sliced
+// forces one where both take the shape.
+static size_t sliced_region_bytes(int64_t rows) { return (sliced_ws_bytes(rows) + 255) & ~(size_t)255; }
+
+static bool use_sliced(int g, int64_t tn, SlicedShape* shp) {
+  SlicedShape tmp;
+  if (!shp) shp = &tmp;
+  const bool ok_s = sliced_shape(g, tn, shp);
+  const bool ok_c = fused_shape(g, tn, nullptr);
+  if (const char* e = getenv("DGFDN_TD_KERNEL")) {
+    if (e[0] == 'c' && ok_c) return false;
+    if (e[0] == 's' && ok_s) return true;
+  }
+  return ok_s && !ok_c;
+}
+
+extern "C" int dgfdn_td_edc_fused_supported(int g, int64_t tn) {
+  return (fused_shape(g, tn, nullptr) || sliced_shape(g, tn, nullptr)) ? 1 : 0;
+}
 
 extern "C" int64_t dgfdn_td_edc_fused_ws_bytes(int g, int64_t rows, int64_t tn) {
   if (g < 1 || rows < 1 || tn < 1) return 0;
-  return (int64_t)ws_layout(g, rows, tn).total;
+  // the two kernels keep disjoint regions: the sliced kernel's carry words must stay "not published" between launches
+  return (int64_t)(sliced_region_bytes(rows) + ws_layout(g, rows, tn).total);
 }
 
-// Diagnostic: the variant chosen for (g, tn) [-1: unsupported], its cluster size, threads per CTA and the number
-// of clusters that are co-resident on the current device.
+extern "C" int dgfdn_td_edc_fused_ws_init(void* ws, int g, int64_t rows, int64_t tn, void* stream) {
+  DGFDN_CHECK(ws && g >= 1 && rows >= 1 && tn >= 1, "td_edc_fused_ws_init: bad arguments");
+  return sliced_ws_init(ws, g, rows, tn, static_cast<cudaStream_t>(stream));
+}
+
+// Diagnostic: the variant chosen for (g, tn) [-1: unsupported; 0..2 cluster tiles; 10 + shape: time-sliced kernel],
+// its cluster size, threads per CTA and the number of clusters (CTAs for the sliced kernel) of a launch.
 extern "C" int dgfdn_td_edc_fused_info(int g, int64_t tn, int* variant, int* cluster_size, int* threads, int* clusters) {
+  SlicedShape ss;
+  if (use_sliced(g, tn, &ss)) {
+    if (variant) *variant = 10 + ss.shape;
+    if (cluster_size) *cluster_size = 1;
+    if (threads) *threads = ss.threads;
+    if (clusters) *clusters = ss.ns;
+    return 0;
+  }
   FusedShape shp;
   if (!fused_shape(g, tn, &shp)) {
     if (variant) *variant = -1;
@@ -790,16 +825,20 @@ extern "C" int dgfdn_td_edc_fused(int g, int64_t rows, int64_t tn, const float* 
                                   int64_t ldhd, const float* target_db, int64_t ldt, const float* mask, double coef,
                                   double* loss_sum, float* gs, float* ghy, int accumulate, void* ws, void* stream) {
   DGFDN_CHECK(rows >= 0 && tn >= 1 && s && hy && target_db && ghy && ws, "td_edc_fused: bad arguments");
+  const bool sliced = use_sliced(g, tn, nullptr);
   FusedShape shp;
-  DGFDN_CHECK(fused_shape(g, tn, &shp), "td_edc_fused: unsupported shape (g=%d in [1,4], tn=%lld multiple of 4 and <= 55296)", g,
-              (long long)tn);
+  DGFDN_CHECK(sliced || fused_shape(g, tn, &shp),
+              "td_edc_fused: unsupported shape (g=%d in [1,4], tn=%lld multiple of 4 and <= 94720)", g, (long long)tn);
   DGFDN_CHECK(ldt >= tn && (hd == nullptr || ldhd >= tn), "td_edc_fused: row stride smaller than tn");
-  DGFDN_CHECK(aligned16(hy) && aligned16(hd) && aligned16(target_db) && aligned16(mask) && ldt % 4 == 0 &&
+  DGFDN_CHECK(aligned16(hy) && aligned16(hd) && aligned16(target_db) && aligned16(mask) && aligned16(ghy) && ldt % 4 == 0 &&
                   (hd == nullptr || ldhd % 4 == 0),
               "td_edc_fused: rows must be 16-byte aligned (pointers and strides)");
   if (rows == 0) return 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (sliced)
+    return sliced_launch(g, rows, tn, s, hy, hd, ldhd, target_db, ldt, mask, coef, loss_sum, gs, ghy, accumulate, ws, st);
   const WsLayout lay = ws_layout(g, rows, tn);
-  unsigned char* base = static_cast<unsigned char*>(ws);
+  unsigned char* base = static_cast<unsigned char*>(ws) + sliced_region_bytes(rows);
   FusedParams p{};
   p.rows = rows;
   p.tn4 = (int)(tn / 4);
@@ -815,7 +854,6 @@ extern "C" int dgfdn_td_edc_fused(int g, int64_t rows, int64_t tn, const float* 
   p.part_ghy = reinterpret_cast<float*>(base);
   p.part_gs = reinterpret_cast<float*>(base + lay.off_gs);
   p.part_loss = reinterpret_cast<double*>(base + lay.off_loss);
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   int ncl = 0;
   if (int rc = dispatch(g, mask != nullptr, shp.variant, 0, p, rows, st, &ncl)) return rc;
   const int c = kVariants[shp.variant].c;

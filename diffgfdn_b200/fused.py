@@ -68,6 +68,7 @@ class ShardedEDCStep:
         self.h2d_bytes = 0
         self._bufs = None
         self.mask = None
+        self._mask_count = None
         self.events = None  # set to a dict of lists to collect per-kernel CUDA events (bench.py)
         self.use_side_stream = os.environ.get("DGFDN_SIDE_STREAM", "1") != "0"
         self.use_fused_colorless = os.environ.get("DGFDN_FUSED_COLORLESS", "1") != "0"
@@ -109,6 +110,17 @@ class ShardedEDCStep:
             self._bufs = dict(gh=torch.empty(r, self.tn, dtype=torch.float32, device=dev),
                               ws=ops.td_contract_workspace(g, r, self.tn, dev),
                               row_sum=torch.empty(self.rows, dtype=torch.float64, device=dev))
+
+    def set_mask(self, mask: Optional[torch.Tensor]):
+        """Fixed 0/1 sample mask of the EDC loss (reference losses.py:221-238 draws one per call; here it is an
+        input). The masked loss is a mean over the KEPT samples, so the normalisation uses mask.sum()."""
+        if mask is None:
+            self.mask, self._mask_count = None, None
+            return
+        m = mask.to(self.dev, torch.float32).contiguous()
+        if m.numel() != self.tn:
+            raise RuntimeError(f"set_mask: mask must have tn = {self.tn} samples")
+        self.mask, self._mask_count = m, float(m.sum().item())
 
     def _window_rows(self, resp: torch.Tensor, to_db: bool) -> torch.Tensor:
         out = torch.empty(resp.shape[0], self.tn, dtype=torch.float32, device=self.dev)
@@ -173,7 +185,9 @@ class ShardedEDCStep:
         hy_d = hy.detach().contiguous()
         ghy = torch.empty_like(hy_d)
         gs = torch.empty_like(s_d)
-        coef = self.w_edc / (self.total_receivers * self.tn)
+        if self.mask is not None and self._mask_count is None:
+            raise RuntimeError("step: attach the EDC mask with set_mask() (the loss is normalised by mask.sum())")
+        coef = self.w_edc / (self.total_receivers * (self.tn if self.mask is None else self._mask_count))
         stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
         pre_rx = torch.cuda.Event()
         pre_rx.record(main)
@@ -330,6 +344,9 @@ class ShardedEDCStep:
         cs = ctypes.c_void_p(copy_stream.cuda_stream)
         main = torch.cuda.current_stream()
         pool = host_d.shape[0]
+        if host_target.shape[0] != pool or pool < min(r, self.rows):
+            raise RuntimeError(f"step: host pools must have the same row count and hold at least one tile "
+                               f"({min(r, self.rows)} rows); got {pool} and {host_target.shape[0]}")
         self.h2d_bytes = 0
         tiles = list(range(0, self.rows, r))
 

@@ -686,8 +686,13 @@ def td_fused_supported(num_groups: int, tn: int) -> bool:
 
 
 def td_fused_workspace(num_groups: int, rows: int, tn: int, device) -> torch.Tensor:
+    """Scratch of dgfdn_td_edc_fused for launches of up to `rows` rows, initialised (K3t's carry words read 'not
+    published')."""
     nbytes = int(_lib.load().dgfdn_td_edc_fused_ws_bytes(num_groups, rows, tn))
-    return torch.empty(max(nbytes // 4, 1), dtype=torch.float32, device=device)
+    ws = torch.empty(max((nbytes + 3) // 4, 1), dtype=torch.float32, device=device)
+    with torch.cuda.device(device):
+        _lib.call("dgfdn_td_edc_fused_ws_init", _ptr(ws), int(num_groups), int(rows), int(tn), _stream())
+    return ws
 
 
 class _TDEDCLossFused(torch.autograd.Function):

@@ -249,10 +249,16 @@ DGFDN_API int dgfdn_td_contract(int g, int64_t rows, int64_t tn, const float* s,
  *   gs[r,g]      = coef * d loss_sum / d s[r,g]                                     float32 [rows, G] (may be NULL)
  *   ghy[g,t]    (+)= coef * d loss_sum / d hy[g,t]                                  float32 [G, tn]
  * accumulate != 0 adds to loss_sum / ghy instead of overwriting them (receiver tiles). Requirements, reported by
- * dgfdn_td_edc_fused_supported(g, tn): 1 <= g <= 4, tn % 4 == 0, tn <= 55296; all rows 16-byte aligned.
- * ws: scratch of dgfdn_td_edc_fused_ws_bytes(g, rows, tn) bytes. */
+ * dgfdn_td_edc_fused_supported(g, tn): 1 <= g <= 4, tn % 4 == 0, tn <= 94720; all rows 16-byte aligned.
+ * Two kernels sit behind this entry point: K3d (a cluster of 8 CTAs per row, tn <= 55296) and K3t (time-sliced
+ * persistent kernel: CTA c owns time slice c of EVERY row, slice totals travel through L2), which takes the longer
+ * windows; DGFDN_TD_KERNEL=cluster|sliced forces one where both take the shape.
+ * ws: scratch of dgfdn_td_edc_fused_ws_bytes(g, rows, tn) bytes, initialised ONCE with dgfdn_td_edc_fused_ws_init
+ * (K3t's carry words double as their own "not published" flags; every launch leaves them reset). A workspace serves
+ * launches of <= rows rows, one at a time. */
 DGFDN_API int dgfdn_td_edc_fused_supported(int g, int64_t tn);
 DGFDN_API int64_t dgfdn_td_edc_fused_ws_bytes(int g, int64_t rows, int64_t tn);
+DGFDN_API int dgfdn_td_edc_fused_ws_init(void* ws, int g, int64_t rows, int64_t tn, void* stream);
 DGFDN_API int dgfdn_td_edc_fused(int g, int64_t rows, int64_t tn, const float* s, const float* hy, const float* hd,
                        int64_t ldhd, const float* target_db, int64_t ldt, const float* mask, double coef,
                        double* loss_sum, float* gs, float* ghy, int accumulate, void* ws, void* stream);

@@ -152,23 +152,36 @@ def _td_reference(rows, g, tn, use_hd, use_mask, gen):
     return s, hy, hd, tdb, mask, float(ref), s_r.grad, hy_r.grad
 
 
-@pytest.mark.parametrize("rows,g,tn,use_hd,use_mask", [
-    (5, 3, 9000, True, True),       # one run per CTA, odd row count (last iteration half empty), ragged last slice
+FUSED_SHAPES = [
+    (5, 3, 9000, True, True),       # odd row count (last task half empty), ragged last slice
     (3, 2, 16384, False, False),    # no early response
     (7, 3, 776, True, False),       # slices shorter than a warp's span
-    (1, 4, 8, True, False),         # 2 segments: six of the eight CTAs own nothing
+    (1, 4, 8, True, False),         # 2 segments: most CTAs of a cluster / most lanes of a slice own nothing
     (2, 1, 4, True, True),          # a single segment
-    (37, 3, 47360, True, False),    # BASELINE window (T60 1.5 s at 32 kHz): two runs per CTA, more iterations than clusters
-    (4, 4, 49152, True, True),      # largest window of the 8-CTA variants
-    (5, 3, 55296, True, False),     # largest supported window (clusters of 6 CTAs, one row per iteration)
-    (3, 2, 50000, True, True),      # 6-CTA variant, ragged last slice, mask
-])
-def test_cluster_fused_receiver_kernel_vs_torch_fp64(rows, g, tn, use_hd, use_mask):
-    """dgfdn_td_edc_fused (K3d: cluster of 8 CTAs per row, DSMEM scan carries, TMA-staged inputs, register-resident
-    ghy accumulators) against the float64 torch restatement of reference losses.py:187-238 / utils.py:16-40 and its
-    autograd, and against K3c on the same inputs."""
+    (37, 3, 47360, True, False),    # BASELINE window (T60 1.5 s at 32 kHz): 148 slices of 320 samples
+    (4, 4, 49152, True, True),      # largest window of the 8-CTA cluster variants; hy slice in shared memory (G x NV > 15)
+    (5, 3, 55296, True, False),     # largest window of the cluster kernel (clusters of 6 CTAs, one row per iteration)
+    (3, 2, 50000, True, True),      # ragged last slice, mask
+    (70, 3, 47360, True, True),     # more rows than one pipeline round of the sliced kernel (11 warps x 2 rows), mask
+    (3, 3, 94720, True, False),     # largest window of the sliced kernel (148 slices of 640 samples)
+    (45, 2, 28416, False, True),    # 148 slices of 192 samples, no early response
+]
+
+
+@pytest.mark.parametrize("kernel", ["sliced", "cluster"])
+@pytest.mark.parametrize("rows,g,tn,use_hd,use_mask", FUSED_SHAPES)
+def test_fused_receiver_kernels_vs_torch_fp64(rows, g, tn, use_hd, use_mask, kernel, monkeypatch):
+    """dgfdn_td_edc_fused -- K3t (time-sliced persistent kernel: CTA c owns slice c of every row, carries through L2,
+    TMA-staged inputs, register-resident ghy accumulators) and K3d (cluster of 8 CTAs per row, DSMEM carries) --
+    against the float64 torch restatement of reference losses.py:187-238 / utils.py:16-40 and its autograd, and
+    against K3c on the same inputs."""
     from diffgfdn_b200 import ops
+    monkeypatch.setenv("DGFDN_TD_KERNEL", kernel)
     assert ops.td_fused_supported(g, tn)
+    info = ops.td_fused_info(g, tn)
+    if kernel == "cluster" and info["variant"] >= 10:
+        pytest.skip("window longer than the cluster kernel's slices")
+    assert (info["variant"] >= 10) == (kernel == "sliced")
     gen = torch.Generator().manual_seed(11)
     s, hy, hd, tdb, mask, ref, gs_ref, ghy_ref = _td_reference(rows, g, tn, use_hd, use_mask, gen)
     cu = lambda t: None if t is None else t.cuda()  # noqa: E731
@@ -191,11 +204,40 @@ def test_cluster_fused_receiver_kernel_vs_torch_fp64(rows, g, tn, use_hd, use_ma
     assert float(out2) == float(out) and torch.equal(s_2.grad, s_c.grad) and torch.equal(hy_2.grad, hy_c.grad)
 
 
+def test_sliced_kernel_workspace_is_reusable_and_accumulates(monkeypatch):
+    """One workspace serves launches of different row counts back to back (the finalize kernel puts the 'not published'
+    flags back), and accumulate=1 adds a second tile's loss / ghy to the first's."""
+    import ctypes
+    monkeypatch.setenv("DGFDN_TD_KERNEL", "sliced")
+
+    from diffgfdn_b200 import _lib, ops
+    gen = torch.Generator().manual_seed(5)
+    rows, g, tn = 29, 3, 47360
+    s, hy, hd, tdb, _, ref, gs_ref, ghy_ref = _td_reference(rows, g, tn, True, False, gen)
+    s, hy, hd, tdb = s.cuda(), hy.cuda(), hd.cuda(), tdb.cuda()
+    assert ops.td_fused_info(g, tn)["variant"] >= 10
+    ws = ops.td_fused_workspace(g, rows, tn, s.device)
+    loss = torch.zeros(1, dtype=torch.float64, device="cuda")
+    gs = torch.empty(rows, g, device="cuda")
+    ghy = torch.empty(g, tn, device="cuda")
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for rep in range(3):  # same workspace, three times, split 18 + 11 rows with accumulate on the second tile
+        for r0, r1, accum in ((0, 18, 0), (18, rows, 1)):
+            _lib.call("dgfdn_td_edc_fused", g, r1 - r0, tn, s[r0:r1].data_ptr(), hy.data_ptr(), hd[r0:r1].data_ptr(), tn,
+                      tdb[r0:r1].data_ptr(), tn, None, 1.0, loss.data_ptr(), gs[r0:r1].data_ptr(), ghy.data_ptr(), accum,
+                      ws.data_ptr(), stream)
+        torch.cuda.synchronize()
+        assert abs(float(loss) - ref) < 2e-5 * abs(ref) + 1e-3, rep
+        assert float((gs.cpu().double() - gs_ref).abs().max() / gs_ref.abs().max()) < 1e-3
+        assert float((ghy.cpu().double() - ghy_ref).abs().max() / ghy_ref.abs().max()) < 1e-3
+
+
 def test_cluster_fused_kernel_rejects_unsupported_shapes():
     from diffgfdn_b200 import _lib, ops
     assert not ops.td_fused_supported(3, 777)      # not a multiple of 4
     assert ops.td_fused_supported(3, 49156)        # longer than 8 slices x 2 runs: clusters of 6 CTAs, 3 x 2 x 384 segments
-    assert not ops.td_fused_supported(3, 55300)    # longer than any variant's slices
+    assert ops.td_fused_supported(3, 55300)        # longer than any cluster variant's slices: the sliced kernel takes it
+    assert not ops.td_fused_supported(3, 94724)    # longer than 148 slices of 640 samples
     assert not ops.td_fused_supported(5, 4096)     # too many groups for the register-resident accumulators
     t = torch.zeros(4, 780, device='cuda')
     with pytest.raises(RuntimeError, match="unsupported shape"):
