@@ -55,13 +55,25 @@ def parse():
     ap.add_argument("--nfft", type=int, default=NFFT)
     ap.add_argument("--tile-rows", type=int, default=int(os.environ.get("DGFDN_TILE_ROWS", "296")))
     ap.add_argument("--e2e-tile-rows", type=int, default=int(os.environ.get("DGFDN_E2E_TILE_ROWS", "128")))
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=0, help="end-to-end steps to time (0: the same count as --steps)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --receivers per GPU; strong: --total-receivers split over the GPUs")
+    ap.add_argument("--total-receivers", type=int, default=100000, help="receivers of the whole job (--scaling strong)")
+    ap.add_argument("--no-shard-bins", action="store_true",
+                    help="N > 1: every rank solves all bins (K1 / K1c replicated) instead of sharding them")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager steps instead of CUDA-graph replays")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-render", action="store_true", help="skip the secondary metric (BASELINE configs[4] renderer)")
-    ap.add_argument("--cpu-sample-receivers", type=int, default=4)
-    return ap.parse_args()
+    ap.add_argument("--cpu-sample-receivers", type=int, default=32,
+                    help="receivers of one CPU-baseline step (32 = the reference's own batch size, trainer batch_size)")
+    args = ap.parse_args()
+    if args.scaling == "strong":
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        args.receivers = (args.total_receivers + world - 1) // world
+    if args.e2e_steps <= 0:
+        args.e2e_steps = args.steps
+    return args
 
 
 def peaks():
@@ -124,12 +136,43 @@ def delays_for(n_lines):
 
 
 def build_net(device, seed=1234):
+    """The configs[3] model. device == "cpu_params_only": the same initialisation drawn on the CPU as float64 oracle
+    parameters (no CUDA, no product code on the reference arm)."""
+    if device == "cpu_params_only":
+        return _oracle_init(seed)
     from diffgfdn_b200.config import FeedbackLoopConfig, OutputFilterConfig
     from diffgfdn_b200.model import DiffGFDNVarReceiverPos
     torch.manual_seed(seed)
     return DiffGFDNVarReceiverPos(FS, N_GROUPS, delays_for(N_LINES), device, FeedbackLoopConfig(use_zero_coupling=False),
                                   OutputFilterConfig(use_svfs=False), use_absorption_filters=False,
                                   common_decay_times=np.array([T60]), use_colorless_loss=True)
+
+
+def _oracle_init(seed, hidden=3, neurons=128, feats=10):
+    """Reference initialisation (model.py:100-106, feedback_loop.py:288-310, dnn.py:331-400 Kaiming-uniform linears,
+    unit LayerNorms) as float64 leaves keyed like the reference state_dict."""
+    gen = torch.Generator().manual_seed(seed)
+    g, n = N_GROUPS, N_LINES
+    l = n // g
+    f64 = torch.float64
+    p = {"feedback_loop.M": (2 * torch.rand(g, l, l, dtype=f64, generator=gen) - 1) / np.sqrt(l),
+         "feedback_loop.alpha": np.pi / 4 * torch.rand(g * (g - 1) // 2, dtype=f64, generator=gen),
+         "input_gains": (2 * torch.randn(n, 1, dtype=f64, generator=gen) - 1) / n,
+         "output_gains": (2 * torch.randn(n, 1, dtype=f64, generator=gen) - 1) / n}
+    dims = [6 * feats] + [neurons] * (hidden + 1)
+    idx = 0
+    for i in range(hidden + 1):
+        bound = np.sqrt(6.0 / dims[i])
+        p[f"output_scalars.mlp.model.{idx}.weight"] = (2 * torch.rand(dims[i + 1], dims[i], dtype=f64, generator=gen) - 1) * bound
+        p[f"output_scalars.mlp.model.{idx}.bias"] = torch.zeros(dims[i + 1], dtype=f64)
+        p[f"output_scalars.mlp.model.{idx + 1}.weight"] = torch.ones(dims[i + 1], dtype=f64)
+        p[f"output_scalars.mlp.model.{idx + 1}.bias"] = torch.zeros(dims[i + 1], dtype=f64)
+        idx += 3
+    p[f"output_scalars.mlp.model.{idx}.weight"] = (2 * torch.rand(g, neurons, dtype=f64, generator=gen) - 1) * np.sqrt(6.0 / neurons)
+    p[f"output_scalars.mlp.model.{idx}.bias"] = torch.zeros(g, dtype=f64)
+    for v in p.values():
+        v.requires_grad_(True)
+    return {"params": p, "delays": torch.tensor(delays_for(n), dtype=f64), "feats": feats}
 
 
 def render_metric(device, hbm_peak):
@@ -183,6 +226,35 @@ def render_metric(device, hbm_peak):
                        "samples": t, "hop": hop, "positions": positions}, "finite": bool(np.isfinite(peak))}
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off (best effort), so that the pinned host pool of
+    the end-to-end mode is allocated next to the GPU's PCIe root. Returns a short description for the JSON line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(torch.cuda.current_device() if local_rank is None else local_rank)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return "gpu reports no NUMA node"
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return f"node {node}: none of its CPUs is available to this process"
+        os.sched_setaffinity(0, allowed)
+        return f"node {node} ({len(allowed)} CPUs)"
+    except Exception as e:  # no NVML / sysfs in the sandbox: run unbound
+        return f"unbound ({type(e).__name__})"
+
+
 def synth_responses(rows, nfft, device, seed):
     """Synthetic targets: 1 s of exponentially decaying noise per receiver -> rfft; the early
     response is the first 20 ms with a fade-out. Generated on the device in chunks. Returns complex64 tensors."""
@@ -230,43 +302,74 @@ def event_breakdown(events, steps):
 # ------------------------------------------------------------------------------------------------------------
 # CPU baseline: the oracle (port of the reference algorithm) on the host cores
 # ------------------------------------------------------------------------------------------------------------
-def cpu_reference_step(nfft, receivers, seed=7):
-    """One fwd + EDC/colorless loss + bwd of the reference algorithm (float64 CPU port, reference batching
-    B <= 32), returning seconds and receiver.bin evals."""
+def oracle_step(params, delays, z, pos, early, target, feats, edc_w=10.0):
+    """One fwd + EDC/colorless loss + bwd of the reference algorithm (oracle/gfdn_oracle.py: float64 CPU port, the
+    reference's own formulation -- dense inverse per bin, projection of every receiver over every bin, one irfft per
+    receiver) on the given parameters (a float64 state_dict; leaves with requires_grad get .grad). Returns the loss
+    terms, and the seconds it took."""
     from oracle import gfdn_oracle as O
-    torch.manual_seed(seed)
-    g, n = N_GROUPS, N_LINES
-    l = n // g
-    delays = torch.tensor(delays_for(n), dtype=torch.float64)
-    m_raw = ((2 * torch.rand(g, l, l, dtype=torch.float64) - 1) / np.sqrt(l)).requires_grad_(True)
-    alpha = (np.pi / 4 * torch.rand(3, dtype=torch.float64)).requires_grad_(True)
-    b = ((2 * torch.randn(n, dtype=torch.float64) - 1) / n).requires_grad_(True)
-    c = ((2 * torch.randn(n, dtype=torch.float64) - 1) / n).requires_grad_(True)
-    s = (2 * torch.rand(receivers, g, dtype=torch.float64) - 1).requires_grad_(True)
-    k = nfft // 2 + 1
-    z = O.z_grid(nfft)
+    g = params["feedback_loop.M"].shape[0]
+    t0 = time.perf_counter()
+    gamma = O.decay_times_to_gain_per_sample(T60, delays.tolist(), FS, g)
+    a = O.coupled_feedback_matrix(params["feedback_loop.M"], params["feedback_loop.alpha"])
+    b, c = params["input_gains"].reshape(-1), params["output_gains"].reshape(-1)
+    s = O.gains_from_mlp(pos, params, feats, g)
+    H = O.omni_response(z, delays, gamma, a, b, c, s, early)
+    h_sub, _ = O.sub_fdn_output(z, delays, params["feedback_loop.M"], b, c)
+    edc = O.edc_loss(target, H, max(T60) * 1e3, FS)
+    spec, spars = O.colorless_losses(h_sub, params["feedback_loop.M"], 1.0, 1.0, asym=True)
+    (edc_w * edc + spec + spars).backward()
+    return dict(edc=float(edc.detach()), spec=float(spec.detach()), spars=float(spars.detach())), time.perf_counter() - t0
+
+
+def oracle_params(net):
+    """float64 CPU copies of net's state_dict; the trainable ones are autograd leaves."""
+    names = {k for k, _ in net.named_parameters()}
+    return {k: v.detach().cpu().to(torch.float64).requires_grad_(k in names) for k, v in net.state_dict().items()
+            if v.dtype.is_floating_point}
+
+
+def cpu_reference_step(nfft, receivers, seed=7):
+    """One CPU step on freshly drawn parameters and data (the --impl reference arm): seconds and receiver.bin evals."""
+    from oracle import gfdn_oracle as O
+    net = build_net("cpu_params_only", seed=seed)
     rng = np.random.default_rng(seed)
     tlen = int(FS)
     rir = rng.standard_normal((receivers, tlen)) * np.exp(-np.arange(tlen)[None, :] / (0.2 * FS))
     target = torch.tensor(np.fft.rfft(rir, n=nfft, axis=-1))
-    d = torch.tensor(np.fft.rfft(rir[:, :640], n=nfft, axis=-1))
-    gamma = O.decay_times_to_gain_per_sample(T60, delays.tolist(), FS, g)
-    t0 = time.perf_counter()
-    a = O.coupled_feedback_matrix(m_raw, alpha)
-    H = O.omni_response(z, delays, gamma, a, b, c, s, d)
-    h_sub, _ = O.sub_fdn_output(z, delays, m_raw, b, c)
-    loss = 10.0 * O.edc_loss(target, H, max(T60) * 1e3, FS)
-    spec, spars = O.colorless_losses(h_sub, m_raw, 1.0, 1.0, asym=True)
-    (loss + spec + spars).backward()
-    return time.perf_counter() - t0, receivers * k
+    early = torch.tensor(np.fft.rfft(rir[:, :640], n=nfft, axis=-1))
+    pos = torch.tensor(rng.uniform(0, 1, (receivers, 3)))
+    _, secs = oracle_step(net["params"], net["delays"], O.z_grid(nfft), pos, early, target, net["feats"])
+    return secs, receivers * (nfft // 2 + 1)
 
 
-def cpu_baseline(nfft, receivers):
+def cpu_baseline(step, net, early_pool, target_pool, positions, args):
+    """The oracle timed on the host cores on a bounded sample of the SAME workload -- the first cpu_sample_receivers
+    receivers of this rank's shard, the GPU net's CURRENT parameters -- and, since both arms then computed the same
+    numbers, the parity of the timed GPU path against it (EDC in dB, worst relative gradient error)."""
+    from diffgfdn_b200.fused import ShardedEDCStep
     torch.set_num_threads(os.cpu_count() or 1)
-    secs, evals = cpu_reference_step(nfft, receivers)
-    return {"value": evals / secs, "unit": "receiver*bin evals/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{receivers} receivers x {nfft // 2 + 1} bins, N={N_LINES}, one fwd+loss+bwd of "
-                      f"oracle/gfdn_oracle.py (float64 torch-CPU port of the reference), {secs:.1f} s"}
+    n = min(args.cpu_sample_receivers, early_pool.shape[0], positions.shape[0])
+    sub = ShardedEDCStep(net, max(T60) * 1e3, edc_weight=10.0)
+    sub.attach(step.z, positions[:n], None, None)
+    sub.attach(step.z, positions[:n], sub.precompute_early_window(early_pool[:n]), sub.precompute_target_db(target_pool[:n]))
+    out = sub.step()
+    torch.cuda.synchronize()
+    params = oracle_params(net)
+    losses, secs = oracle_step(params, net.delays.cpu().to(torch.float64), step.z.cpu(), positions[:n].cpu().to(torch.float64),
+                               early_pool[:n].cpu().to(torch.complex128), target_pool[:n].cpu().to(torch.complex128),
+                               net.output_scalars.encoder.num_fourier_features)
+    worst = max(float((q.grad.detach().cpu().double() - params[k].grad).abs().max() / params[k].grad.abs().max())
+                for k, q in net.named_parameters())
+    k = args.nfft // 2 + 1
+    return {"value": n * k / secs, "unit": "receiver*bin evals/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{n} receivers x {k} bins, N={N_LINES}, one fwd+loss+bwd of oracle/gfdn_oracle.py (float64 "
+                      f"torch-CPU port of the reference) on the GPU net's parameters, {secs:.1f} s",
+            "parity_vs_gpu_step": {"receivers": n, "edc_db_gpu": float(out["edc_loss"]) / 10.0, "edc_db_oracle": losses["edc"],
+                                   "edc_db_abs_diff": abs(float(out["edc_loss"]) / 10.0 - losses["edc"]),
+                                   "spectral_rel_diff": abs(float(out["spectral_loss"]) - losses["spec"]) / abs(losses["spec"]),
+                                   "worst_grad_rel_err": worst, "at": "initial parameters",
+                                   "tolerances": "EDC 0.01 dB, gradients 1e-3 relative (BASELINE.json)"}}
 
 
 def run_reference(args, rank):
@@ -294,11 +397,15 @@ def run_reference(args, rank):
 
 
 def workload_config(args):
-    return {"workload": f"BASELINE configs[3] per-GPU shard: N={N_LINES} lines, G={N_GROUPS} groups, "
-                        f"{args.receivers} receivers/GPU x {args.nfft // 2 + 1} bins (nfft={args.nfft}), "
-                        "EDC(w=10)+colorless losses, fwd+bwd",
+    shard = (f"{args.total_receivers} receivers split over the GPUs ({args.receivers}/GPU)" if args.scaling == "strong"
+             else f"per-GPU shard of {args.receivers} receivers")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    bins = "bins of the per-bin solves sharded over the ranks" if world > 1 and not args.no_shard_bins else "per-bin solves on every rank"
+    return {"workload": f"BASELINE configs[3], {shard}: N={N_LINES} lines, G={N_GROUPS} groups, "
+                        f"x {args.nfft // 2 + 1} bins (nfft={args.nfft}), EDC(w=10)+colorless losses, fwd+bwd+Adam",
             "receivers_per_gpu": args.receivers, "bins": args.nfft // 2 + 1, "delay_lines": N_LINES,
-            "groups": N_GROUPS, "tile_rows": args.tile_rows, "parallelism": f"receiver-sharded dp{args.gpus}",
+            "groups": N_GROUPS, "tile_rows": args.tile_rows,
+            "parallelism": f"receiver-sharded dp{args.gpus}, {bins}",
             "l2_policy": "inputs larger than L2 (resident hd + target dB = 2 x receivers x tn x 4 B >> 126 MB, "
                          "streamed once per step), no explicit flush"}
 
@@ -320,6 +427,7 @@ def main():
         raise RuntimeError("bench.py needs a CUDA device: the kernels have no CPU fallback")
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(local)  # before any pinned allocation: first touch decides where the pool lives
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     barrier = (lambda: dist.barrier()) if world > 1 else (lambda: None)
@@ -330,8 +438,9 @@ def main():
     if world > 1:  # identical parameters on every rank
         for p in net.parameters():
             dist.broadcast(p.data, 0)
+    shard_bins = world > 1 and not args.no_shard_bins
     step = ShardedEDCStep(net, max(T60) * 1e3, tile_rows=args.tile_rows, edc_weight=10.0, world_size=world,
-                          total_receivers=args.receivers * world, e2e_tile_rows=args.e2e_tile_rows)
+                          total_receivers=args.receivers * world, e2e_tile_rows=args.e2e_tile_rows, shard_bins=shard_bins)
     k = args.nfft // 2 + 1
     z = unit_circle_grid(args.nfft, device=device)
     gen = torch.Generator(device=device).manual_seed(100 + rank)
@@ -347,6 +456,11 @@ def main():
     hd = hd_pool.repeat(reps, 1)[:args.receivers].contiguous()
     target_db = tdb_pool.repeat(reps, 1)[:args.receivers].contiguous()
     step.attach(z, positions, hd, target_db)
+    # CPU baseline + parity of the timed path, on the INITIAL parameters (before any optimizer step), rank 0 only
+    cpu_base = None
+    if rank == 0 and not args.no_cpu_baseline:
+        cpu_base = cpu_baseline(step, net, early_pool, target_pool, positions, args)
+    barrier()
     opt = torch.optim.Adam(net.parameters(), lr=1e-3, capturable=True, fused=True)  # one multi-tensor kernel per step
 
     def eager_step():
@@ -406,15 +520,20 @@ def main():
         for _ in range(args.e2e_steps):
             e2e_step()
         torch.cuda.synchronize()
-        te = torch.tensor([(time.perf_counter() - t0) / args.e2e_steps], device=device, dtype=torch.float64)
+        mine = (time.perf_counter() - t0) / args.e2e_steps
+        te = torch.tensor([mine], device=device, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        h2d = int(step.h2d_bytes) + int(positions.numel() * 4)
         e2e = {"value": evals_per_step / float(te.item()), "unit": "receiver*bin evals/s",
-               "h2d_bytes_per_step": int(step.h2d_bytes) + int(positions.numel() * 4), "d2h_bytes_per_step": 8,
-               "ms_per_step": 1e3 * float(te.item()),
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
+               "ms_per_step": 1e3 * float(te.item()), "steps": args.e2e_steps,
+               "h2d_GBps_per_rank": h2d / float(te.item()) / 1e9, "h2d_GBps_all_ranks": world * h2d / float(te.item()) / 1e9,
+               "host_numa_binding": numa,
                "note": "early + target responses ((B, K) complex64, reference layout) streamed from a pinned host pool "
                        "every step (bins 0..K/2, the ones irfft(X, n=K) reads), early window + target EDC rebuilt on "
-                       "the device, loss read back"}
+                       "the device, loss read back. Bound by host->device copies: one PCIe 5 x16 link per GPU (~55 GB/s) "
+                       "at N <= 2; at N >= 4 GPUs behind the same PCIe switch share its uplink (see h2d_GBps_all_ranks)"}
 
     if rank == 0:
         hbm, how = peaks()
@@ -438,7 +557,7 @@ def main():
         out = {
             "metric": "DiffGFDN receiver*bin evals/s fwd+bwd", "value": value, "unit": "receiver*bin evals/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32 storage / f64 per-bin solve and scans",
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f32 storage / f64 per-bin solve and scans",
             "data": "synthetic", "config": workload_config(args), "loss": loss_val, "clocks": clocks.summary(),
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
@@ -459,18 +578,30 @@ def main():
         }
         if not args.no_render:
             out["render"] = render_metric(device, hbm)
-        if not args.no_cpu_baseline:
-            out["cpu_baseline"] = cpu_baseline(args.nfft, args.cpu_sample_receivers)
+        if cpu_base is not None:
+            out["cpu_baseline"] = cpu_base
         print(json.dumps(out), flush=True)
     if world > 1:
-        # Leave without tearing the NCCL communicator down: destroy_process_group() after a CUDA-graph capture that
-        # holds an all-reduce node hung for the full gpurun limit at N=2 (the JSON line was already out). Every rank
-        # waits for the others first, so no peer is still inside a collective when a process disappears.
+        # The captured graph holds NCCL all-reduce nodes: release it (and everything that keeps its memory pool alive)
+        # before the communicator goes away, then tear down in order.
         dist.barrier()
+        torch.cuda.synchronize()
+        step.release_graph()
+        del opt
         torch.cuda.synchronize()
         sys.stdout.flush()
         sys.stderr.flush()
-        os._exit(0)
+        done = threading.Event()
+
+        def _teardown():
+            try:
+                dist.destroy_process_group()
+            finally:
+                done.set()
+
+        threading.Thread(target=_teardown, daemon=True).start()
+        if not done.wait(30.0):  # a wedged communicator must not hold the box: the JSON line is out, leave
+            os._exit(0)
 
 
 if __name__ == "__main__":

@@ -43,6 +43,24 @@ from .model import DiffGFDNVarReceiverPos
 C64 = torch.complex64
 
 
+class _GatherBins(torch.autograd.Function):
+    """y (K, G) from this rank's bin slice y_loc = y[lo:hi]: zero-padded SUM all-reduce (an all-gather that also runs
+    on backends without one for CUDA tensors, 8 K G bytes over NVLink). The caller all-reduces the gradient of
+    everything downstream (dL/dhy) BEFORE the backward, so the backward is the slice of the total gradient."""
+
+    @staticmethod
+    def forward(ctx, y_loc, lo, hi, k, group):
+        y = torch.zeros(k, y_loc.shape[1], dtype=y_loc.dtype, device=y_loc.device)
+        y[lo:hi] = y_loc
+        dist.all_reduce(torch.view_as_real(y), op=dist.ReduceOp.SUM, group=group)
+        ctx.lo, ctx.hi = lo, hi
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        return gy[ctx.lo:ctx.hi].contiguous(), None, None, None, None
+
+
 def _p(t):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
@@ -53,7 +71,8 @@ class ShardedEDCStep:
     def __init__(self, net: DiffGFDNVarReceiverPos, max_ir_len_ms: float, tile_rows: int = 296,
                  edc_weight: float = 1.0, spectral_weight: float = 1.0, sparsity_weight: float = 1.0,
                  asym_spectral: bool = True, mixing_time_ms: float = 20.0, world_size: int = 1,
-                 total_receivers: Optional[int] = None, process_group=None, e2e_tile_rows: int = 128):
+                 total_receivers: Optional[int] = None, process_group=None, e2e_tile_rows: int = 128,
+                 shard_bins: bool = False):
         self.net = net
         self.dev = net.device
         self.crit = edc_loss(max_ir_len_ms, net.sample_rate, mixing_time_ms=mixing_time_ms)
@@ -64,6 +83,11 @@ class ShardedEDCStep:
         self.world_size = world_size
         self.total_receivers = total_receivers
         self.pg = process_group
+        # shard_bins: the receiver-independent per-bin work (coupled solve K1 + its adjoint, colorless branch K1c) is
+        # split over the ranks by bins instead of repeated on every rank: y is gathered before the inverse DFT and
+        # dL/dhy summed before the adjoint -- two small all-reduces (8 K G and 4 G tn bytes) on the critical path
+        self.shard_bins = bool(shard_bins) and world_size > 1
+        self.rank = dist.get_rank(process_group) if self.shard_bins else 0
         self.kernel_launches = 0
         self.h2d_bytes = 0
         self._bufs = None
@@ -163,7 +187,13 @@ class ShardedEDCStep:
         # irfft(X, n=K) reads bins 0..K/2 only (reference losses.py:207-213, quirk Q3), so the coupled system is
         # solved on those kx bins; the other bins of H reach no loss term (the colorless loss has its own solve)
         z_edc = self.z if net.feedback_loop.delay_line_gain_response is not None else self.z[:self.kx]
-        _, y = net.feedback_loop.solve(z_edc, net.input_gains.reshape(-1), net.output_gains.reshape(-1))
+        if self.shard_bins:  # this rank's bins of the coupled solve; y is completed over the ranks
+            ke = z_edc.shape[0]
+            lo, hi = self._bin_slice(ke)
+            _, y_loc = net.feedback_loop.solve(z_edc[lo:hi], net.input_gains.reshape(-1), net.output_gains.reshape(-1))
+            y = _GatherBins.apply(y_loc, lo, hi, ke, self.pg)
+        else:
+            _, y = net.feedback_loop.solve(z_edc, net.input_gains.reshape(-1), net.output_gains.reshape(-1))
         hy = ops.irfft_window(y.transpose(0, 1), self.n_fft, self.t0, self.tn)  # (G, tn)
         # own kernels of the front: position network, 2 x skew-expm (coupled matrix, sparsity term), matrix assembly,
         # coupled solve, chirp-z (pre, mul, post; the 2 cuFFT launches are not counted), colorless branch
@@ -215,19 +245,25 @@ class ShardedEDCStep:
         # for the whole chip = 1.5 ms on 28 SMs, the length of K3d), instead of competing with the coupled solve.
         side.wait_event(pre_rx)
         with torch.cuda.stream(side):
+            zc, share = self.z, 1.0 / self.world_size
+            if self.shard_bins:  # mean over ALL bins = sum over ranks of (bins of the rank / K) x mean over its bins
+                lo_c, hi_c = self._bin_slice(self.k)
+                zc, share = self.z[lo_c:hi_c], (hi_c - lo_c) / self.k
             if self.use_fused_colorless and net.num_delay_lines_per_group <= 16:
                 # K1c: solve, loss, dL/dy and the adjoint in one pass per bin (no H_sub, no second elimination)
-                per_group = ops.colorless_solve_loss(self.z, net.delays.to(torch.int32), net.feedback_loop.M,
+                per_group = ops.colorless_solve_loss(zc, net.delays.to(torch.int32), net.feedback_loop.M,
                                                      net.input_gains.reshape(-1), net.output_gains.reshape(-1), self.asym)
             else:
                 keep = net.return_per_delay_outputs
                 net.return_per_delay_outputs = False
-                h_sub, _ = net.sub_fdn_output(self.z)
+                h_sub, _ = net.sub_fdn_output(zc)
                 net.return_per_delay_outputs = keep
                 per_group = ops.colorless_loss_per_group(h_sub, self.asym)
-            spectral = self.w_spec * per_group.sum()
-            aux = (spectral + sparsity.to(spectral.dtype)) / self.world_size
+            spectral = self.w_spec * per_group.sum() * share  # this rank's share: the ranks' values add up to the loss
+            aux = spectral + sparsity.to(spectral.dtype) / self.world_size
         edc = (self._bufs["loss_sum"][0] if self.use_fused else self._bufs["row_sum"].sum()) * coef
+        if self.shard_bins:  # every rank needs the TOTAL dL/dhy for the adjoint solve of its bins
+            dist.all_reduce(ghy, op=dist.ReduceOp.SUM, group=self.pg)
         # no join before the backward: the engine runs each node on its forward's stream and orders producers and
         # consumers itself, so the adjoint solve of the EDC branch does not wait for the tail of the colorless branch
         # two calls: the EDC branch first, so that its nodes are enqueued (and captured) ahead of the colorless tail --
@@ -246,7 +282,10 @@ class ShardedEDCStep:
             ev.setdefault("front(MLP+solves+irfft of G rows)", []).append((sec[0], sec[1]))
             ev.setdefault("receiver tiles", []).append((sec[1], sec[2]))
             ev.setdefault("back(irfft^T+adjoint solves+autograd)", []).append((sec[2], sec[3]))
-        return {'edc_loss': edc, 'spectral_loss': spectral.detach(), 'sparsity_loss': sparsity.detach()}
+        # losses as reported: 'edc_loss' and (with shard_bins) 'spectral_loss' are this rank's share -- they add up over the
+        # ranks; without shard_bins every rank evaluates the whole spectral loss
+        spectral_rep = spectral.detach() if self.shard_bins else spectral.detach() * self.world_size
+        return {'edc_loss': edc, 'spectral_loss': spectral_rep, 'sparsity_loss': sparsity.detach()}
 
     # ---- CUDA graph: the whole resident step (+ optimizer) as one launch ----------------------------------
     def capture(self, optimizer: Optional[torch.optim.Optimizer] = None, warmup: int = 3):
@@ -277,6 +316,11 @@ class ShardedEDCStep:
                 optimizer.step()
         self.launches_per_replay = self.kernel_launches - before
         return self._graph
+
+    def release_graph(self):
+        """Drop the captured graph and its static outputs (before tearing down a process group it holds nodes of)."""
+        self._graph = None
+        self._static_losses = None
 
     def replay(self) -> Dict:
         """Run the captured step once; returns the (static) loss tensors, overwritten by every replay."""
@@ -313,6 +357,12 @@ class ShardedEDCStep:
             ev.setdefault("td_edc_step", []).append((marks[0], marks[1]))
             ev.setdefault("td_contract", []).append((marks[1], marks[2]))
         self.kernel_launches += 3  # td_edc_step, td_contract, td_contract_reduce
+
+    def _bin_slice(self, k: int):
+        """Contiguous bins [lo, hi) of this rank out of k (ranks at the end may get one bin less)."""
+        per = (k + self.world_size - 1) // self.world_size
+        lo = min(k, self.rank * per)
+        return lo, min(k, lo + per)
 
     @staticmethod
     def _sparsity(a: torch.Tensor) -> torch.Tensor:
