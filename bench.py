@@ -65,6 +65,10 @@ def parse():
     ap.add_argument("--no-graph", action="store_true", help="time eager steps instead of CUDA-graph replays")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-render", action="store_true", help="skip the secondary metric (BASELINE configs[4] renderer)")
+    ap.add_argument("--config", default="c4", choices=["c1", "c1svf", "c2", "c3", "c4"],
+                    help="c4 (default): BASELINE configs[3], the headline; c1 / c1svf / c2 / c3: one JSON line for the "
+                         "reference's own batch-32 configurations (configs[0..2]) through the drop-in trainer")
+    ap.add_argument("--no-configs", action="store_true", help="default run: skip the configs[0..2] lines under 'configs'")
     ap.add_argument("--cpu-sample-receivers", type=int, default=32,
                     help="receivers of one CPU-baseline step (32 = the reference's own batch size, trainer batch_size)")
     args = ap.parse_args()
@@ -255,6 +259,103 @@ def bind_to_gpu_numa_node(local_rank):
         return f"unbound ({type(e).__name__})"
 
 
+# ------------------------------------------------------------------------------------------------------------
+# BASELINE configs[0..2]: the reference's own training configurations (batch 32, nfft 2^17) through the drop-in API
+# ------------------------------------------------------------------------------------------------------------
+SMALL_CONFIGS = {
+    "c1": "configs[0] omni full-band, N=12 (3x4), B=32 x 65537 bins, EDC(w=10)+EDR+colorless losses, scalar receiver gains",
+    "c1svf": "configs[0] as shipped (use_svfs: True): SVF output filters from the MLP (11 sections per group and receiver)",
+    "c2": "configs[1] one octave band of the sub-band training: configs[0] with the band filter F[k] applied to H (8 such "
+          "models are independent: one per GPU, replicas only)",
+    "c3": "configs[2] directional FDN, ambisonic order 2 (N=27 = 3x9), J=12 directions, B=32 x 65537 bins, "
+          "directional EDC + colorless losses",
+}
+
+
+def module_path_metric(name, device, hbm_peak, steps=20, warmup=5, batch=32, nfft=131072):
+    """One training step (normalize + forward + losses + backward + Adam) of the reference's trainer API at a
+    configs[0..2] shape: `Trainer.train_step(data, with_norm=True)`, i.e. the CUDA-graph replay of the module path.
+    Timed with CUDA events around `steps` calls, batch resident on the device. Also timed with host-resident batches
+    (the DataLoader case): e2e."""
+    import tempfile
+
+    from diffgfdn_b200.config import FeedbackLoopConfig, OutputFilterConfig, TrainerConfig
+    from diffgfdn_b200.model import DiffDirectionalFDNVarReceiverPos, DiffGFDNVarReceiverPos
+    from diffgfdn_b200.trainer import DirectionalFDNVarReceiverPosTrainer, VarReceiverPosTrainer
+    from diffgfdn_b200.utils import unit_circle_grid
+    torch.manual_seed(0)
+    t60 = np.array([list(T60)])
+    k = nfft // 2 + 1
+    tmp = tempfile.mkdtemp()
+    gen = torch.Generator(device=device).manual_seed(1)
+    pos = torch.rand(batch, 3, device=device, generator=gen)
+    z = unit_circle_grid(nfft).to(device)
+    directional = name == "c3"
+    if directional:
+        n_lines = 27
+        net = DiffDirectionalFDNVarReceiverPos(FS, N_GROUPS, delays_for(n_lines), device, FeedbackLoopConfig(use_zero_coupling=False),
+                                               OutputFilterConfig(use_svfs=False, num_hidden_layers=3, num_neurons_per_layer=128,
+                                                                  num_fourier_features=10), 2, None, common_decay_times=t60,
+                                               use_colorless_loss=True,
+                                               analysis_matrix=(torch.randn(12, 9, generator=torch.Generator().manual_seed(2)) / 3).numpy())
+        tr = DirectionalFDNVarReceiverPosTrainer(net, TrainerConfig(train_dir=tmp + "/o", ir_dir=tmp + "/i", num_freq_bins=nfft,
+                                                                    use_colorless_loss=True, edc_loss_weight=10.0))
+        data = dict(z_values=z, listener_position=pos, norm_listener_position=pos,
+                    target_common_slope_amps=1e-4 + torch.rand(batch, 12, N_GROUPS, device=device, generator=gen))
+    else:
+        n_lines = 12
+        net = DiffGFDNVarReceiverPos(FS, N_GROUPS, delays_for(n_lines), device, FeedbackLoopConfig(use_zero_coupling=False),
+                                     OutputFilterConfig(use_svfs=name == "c1svf", num_hidden_layers=3, num_neurons_per_layer=128,
+                                                        num_fourier_features=10), use_absorption_filters=False,
+                                     common_decay_times=t60, use_colorless_loss=True)
+        tr = VarReceiverPosTrainer(net, TrainerConfig(train_dir=tmp + "/o", ir_dir=tmp + "/i", num_freq_bins=nfft,
+                                                      use_colorless_loss=True, use_asym_spectral_loss=True, edc_loss_weight=10.0))
+        early, target = synth_responses(batch, nfft, device, 300)
+        data = dict(z_values=z, listener_position=pos, norm_listener_position=pos, target_early_response=early,
+                    target_rir_response=target)
+        if name == "c2":  # a synthetic octave-band filter (SURVEY 8d): rfft of a hann-windowed sinc band-pass around 1 kHz
+            taps = 2047
+            n = torch.arange(taps, dtype=torch.float64) - taps // 2
+            lo, hi = 707.0 / FS, 1414.0 / FS
+            fir = (2 * hi * torch.sinc(2 * hi * n) - 2 * lo * torch.sinc(2 * lo * n)) * torch.hann_window(taps, periodic=False,
+                                                                                                       dtype=torch.float64)
+            tr.set_subband_filter(torch.fft.rfft(fir, n=nfft).to(torch.complex64))
+    with_norm = not getattr(net, "use_svf_in_output", False)
+    for _ in range(max(3, warmup)):  # the first two calls are eager (second one captures), then replays
+        tr.train_step(data, with_norm=with_norm)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss, _ = tr.train_step(data, with_norm=with_norm)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    # end to end: the batch arrives from (pinned) host memory every step, as from the reference's DataLoader
+    host = {kk: (v.cpu().pin_memory() if torch.is_tensor(v) and kk != "z_values" else v) for kk, v in data.items()}
+    h2d = sum(v.numel() * v.element_size() for kk, v in host.items() if torch.is_tensor(v) and kk != "z_values")
+    for _ in range(3):
+        tr.train_step(host, with_norm=with_norm)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        tr.train_step(host, with_norm=with_norm)
+    torch.cuda.synchronize()
+    ms_e2e = 1e3 * (time.perf_counter() - t0) / steps
+    evals = float(batch) * k
+    graphed = any(isinstance(v, dict) for v in tr._graphs.values())
+    return {"metric": "DiffGFDN receiver*bin evals/s fwd+bwd", "value": evals / (ms * 1e-3), "unit": "receiver*bin evals/s",
+            "ms_per_step": ms, "steps": steps, "loss": float(loss), "cuda_graph": graphed,
+            "config": {"workload": SMALL_CONFIGS[name], "batch": batch, "bins": k, "delay_lines": n_lines, "groups": N_GROUPS,
+                       "api": "Trainer.train_step(data, with_norm=True): normalize + forward + losses + backward + Adam"},
+            "e2e": {"value": evals / (ms_e2e * 1e-3), "unit": "receiver*bin evals/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4},
+            "roofline": {"bound": "hbm", "achieved": evals * SURVEY_BYTES_PER_EVAL / (ms * 1e-3) / 1e9, "peak": hbm_peak,
+                         "unit": "GB/s", "frac": evals * SURVEY_BYTES_PER_EVAL / (ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+                         "note": "whole step against SURVEY 8(d)'s 64 B per receiver.bin of the project -> irfft -> loss "
+                                 "pipeline; at batch 32 the step is ~100 small kernels (latency bound), not bandwidth bound"}}
+
+
 def synth_responses(rows, nfft, device, seed):
     """Synthetic targets: 1 s of exponentially decaying noise per receiver -> rfft; the early
     response is the first 20 ms with a fade-out. Generated on the device in chunks. Returns complex64 tensors."""
@@ -432,6 +533,28 @@ def main():
         dist.init_process_group("nccl", device_id=device)
     barrier = (lambda: dist.barrier()) if world > 1 else (lambda: None)
 
+    if args.config != "c4":  # one line for a configs[0..2] shape; N > 1 = independent replicas (sub-band models: one per GPU)
+        hbm, how = peaks()
+        with ClockSampler(local) as clocks:
+            line = module_path_metric(args.config, device, hbm, steps=args.steps, warmup=args.warmup)
+        vals = torch.tensor([line["value"], line["e2e"]["value"]], device=device, dtype=torch.float64)
+        worst = torch.tensor([line["ms_per_step"]], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(vals, op=dist.ReduceOp.SUM)
+            dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            line.update({"value": float(vals[0]), "ms_per_step": float(worst[0]), "n_gpus": world, "warmup": args.warmup,
+                         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "data": "synthetic",
+                         "dtype": "f32 storage / f64 per-bin solve", "clocks": clocks.summary(), "gpu_launches": args.steps,
+                         "parallelism": f"{world} independent replicas" if world > 1 else "single GPU"})
+            line["e2e"]["value"] = float(vals[1])
+            line["roofline"]["peak_source"] = how
+            print(json.dumps(line), flush=True)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
     from diffgfdn_b200.fused import ShardedEDCStep
     from diffgfdn_b200.utils import unit_circle_grid
     net = build_net(device)
@@ -578,6 +701,8 @@ def main():
         }
         if not args.no_render:
             out["render"] = render_metric(device, hbm)
+        if not args.no_configs:  # the reference's own batch-32 configurations through the drop-in trainer (graph replay)
+            out["configs"] = {c: module_path_metric(c, device, hbm, steps=max(5, min(args.steps, 20))) for c in SMALL_CONFIGS}
         if cpu_base is not None:
             out["cpu_baseline"] = cpu_base
         print(json.dumps(out), flush=True)

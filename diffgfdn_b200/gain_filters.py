@@ -38,10 +38,11 @@ def svf_to_biquads(svf_params: torch.Tensor, cutoffs: torch.Tensor, compress_pol
     svf_params = svf_params.to(torch.float64)
     res, gain_db = svf_params[..., 0], svf_params[..., 1]
     gain = torch.pow(10.0, gain_db * 0.05)
-    f = cutoffs.to(device=svf_params.device, dtype=svf_params.dtype)
+    f = cutoffs if cutoffs.device == svf_params.device and cutoffs.dtype == svf_params.dtype else \
+        cutoffs.to(device=svf_params.device, dtype=svf_params.dtype)
     ns = f.numel()
-    kind = torch.zeros(ns, dtype=torch.long, device=svf_params.device)
-    kind[0], kind[-1] = 1, 2
+    sec = torch.arange(ns, device=svf_params.device)
+    kind = (sec == 0).long() + 2 * (sec == ns - 1).long()  # 1: low shelf, 2: high shelf, 0: peaking (no host scalars)
     one = torch.ones_like(gain)
     m_lp = torch.where(kind == 1, gain, one)
     m_hp = torch.where(kind == 2, gain, one)
@@ -145,6 +146,8 @@ class SVF_from_MLP(nn.Module):
     def coefficients(self, x: Dict) -> torch.Tensor:
         """(B, G, S, 6) biquad coefficients of this batch; remembers the detached tables for get_parameters()."""
         svf = self.svf_parameters(x)
+        if self.svf_cutoff_freqs.device != svf.device:  # moved once: no host -> device copy inside a step
+            self.svf_cutoff_freqs = self.svf_cutoff_freqs.to(svf.device)
         coef = svf_to_biquads(svf, self.svf_cutoff_freqs, self.compress_pole_factor)
         self.svf_params = svf.detach()
         self.biquad_coeffs_ = coef.detach()

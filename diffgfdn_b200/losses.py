@@ -47,7 +47,7 @@ class edc_loss(nn.Module):
         self.band_centre_hz = band_centre_hz
         self.mixing_time_samps = ms_to_samps(mixing_time_ms, sample_rate)
         self.use_mask = use_mask
-        self._target_cache = TensorKeyedCache()
+        self._target_cache = TensorKeyedCache(max_entries=2)  # batch-sized entries: a loader hands out new tensors per step
 
     def window(self, num_bins: int):
         """(n, t0, tn) of the reference's slice irfft(X, n=K)[mix : min(max_len, K)]."""
@@ -156,7 +156,8 @@ class edr_loss(nn.Module):
         self.win_size = win_size
         self.hop_size = hop_size
         self.reduced_pole_radius = reduced_pole_radius
-        self._target_cache = TensorKeyedCache()
+        self._pole_weights = None
+        self._target_cache = TensorKeyedCache(max_entries=2)  # batch-sized entries: a loader hands out new tensors per step
 
     def _stft(self, rir: torch.Tensor) -> torch.Tensor:
         """(R, T_f, F) complex64: zero-pad to a hop multiple, hann(win), center=False (reference :501-553). The
@@ -179,7 +180,13 @@ class edr_loss(nn.Module):
             self._target_cache.put(target_response, hit)
         tgt, den = hit
         rir = ops.irfft_window(achieved_response, k, 0, k)
-        if self.reduced_pole_radius is not None:
-            rir = rir * torch.pow(torch.tensor(1.0 / self.reduced_pole_radius, device=rir.device),
-                                  torch.arange(k, device=rir.device))
+        if self.reduced_pole_radius is not None and self.reduced_pole_radius != 1.0:
+            # r^-n de-emphasis (reference losses.py:446-450); 1^-n is an exact identity and is skipped. The vector is
+            # built once per (length, device): no host scalar reaches the device inside a step (graph capture)
+            key = (k, str(rir.device))
+            if self._pole_weights is None or self._pole_weights[0] != key:
+                w = torch.pow(torch.full((), 1.0 / self.reduced_pole_radius, device=rir.device),
+                              torch.arange(k, device=rir.device))
+                self._pole_weights = (key, w)
+            rir = rir * self._pole_weights[1]
         return ops.edr_l1_normalised(self._stft(rir), tgt, den)

@@ -160,9 +160,10 @@ class DiffGFDN(nn.Module):
         if not self.return_per_delay_outputs:
             return hout, None
         per = (xs * self._gains_vec(self.output_gains).to(xs.dtype)).transpose(0, 1)  # (N, K)
-        onehot = torch.zeros(self.num_delay_lines, 1, self.num_groups, dtype=per.dtype, device=per.device)
         idx = torch.arange(self.num_delay_lines, device=per.device)
-        onehot[idx, 0, idx // self.num_delay_lines_per_group] = 1.0
+        groups = torch.arange(self.num_groups, device=per.device)
+        # one-hot of each delay line's group, built from comparisons (no host scalar: this runs inside graph captures)
+        onehot = ((idx // self.num_delay_lines_per_group).unsqueeze(-1) == groups).to(per.dtype).unsqueeze(1)
         return hout, per.unsqueeze(-1) * onehot
 
     @torch.no_grad()

@@ -60,6 +60,13 @@ class Trainer:
             self.colorless_criterion = [amse_loss() if trainer_config.use_asym_spectral_loss else mse_loss(),
                                         sparsity_loss()]
             self.colorless_loss_weights = [trainer_config.spectral_loss_weight, trainer_config.sparsity_loss_weight]
+        # The module path is ~120 kernel launches per step at batch size 32 and was launch bound (1.9 ms of kernels in
+        # 5.2 ms of wall time): normalize + forward + losses + backward + Adam of a batch shape are captured once in a
+        # CUDA graph and replayed (DGFDN_GRAPH_STEP=0 keeps every step eager). The random EDC mask is drawn on the
+        # host per step (reference losses.py:221-223), which a replay cannot do: such configs stay eager.
+        self.use_cuda_graph = (os.environ.get("DGFDN_GRAPH_STEP", "1") != "0" and not trainer_config.use_edc_mask
+                               and torch.device(self.device).type == "cuda")
+        self._graphs = {}
 
     def set_subband_filter(self, freq_resp: torch.Tensor):
         """Frequency response F[k] of the octave-band filter applied to H before the losses (trainer.py:112-150
@@ -86,7 +93,9 @@ class Trainer:
         others = pick(lambda n: not any(k in n for k in keys))
         if others:
             groups.append({'params': others, 'lr': trainer_config.lr})
-        self.optimizer = torch.optim.Adam(groups)
+        # capturable: the step counters live on the device, so optimizer.step() can sit inside a CUDA graph
+        cuda = torch.device(self.device).type == "cuda"
+        self.optimizer = torch.optim.Adam([g for g in groups if g['params']], capturable=cuda)
         self.scheduler = torch.optim.lr_scheduler.StepLR(self.optimizer, step_size=10, gamma=0.1)
 
     def save_model(self, e: int):
@@ -131,7 +140,7 @@ class Trainer:
         """complex128 dataset tensors are converted once and remembered (targets are constant over training)."""
         cache = self.__dict__.get("_c64_cache")
         if cache is None:
-            cache = self.__dict__["_c64_cache"] = TensorKeyedCache(max_entries=8)
+            cache = self.__dict__["_c64_cache"] = TensorKeyedCache(max_entries=2)
         out = cache.get(t)
         if out is None:
             out = cache.put(t, t.to(torch.complex64))
@@ -163,14 +172,87 @@ class Trainer:
             H = self.convert_ambi_rir_to_directional_rir(H)
         return self.calculate_losses(data, H, H_sub)
 
-    def train_step(self, data: Dict):
-        """reference trainer.py:452-477 / 795-825"""
-        self.optimizer.zero_grad()
+    def _step_body(self, data: Dict, with_norm: bool):
+        if with_norm:
+            self.normalize(data)
+        self.optimizer.zero_grad(set_to_none=True)
         all_losses = self._forward_losses(data)
         loss = sum(all_losses.values())
         loss.backward()
         self.optimizer.step()
-        return loss.item(), all_losses
+        return loss, all_losses
+
+    def train_step(self, data: Dict, with_norm: bool = False):
+        """reference trainer.py:452-477 / 795-825. with_norm=True runs normalize(data) first (what the epoch loop does
+        before every step, trainer.py:366-377) inside the same captured graph."""
+        if not self.use_cuda_graph:
+            loss, all_losses = self._step_body(data, with_norm)
+            return loss.item(), all_losses
+        return self._graphed_step(data, with_norm)
+
+    # ---- CUDA-graph replay of a whole step ---------------------------------------------------------------
+    def _clear_target_caches(self):
+        for crit in self.criterion:
+            cache = getattr(crit, "_target_cache", None)
+            if cache is not None:
+                cache.clear()
+        cache = self.__dict__.get("_c64_cache")
+        if cache is not None:
+            cache.clear()
+
+    def _graphed_step(self, data: Dict, with_norm: bool):
+        """First sighting of a batch signature: eager. Second: the batch is copied into static device buffers, the step
+        runs eagerly on them (warming every cache keyed on the constant inputs) and is then captured. From the third on:
+        copy + one graph launch. A change of learning rate (StepLR) re-captures."""
+        tensors = {k: v for k, v in data.items() if torch.is_tensor(v)}
+        sig = tuple(sorted((k, tuple(v.shape), str(v.dtype)) for k, v in tensors.items()))
+        lrs = tuple(float(g['lr']) for g in self.optimizer.param_groups)
+        key = (sig, with_norm)
+        entry = self._graphs.get(key)
+        if entry is not None and entry != "seen" and entry["lrs"] != lrs:
+            entry = self._graphs[key] = "seen"  # the captured Adam kernels hold the old learning rates
+        # Every eager step of a graphed trainer runs on ONE side stream, the stream of the later capture: autograd binds
+        # the parameters' AccumulateGrad nodes to the stream they are first used on, and a captured backward that has
+        # to synchronise with another (the default) stream invalidates the capture.
+        if self.__dict__.get("_stream") is None:
+            self._stream = torch.cuda.Stream(device=self.device)
+        cur = torch.cuda.current_stream(self.device)
+        if entry is None:
+            self._graphs[key] = "seen"
+            self._stream.wait_stream(cur)
+            with torch.cuda.stream(self._stream):
+                loss, all_losses = self._step_body(data, with_norm)
+            cur.wait_stream(self._stream)
+            return loss.item(), all_losses
+        if entry == "seen":
+            static = dict(data)
+            self._stream.wait_stream(cur)
+            with torch.cuda.stream(self._stream):
+                for k, v in tensors.items():
+                    static[k] = v.to(self.device, copy=True)
+                loss, all_losses = self._step_body(static, with_norm)  # this call's real step, and the warm-up
+                result = loss.item(), {k: v.detach().clone() if torch.is_tensor(v) else v for k, v in all_losses.items()}
+                del loss, all_losses  # nothing may keep this step's autograd graph (and its AccumulateGrad nodes) alive
+                self._clear_target_caches()  # the capture must recompute everything derived from the batch
+                torch.cuda.synchronize(self.device)
+                graph = torch.cuda.CUDAGraph()
+                self.optimizer.zero_grad(set_to_none=True)
+                with torch.cuda.graph(graph, stream=self._stream):
+                    g_loss, g_all = self._step_body(static, with_norm)
+                self._clear_target_caches()  # they now point into the graph's memory pool
+            cur.wait_stream(self._stream)
+            self._graphs[key] = dict(graph=graph, static=static, loss=g_loss, all=g_all, lrs=lrs,
+                                     src={k: None for k in tensors})
+            return result
+        static, src = entry["static"], entry["src"]
+        for k, v in tensors.items():
+            ident = (v.data_ptr(), v._version)
+            if k == 'z_values' and src[k] == ident:
+                continue  # the frequency grid is the same tensor every step
+            static[k].copy_(v, non_blocking=True)
+            src[k] = ident
+        entry["graph"].replay()
+        return entry["loss"].item(), entry["all"]
 
     @torch.no_grad()
     def valid_step(self, data: Dict):
@@ -194,9 +276,7 @@ class Trainer:
             if svf:  # full-band (SVF) models normalise b, c once per epoch, the others before every step (:366-377)
                 self.normalize(next(iter(train_dataset)))
             for data in train_dataset:
-                if not svf:
-                    self.normalize(data)
-                cur, cur_all = self.train_step(data)
+                cur, cur_all = self.train_step(data, with_norm=not svf)
                 tot += cur
                 for k, v in cur_all.items():
                     parts[k] = parts.get(k, 0.0) + float(v)
