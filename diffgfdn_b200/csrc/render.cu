@@ -173,85 +173,149 @@ __global__ void __launch_bounds__(256) render_mix_kernel(int bands, int g, int64
 }
 
 // Tiled listener mix (hop % 4 == 0): a block owns up to 1024 samples of ONE hop and kMixTile listeners. A thread keeps
-// 4 samples x kMixTile listeners of accumulators in registers, reads the 4 x G group samples of a band with G 128-bit
-// loads (q is [band][t][g], so 4 consecutive samples are 4 G contiguous floats) and reuses them for every listener
-// of the tile; the listeners' gains for this hop sit in shared memory (one broadcast LDS per gain). Per output
-// sample that is the bands x G FMAs the sum needs plus ~1/kMixTile of a load: the kernel streams its 4 B per
-// listener.sample at HBM write speed instead of re-reading q and s from L2 for every listener.
-constexpr int kMixTile = 8;
+// 4 samples x kMixTile listeners of accumulators in registers (as packed float2 pairs of samples: FFMA2), reads the
+// 4 x G group samples of a band with G 128-bit loads (q is [band][t][g], so 4 consecutive samples are 4 G contiguous
+// floats) and reuses them for every listener of the tile; the listeners' gains for this hop sit in shared memory as
+// [band * G + g][listener], so the 8 gains one (band, g) needs are two 128-bit broadcast loads. Per output sample that
+// is bands x G / 2 packed FMAs plus ~1/20 of a load. Measured at BASELINE configs[4] (profiles/r02_render_mix.txt):
+// 8 listeners x scalar FMAs 2.75 ms -> FFMA2 over listener pairs 2.53 -> 16 listeners per tile, persistent blocks with
+// prefetched gains and group samples 1.86 ms; staging the group samples of 64 listeners in shared memory by TMA
+// (a quarter of the L2 reads) measured 2.0 ms and was dropped. The packed-FMA floor of the 24-term sum is 0.87 ms.
+constexpr int kMixTile = 16;
 
 template <int G>
 __global__ void __launch_bounds__(256) render_mix_tiled_kernel(int bands, int64_t tlen, int64_t listeners,
                                                                int64_t positions, int64_t hop, int64_t nhops,
-                                                               int blocks_per_hop, const float* __restrict__ s,
+                                                               const float* __restrict__ s,
                                                                const int32_t* __restrict__ traj,
                                                                const float* __restrict__ q, float* __restrict__ out) {
-  extern __shared__ float s_tile[];  // [kMixTile][bands * G]
+  // PERSISTENT: a block walks over (hop, listener tile) items, hop-major (concurrent blocks share a hop's q slice in
+  // L2). The gains of the NEXT item -- a dependent traj -> s gather, ~2 us of latency -- are fetched into registers
+  // while the current item is computed, then parked in the other half of shared memory.
+  extern __shared__ __align__(16) float s_tile[];  // [2][bands * G][kMixTile]
   const int bg = bands * G;
-  const int64_t hidx = blockIdx.x / blocks_per_hop;
-  const int sub = blockIdx.x % blocks_per_hop;
-  const int64_t r0 = (int64_t)blockIdx.y * kMixTile;
-  const int nl = (int)min((int64_t)kMixTile, listeners - r0);
-  for (int i = threadIdx.x; i < kMixTile * bg; i += 256) {
-    const int l = i / bg, j = i % bg;
-    float v = 0.f;
-    if (l < nl) {
-      const int64_t pos = traj[(r0 + l) * nhops + hidx];
-      v = s[((size_t)(j / G) * positions + pos) * G + (j % G)];
-    }
-    s_tile[i] = v;
-  }
+  const int64_t ntl = (listeners + kMixTile - 1) / kMixTile;
+  const int64_t nitems = nhops * ntl;
+  const int tile_floats = kMixTile * bg;
+  auto gather = [&](int64_t item, int i) -> float {  // gain i = (band g, listener) of an item
+    const int64_t hidx = item / ntl, r0 = (item % ntl) * kMixTile;
+    const int j = i / kMixTile, l = i % kMixTile;
+    if (r0 + l >= listeners) return 0.f;
+    const int64_t pos = __ldg(traj + (r0 + l) * nhops + hidx);
+    return __ldg(s + ((size_t)(j / G) * positions + pos) * G + (j % G));
+  };
+  const int nthreads = blockDim.x;  // chosen on the host so that the threads x iterations cover a hop with little waste
+  int cur = 0;
+  if ((int64_t)blockIdx.x < nitems)
+    for (int i = threadIdx.x; i < tile_floats; i += nthreads) s_tile[i] = gather(blockIdx.x, i);
   __syncthreads();
-  const int64_t hop_end = min(tlen, (hidx + 1) * hop);
-  const int64_t t0 = hidx * hop + 4 * ((int64_t)sub * 256 + threadIdx.x);
-  if (t0 >= hop_end) return;
-  const bool full = t0 + 3 < hop_end;
-  float acc[kMixTile][4];
+  const bool aligned = (tlen * G) % 4 == 0 && (reinterpret_cast<uintptr_t>(q) & 15u) == 0;  // every band / row 16-byte aligned
+  for (int64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
+    const int64_t next = item + gridDim.x;
+    float pre[4] = {0.f, 0.f, 0.f, 0.f};  // tile_floats <= 4 x blockDim (checked on the host)
+    if (next < nitems) {
 #pragma unroll
-  for (int l = 0; l < kMixTile; ++l)
+      for (int u = 0; u < 4; ++u)
+        if ((int)threadIdx.x + nthreads * u < tile_floats) pre[u] = gather(next, threadIdx.x + nthreads * u);
+    }
+    const float* tile = s_tile + cur * tile_floats;
+    const int64_t hidx = item / ntl, r0 = (item % ntl) * kMixTile;
+    const int nl = (int)min((int64_t)kMixTile, listeners - r0);
+    const int64_t hop_end = min(tlen, (hidx + 1) * hop);
+    for (int64_t t0 = hidx * hop + 4 * (int64_t)threadIdx.x; t0 < hop_end; t0 += 4 * nthreads) {
+      const bool full = aligned && t0 + 3 < hop_end;
+      auto load_q = [&](int bd, float* v) {  // the 4 x G group samples of band bd at t0..t0+3
+        const float* qp = q + ((size_t)bd * tlen + t0) * G;
+        if (full) {
 #pragma unroll
-    for (int e = 0; e < 4; ++e) acc[l][e] = 0.f;
-  for (int bd = 0; bd < bands; ++bd) {
-    float v[4 * G];
-    const float* qp = q + ((size_t)bd * tlen + t0) * G;
-    if (full && (reinterpret_cast<uintptr_t>(qp) & 15u) == 0) {  // (a band starts 16-byte aligned only if tlen G % 4 == 0)
+          for (int i = 0; i < G; ++i) {
+            const float4 w = __ldg(reinterpret_cast<const float4*>(qp) + i);
+            v[4 * i] = w.x, v[4 * i + 1] = w.y, v[4 * i + 2] = w.z, v[4 * i + 3] = w.w;
+          }
+        } else {
 #pragma unroll
-      for (int i = 0; i < G; ++i) {
-        const float4 w = __ldg(reinterpret_cast<const float4*>(qp) + i);
-        v[4 * i] = w.x, v[4 * i + 1] = w.y, v[4 * i + 2] = w.z, v[4 * i + 3] = w.w;
+          for (int i = 0; i < 4 * G; ++i) v[i] = (t0 + i / G < hop_end) ? __ldg(qp + i) : 0.f;
+        }
+      };
+      float2 acc[kMixTile / 2][4];  // [listener pair][sample]: the pair's gains are adjacent in shared memory
+#pragma unroll
+      for (int l = 0; l < kMixTile / 2; ++l)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[l][e] = make_float2(0.f, 0.f);
+      float vn[4 * G];
+      load_q(0, vn);
+      for (int bd = 0; bd < bands; ++bd) {
+        float v[4 * G];
+#pragma unroll
+        for (int i = 0; i < 4 * G; ++i) v[i] = vn[i];
+        if (bd + 1 < bands) load_q(bd + 1, vn);  // the next band's samples travel while this band is accumulated
+#pragma unroll
+        for (int gi = 0; gi < G; ++gi) {
+          const float4* wp = reinterpret_cast<const float4*>(tile + (bd * G + gi) * kMixTile);
+          float2 w2[kMixTile / 2];
+#pragma unroll
+          for (int l = 0; l < kMixTile / 4; ++l) {
+            const float4 wv = wp[l];
+            w2[2 * l] = make_float2(wv.x, wv.y);
+            w2[2 * l + 1] = make_float2(wv.z, wv.w);
+          }
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float x = v[e * G + gi];
+            const float2 x2 = make_float2(x, x);
+#pragma unroll
+            for (int l = 0; l < kMixTile / 2; ++l) acc[l][e] = __ffma2_rn(w2[l], x2, acc[l][e]);
+          }
+        }
       }
-    } else {
 #pragma unroll
-      for (int i = 0; i < 4 * G; ++i) v[i] = (t0 + i / G < hop_end) ? __ldg(qp + i) : 0.f;
-    }
-#pragma unroll
-    for (int l = 0; l < kMixTile; ++l) {
-#pragma unroll
-      for (int gi = 0; gi < G; ++gi) {
-        const float w = s_tile[l * bg + bd * G + gi];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) acc[l][e] = fmaf(w, v[e * G + gi], acc[l][e]);
+      for (int l = 0; l < kMixTile; ++l) {
+        if (l < nl) {
+          float* o = out + (r0 + l) * tlen + t0;
+          const float a0 = (l & 1) ? acc[l >> 1][0].y : acc[l >> 1][0].x, a1 = (l & 1) ? acc[l >> 1][1].y : acc[l >> 1][1].x;
+          const float a2 = (l & 1) ? acc[l >> 1][2].y : acc[l >> 1][2].x, a3 = (l & 1) ? acc[l >> 1][3].y : acc[l >> 1][3].x;
+          if (full && ((reinterpret_cast<uintptr_t>(o) & 15u) == 0)) {
+            st_stream(reinterpret_cast<float4*>(o), make_float4(a0, a1, a2, a3));
+          } else {
+            if (t0 < hop_end) o[0] = a0;
+            if (t0 + 1 < hop_end) o[1] = a1;
+            if (t0 + 2 < hop_end) o[2] = a2;
+            if (t0 + 3 < hop_end) o[3] = a3;
+          }
+        }
       }
     }
-  }
-  for (int l = 0; l < nl; ++l) {
-    float* o = out + (r0 + l) * tlen + t0;
-    if (full && ((reinterpret_cast<uintptr_t>(o) & 15u) == 0)) {
-      st_stream(reinterpret_cast<float4*>(o), make_float4(acc[l][0], acc[l][1], acc[l][2], acc[l][3]));
-    } else {
-      for (int e = 0; e < 4 && t0 + e < hop_end; ++e) o[e] = acc[l][e];
-    }
+    float* nxt = s_tile + (cur ^ 1) * tile_floats;
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if ((int)threadIdx.x + nthreads * u < tile_floats) nxt[threadIdx.x + nthreads * u] = pre[u];
+    __syncthreads();
+    cur ^= 1;
   }
 }
 
 template <int G>
 int launch_mix_tiled(int bands, int64_t t, int64_t listeners, int64_t positions, int64_t hop, int64_t nhops,
                      const float* s, const int32_t* traj, const float* q, float* out, cudaStream_t st) {
-  const int blocks_per_hop = (int)((std::min(hop, t) + 1023) / 1024);
-  const dim3 grid((unsigned)(nhops * blocks_per_hop), (unsigned)((listeners + kMixTile - 1) / kMixTile));
-  const size_t smem = (size_t)kMixTile * bands * G * sizeof(float);
-  render_mix_tiled_kernel<G><<<grid, 256, smem, st>>>(bands, t, listeners, positions, hop, nhops, blocks_per_hop, s, traj,
-                                                      q, out);
+  const int64_t nitems = nhops * ((listeners + kMixTile - 1) / kMixTile);
+  // threads per block: a multiple of 32 <= 256 such that threads x iterations covers the hop's 128-bit words with
+  // the least idle lanes (3200 samples: 160 threads x 5 iterations exactly, instead of 256 x 4 with 22 % idle)
+  const int64_t n4 = (std::min(hop, t) + 3) / 4;
+  int threads = 256;
+  double best = 1e30;
+  for (int64_t it = (n4 + 255) / 256; it <= (n4 + 255) / 256 + 3; ++it) {
+    const int64_t th = std::min<int64_t>(256, std::max<int64_t>(32, ((n4 + it - 1) / it + 31) / 32 * 32));
+    const double waste = (double)(th * ((n4 + th - 1) / th)) / (double)n4 + 0.002 * (256 - th) / 32;  // prefer fuller blocks on ties
+    if (waste < best) best = waste, threads = (int)th;
+  }
+  DGFDN_CHECK(kMixTile * bands * G <= 4 * threads, "render_mix: too many (band, group) gains for the tile prefetch");
+  const size_t smem = (size_t)2 * kMixTile * bands * G * sizeof(float);
+  int per_sm = 0;
+  DGFDN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, render_mix_tiled_kernel<G>, threads, smem));
+  if (per_sm < 1) per_sm = 1;
+  const int64_t resident = (int64_t)sm_count() * per_sm;
+  render_mix_tiled_kernel<G><<<(unsigned)std::min(nitems, resident), threads, smem, st>>>(bands, t, listeners, positions, hop,
+                                                                                          nhops, s, traj, q, out);
   DGFDN_LAUNCH_CHECK();
   return 0;
 }
@@ -300,9 +364,7 @@ extern "C" int dgfdn_render_mix(int bands, int g, int64_t t, int64_t listeners, 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   // tiled kernel: hops of a multiple of 4 samples (128-bit accesses never straddle a hop), 16-byte aligned q, and a
   // grid.x that fits; anything else takes the per-sample kernel below
-  const int64_t gx = nhops * ((std::min(hop, t) + 1023) / 1024);
-  if (hop % 4 == 0 && g <= 4 && (reinterpret_cast<uintptr_t>(q) & 15u) == 0 && gx < (int64_t)1 << 31 &&
-      (size_t)kMixTile * bands * g * sizeof(float) <= 48 * 1024) {
+  if (hop % 4 == 0 && g <= 4 && kMixTile * bands * g <= 4 * 128) {
     switch (g) {
       case 1: return launch_mix_tiled<1>(bands, t, listeners, positions, hop, nhops, s, traj, q, out, st);
       case 2: return launch_mix_tiled<2>(bands, t, listeners, positions, hop, nhops, s, traj, q, out, st);
