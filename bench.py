@@ -220,7 +220,29 @@ def render_metric(device, hbm_peak):
     ms_groups, ms_mix = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])
     peak = float(out.abs().max())
     total = listeners * t
+    # the reference's own moving-listener semantics (sound_examples.py:163-226 filter_overlap_add + the sub-band FIRs of
+    # run_subband_training_treble.py:316-358): a 10 s stimulus through 2 s tails, hops of 100 ms cross-faded over 50 ms
+    from diffgfdn_b200.inference import GFDNAuraliser
+    firs = torch.randn(bands, 1025, device=device, generator=gen) * torch.hann_window(1025, periodic=False, device=device)
+    aur = GFDNAuraliser(dl, a, gam, b, c, N_GROUPS, firs, device=device)
+    stim = torch.randn(int(2.5 * FS), device=device, generator=gen)
+    traj_ola = traj[:, :t // hop].long()
+    ola_ms = []
+    for it in range(2):
+        ev2 = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        ev2[0].record()
+        y = aur.moving_listeners(stim, s, traj_ola, hop, int(2.0 * FS), int(0.05 * FS), 0.5)
+        ev2[1].record()
+        torch.cuda.synchronize()
+        ola_ms.append(ev2[0].elapsed_time(ev2[1]))
+    ola = {"metric": "moving-listener overlap-add, reference semantics (filter_overlap_add + sub-band FIRs)",
+           "value": float(y.numel()) / (ola_ms[-1] * 1e-3), "unit": "listener*samples/s", "ms": ola_ms[-1],
+           "finite": bool(torch.isfinite(y).all()),
+           "note": "block recursion + batched cuFFT block responses + one (listeners x blocks.channels) x (blocks.channels x hop) "
+                   "GEMM per output hop as 3 x TF32 on the tensor cores (cuBLAS); the reference convolves per listener and hop"}
+    del y
     return {"metric": "render listener*samples/s (10 s late tail, 4096 moving listeners x 8 octave bands)",
+            "moving_listeners_reference_semantics": ola,
             "value": total / ((ms_groups + ms_mix) * 1e-3), "unit": "listener*samples/s",
             "ms": {"render_groups(recursion, 8 bands)": ms_groups, "render_mix(4096 listeners)": ms_mix},
             "roofline": {"bound": "hbm", "kernel": "render_mix", "achieved": 4.0 * total / (ms_mix * 1e-3) / 1e9,
