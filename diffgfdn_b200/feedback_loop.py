@@ -113,9 +113,10 @@ class FeedbackLoop(nn.Module):
         self.device = device
         self.coupling_matrix_type = coupling_matrix_type or CouplingMatrixType.SCALAR
         self.coupling_matrix_order = coupling_matrix_order
-        if self.coupling_matrix_type == CouplingMatrixType.FILTER:
-            raise NotImplementedError("paraunitary FIR coupling A(z) is not built (no shipped config uses it; "
-                                      "SURVEY.md a-5); scalar and random (unstructured orthogonal) coupling are")
+        self._eps = 1e-9
+        if self.coupling_matrix_type == CouplingMatrixType.FILTER and not coupling_matrix_order or \
+                (self.coupling_matrix_type == CouplingMatrixType.FILTER and coupling_matrix_order < 2):
+            raise ValueError("filter_matrix coupling needs coupling_matrix_order (pu_matrix_order) >= 2")
         self._init_absorption(gains, common_decay_times)
         self._init_feedback_matrix(colorless_feedback_matrix)
 
@@ -201,6 +202,13 @@ class FeedbackLoop(nn.Module):
         else:
             self.M = nn.Parameter(((2 * torch.rand(self.num_groups, L, L) - 1) / np.sqrt(L)).to(self.device))
         self.nd_unitary = ND_Unitary()
+        if self.coupling_matrix_type == CouplingMatrixType.FILTER:
+            # paraunitary FIR coupling Phi(z): order - 1 Householder vectors and the order-0 unitary factor
+            # (reference feedback_loop.py:311-324; same parameter names and shapes)
+            self.unit_vectors = nn.Parameter(torch.randn(self.num_groups, self.coupling_matrix_order - 1).to(self.device))
+            self.unitary_matrix = nn.Parameter(((2 * torch.rand(self.num_groups, self.num_groups) - 1) /
+                                                np.sqrt(self.num_groups)).to(self.device))
+            return
         n_alpha = self.num_groups * (self.num_groups - 1) // 2
         if self.use_zero_coupling:
             self.register_buffer("alpha", torch.zeros(n_alpha, device=self.device))
@@ -229,7 +237,57 @@ class FeedbackLoop(nn.Module):
         blocks = torch.einsum('iab,jbc->iajc', U, U)  # (G, L, G, L)
         return blocks.reshape(G * L, G * L)
 
+    def construct_paraunitary_coupling(self, dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+        """Phi(z) = H_{P-2}(z) ... H_0(z) U as (G, G, P) real taps: H_k(z) = (I - v_k v_k^T) + v_k v_k^T z^-1 with v_k
+        the k-th column of `unit_vectors` scaled to unit length, U = expm(skew(unitary_matrix)) (reference
+        FIRParaunitary, feedback_loop.py:90-143, called at :414-421). The polynomial product is a handful of G x G
+        matmuls (the reference convolves entry by entry, utils.py:216-239)."""
+        dt = dtype or self.unit_vectors.dtype
+        uv = self.unit_vectors.to(dt)
+        v = uv / (torch.norm(uv, dim=0, keepdim=True) + self._eps)
+        eye = torch.eye(self.num_groups, dtype=dt, device=uv.device)
+        taps = [eye]
+        for k in range(v.shape[1]):
+            vv = torch.outer(v[:, k], v[:, k])
+            h0 = eye - vv
+            nxt = [h0 @ taps[0]] + [h0 @ taps[i] + vv @ taps[i - 1] for i in range(1, len(taps))] + [vv @ taps[-1]]
+            taps = nxt
+        u = self.ortho_param(self.unitary_matrix.to(dt))
+        return torch.stack([t @ u for t in taps], dim=-1)
+
+    def coupled_feedback_taps(self, dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+        """Taps of A(z) = sum_p A_p z^-p, (N, N, P) real: A_p = block_M o (Phi_p (x) 1_{LxL}) (reference :447-453)."""
+        block_M = self.construct_block_mixing_matrix(dtype)
+        phi = self.construct_paraunitary_coupling(dtype)
+        self.phi = phi.detach()
+        G, L = self.num_groups, self.num_delay_lines_per_group
+        taps = block_M.view(G, L, G, L, 1) * phi.view(G, 1, G, 1, -1)
+        return taps.reshape(G * L, G * L, -1)
+
+    def _solve_filter_coupling(self, z: torch.Tensor, b: torch.Tensor, c: torch.Tensor, transpose: bool):
+        """filter_matrix coupling: the system matrix D(z_k) Gamma^-1 - A(z_k) has a different complex A per bin
+        (reference :362-373, A(z) cast to complex64 like there). No shipped configuration uses this variant and it is
+        not on the kernel hot path: the per-bin matrices are formed and solved by a batched LU on the device
+        (torch.linalg.solve, complex128), differentiable through autograd."""
+        taps = self.coupled_feedback_taps(torch.float64)
+        self.coupled_feedback_matrix = taps.detach()
+        zc = z.to(device=taps.device, dtype=torch.complex128)
+        p = torch.arange(taps.shape[-1], device=taps.device, dtype=torch.float64)
+        az = torch.einsum('nmp,kp->knm', taps.to(torch.complex128), zc.unsqueeze(-1)**(-p))
+        az = az.to(torch.complex64).to(torch.complex128)
+        gamma_z = self.absorption_response(z)
+        d = zc.unsqueeze(-1)**self.delays.to(torch.float64)
+        dd = d / (self.delay_line_gains.to(torch.complex128) if gamma_z is None else gamma_z.to(torch.complex128).transpose(0, 1))
+        m = torch.diag_embed(dd) - az
+        if transpose:
+            m = m.transpose(-1, -2)
+        x = torch.linalg.solve(m, b.reshape(-1).to(torch.complex128).expand(m.shape[0], -1).unsqueeze(-1)).squeeze(-1)
+        y = (x * c.reshape(-1).to(torch.complex128)).reshape(x.shape[0], self.num_groups, -1).sum(-1)
+        return x.to(torch.complex64), y.to(torch.complex64)
+
     def construct_coupling_matrix(self, dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+        if self.coupling_matrix_type == CouplingMatrixType.FILTER:
+            return self.construct_paraunitary_coupling(dtype)
         alpha = self.alpha.clamp(min=-np.pi, max=np.pi)
         if dtype is not None:
             alpha = alpha.to(dtype)
@@ -271,11 +329,16 @@ class FeedbackLoop(nn.Module):
         return a
 
     def get_coupled_feedback_matrix(self) -> torch.Tensor:
-        a = self.coupled_feedback_matrix_real()
+        if self.coupling_matrix_type == CouplingMatrixType.FILTER:  # (N, N, order) taps of A(z)
+            a = self.coupled_feedback_taps()
+        else:
+            a = self.coupled_feedback_matrix_real()
         return torch.complex(a, torch.zeros_like(a))
 
     def solve(self, z: torch.Tensor, b: torch.Tensor, c: torch.Tensor, transpose: bool = False):
         """x_k = (D(z_k) Gamma^-1 - A)^-1 b and y[k,g] = sum_{n in g} c_n x_k[n] on the GPU (one warp per bin)."""
+        if self.coupling_matrix_type == CouplingMatrixType.FILTER:
+            return self._solve_filter_coupling(z, b, c, transpose)
         a = self._assembled()
         gamma_z = self.absorption_response(z)
         gamma = None if gamma_z is not None else self.delay_line_gains
@@ -287,16 +350,19 @@ class FeedbackLoop(nn.Module):
         source group g' (b masked to that group), A assembled once. The model variants with source-side gains or
         filters (reference model.py:402-452, 779-836) are bilinear in the per-group factors of both sides, so these
         G x G functions per bin are all they need of the feedback loop."""
+        L = self.num_delay_lines_per_group
+        b = b.reshape(-1)
+        group_of_line = torch.arange(self.num_delays, device=b.device) // L
+        if self.coupling_matrix_type == CouplingMatrixType.FILTER:
+            return [self._solve_filter_coupling(z, b * (group_of_line == gp).to(b.dtype), c, False)[1]
+                    for gp in range(self.num_groups)]
         a = self._assembled()
         gamma_z = self.absorption_response(z)
         gamma = None if gamma_z is not None else self.delay_line_gains
         delays = self.delays.to(torch.int32)
-        L = self.num_delay_lines_per_group
-        b = b.reshape(-1)
         out = []
         for gp in range(self.num_groups):
-            mask = torch.zeros_like(b)
-            mask[gp * L:(gp + 1) * L] = 1.0
+            mask = (group_of_line == gp).to(b.dtype)
             out.append(ops.gfdn_solve(z, delays, a, gamma, b * mask, c, self.num_groups, gamma_z=gamma_z)[1])
         return out
 
@@ -328,6 +394,11 @@ class FeedbackLoop(nn.Module):
              'coupled_feedback_matrix': coupled.squeeze().cpu().numpy()}
         if hasattr(self, 'common_decay_times'):
             d['common_decay_times'] = self.common_decay_times
+        if self.coupling_matrix_type == CouplingMatrixType.FILTER:  # reference :481-488
+            uv = self.unit_vectors / (torch.norm(self.unit_vectors, dim=0, keepdim=True) + self._eps)
+            d['unitary_matrix'] = self.ortho_param(self.unitary_matrix).squeeze().cpu().numpy()
+            d['unit_vectors'] = uv.squeeze().cpu().numpy()
+            return d
         if not self.use_zero_coupling:
             d['coupling_coefficient'] = self.alpha.squeeze().cpu().numpy()
         return d

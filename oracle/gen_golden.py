@@ -340,6 +340,47 @@ def case_random_coupling(name, n_lines, nfft, bsz, t60, seed):
     print(name, {k: v for k, v in out.items() if k.startswith("loss/")})
 
 
+def case_filter_coupling(name, n_lines, nfft, bsz, t60, seed, order):
+    """coupling_matrix_type: filter_matrix (feedback_loop.py:90-143, 311-324, 362-373, 414-421, 447-453): the coupling
+    between groups is a paraunitary FIR matrix Phi(z) of `order` taps built from Householder stages, A(z) per bin."""
+    from diff_gfdn.config.config import CouplingMatrixType
+    cfg = DiffGFDNConfig(seed=235265, num_delay_lines=n_lines)
+    delays = cfg.delay_length_samps
+    torch.manual_seed(seed)
+    np.random.seed(seed)
+    g = len(t60)
+    net = DiffGFDNVarReceiverPos(FS, g, delays, 'cpu',
+                                 FeedbackLoopConfig(coupling_matrix_type=CouplingMatrixType.FILTER, pu_matrix_order=order,
+                                                    use_zero_coupling=False),
+                                 OutputFilterConfig(use_svfs=False, num_hidden_layers=1, num_neurons_per_layer=16,
+                                                    num_fourier_features=4),
+                                 use_absorption_filters=False, common_decay_times=np.array([t60]), use_colorless_loss=True)
+    data = synth_batch(nfft, bsz, seed + 1, early_scale=1e-3)
+    trainer = make_trainer(VarReceiverPosTrainer, net, use_colorless_loss=True, use_asym_spectral_loss=True,
+                           edc_loss_weight=10.0, num_freq_bins=nfft)
+    out = {"meta/delays": np.array(delays), "meta/nfft": nfft, "meta/fs": FS, "meta/t60": np.array(t60),
+           "meta/feats": 4, "meta/edc_w": 10.0, "meta/edr_w": 1.0, "meta/order": order,
+           "meta/max_ir_len_ms": float(np.max(t60) * 1e3)}
+    for key in ("listener_position", "norm_listener_position", "target_early_response", "target_rir_response"):
+        out[f"data/{key}"] = data[key].numpy()
+    out.update(np_state(net))
+    net.zero_grad()
+    H, (Hs, Hsd) = net(data)
+    losses = trainer.calculate_losses(data, H, (Hs, Hsd))
+    total = sum(losses.values())
+    total.backward()
+    out["out/H"] = H.detach().numpy()
+    out["out/H_sub"] = Hs.detach().numpy()
+    out["out/A"] = net.feedback_loop.coupled_feedback_matrix.detach().numpy()  # (N, N, order) complex
+    out["out/phi"] = net.feedback_loop.phi.detach().numpy()  # (G, G, order)
+    for kk, v in losses.items():
+        out[f"loss/{kk}"] = float(v.detach())
+    out["loss/total"] = float(total.detach())
+    out.update(grads_of(net))
+    np.savez_compressed(os.path.join(OUT, f"{name}.npz"), **out)
+    print(name, {k: v for k, v in out.items() if k.startswith("loss/")})
+
+
 def case_dataloader(name):
     """Data boundary (dataloader.py:185-325, 515-600, 674-745): a small two-room grid through the reference classes."""
     from diff_gfdn.dataloader import (MultiRIRDataset, RIRData, RoomDataset, SingleRIRDataset, create_fixed_test_split,
@@ -402,6 +443,7 @@ if __name__ == "__main__":
     case_single("single_n12", 12, 8192, [0.05, 0.08, 0.12], 16, False, False)
     case_single("single_n12_svf", 12, 8192, [0.05, 0.08, 0.12], 17, True, True)
     case_random_coupling("random_coupling_n8", 8, 8192, 3, [0.06, 0.11], 19)
+    case_filter_coupling("filter_coupling_n12", 12, 8192, 3, [0.05, 0.08, 0.12], 23, 4)
     case_dataloader("dataloader_small")
     case_directional("directional_n27", 8192, 2, [0.05, 0.08, 0.1], 21, 1, 16, 4, skip=False)
     case_directional("directional_n27_skip", 4096, 2, [0.03, 0.04, 0.05], 22, 2, 16, 4, skip=True)

@@ -112,18 +112,53 @@ def z_grid(nfft: int, radius: float = 1.0) -> torch.Tensor:
 # --------------------------------------------------------------------------------------
 # feedback loop (a-6) and transfer functions (a-8, a-8b, a-9)
 # --------------------------------------------------------------------------------------
+def paraunitary_coupling(unitary_matrix: torch.Tensor, unit_vectors: torch.Tensor, eps: float = 1e-9) -> torch.Tensor:
+    """feedback_loop.py:90-143 (FIRParaunitary) as called by construct_coupling_matrix (:414-421):
+    Phi(z) = H_{P-2}(z) ... H_0(z) U,  H_k(z) = (I - v_k v_k^T) + v_k v_k^T z^-1 with v_k the k-th column of
+    unit_vectors normalised to unit length (+ eps), U = expm(skew(unitary_matrix)). Returns (G, G, P) real taps."""
+    g = unitary_matrix.shape[0]
+    v = unit_vectors / (torch.norm(unit_vectors, dim=0, keepdim=True) + eps)
+    poly = [torch.eye(g, dtype=unitary_matrix.dtype)]  # taps of the running product
+    for k in range(unit_vectors.shape[1]):
+        vv = torch.outer(v[:, k], v[:, k])
+        h0, h1 = torch.eye(g, dtype=vv.dtype) - vv, vv
+        nxt = [torch.zeros(g, g, dtype=vv.dtype) for _ in range(len(poly) + 1)]
+        for i, tap in enumerate(poly):  # matrix_convolution(H_k, poly): H_k on the left (utils.py:216-239)
+            nxt[i] = nxt[i] + h0 @ tap
+            nxt[i + 1] = nxt[i + 1] + h1 @ tap
+        poly = nxt
+    u = ortho_param(unitary_matrix)
+    return torch.stack([tap @ u for tap in poly], dim=-1)
+
+
+def coupled_feedback_matrix_filter(m_raw: torch.Tensor, phi: torch.Tensor) -> torch.Tensor:
+    """feedback_loop.py:447-453: A[..., p] = block_M o (Phi[..., p] (x) 1_{LxL}); (N, N, P) real taps of A(z)."""
+    g, l, _ = m_raw.shape
+    u = ortho_param(m_raw)
+    block_m = torch.cat([torch.cat([u[i] @ u[j] for j in range(g)], dim=1) for i in range(g)], dim=0)
+    ones = torch.ones(l, l, dtype=m_raw.dtype)
+    return torch.stack([block_m * torch.kron(phi[..., p], ones) for p in range(phi.shape[-1])], dim=-1)
+
+
 def feedback_loop_inverse(z: torch.Tensor, delays: torch.Tensor, gamma: torch.Tensor,
                           a: torch.Tensor) -> torch.Tensor:
     """feedback_loop.py:326-391: P_k = (diag(z_k^m) Gamma^-1 - A)^-1  (quirk Q5: D Gamma^-1, not D - A Gamma).
 
-    gamma is (N,) real (scalar absorption) or (N, K) complex (filter absorption Gamma_i(z_k))."""
+    gamma is (N,) real (scalar absorption) or (N, K) complex (filter absorption Gamma_i(z_k)). a is (N, N), or
+    (N, N, P) taps of a FIR coupling A(z_k) = sum_p a[..., p] z_k^-p (filter_matrix coupling, :362-373)."""
     z = z.to(C128)
     d = z.unsqueeze(-1)**delays.to(F64)  # (K, N)                      feedback_loop.py:330
     if gamma.dim() == 1:
         dd = d / gamma.to(C128).unsqueeze(0)  #                        feedback_loop.py:385-386
     else:
         dd = d / gamma.to(C128).transpose(0, 1)  #                     feedback_loop.py:378-381
-    m = torch.diag_embed(dd) - a.to(C128).unsqueeze(0)
+    if a.dim() == 3:
+        zp = z.unsqueeze(-1)**(-torch.arange(a.shape[-1], dtype=F64))  # (K, P)
+        # the reference casts A(z) to complex64 before the subtraction (:373)
+        az = torch.einsum('nmp,kp->knm', a.to(C128), zp).to(torch.complex64).to(C128)
+    else:
+        az = a.to(C128).unsqueeze(0)
+    m = torch.diag_embed(dd) - az
     return torch.linalg.inv(m)  #                                      feedback_loop.py:391
 
 

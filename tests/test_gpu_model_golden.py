@@ -274,6 +274,44 @@ def test_random_coupling_matches_reference(tmp_path):
     assert set(net.feedback_loop.get_param_dict()) >= {"coupled_feedback_matrix", "delay_line_gains"}
 
 
+def test_filter_coupling_matches_reference(tmp_path):
+    """coupling_matrix_type: filter_matrix (reference feedback_loop.py:90-143, 362-373, 447-453): paraunitary FIR coupling,
+    A(z_k) per bin. Forward, losses and every gradient vs the reference golden; reference state_dict loads strictly."""
+    from diffgfdn_b200.config import CouplingMatrixType, FeedbackLoopConfig, OutputFilterConfig
+    from diffgfdn_b200.model import DiffGFDNVarReceiverPos
+    from diffgfdn_b200.trainer import VarReceiverPosTrainer
+    g = load("filter_coupling_n12")
+    net = DiffGFDNVarReceiverPos(float(g["meta/fs"]), len(g["meta/t60"]), [int(v) for v in g["meta/delays"]], 'cuda',
+                                 FeedbackLoopConfig(coupling_matrix_type=CouplingMatrixType.FILTER,
+                                                    pu_matrix_order=int(g["meta/order"]), use_zero_coupling=False),
+                                 OutputFilterConfig(use_svfs=False, num_hidden_layers=1, num_neurons_per_layer=16,
+                                                    num_fourier_features=4),
+                                 use_absorption_filters=False, common_decay_times=np.array([g["meta/t60"]]),
+                                 use_colorless_loss=True)
+    net.load_state_dict({k[len("param/"):]: torch.tensor(v) for k, v in g.items() if k.startswith("param/")},
+                        strict=True)
+    data = omni_data({**g, "meta/radius": 1.0})
+    trainer = make_trainer(VarReceiverPosTrainer, net, tmp_path, use_colorless_loss=True, use_asym_spectral_loss=True,
+                           edc_loss_weight=10.0, num_freq_bins=int(g["meta/nfft"]))
+    net.zero_grad()
+    H, (Hs, Hsd) = net(data)
+    d = g["data/target_early_response"]
+    assert rel(H.detach().cpu().to(torch.complex128).numpy() - d, g["out/H"] - d) < 1e-4
+    assert rel(Hs, g["out/H_sub"]) < 1e-4
+    assert rel(net.feedback_loop.phi, g["out/phi"]) < 1e-5
+    assert rel(net.feedback_loop.coupled_feedback_matrix, g["out/A"].real) < 1e-5
+    losses = trainer.calculate_losses(data, H, (Hs, Hsd))
+    total = sum(losses.values())
+    total.backward()
+    assert abs(float(losses["edc_loss"]) - g["loss/edc_loss"]) < 0.01 * float(g["meta/edc_w"])
+    assert abs(float(total) - g["loss/total"]) < 2e-3 * g["loss/total"]
+    for k, p in net.named_parameters():
+        assert rel(p.grad, g[f"grad/{k}"]) < 1e-3, k
+    pd = net.feedback_loop.get_param_dict()
+    assert set(pd) >= {"coupled_feedback_matrix", "unitary_matrix", "unit_vectors", "coupling_matrix"}
+    assert pd["coupled_feedback_matrix"].shape == g["out/A"].shape
+
+
 def test_feedback_loop_dense_inverse_api():
     """FeedbackLoop.forward(z) keeps the reference's (K, N, N) inverse for API compatibility."""
     from oracle import gfdn_oracle as O
