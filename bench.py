@@ -685,9 +685,12 @@ def main():
         # dominant receiver-scaling kernel: 8 algorithmic bytes per receiver.sample
         if step.use_fused:
             td_key, rows_per_launch = "td_edc_fused", args.receivers
-            td_name = ("td_fused_kernel<3,2,false> (K3d: cluster of 8 CTAs per receiver row, TMA-staged inputs, mix + EDC + "
-                       "dB loss + whole backward, register-resident ghy accumulators; its finalize launch is inside the "
-                       "timed pair)")
+            from diffgfdn_b200 import ops
+            info = ops.td_fused_info(net.num_groups, step.tn)
+            td_name = ("td_fused_kernel<G=3, variant %d: %d threads, cluster of %d> (K3d: cluster of 8 CTAs per receiver "
+                       "row, TMA-staged inputs, three rows per iteration, mix + EDC + dB loss + whole backward, ghy "
+                       "accumulators resident in tensor memory (tcgen05.ld/st); its finalize launch is inside the timed "
+                       "pair)" % (info["variant"], info["threads"], info["cluster_size"]))
         else:
             td_key, rows_per_launch = "td_edc_step", min(args.tile_rows, args.receivers)
             td_name = "td_edc_step_kernel<3,true> (K3c: mix + EDC + dB loss + backward per receiver row)"

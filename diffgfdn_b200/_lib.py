@@ -36,7 +36,7 @@ SIGNATURES = {
                                        c_void_p, c_void_p]),
     "dgfdn_solve_colorless_ws_bytes": (c_int64, [c_int]),
     "dgfdn_solve_colorless": (c_int, [c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                      c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+                                      c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dgfdn_project_fwd": (c_int, [c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64,
                                   c_void_p]),
     "dgfdn_project_bwd": (c_int, [c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int,

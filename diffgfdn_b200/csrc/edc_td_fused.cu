@@ -12,7 +12,10 @@
 // HBM traffic is the algorithmic minimum, 8 B per receiver.sample (hd + target dB), moved by 1-D TMA bulk copies
 // (cp.async.bulk + mbarrier) into shared memory one iteration ahead of their use.
 //
-// Per iteration a cluster handles kRows = 2 rows. The two scans (suffix sum of h^2, prefix sum of dL/dEDC) run
+// Per iteration a cluster handles kRows = 2 or 3 rows. With Tile::TMEM the ghy accumulators live in TENSOR MEMORY
+// (tcgen05.alloc / tcgen05.ld / tcgen05.st, 32x32b shape: one TMEM lane per thread, 4 G NRUN RUN columns) and stream
+// through registers one 4 G-word chunk at a time in phase C; the 72 registers this frees hold a third row, over
+// which the two barriers + two exchanges of an iteration amortise (1.46 -> 1.35 ms at the BASELINE shard). The two scans (suffix sum of h^2, prefix sum of dL/dEDC) run
 // thread -> warp (shuffles) -> CTA (every warp scans the 16 warp totals) -> cluster: every CTA stores its slice total into
 // the other CTAs' shared memory with st.async (DSMEM store that completes tx-bytes on the receiver's mbarrier), so
 // the row loop has no barrier.cluster and no cluster-scope fence. The second exchange is hidden behind the part of the backward that does not need the carry
@@ -37,15 +40,20 @@ constexpr double kDbFactor = 4.342944819032518;    // 10 / ln(10)
 // Compile-time shape of one variant of the kernel. A CTA of FT threads owns one of C time slices of a row; thread t
 // owns, in each of NRUN runs, RUN consecutive 128-bit segments (RUN odd: the 16 RUN-byte thread stride is then
 // conflict-free for 128-bit shared-memory accesses); ROWS rows are processed per iteration.
-template <int FT_, int RUN_, int NRUN_, int ROWS_, int C_, int MINB_ = 1>
+template <int FT_, int RUN_, int NRUN_, int ROWS_, int C_, int MINB_ = 1, bool TMEM_ = false>
 struct Tile {
   static constexpr int FT = FT_, FW = FT_ / 32, RUN = RUN_, NRUN = NRUN_, ROWS = ROWS_, C = C_, MINB = MINB_;
+  // TMEM: the ghy accumulators live in tensor memory (tcgen05.ld / tcgen05.st, 32 lanes x 32 bit: lane = thread) instead
+  // of registers; the registers they free hold a third row per iteration.
+  static constexpr bool TMEM = TMEM_;
   static constexpr int CPAD = C_ <= 8 ? 8 : 16;  // exchange slots per row (entries >= C stay 0)
   static constexpr int RUNSEGS = FT * RUN;     // segments per run
   static constexpr int SLOT = NRUN * RUNSEGS;  // padded segments per slot
-  static constexpr int POS = 32 / ROWS;        // lanes per row in the CTA-level scan
-  static_assert(ROWS == 1 || ROWS == 2, "CTA-level scan is one warp: rows x positions = 32 lanes");
-  static_assert(NRUN * FW <= POS, "too many (run, warp) positions for the one-warp CTA scan");
+  static constexpr int NPOS = NRUN * FW;       // (run, warp) positions of a row
+  static constexpr int POS = NPOS <= 8 ? 8 : (NPOS <= 16 ? 16 : 32);  // lanes per row in the CTA-level scan
+  static constexpr int RPP = 32 / POS;                                // rows per pass of that scan
+  static constexpr int PASSES = (ROWS + RPP - 1) / RPP;
+  static_assert(NPOS <= 32, "too many (run, warp) positions for the one-warp CTA scan");
   static_assert(ROWS * C <= 32 && C <= kMaxC, "carry exchange is issued by one warp");
   static_assert(RUN % 2 == 1, "odd segment count per thread: conflict-free 128-bit shared-memory accesses");
 };
@@ -96,6 +104,22 @@ __device__ __forceinline__ float rcp_ftz(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
+// ---- tensor memory as accumulator storage: 32x32b shape, thread i of warp w owns lane 32 (w % 4) + i, x4 = four
+// consecutive 32-bit columns (one float4). The loads are asynchronous: tmem_wait_ld() before the registers are read.
+__device__ __forceinline__ void tmem_ld4(float4& a, uint32_t taddr) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w)
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, float4 a) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "f"(a.x), "f"(a.y), "f"(a.z),
+               "f"(a.w));
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// ties the loaded registers to the wait that precedes it (volatile asms keep their order): no use can move above it
+__device__ __forceinline__ void tmem_loaded(float4& a) { asm volatile("" : "+f"(a.x), "+f"(a.y), "+f"(a.z), "+f"(a.w)); }
+
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
@@ -147,6 +171,7 @@ struct FusedSmem {                      // static part; the slots follow in dyna
   double red[T::FW];
   unsigned long long bar_hd, bar_td;    // mbarriers of the hd / target-dB slots (TMA complete_tx)
   unsigned long long bar_x[2];          // mbarriers of the two carry exchanges (st.async complete_tx)
+  uint32_t tmem_base;                   // tensor-memory allocation (Tile::TMEM)
 };
 
 // CTA level of a scan, done redundantly by every warp (one barrier per scan instead of two): lane = row * POS + pos
@@ -222,8 +247,27 @@ __global__ void __launch_bounds__(T::FT, T::MINB) td_fused_kernel(FusedParams p)
     mbar_init(bar_xb, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  // accumulator columns of one thread, and of the CTA: warps w and w + 4 share a lane quarter of tensor memory
+  constexpr int kAccCols = G * NRUN * kRun * 4;
+  constexpr int kTmemNeed = ((kFW + 3) / 4) * kAccCols;
+  constexpr int kTmemCols = kTmemNeed <= 32 ? 32 : (kTmemNeed <= 64 ? 64 : (kTmemNeed <= 128 ? 128 : (kTmemNeed <= 256 ? 256 : 512)));
+  static_assert(!T::TMEM || kTmemNeed <= 512, "accumulators exceed the 512 columns of tensor memory");
+  if constexpr (T::TMEM) {
+    if (warp == 0) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)),
+                   "n"(kTmemCols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic zero-fill before async-proxy (TMA) writes
   __syncthreads();
+  uint32_t tacc = 0;  // this thread's accumulator columns: lane field = bits 31..16, column = bits 15..0
+  if constexpr (T::TMEM) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    tacc = sm.tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * kAccCols);
+  }
   cluster_arrive();  // every CTA of the cluster is resident and initialised before any DSMEM store
   cluster_wait();
 
@@ -245,13 +289,20 @@ __global__ void __launch_bounds__(T::FT, T::MINB) td_fused_kernel(FusedParams p)
     }
   };
 
-  float4 acc[G][NRUN][kRun];
+  // chunk (u, k) of the accumulators = G float4 = 4 G consecutive columns when they live in tensor memory
+  auto acc_col = [&](int g, int u, int k) { return tacc + (uint32_t)(((u * kRun + k) * G + g) * 4); };
+  float4 acc[T::TMEM ? 1 : G][T::TMEM ? 1 : NRUN][T::TMEM ? 1 : kRun];
 #pragma unroll
   for (int g = 0; g < G; ++g)
 #pragma unroll
     for (int u = 0; u < NRUN; ++u)
 #pragma unroll
-      for (int k = 0; k < kRun; ++k) acc[g][u][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int k = 0; k < kRun; ++k) {
+        if constexpr (T::TMEM)
+          tmem_st4(acc_col(g, u, k), make_float4(0.f, 0.f, 0.f, 0.f));
+        else
+          acc[g][u][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
   double loss_acc = 0.0;
 
   const int64_t niter = (p.rows + kRows - 1) / kRows;
@@ -362,18 +413,29 @@ __global__ void __launch_bounds__(T::FT, T::MINB) td_fused_kernel(FusedParams p)
     if (tid == 0 && has_next && has_hd) issue(true, it + ncl);
     float offl[kRows][NRUN];  // CTA-local exclusive offsets: later (run, warp) positions of this slice
     {
-      const float v = cta_scan<kPos, true>(sm.wtot[0][lane / kPos][lane & (kPos - 1)], lane);
+      float v[T::PASSES];  // pass ps scans rows ps * RPP ..: lane = (row % RPP) * POS + position
+#pragma unroll
+      for (int ps = 0; ps < T::PASSES; ++ps) {
+        const int row = ps * T::RPP + lane / kPos;
+        const float t = sm.wtot[0][min(row, kRows - 1)][lane & (kPos - 1)];
+        v[ps] = cta_scan<kPos, true>(row < kRows ? t : 0.f, lane);
+      }
 #pragma unroll
       for (int q = 0; q < kRows; ++q)
 #pragma unroll
         for (int u = 0; u < NRUN; ++u) {
           const int pos = u * kFW + warp + 1;
-          const float t = __shfl_sync(0xffffffffu, v, q * kPos + (pos & (kPos - 1)));
+          const float t = __shfl_sync(0xffffffffu, v[q / T::RPP], (q % T::RPP) * kPos + (pos & (kPos - 1)));
           offl[q][u] = pos < kPos ? t : 0.f;
         }
       if (warp == 0) {  // lane = row * C + peer; receiver `peer` sums the slices later than its own
         const int xrow = min(lane / kC, kRows - 1);
-        const float total = __shfl_sync(0xffffffffu, v, xrow * kPos);
+        float total = 0.f;
+#pragma unroll
+        for (int ps = 0; ps < T::PASSES; ++ps) {
+          const float t = __shfl_sync(0xffffffffu, v[ps], (xrow % T::RPP) * kPos);
+          if (xrow / T::RPP == ps) total = t;
+        }
         const uint32_t peer = (uint32_t)(lane % kC);
         if (lane < kRows * kC)
           st_async_f32(smem_u32(&sm.xchg[0][parity][xrow][rank]), bar_xa, peer, rank > peer ? total : 0.f);
@@ -473,18 +535,29 @@ __global__ void __launch_bounds__(T::FT, T::MINB) td_fused_kernel(FusedParams p)
     if (tid == 0 && has_next && has_td) issue(false, it + ncl);
     float offp[kRows][NRUN];  // exclusive offsets inside the CTA: earlier (run, warp) positions + earlier lanes
     {
-      const float v = cta_scan<kPos, false>(sm.wtot[1][lane / kPos][lane & (kPos - 1)], lane);
+      float v[T::PASSES];
+#pragma unroll
+      for (int ps = 0; ps < T::PASSES; ++ps) {
+        const int row = ps * T::RPP + lane / kPos;
+        const float t = sm.wtot[1][min(row, kRows - 1)][lane & (kPos - 1)];
+        v[ps] = cta_scan<kPos, false>(row < kRows ? t : 0.f, lane);
+      }
 #pragma unroll
       for (int q = 0; q < kRows; ++q)
 #pragma unroll
         for (int u = 0; u < NRUN; ++u) {
           const int pos = u * kFW + warp - 1;
-          const float t = __shfl_sync(0xffffffffu, v, q * kPos + (pos & (kPos - 1)));
+          const float t = __shfl_sync(0xffffffffu, v[q / T::RPP], (q % T::RPP) * kPos + (pos & (kPos - 1)));
           offp[q][u] = (pos >= 0 ? t : 0.f) + inc[q][u];
         }
       if (warp == 0) {  // receiver `peer` sums the slices earlier than its own
         const int xrow = min(lane / kC, kRows - 1);
-        const float total = __shfl_sync(0xffffffffu, v, xrow * kPos + kPos - 1);
+        float total = 0.f;
+#pragma unroll
+        for (int ps = 0; ps < T::PASSES; ++ps) {
+          const float t = __shfl_sync(0xffffffffu, v[ps], (xrow % T::RPP) * kPos + kPos - 1);
+          if (xrow / T::RPP == ps) total = t;
+        }
         const uint32_t peer = (uint32_t)(lane % kC);
         if (lane < kRows * kC)
           st_async_f32(smem_u32(&sm.xchg[1][parity][xrow][rank]), bar_xb, peer, rank < peer ? total : 0.f);
@@ -520,20 +593,51 @@ __global__ void __launch_bounds__(T::FT, T::MINB) td_fused_kernel(FusedParams p)
     mbar_wait(bar_xb, parity);
 
     // ================= phase C: dL/dh = u + c h ; ghy accumulators ; dL/ds partials ============================
+    float cq[kRows];  // slices earlier than this one (senders masked their totals)
 #pragma unroll
     for (int q = 0; q < kRows; ++q) {
-      const float c = sum_slots<T::CPAD>(sm.xchg[1][parity][q]);  // slices earlier than this one (senders masked their totals)
-#pragma unroll
-      for (int u = 0; u < NRUN; ++u)
-#pragma unroll
-        for (int k = 0; k < kRun; ++k) {
-          const float4 gh = fma4(c, h[q][u][k], w[q][u][k]);
-#pragma unroll
-          for (int g = 0; g < G; ++g) acc[g][u][k] = fma4(sv[q][g], gh, acc[g][u][k]);
-        }
+      cq[q] = sum_slots<T::CPAD>(sm.xchg[1][parity][q]);
 #pragma unroll
       for (int g = 0; g < G; ++g)
-        red_s[(q * G + g) * kFT + tid] = (du[q][g].x + du[q][g].y) + c * (dv[q][g].x + dv[q][g].y);
+        red_s[(q * G + g) * kFT + tid] = (du[q][g].x + du[q][g].y) + cq[q] * (dv[q][g].x + dv[q][g].y);
+    }
+    if constexpr (T::TMEM) {
+      // accumulators through tensor memory, one chunk (u, k) of G float4 at a time, the next chunk's load in flight
+      constexpr int kChunks = NRUN * kRun;
+      float4 a[2][G];
+      tmem_wait_st();  // the stores of the previous iteration (or of the zero fill)
+#pragma unroll
+      for (int g = 0; g < G; ++g) tmem_ld4(a[0][g], acc_col(g, 0, 0));
+#pragma unroll
+      for (int ch = 0; ch < kChunks; ++ch) {
+        const int u = ch / kRun, k = ch % kRun;
+        tmem_wait_ld();
+#pragma unroll
+        for (int g = 0; g < G; ++g) tmem_loaded(a[ch & 1][g]);
+        if (ch + 1 < kChunks) {
+#pragma unroll
+          for (int g = 0; g < G; ++g) tmem_ld4(a[(ch + 1) & 1][g], acc_col(g, (ch + 1) / kRun, (ch + 1) % kRun));
+        }
+#pragma unroll
+        for (int q = 0; q < kRows; ++q) {
+          const float4 gh = fma4(cq[q], h[q][u][k], w[q][u][k]);
+#pragma unroll
+          for (int g = 0; g < G; ++g) a[ch & 1][g] = fma4(sv[q][g], gh, a[ch & 1][g]);
+        }
+#pragma unroll
+        for (int g = 0; g < G; ++g) tmem_st4(acc_col(g, u, k), a[ch & 1][g]);
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < kRows; ++q)
+#pragma unroll
+        for (int u = 0; u < NRUN; ++u)
+#pragma unroll
+          for (int k = 0; k < kRun; ++k) {
+            const float4 gh = fma4(cq[q], h[q][u][k], w[q][u][k]);
+#pragma unroll
+            for (int g = 0; g < G; ++g) acc[g][u][k] = fma4(sv[q][g], gh, acc[g][u][k]);
+          }
     }
     it_prev = it;
   }
@@ -549,8 +653,16 @@ __global__ void __launch_bounds__(T::FT, T::MINB) td_fused_kernel(FusedParams p)
 #pragma unroll
         for (int k = 0; k < kRun; ++k) {
           const int idx = u * kRunSegs + tid * kRun + k;
-          if (idx < len4)
-            reinterpret_cast<float4*>(p.part_ghy)[((int64_t)cid * G + g) * tn4 + seg0 + idx] = acc[g][u][k];
+          float4 v;
+          if constexpr (T::TMEM) {  // (warp-uniform code path: tcgen05.ld is warp collective)
+            tmem_wait_st();
+            tmem_ld4(v, acc_col(g, u, k));
+            tmem_wait_ld();
+            tmem_loaded(v);
+          } else {
+            v = acc[g][u][k];
+          }
+          if (idx < len4) reinterpret_cast<float4*>(p.part_ghy)[((int64_t)cid * G + g) * tn4 + seg0 + idx] = v;
         }
   }
   {
@@ -562,6 +674,12 @@ __global__ void __launch_bounds__(T::FT, T::MINB) td_fused_kernel(FusedParams p)
       for (int i = 0; i < T::FW; ++i) t += sm.red[i];
       p.part_loss[blockIdx.x] = t;
     }
+  }
+  if constexpr (T::TMEM) {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();  // every warp has read its accumulators back
+    if (warp == 0)
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(sm.tmem_base), "n"(kTmemCols) : "memory");
   }
   cluster_arrive();  // no CTA may exit while a peer can still store into its shared memory
   cluster_wait();
@@ -609,7 +727,10 @@ using TileA2 = Tile<256, 3, 2, 2, 8>;  // 1: two runs per thread, rows up to 49 
 using TileD = Tile<384, 3, 2, 1, 6>;   // 2: clusters of 6 (22 resident clusters = 132 SMs), rows up to 55 296 samples
 // Also tried (same file, same run): clusters of 16 with two 128-register CTAs per SM (Tile<256,3,1,2,16,2>: 14 resident
 // clusters, 1.71 ms) and clusters of 8 with one row per iteration at 128 registers (2.70 ms).
-constexpr int kNumVariants = 3;
+// 3: ghy accumulators in tensor memory, three rows per iteration (the two barriers + two DSMEM exchanges amortise over 3 rows)
+using TileT3 = Tile<256, 3, 2, 3, 8, 1, true>;
+using TileT2 = Tile<256, 3, 2, 2, 8, 1, true>;  // 4: tensor-memory accumulators at two rows per iteration (A/B of the storage alone)
+constexpr int kNumVariants = 5;
 
 struct VariantInfo {
   int c, slot, ft, rows;
@@ -618,12 +739,22 @@ template <class T>
 constexpr VariantInfo info_of() {
   return VariantInfo{T::C, T::SLOT, T::FT, T::ROWS};
 }
-constexpr VariantInfo kVariants[kNumVariants] = {info_of<TileA1>(), info_of<TileA2>(), info_of<TileD>()};
-constexpr int kOrder[kNumVariants] = {0, 1, 2};
+constexpr VariantInfo kVariants[kNumVariants] = {info_of<TileA1>(), info_of<TileA2>(), info_of<TileD>(), info_of<TileT3>(),
+                                                 info_of<TileT2>()};
+// preference order: short rows, then three rows per iteration with tensor-memory accumulators (1.35 ms at the BASELINE
+// shard vs 1.46 ms for two rows with register accumulators; G = 4 or a mask slot exceed its shared memory), ...
+constexpr int kOrder[kNumVariants] = {0, 3, 1, 2, 4};
 
-bool variant_fits(int v, int64_t tn4) {
+// dynamic shared memory of variant v (what fused_dyn_smem<T> returns for its tile)
+size_t variant_smem(int v, int g, bool masked) {
+  const VariantInfo& t = kVariants[v];
+  return (size_t)t.slot * sizeof(float4) * (2 * t.rows + g + (masked ? 1 : 0)) + (size_t)t.rows * g * t.ft * sizeof(float);
+}
+constexpr size_t kSmemBudget = 227 * 1024 - 1024;  // opt-in maximum per CTA minus the static part (FusedSmem < 1 KB)
+
+bool variant_fits(int v, int64_t tn4, int g, bool masked) {
   const int64_t slice4 = (tn4 + kVariants[v].c - 1) / kVariants[v].c;
-  return slice4 <= kVariants[v].slot;
+  return slice4 <= kVariants[v].slot && variant_smem(v, g, masked) <= kSmemBudget;
 }
 
 struct FusedShape {
@@ -631,16 +762,16 @@ struct FusedShape {
   int slice4;
 };
 // The fused kernel needs tn % 4 == 0 and a row that fits the slices of one variant (tn <= 6 * 2304 * 4 = 55296).
-bool fused_shape(int g, int64_t tn, FusedShape* out) {
+bool fused_shape(int g, int64_t tn, bool masked, FusedShape* out) {
   if (g < 1 || g > 4 || tn < 4 || tn % 4 != 0) return false;
   const int64_t tn4 = tn / 4;
   int v = -1;
   if (const char* e = getenv("DGFDN_TD_VARIANT")) {
     const int want = atoi(e);
-    if (want >= 0 && want < kNumVariants && variant_fits(want, tn4)) v = want;
+    if (want >= 0 && want < kNumVariants && variant_fits(want, tn4, g, masked)) v = want;
   }
   for (int i = 0; v < 0 && i < kNumVariants; ++i)
-    if (variant_fits(kOrder[i], tn4)) v = kOrder[i];
+    if (variant_fits(kOrder[i], tn4, g, masked)) v = kOrder[i];
   if (v < 0) return false;
   if (out) {
     out->variant = v;
@@ -743,6 +874,8 @@ int by_variant(int variant, int op, const FusedParams& p, int64_t rows, cudaStre
     DGFDN_TD_CASE(0, TileA1)
     DGFDN_TD_CASE(1, TileA2)
     DGFDN_TD_CASE(2, TileD)
+    DGFDN_TD_CASE(3, TileT3)
+    DGFDN_TD_CASE(4, TileT2)
   }
 #undef DGFDN_TD_CASE
   return 1;
@@ -772,7 +905,7 @@ static bool use_sliced(int g, int64_t tn, SlicedShape* shp) {
   SlicedShape tmp;
   if (!shp) shp = &tmp;
   const bool ok_s = sliced_shape(g, tn, shp);
-  const bool ok_c = fused_shape(g, tn, nullptr);
+  const bool ok_c = fused_shape(g, tn, false, nullptr);
   if (const char* e = getenv("DGFDN_TD_KERNEL")) {
     if (e[0] == 'c' && ok_c) return false;
     if (e[0] == 's' && ok_s) return true;
@@ -781,7 +914,7 @@ static bool use_sliced(int g, int64_t tn, SlicedShape* shp) {
 }
 
 extern "C" int dgfdn_td_edc_fused_supported(int g, int64_t tn) {
-  return (fused_shape(g, tn, nullptr) || sliced_shape(g, tn, nullptr)) ? 1 : 0;
+  return (fused_shape(g, tn, false, nullptr) || sliced_shape(g, tn, nullptr)) ? 1 : 0;
 }
 
 extern "C" int64_t dgfdn_td_edc_fused_ws_bytes(int g, int64_t rows, int64_t tn) {
@@ -807,7 +940,7 @@ extern "C" int dgfdn_td_edc_fused_info(int g, int64_t tn, int* variant, int* clu
     return 0;
   }
   FusedShape shp;
-  if (!fused_shape(g, tn, &shp)) {
+  if (!fused_shape(g, tn, false, &shp)) {
     if (variant) *variant = -1;
     return 0;
   }
@@ -827,7 +960,7 @@ extern "C" int dgfdn_td_edc_fused(int g, int64_t rows, int64_t tn, const float* 
   DGFDN_CHECK(rows >= 0 && tn >= 1 && s && hy && target_db && ghy && ws, "td_edc_fused: bad arguments");
   const bool sliced = use_sliced(g, tn, nullptr);
   FusedShape shp;
-  DGFDN_CHECK(sliced || fused_shape(g, tn, &shp),
+  DGFDN_CHECK(sliced || fused_shape(g, tn, mask != nullptr, &shp),
               "td_edc_fused: unsupported shape (g=%d in [1,4], tn=%lld multiple of 4 and <= 94720)", g, (long long)tn);
   DGFDN_CHECK(ldt >= tn && (hd == nullptr || ldhd >= tn), "td_edc_fused: row stride smaller than tn");
   DGFDN_CHECK(aligned16(hy) && aligned16(hd) && aligned16(target_db) && aligned16(mask) && aligned16(ghy) && ldt % 4 == 0 &&

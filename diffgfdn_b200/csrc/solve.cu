@@ -679,14 +679,45 @@ __global__ void __launch_bounds__(kWarps * 32, 3) solve_colorless_kernel(SolvePa
   if (sl == 0) loss_part[gi.sgid] = loss_acc;
 }
 
-// loss[q] = (1/K) sum over the lane groups that served system type q (fixed order)
+// loss[q] = (1/K) sum over the lane groups that served system type q (fixed order); one block of 256 threads per q
 __global__ void colorless_loss_reduce_kernel(const double* part, int64_t ngroups, int nsys, int64_t k, double* loss) {
+  __shared__ double red[8];
   const int q = blockIdx.x;
-  const int lane = threadIdx.x;
+  const int t = threadIdx.x;
   double s = 0.0;
-  for (int64_t sg = q + (int64_t)lane * nsys; sg < ngroups; sg += 32 * (int64_t)nsys) s += part[sg];
+  for (int64_t sg = q + (int64_t)t * nsys; sg < ngroups; sg += (int64_t)blockDim.x * nsys) s += part[sg];
   s = warp_sum(s);
-  if (lane == 0) loss[q] = s / (double)k;
+  if ((t & 31) == 0) red[t >> 5] = s;
+  __syncthreads();
+  if (t == 0) {
+    double v = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) v += red[i];
+    loss[q] = v / (double)k;
+  }
+}
+
+// First stage of the gradient reduction for large grids: block (q, c) adds the rows of chunk c among the lane groups
+// that served system type q (rows q, q + nsys, ...), thread i the elements i, i + blockDim, ... of a row (coalesced).
+// out row c * nsys + q, so that solve_bwd_reduce_kernel finishes on `chunks * nsys` rows with the same row -> q rule.
+constexpr int kReduceChunks = 64;
+__global__ void solve_bwd_prereduce_kernel(const double* __restrict__ ws, int64_t ngroups, int per, int nsys,
+                                           double* __restrict__ out) {
+  const int q = blockIdx.x, c = blockIdx.y;
+  const int64_t rows_q = (ngroups - q + nsys - 1) / nsys;  // rows of this system type
+  const int64_t chunk = (rows_q + kReduceChunks - 1) / kReduceChunks;
+  const int64_t r0 = (int64_t)c * chunk, r1 = r0 + chunk < rows_q ? r0 + chunk : rows_q;
+  const int i = blockIdx.z * blockDim.x + threadIdx.x;
+  if (i >= per) return;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;  // four loads in flight; the order of the sum stays fixed
+  int64_t r = r0;
+  for (; r + 4 <= r1; r += 4) {
+    s0 += ws[(size_t)(q + r * nsys) * per + i];
+    s1 += ws[(size_t)(q + (r + 1) * nsys) * per + i];
+    s2 += ws[(size_t)(q + (r + 2) * nsys) * per + i];
+    s3 += ws[(size_t)(q + (r + 3) * nsys) * per + i];
+  }
+  for (; r < r1; ++r) s0 += ws[(size_t)(q + r * nsys) * per + i];
+  out[(size_t)(c * nsys + q) * per + i] = (s0 + s1) + (s2 + s3);
 }
 
 // One warp per output element: lanes stride over the partial rows of the lane groups that served system type q
@@ -722,9 +753,23 @@ __global__ void solve_bwd_reduce_kernel(const double* ws, int64_t ngroups, int n
   }
 }
 
+// Reduction of `groups` partial rows of (n^2 + 3 n) doubles per system type: directly for small grids, through the
+// chunked first stage (scratch `pre`, kReduceChunks * nsys rows) for large ones.
+void launch_bwd_reduce(const double* ws, double* pre, int64_t groups, int n, int nsys, int transpose_a, double* ga,
+                       double* gb, double* gc, double* gig, cudaStream_t st) {
+  const int per = n * n + 3 * n;
+  const double* rows = ws;
+  if (groups > 4 * (int64_t)kReduceChunks * nsys) {
+    solve_bwd_prereduce_kernel<<<dim3(nsys, kReduceChunks, (per + 127) / 128), 128, 0, st>>>(ws, groups, per, nsys, pre);
+    rows = pre;
+    groups = (int64_t)kReduceChunks * nsys;
+  }
+  solve_bwd_reduce_kernel<<<(per * nsys * 32 + 255) / 256, 256, 0, st>>>(rows, groups, n, nsys, transpose_a, ga, gb, gc, gig);
+}
+
 constexpr int lanes_for(int np) { return np <= 4 ? 4 : (np <= 8 ? 8 : (np <= 16 ? 16 : 32)); }
 
-constexpr int kMaxBlocksPerSm = 8;  // the backward workspace is sized for this many resident blocks per SM
+constexpr int kMaxBlocksPerSm = 12;  // the backward workspace is sized for this many blocks per SM in a grid
 
 // One resident wave: `per_sm` is the occupancy of the instantiation being launched (a grid of 4 blocks per SM with
 // only 3 resident leaves a 148-block second wave that runs at a third of the SM's throughput).
@@ -892,6 +937,8 @@ int fill_params(SolveParams& p, int n, int nsys, int g, int64_t k, const void* z
 
 using namespace dgfdn;
 
+static int64_t bwd_rows_bytes(int n);
+
 static int solve_fwd_impl(int n, int nsys, int g, int64_t k, const void* z, const int32_t* delays, const float* a,
                           int transpose_a, const float* gamma, const void* gamma_z, const float* b, const float* c,
                           void* x, void* y, void* factors, void* stream) {
@@ -925,10 +972,9 @@ static int solve_bwd_impl(int n, int nsys, int g, int64_t k, const void* z, cons
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   bind_factors(p, const_cast<void*>(factors), n, nsys, k);
   if (factors != nullptr ? dispatch_bwd_replay(p, &blocks, st) : dispatch_bwd(p, &blocks, st)) return 1;
-  const int per = (n * n + 3 * n) * nsys;
   const int64_t groups = (int64_t)blocks * kWarps * (32 / w);  // lane groups of the grid that was launched
-  solve_bwd_reduce_kernel<<<(per * 32 + 255) / 256, 256, 0, st>>>(p.ws, groups, n, nsys, transpose_a, ga, gb, gc,
-                                                                 ginvgamma);
+  launch_bwd_reduce(p.ws, reinterpret_cast<double*>(static_cast<unsigned char*>(ws) + bwd_rows_bytes(n)), groups, n, nsys,
+                    transpose_a, ga, gb, gc, ginvgamma, st);
   DGFDN_LAUNCH_CHECK();
   return 0;
 }
@@ -949,18 +995,27 @@ extern "C" int64_t dgfdn_solve_groups_factors_bytes(int l, int g, int64_t k) {
 }
 
 // one row of (n^2 + 3n) doubles per lane group of the largest grid the backward kernel launches
-static int64_t bwd_ws_bytes(int n) {
-  if (n < 1 || n > DGFDN_MAX_LINES) return 0;
+static int64_t bwd_rows_bytes(int n) {
   const int64_t groups = (int64_t)sm_count() * kMaxBlocksPerSm * kWarps * (32 / lanes_runtime(n));
   return groups * ((int64_t)n * n + 3 * (int64_t)n) * (int64_t)sizeof(double);
 }
+// ... followed by the rows of the first reduction stage (kReduceChunks per system type)
+static int64_t bwd_ws_bytes(int n) {
+  if (n < 1 || n > DGFDN_MAX_LINES) return 0;
+  return bwd_rows_bytes(n) + (int64_t)kReduceChunks * DGFDN_MAX_GROUPS * ((int64_t)n * n + 3 * (int64_t)n) * (int64_t)sizeof(double);
+}
 
 template <int NP>
-int launch_colorless(const SolveParams& p, int asym, double* loss_part, int* blocks_out, cudaStream_t st) {
+int launch_colorless(const SolveParams& p, int asym, double* loss_part, int max_sms, int* blocks_out, cudaStream_t st) {
   constexpr int W = lanes_for(NP);
   const size_t smem = smem_bytes<NP>(p, true);
   DGFDN_CUDA(cudaFuncSetAttribute(solve_colorless_kernel<NP, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int blocks = grid_blocks(p.k * p.nsys, W, blocks_per_sm(solve_colorless_kernel<NP, W>, smem));
+  // max_sms > 0: a grid of at most max_sms resident waves' worth of blocks. The fused step runs K1c in the shadow of the
+  // receiver kernel on the SMs its clusters cannot use; a grid sized for the whole chip would leave blocks waiting that
+  // flood the SMs the receiver kernel frees and hold back the adjoint chain behind them.
+  const int bpsm = blocks_per_sm(solve_colorless_kernel<NP, W>, smem);
+  int blocks = grid_blocks(p.k * p.nsys, W, bpsm);
+  if (max_sms > 0 && blocks > max_sms * bpsm) blocks = max_sms * bpsm;
   *blocks_out = blocks;
   solve_colorless_kernel<NP, W><<<blocks, kWarps * 32, smem, st>>>(p, asym, loss_part);
   DGFDN_LAUNCH_CHECK();
@@ -975,8 +1030,8 @@ extern "C" int64_t dgfdn_solve_colorless_ws_bytes(int l) {
 }
 
 extern "C" int dgfdn_solve_colorless(int l, int g, int64_t k, const void* z, const int32_t* delays, const float* m_raw,
-                                     const float* gamma, const float* b, const float* c, int asym, double* loss,
-                                     double* gm, double* gb, double* gc, void* ws, void* stream) {
+                                     const float* gamma, const float* b, const float* c, int asym, int max_sms,
+                                     double* loss, double* gm, double* gb, double* gc, void* ws, void* stream) {
   if (check_common(l, g, g, k)) return 1;
   DGFDN_CHECK(z && delays && m_raw && b && c && loss && gm && gb && gc && ws, "solve_colorless: null pointer");
   SolveParams p{};
@@ -988,10 +1043,10 @@ extern "C" int dgfdn_solve_colorless(int l, int g, int64_t k, const void* z, con
   const int np = (l + 3) & ~3;
   int rc = 1;
   switch (np) {
-    case 4: rc = launch_colorless<4>(p, asym, loss_part, &blocks, st); break;
-    case 8: rc = launch_colorless<8>(p, asym, loss_part, &blocks, st); break;
-    case 12: rc = launch_colorless<12>(p, asym, loss_part, &blocks, st); break;
-    case 16: rc = launch_colorless<16>(p, asym, loss_part, &blocks, st); break;
+    case 4: rc = launch_colorless<4>(p, asym, loss_part, max_sms, &blocks, st); break;
+    case 8: rc = launch_colorless<8>(p, asym, loss_part, max_sms, &blocks, st); break;
+    case 12: rc = launch_colorless<12>(p, asym, loss_part, max_sms, &blocks, st); break;
+    case 16: rc = launch_colorless<16>(p, asym, loss_part, max_sms, &blocks, st); break;
     default:
       set_error("solve_colorless: at most 16 lines per group (got %d)", l);
       return 1;
@@ -999,10 +1054,10 @@ extern "C" int dgfdn_solve_colorless(int l, int g, int64_t k, const void* z, con
   if (rc) return rc;
   const int w = lanes_runtime(l);
   const int64_t groups = (int64_t)blocks * kWarps * (32 / w);
-  const int per = (l * l + 3 * l) * g;
-  solve_bwd_reduce_kernel<<<(per * 32 + 255) / 256, 256, 0, st>>>(p.ws, groups, l, g, 0, gm, gb, gc, nullptr);
+  launch_bwd_reduce(p.ws, reinterpret_cast<double*>(static_cast<unsigned char*>(ws) + bwd_rows_bytes(l)), groups, l, g, 0,
+                    gm, gb, gc, nullptr, st);
   DGFDN_LAUNCH_CHECK();
-  colorless_loss_reduce_kernel<<<g, 32, 0, st>>>(loss_part, groups, g, k, loss);
+  colorless_loss_reduce_kernel<<<g, 256, 0, st>>>(loss_part, groups, g, k, loss);
   DGFDN_LAUNCH_CHECK();
   return 0;
 }

@@ -97,11 +97,34 @@ class ShardedEDCStep:
         self.use_side_stream = os.environ.get("DGFDN_SIDE_STREAM", "1") != "0"
         self.use_fused_colorless = os.environ.get("DGFDN_FUSED_COLORLESS", "1") != "0"
         self._side = None
+        self._side2 = None
 
     def _side_stream(self) -> torch.cuda.Stream:
         if self._side is None:
-            self._side = torch.cuda.Stream(device=self.dev)
+            # between the main chain (captured at the highest priority) and the colorless branch: the position network's
+            # backward has a big grid that would otherwise sit in front of the first kernels of the adjoint chain
+            self._side = torch.cuda.Stream(device=self.dev, priority=-1)
         return self._side
+
+    def _colorless_sms(self, bins: int) -> int:
+        """Grid bound of K1c: the SMs the receiver kernel leaves idle when the branch can finish in that kernel's shadow
+        (estimates from the measured rates: K1c 0.27 ms on 148 SMs for 131 073 bins x 3 groups of 8 lines; receiver
+        kernel 3.4 TB/s of its 8 B per receiver.sample), else 0 = the whole device."""
+        if not self._shadow_sms:
+            return 0
+        net = self.net
+        sms = torch.cuda.get_device_properties(self.dev).multi_processor_count
+        work = bins * net.num_groups * net.num_delay_lines_per_group**3 / (131073 * 3 * 512)
+        t_k1c = 0.27e-3 * work * sms / self._shadow_sms
+        t_rx = self.rows * self.tn * 8 / 3.4e12
+        return self._shadow_sms if t_k1c <= 1.15 * t_rx else 0
+
+    def _colorless_stream(self) -> torch.cuda.Stream:
+        """The colorless branch has its own stream: on the position network's stream its 1.4 ms in the shadow of the
+        receiver kernel would hold back that network's backward, which only waits for dL/ds."""
+        if self._side2 is None:
+            self._side2 = torch.cuda.Stream(device=self.dev, priority=0)  # lowest: it only fills what the main chain leaves
+        return self._side2
 
     # ---- data ------------------------------------------------------------------------------------------
     def attach(self, z: torch.Tensor, positions: torch.Tensor, early_window: Optional[torch.Tensor],
@@ -127,7 +150,15 @@ class ShardedEDCStep:
         dev = self.dev
         # K3d (cluster-fused kernel, no dL/dh in memory) when the shape allows it; DGFDN_TD_FUSED=0 forces K3c
         self.use_fused = ops.td_fused_supported(g, self.tn) and os.environ.get("DGFDN_TD_FUSED", "1") != "0"
+        # SMs the receiver kernel's clusters cannot use (15 clusters of 8 CTAs on 148 SMs leave 28): the colorless branch
+        # runs there with a grid bounded to them, so none of its blocks is left waiting for the SMs that kernel frees
+        self._shadow_sms = 0
         if self.use_fused:
+            info = ops.td_fused_info(g, self.tn)
+            sms = torch.cuda.get_device_properties(dev).multi_processor_count
+            idle = sms - info["clusters"] * info["cluster_size"]
+            if info["cluster_size"] > 1 and idle >= 16:
+                self._shadow_sms = idle
             self._bufs = dict(fws=ops.td_fused_workspace(g, self.rows, self.tn, dev),
                               loss_sum=torch.zeros(1, dtype=torch.float64, device=dev))
         else:
@@ -182,6 +213,7 @@ class ShardedEDCStep:
             sec[0].record()
         main = torch.cuda.current_stream()
         side = self._side_stream() if self.use_side_stream else main
+        side2 = self._colorless_stream() if self.use_side_stream else main
         start = torch.cuda.Event()
         start.record(main)
         # irfft(X, n=K) reads bins 0..K/2 only (reference losses.py:207-213, quirk Q3), so the coupled system is
@@ -209,7 +241,6 @@ class ShardedEDCStep:
             s = net.output_scalars.gains({'norm_listener_position': self.positions})
             s_ready = torch.cuda.Event()
             s_ready.record(side)
-            sparsity = self.w_spars * self._sparsity(net.feedback_loop.ortho_param(net.feedback_loop.M[g - 1]))
         main.wait_event(s_ready)
         s_d = s.detach().contiguous()
         hy_d = hy.detach().contiguous()
@@ -243,8 +274,9 @@ class ShardedEDCStep:
         # is enqueued on the side stream AFTER the receiver kernel, gated only on what precedes that kernel: K3d's
         # 15 clusters of 8 CTAs take their 120 SMs first and K1c runs on the 28 SMs they cannot use (0.29 ms of work
         # for the whole chip = 1.5 ms on 28 SMs, the length of K3d), instead of competing with the coupled solve.
-        side.wait_event(pre_rx)
-        with torch.cuda.stream(side):
+        side2.wait_event(pre_rx)
+        with torch.cuda.stream(side2):
+            sparsity = self.w_spars * self._sparsity(net.feedback_loop.ortho_param(net.feedback_loop.M[g - 1]))
             zc, share = self.z, 1.0 / self.world_size
             if self.shard_bins:  # mean over ALL bins = sum over ranks of (bins of the rank / K) x mean over its bins
                 lo_c, hi_c = self._bin_slice(self.k)
@@ -252,7 +284,8 @@ class ShardedEDCStep:
             if self.use_fused_colorless and net.num_delay_lines_per_group <= 16:
                 # K1c: solve, loss, dL/dy and the adjoint in one pass per bin (no H_sub, no second elimination)
                 per_group = ops.colorless_solve_loss(zc, net.delays.to(torch.int32), net.feedback_loop.M,
-                                                     net.input_gains.reshape(-1), net.output_gains.reshape(-1), self.asym)
+                                                     net.input_gains.reshape(-1), net.output_gains.reshape(-1), self.asym,
+                                                     max_sms=self._colorless_sms(zc.numel()) if host_d is None else 0)
             else:
                 keep = net.return_per_delay_outputs
                 net.return_per_delay_outputs = False
@@ -269,9 +302,10 @@ class ShardedEDCStep:
         # two calls: the EDC branch first, so that its nodes are enqueued (and captured) ahead of the colorless tail --
         # the branches share nothing but leaf parameters
         torch.autograd.backward([hy, s], [ghy, gs])
-        with torch.cuda.stream(side):
+        with torch.cuda.stream(side2):
             torch.autograd.backward([aux], [torch.ones_like(aux)])
         main.wait_stream(side)  # the engine joins the streams of the leaves; this makes the join explicit for capture
+        main.wait_stream(side2)
         # chirp-z adjoint, coupled adjoint solve (+ reduce), assembly bwd, 2 x skew-expm bwd, position network bwd
         # (+ reduce); the separate colorless path adds its adjoint solve (+ reduce) and the loss backward
         self.kernel_launches += 3 + 2 + 1 + 2 + 2 + (0 if fused_cl else 3)
@@ -297,7 +331,10 @@ class ShardedEDCStep:
         if self.target_db is None:
             raise RuntimeError("capture: attach() resident inputs first")
         self.events = None
-        side = torch.cuda.Stream(device=self.dev)
+        # the captured main chain runs at high stream priority (kernel nodes keep the priority of the stream they were
+        # captured on): when the receiver kernel frees its SMs, the adjoint chain is placed ahead of the waiting blocks of
+        # the low-priority colorless branch
+        side = torch.cuda.Stream(device=self.dev, priority=-3)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(max(1, warmup)):

@@ -841,7 +841,7 @@ class _ColorlessSolve(torch.autograd.Function):
     colorless_fdn/losses.py:20-73, trainer.py:298-303)."""
 
     @staticmethod
-    def forward(ctx, z, delays, m, b, c, asym):
+    def forward(ctx, z, delays, m, b, c, asym, max_sms=0):
         z = _cuda("z", z, C128)
         delays = _cuda("delays", delays, torch.int32)
         m_ = _cuda("M", m, torch.float32)
@@ -858,7 +858,7 @@ class _ColorlessSolve(torch.autograd.Function):
         with torch.cuda.device(dev):
             ws = torch.empty(_lib.load().dgfdn_solve_colorless_ws_bytes(l) // 8, dtype=torch.float64, device=dev)
             _lib.call("dgfdn_solve_colorless", l, g, k, _ptr(z), _ptr(delays), _ptr(m_), None, _ptr(b_), _ptr(c_),
-                      int(asym), _ptr(loss), _ptr(gm), _ptr(gb), _ptr(gc), _ptr(ws), _stream())
+                      int(asym), int(max_sms), _ptr(loss), _ptr(gm), _ptr(gb), _ptr(gc), _ptr(ws), _stream())
         ctx.save_for_backward(gm.reshape(g, l, l), gb.reshape(g, l), gc.reshape(g, l))
         ctx.shapes = (b.shape, c.shape)
         return loss
@@ -871,13 +871,14 @@ class _ColorlessSolve(torch.autograd.Function):
         g_m = (gm * gl.view(-1, 1, 1)).to(torch.float32) if ctx.needs_input_grad[2] else None
         g_b = (gb * gl.view(-1, 1)).to(torch.float32).reshape(bshape) if ctx.needs_input_grad[3] else None
         g_c = (gc * gl.view(-1, 1)).to(torch.float32).reshape(cshape) if ctx.needs_input_grad[4] else None
-        return None, None, g_m, g_b, g_c, None
+        return None, None, g_m, g_b, g_c, None, None
 
 
 def colorless_solve_loss(z: torch.Tensor, delays: torch.Tensor, m: torch.Tensor, b: torch.Tensor, c: torch.Tensor,
-                         asym: bool) -> torch.Tensor:
-    """Per-group colorless loss (G,) float64 of the lossless sub-FDNs, differentiable w.r.t. m (G,L,L), b, c."""
-    return _ColorlessSolve.apply(z, delays, m, b, c, bool(asym))
+                         asym: bool, max_sms: int = 0) -> torch.Tensor:
+    """Per-group colorless loss (G,) float64 of the lossless sub-FDNs, differentiable w.r.t. m (G,L,L), b, c.
+    max_sms > 0 bounds the grid to that many SMs' worth of resident blocks (see dgfdn_solve_colorless)."""
+    return _ColorlessSolve.apply(z, delays, m, b, c, bool(asym), int(max_sms))
 
 
 def colorless_loss_per_group(h_sub: torch.Tensor, asym: bool) -> torch.Tensor:

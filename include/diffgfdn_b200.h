@@ -120,11 +120,13 @@ DGFDN_API int dgfdn_solve_groups_bwd(int l, int g, int64_t k, const void* z, con
  * model.py:209-252, and mse_loss / amse_loss, colorless_fdn/losses.py:20-73):
  *   loss[g] = mean_k (|y[k,g]| - 1)^p,  y[k,g] = c_g^T (diag(z_k^{m_g} / gamma_g) - M_g)^{-1} b_g,  p = 4 where asym and
  *   |y| - 1 > 1, else 2 -- together with dloss[g]/dM_g, /db, /dc (float64: gm [G,L,L], gb, gc [G*L]), the adjoint solved with
- * the elimination still in registers. L <= 16. ws: dgfdn_solve_colorless_ws_bytes(l) bytes. */
+ * the elimination still in registers. L <= 16. ws: dgfdn_solve_colorless_ws_bytes(l) bytes.
+ * max_sms: 0 = a grid for the whole device; > 0 = at most that many SMs' worth of resident blocks (the fused step runs this
+ * kernel next to the receiver kernel, on the SMs its thread-block clusters leave idle). */
 DGFDN_API int64_t dgfdn_solve_colorless_ws_bytes(int l);
 DGFDN_API int dgfdn_solve_colorless(int l, int g, int64_t k, const void* z, const int32_t* delays, const float* m_raw,
-                          const float* gamma, const float* b, const float* c, int asym, double* loss, double* gm,
-                          double* gb, double* gc, void* ws, void* stream);
+                          const float* gamma, const float* b, const float* c, int asym, int max_sms, double* loss,
+                          double* gm, double* gb, double* gc, void* ws, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K2: receiver projection.  Replaces the (B,N,K) expansion + einsums of model.py:583-619.

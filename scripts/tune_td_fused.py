@@ -28,7 +28,7 @@ def main():
     ref = ops.td_edc_abs_db_sum(s_o, hy_o, hd[:n_ref], tdb[:n_ref], None, tile_rows=32)
     ref.backward()
     out = {}
-    for v in range(7):
+    for v in range(12):
         os.environ["DGFDN_TD_VARIANT"] = str(v)
         info = ops.td_fused_info(g, tn)
         if info["variant"] != v:
