@@ -5,6 +5,7 @@ parameter pre-processing (matrix exponential, Givens rotations, Kronecker mask) 
 the device, differentiable for free; the O(K N^3) part -- the reference's `torch.linalg.inv` over K dense matrices
 (feedback_loop.py:391) -- is the sm_100a kernel behind `ops.gfdn_solve`."""
 import os
+import warnings
 from typing import List, Optional
 
 import numpy as np
@@ -132,7 +133,13 @@ class FeedbackLoop(nn.Module):
                 t60 = torch.as_tensor(np.asarray(common_decay_times).squeeze(), dtype=torch.float32)
             self.common_decay_times = nn.Parameter(t60.to(self.device))
             per = self.num_delay_lines_per_group
-            # computed once at construction like the reference (quirk Q9: never refreshed)
+            # computed once at construction like the reference (quirk Q9: never refreshed). The reference keeps the graph
+            # of this one-off computation alive (loss.backward(retain_graph=learn_common_decay_times)), so ITS optimizer
+            # moves `common_decay_times` although no forward pass ever reads the new value; here the gains are detached:
+            # identical outputs, but the parameter (and the checkpoint entry of that name) stays at its initial value.
+            warnings.warn("FeedbackLoop: common_decay_times is a parameter without effect -- the delay-line gains are "
+                          "computed once at construction (as in the reference) and detached; it receives no gradient",
+                          stacklevel=2)
             self.delay_line_gains = torch.cat([
                 decay_times_to_gain_per_sample(self.common_decay_times[i], self.delays[i * per:(i + 1) * per],
                                                torch.tensor(self.sample_rate)) for i in range(self.num_groups)

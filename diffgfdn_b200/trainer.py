@@ -116,11 +116,7 @@ class Trainer:
             amps = data['target_common_slope_amps']
             all_losses = {'edc_loss': self.loss_weights[0] * self.criterion[0](H, amps)}
         else:
-            target = data['target_rir_response']
-            if not target.is_cuda:
-                target = target.to(self.device, non_blocking=True)
-            if target.dtype != torch.complex64:
-                target = self._as_c64(target)
+            target = self._device_c64(data['target_rir_response'])
             edr_val = self.loss_weights[0] * self.criterion[0](target, H)
             edc_val = self.loss_weights[1] * self.criterion[1](target, H)
             all_losses = {'edc_loss': edc_val, 'edr_loss': edr_val}
@@ -136,14 +132,18 @@ class Trainer:
             all_losses.update({'spectral_loss': spectral, 'sparsity_loss': sparsity})
         return all_losses
 
-    def _as_c64(self, t: torch.Tensor) -> torch.Tensor:
-        """complex128 dataset tensors are converted once and remembered (targets are constant over training)."""
+    def _device_c64(self, t: torch.Tensor) -> torch.Tensor:
+        """Targets as complex64 device tensors, moved / converted once per SOURCE tensor (host or complex128 dataset
+        fields are constant over training): the loss callables key their target-EDC / EDR caches on the tensor they are
+        handed, so a fresh `.to(device)` copy per step would miss them every time and pile up stale entries."""
+        if t.is_cuda and t.dtype == torch.complex64:
+            return t
         cache = self.__dict__.get("_c64_cache")
         if cache is None:
             cache = self.__dict__["_c64_cache"] = TensorKeyedCache(max_entries=2)
         out = cache.get(t)
         if out is None:
-            out = cache.put(t, t.to(torch.complex64))
+            out = cache.put(t, t.to(device=self.device, dtype=torch.complex64))
         return out
 
     @torch.no_grad()
