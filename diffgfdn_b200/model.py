@@ -287,9 +287,6 @@ class DiffGFDNVarSourceReceiverPos(DiffGFDN):
                          use_colorless_loss)
         self.use_svf_in_output = output_filter_config.use_svfs
         self.use_svf_in_input = input_filter_config.use_svfs
-        if self.use_svf_in_input:
-            raise NotImplementedError("SVF cascades on the SOURCE side of DiffGFDNVarSourceReceiverPos: no shipped "
-                                      "config enables them (the multi-source YAML uses gains on both sides)")
         if self.use_svf_in_output:
             self.output_filters = SVF_from_MLP(self.sample_rate, self.num_groups, self.num_delay_lines_per_group,
                                                output_filter_config.num_fourier_features,
@@ -305,23 +302,43 @@ class DiffGFDNVarSourceReceiverPos(DiffGFDN):
                                                  output_filter_config.num_neurons_per_layer,
                                                  output_filter_config.encoding_type, position_type="output_gains",
                                                  device=self.device).to(self.device)
-        self.input_scalars = Gains_from_MLP(self.num_groups, self.num_delay_lines_per_group,
-                                            input_filter_config.num_fourier_features,
-                                            input_filter_config.num_hidden_layers,
-                                            input_filter_config.num_neurons_per_layer,
-                                            input_filter_config.encoding_type, position_type="input_gains",
-                                            device=self.device).to(self.device)
+        if self.use_svf_in_input:  # reference model.py:376-388: cascades driven by x['source_position']
+            self.input_filters = SVF_from_MLP(self.sample_rate, self.num_groups, self.num_delay_lines_per_group,
+                                              input_filter_config.num_fourier_features,
+                                              input_filter_config.num_hidden_layers,
+                                              input_filter_config.num_neurons_per_layer,
+                                              input_filter_config.encoding_type,
+                                              input_filter_config.compress_pole_factor,
+                                              position_type="input_gains", device=self.device).to(self.device)
+        else:
+            self.input_scalars = Gains_from_MLP(self.num_groups, self.num_delay_lines_per_group,
+                                                input_filter_config.num_fourier_features,
+                                                input_filter_config.num_hidden_layers,
+                                                input_filter_config.num_neurons_per_layer,
+                                                input_filter_config.encoding_type, position_type="input_gains",
+                                                device=self.device).to(self.device)
 
     def forward(self, x: Dict):
+        """H[r,k] = sum_{g,g'} C[r,g,k] T[k,g,g'] B[r,g',k] + d[r,k] with T the G x G group-to-group transfer functions of
+        the loop (one K1 solve per source group) and C / B the receiver / source factors: (B, G) gains or the responses
+        of the (receiver, group) SVF cascades (reference model.py:402-452 expands both to (B, N, K))."""
         z = self._on_device(x['z_values'], torch.complex128)
         self.batch_size = x['listener_position'].shape[0]
-        s_src = self.input_scalars.gains(x)  # (B, G) from x['source_position']
         coef = self.output_filters.coefficients(x) if self.use_svf_in_output else None
         s_rx = None if self.use_svf_in_output else self.output_scalars.gains(x)
+        if self.use_svf_in_input:  # source-side cascade responses F_in[r,g',k], (B, G, K) complex64 (K2s, differentiable)
+            f_src = cascade_response(self.input_filters.coefficients(x), z)
+        else:
+            s_src = self.input_scalars.gains(x)  # (B, G) from x['source_position']
         T = self.feedback_loop.transfer_matrix(z, self._gains_vec(self.input_gains), self._gains_vec(self.output_gains))
         d = x.get('target_early_response')
         H = None if d is None else self._on_device(d, torch.complex64)
         for gp in range(self.num_groups):
+            if self.use_svf_in_input:  # receiver side of source group gp, then the per-receiver, per-bin source factor
+                part = ops.svf_project(coef, z, T[gp], None) if coef is not None else ops.receiver_project(s_rx, T[gp], None)
+                part = part * f_src[:, gp]
+                H = part if H is None else H + part
+                continue
             w = s_src[:, gp]
             if coef is not None:  # scale the cascade by the source gain through its first numerator
                 scale = torch.ones_like(coef)
@@ -335,7 +352,11 @@ class DiffGFDNVarSourceReceiverPos(DiffGFDN):
 
     @torch.no_grad()
     def get_param_dict_inference(self, data: Dict) -> Dict:
-        out = {'input_scalars': self.input_scalars.get_param_dict(data)['gains']}
+        if self.use_svf_in_input:
+            i = self.input_filters.get_param_dict(data)
+            out = {'input_svf_params': i['svf_params'], 'input_biquad_coeffs': i['biquad_coeffs']}
+        else:
+            out = {'input_scalars': self.input_scalars.get_param_dict(data)['gains']}
         if self.use_svf_in_output:
             o = self.output_filters.get_param_dict(data)
             out.update({'output_svf_params': o['svf_params'], 'output_biquad_coeffs': o['biquad_coeffs']})

@@ -201,15 +201,19 @@ def _finish_variant(name, net, trainer, data, out, t60, nfft):
     print(name, {k: v for k, v in out.items() if k.startswith("loss/")})
 
 
-def case_src_rx(name, n_lines, nfft, bsz, t60, seed, hidden, neurons, feats):
-    """DiffGFDNVarSourceReceiverPos (model.py:303-452): MLP-driven gains on the source AND the receiver side."""
+def case_src_rx(name, n_lines, nfft, bsz, t60, seed, hidden, neurons, feats, svf_in=False, svf_out=False,
+                pole_factor=0.998):
+    """DiffGFDNVarSourceReceiverPos (model.py:303-452): MLP-driven gains -- or SVF cascades (svf_in / svf_out) -- on the
+    source AND the receiver side."""
     cfg = DiffGFDNConfig(seed=235265, num_delay_lines=n_lines)
     delays = cfg.delay_length_samps
     torch.manual_seed(seed)
     np.random.seed(seed)
-    ofc = OutputFilterConfig(use_svfs=False, num_hidden_layers=hidden, num_neurons_per_layer=neurons,
-                             num_fourier_features=feats)
-    net = DiffGFDNVarSourceReceiverPos(FS, 3, delays, 'cpu', FeedbackLoopConfig(use_zero_coupling=False), ofc, ofc,
+    ofc_out = OutputFilterConfig(use_svfs=svf_out, num_hidden_layers=hidden, num_neurons_per_layer=neurons,
+                                 num_fourier_features=feats, compress_pole_factor=pole_factor)
+    ofc_in = OutputFilterConfig(use_svfs=svf_in, num_hidden_layers=hidden, num_neurons_per_layer=neurons,
+                                num_fourier_features=feats, compress_pole_factor=pole_factor)
+    net = DiffGFDNVarSourceReceiverPos(FS, 3, delays, 'cpu', FeedbackLoopConfig(use_zero_coupling=False), ofc_out, ofc_in,
                                        use_absorption_filters=False, learn_common_decay_times=False,
                                        common_decay_times=np.array([t60]), use_colorless_loss=True)
     data = synth_batch(nfft, bsz, seed + 1, early_scale=1e-3)
@@ -219,7 +223,17 @@ def case_src_rx(name, n_lines, nfft, bsz, t60, seed, hidden, neurons, feats):
                            edc_loss_weight=10.0, num_freq_bins=nfft)
     out = {"meta/delays": np.array(delays), "meta/nfft": nfft, "meta/fs": FS, "meta/t60": np.array(t60),
            "meta/radius": 1.0, "meta/feats": feats, "meta/edc_w": 10.0, "meta/edr_w": 1.0,
-           "meta/max_ir_len_ms": float(np.max(t60) * 1e3)}
+           "meta/max_ir_len_ms": float(np.max(t60) * 1e3), "meta/svf_in": svf_in, "meta/svf_out": svf_out,
+           "meta/pole_factor": pole_factor}
+    if svf_in or svf_out:  # the float32 cascades the reference builds for this batch, (B, G, S, 6) each
+        with torch.no_grad():
+            for tag, on in (("in", svf_in), ("out", svf_out)):
+                if on:
+                    filt = net.input_filters if tag == "in" else net.output_filters
+                    filt(data)
+                    out[f"out/biquads_{tag}"] = np.stack([np.stack([np.concatenate(
+                        [c.num_coeffs.detach().numpy(), c.den_coeffs.detach().numpy()], axis=-1) for c in row])
+                        for row in filt.biquad_cascade])
     for key in ("listener_position", "norm_listener_position", "source_position", "target_early_response",
                 "target_rir_response"):
         out[f"data/{key}"] = data[key].numpy()
@@ -440,6 +454,8 @@ if __name__ == "__main__":
     case_omni("omni_n12_geq_svf", 12, 8192, 2, t60_bands, 18, 1, 16, 4, svf=True, pole_factor=0.998, early_scale=1e-3,
               geq_bands=bands, steps=1)
     case_src_rx("src_rx_n12", 12, 8192, 3, [0.05, 0.08, 0.12], 15, 1, 16, 4)
+    case_src_rx("src_rx_n12_svf", 12, 4096, 2, [0.04, 0.06, 0.09], 24, 1, 16, 4, svf_in=True, svf_out=True)
+    case_src_rx("src_rx_n12_svf_in", 12, 4096, 2, [0.04, 0.06, 0.09], 25, 1, 16, 4, svf_in=True, svf_out=False)
     case_single("single_n12", 12, 8192, [0.05, 0.08, 0.12], 16, False, False)
     case_single("single_n12_svf", 12, 8192, [0.05, 0.08, 0.12], 17, True, True)
     case_random_coupling("random_coupling_n8", 8, 8192, 3, [0.06, 0.11], 19)

@@ -377,15 +377,22 @@ def omni_response_svf(z, delays, gamma, a, b, c, coef, d=None) -> torch.Tensor:
 
 
 def source_receiver_response(z, delays, gamma, a, b, c, s_rx, s_src, d=None) -> torch.Tensor:
-    """model.py:402-452 (DiffGFDNVarSourceReceiverPos.forward, gains on both sides):
-    H[r,k] = sum_{n,m} (s_rx[r,g(n)] c_n) P_k[n,m] (s_src[r,g(m)] b_m) + d[r,k]."""
+    """model.py:402-452 (DiffGFDNVarSourceReceiverPos.forward):
+    H[r,k] = sum_{n,m} (C[r,g(n),k] c_n) P_k[n,m] (B[r,g(m),k] b_m) + d[r,k].
+    s_rx / s_src are (B, G) real gains (Gains_from_MLP) or (B, G, K) complex filter responses (SVF_from_MLP,
+    use_svf_in_output / use_svf_in_input: every delay line of a group shares the group's cascade)."""
     p = feedback_loop_inverse(z, delays, gamma, a)
     n = delays.numel()
-    g = s_rx.shape[1]
-    cfull = (s_rx.to(F64).repeat_interleave(n // g, dim=1) * c.to(F64).unsqueeze(0)).to(C128)
-    bfull = (s_src.to(F64).repeat_interleave(n // g, dim=1) * b.to(F64).unsqueeze(0)).to(C128)
-    htemp = torch.einsum('bn,knm->bmk', cfull, p)
-    h = torch.einsum('bmk,bm->bk', htemp, bfull)
+
+    def expand(f, v):  # (B, N, K) complex
+        g = f.shape[1]
+        if f.dim() == 2:
+            f = f.to(C128).unsqueeze(-1).expand(-1, -1, z.numel())
+        return f.to(C128).repeat_interleave(n // g, dim=1) * v.to(C128).reshape(1, n, 1)
+
+    cfull, bfull = expand(s_rx, c), expand(s_src, b)
+    htemp = torch.einsum('bnk,knm->bmk', cfull, p)  #                  model.py:442-443
+    h = torch.einsum('bmk,bmk->bk', htemp, bfull)  #                   model.py:449
     if d is not None:
         h = h + d.to(C128)
     return h

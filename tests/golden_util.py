@@ -11,6 +11,7 @@ OMNI_CASES = ["omni_n12", "omni_n12_subband_r", "omni_n24"]
 SVF_CASES = ["omni_n12_svf", "omni_n12_geq_svf"]  # the second adds GEQ absorption filters (the full-band YAML)
 DIR_CASES = ["directional_n27", "directional_n27_skip"]
 VARIANT_CASES = ["src_rx_n12", "single_n12", "single_n12_svf"]  # a-8c: source+receiver gains, single position
+SRC_RX_SVF_CASES = ["src_rx_n12_svf", "src_rx_n12_svf_in"]  # SVF cascades on both sides / on the source side only
 
 
 def load(name):
@@ -79,10 +80,20 @@ def oracle_variant(g, p, biquads_from_golden=False):
     d = torch.tensor(g["data/target_early_response"])
     if "data/source_position" in g:
         feats = int(g["meta/feats"])
-        s_rx = O.gains_from_mlp(torch.tensor(g["data/norm_listener_position"]), p, feats, G,
-                                prefix='output_scalars.mlp.model.')
-        s_src = O.gains_from_mlp(torch.tensor(g["data/source_position"]), p, feats, G,
-                                 prefix='input_scalars.mlp.model.')
+        def side(tag, svf, pos_gain, pos_svf):
+            if not svf:
+                return O.gains_from_mlp(torch.tensor(g[pos_gain]), p, feats, G, prefix=f'{tag}_scalars.mlp.model.')
+            if biquads_from_golden:  # the reference's own float32 cascades
+                coef = torch.tensor(g[f"out/biquads_{'in' if tag == 'input' else 'out'}"])
+            else:
+                svfp = O.svf_params_from_mlp(torch.tensor(g[pos_svf]), p, feats, G, prefix=f'{tag}_filters.mlp.model.')
+                coef = O.svf_to_biquads(svfp, O.svf_cutoffs(fs), float(g["meta/pole_factor"]))
+            return O.sos_response(z, coef)
+        svf_out = bool(g["meta/svf_out"]) if "meta/svf_out" in g else False
+        svf_in = bool(g["meta/svf_in"]) if "meta/svf_in" in g else False
+        # receiver side: Gains_from_MLP reads the normalised position, SVF_from_MLP the raw one (gain_filters.py:341, 504)
+        s_rx = side("output", svf_out, "data/norm_listener_position", "data/listener_position")
+        s_src = side("input", svf_in, "data/source_position", "data/source_position")
         H = O.source_receiver_response(z, delays, gamma, A, b, c, s_rx, s_src, d)
     else:
         def factor(tag, svf):

@@ -241,6 +241,52 @@ def test_source_receiver_and_single_position_variants_match_reference(name, tmp_
         assert rel(p.grad, ref) < 1e-3, k
 
 
+@pytest.mark.parametrize("name", ["src_rx_n12_svf", "src_rx_n12_svf_in"])
+def test_source_receiver_svf_cascades_match_reference(name, tmp_path):
+    """DiffGFDNVarSourceReceiverPos with SVF cascades on the source side (reference model.py:376-388, 432-449), with
+    gains or cascades on the receiver side: forward, losses and gradients vs the reference golden and the oracle."""
+    from diffgfdn_b200.config import FeedbackLoopConfig, OutputFilterConfig
+    from diffgfdn_b200.model import DiffGFDNVarSourceReceiverPos
+    from diffgfdn_b200.trainer import VarReceiverPosTrainer
+    from diffgfdn_b200.utils import unit_circle_grid
+    from golden_util import oracle_variant
+    g = load(name)
+    pf = float(g["meta/pole_factor"])
+    mk = lambda svf: OutputFilterConfig(use_svfs=bool(svf), num_hidden_layers=1, num_neurons_per_layer=16,  # noqa: E731
+                                        num_fourier_features=int(g["meta/feats"]), compress_pole_factor=pf)
+    net = DiffGFDNVarSourceReceiverPos(float(g["meta/fs"]), 3, [int(v) for v in g["meta/delays"]], 'cuda',
+                                       FeedbackLoopConfig(use_zero_coupling=False), mk(g["meta/svf_out"]),
+                                       mk(g["meta/svf_in"]), use_absorption_filters=False, learn_common_decay_times=False,
+                                       common_decay_times=np.array([g["meta/t60"]]), use_colorless_loss=True)
+    net.load_state_dict({k[len("param/"):]: torch.tensor(v) for k, v in g.items() if k.startswith("param/")},
+                        strict=True)
+    data = {k[len("data/"):]: torch.tensor(v) for k, v in g.items() if k.startswith("data/")}
+    data["z_values"] = unit_circle_grid(int(g["meta/nfft"]))
+    data["target_rir_response"] = data["target_rir_response"].cuda()
+    trainer = make_trainer(VarReceiverPosTrainer, net, tmp_path, use_colorless_loss=True, use_asym_spectral_loss=True,
+                           edc_loss_weight=10.0, num_freq_bins=int(g["meta/nfft"]))
+    net.zero_grad()
+    H, (Hs, Hsd) = net(data)
+    d = g["data/target_early_response"]
+    assert tuple(H.shape) == d.shape and H.dtype == torch.complex64
+    Hn = H.detach().cpu().to(torch.complex128).numpy()
+    assert rel(Hn - d, g["out/H"] - d) < 5e-3  # the reference's float32 biquad coefficients (DESIGN.md section 8)
+    po = params_of(g, requires_grad=True)
+    o = oracle_variant(g, po)
+    assert rel(Hn - d, o["H"].detach().numpy() - d) < 1e-4  # float64 oracle
+    assert rel(Hs, g["out/H_sub"]) < 1e-4
+    losses = trainer.calculate_losses(data, H, (Hs, Hsd))
+    total = sum(losses.values())
+    total.backward()
+    assert abs(float(total) - g["loss/total"]) < 2e-3 * g["loss/total"]
+    o["total"].backward()
+    for k, p in net.named_parameters():
+        assert rel(p.grad, po[k].grad) < 1e-3, k          # float64 oracle
+        assert rel(p.grad, g[f"grad/{k}"]) < 5e-3, k      # reference (float32 coefficient noise)
+    pd = net.get_param_dict_inference(data)
+    assert "input_svf_params" in pd and "input_biquad_coeffs" in pd
+
+
 def test_random_coupling_matches_reference(tmp_path):
     """coupling_matrix_type: random_matrix (the single-room sub-band YAML): forward, losses and gradients vs the
     reference golden; checkpoint key 'feedback_loop.random_feedback_matrix'."""
