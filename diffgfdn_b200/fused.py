@@ -44,16 +44,28 @@ C64 = torch.complex64
 
 
 class _GatherBins(torch.autograd.Function):
-    """y (K, G) from this rank's bin slice y_loc = y[lo:hi]: zero-padded SUM all-reduce (an all-gather that also runs
-    on backends without one for CUDA tensors, 8 K G bytes over NVLink). The caller all-reduces the gradient of
-    everything downstream (dL/dhy) BEFORE the backward, so the backward is the slice of the total gradient."""
+    """y (K, G) from this rank's bin slice y_loc = y[lo:hi]: an all-gather of equal (padded) slices over NCCL, a
+    zero-padded SUM all-reduce on other backends. The caller all-reduces the gradient of everything downstream
+    (dL/dhy) BEFORE the backward, so the backward is the slice of the total gradient."""
 
     @staticmethod
     def forward(ctx, y_loc, lo, hi, k, group):
+        world = dist.get_world_size(group)
+        per = (k + world - 1) // world
+        ctx.lo, ctx.hi = lo, hi
+        if dist.get_backend(group) == "nccl":
+            # equal slices of `per` bins (the last ranks' slices are padded): one all-gather into a (world * per, G)
+            # buffer, no zero fill and half the traffic of the all-reduce formulation
+            buf = torch.empty(world * per, y_loc.shape[1], dtype=y_loc.dtype, device=y_loc.device)
+            mine = y_loc
+            if hi - lo < per:
+                mine = torch.zeros(per, y_loc.shape[1], dtype=y_loc.dtype, device=y_loc.device)
+                mine[:hi - lo] = y_loc
+            dist.all_gather_into_tensor(torch.view_as_real(buf), torch.view_as_real(mine.contiguous()), group=group)
+            return buf[:k]
         y = torch.zeros(k, y_loc.shape[1], dtype=y_loc.dtype, device=y_loc.device)
         y[lo:hi] = y_loc
         dist.all_reduce(torch.view_as_real(y), op=dist.ReduceOp.SUM, group=group)
-        ctx.lo, ctx.hi = lo, hi
         return y
 
     @staticmethod
@@ -481,8 +493,9 @@ class ShardedEDCStep:
                 p.grad = torch.zeros_like(p)
         flat = torch.cat([p.grad.reshape(-1).to(torch.float32) for p in params])
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.pg)
-        off = 0
+        views, off = [], 0
         for p in params:
             n = p.numel()
-            p.grad.copy_(flat[off:off + n].view_as(p.grad))
+            views.append(flat[off:off + n].view_as(p.grad))
             off += n
+        torch._foreach_copy_([p.grad for p in params], views)  # one multi-tensor kernel, not one copy per parameter
