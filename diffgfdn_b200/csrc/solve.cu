@@ -65,6 +65,9 @@ struct Smem {
   static constexpr size_t kConstPerSys = 2 * (size_t)NP * NP + 4 * NP;
   static constexpr size_t kGroupFwd = 2 * 2 * (NP + 1);
   static constexpr size_t kGroupBwd = kGroupFwd + 4 * NP + (size_t)NP * NP;
+  // mixed-precision forward: two float2 pivot lines (NP + 1) | solution by column, double2 [NP] | pivot lane per step, int [NP]
+  // (an even number of doubles: the double2 part stays 16-byte aligned from group to group)
+  static constexpr size_t kGroupMixed = (2 * (NP + 1) + 2 * NP + (NP + 1) / 2 + 2) & ~(size_t)1;
 };
 
 __device__ __forceinline__ double fast_rcp(double d) {
@@ -337,6 +340,216 @@ __global__ void __launch_bounds__(kWarps * 32, (NP <= 24 ? 3 : 2)) solve_fwd_ker
     }
   }
   (void)my_c;
+}
+
+// ---- mixed-precision forward: float32 elimination + one float64 residual-refinement step ---------------------------
+// The forward solve of the coupled system is bound by instruction issue / latency, not by the FP64 pipe's peak (35 % of it):
+// 24 dependent elimination steps per bin with 96 registers of row state per lane. Here the ROW lives in float32 (half the
+// registers, FFMA latency, 128-bit pivot-line reads carry two complex entries) while everything that fixes the accuracy
+// stays float64: z^m by binary powering, the diagonal z^m / gamma, and the residual r = b - M x0 of the float32 solution
+// x0, formed against the float64 A in shared memory. The correction M delta = r is solved by replaying the saved
+// elimination (the multipliers are still in registers): delta = E^-1 T_N ... T_1 r, one shuffle + one complex FMA per
+// step. x = x0 + delta is then accurate to ~(cond(M) eps_32)^2 -- the same multipliers, stored as float32, are what the
+// adjoint replay (solve_bwd_replay_kernel) has always used. DGFDN_SOLVE_MIXED=0 keeps the all-float64 kernel.
+struct GJStateF {
+  float2 rhs;
+  float2 diag;
+  int mycol;
+  bool used;
+};
+
+template <int NP, int W, int K>
+struct GJStepF {
+  static __device__ __forceinline__ void run(float2 (&m)[NP], GJStateF& st, int sl, float2* line0, float2* line1, float2* fac,
+                                             float2 (&fm)[NP]) {
+    float2* line = (K & 1) ? line1 : line0;
+    unsigned key = 0u;
+    const float nrm = m[K].x * m[K].x + m[K].y * m[K].y;
+    if (!st.used)  // monotone in |m|^2 for non-negative floats; the low bits carry the lane
+      key = 0x80000000u | ((__float_as_uint(nrm) >> 1) & ~(unsigned)(W - 1)) | (unsigned)(W - 1 - sl);
+    const float rn = __frcp_rn(nrm);  // every lane inverts its own candidate while the search is in flight
+    const float2 myinv = make_float2(m[K].x * rn, -m[K].y * rn);
+    const int piv = pivot_sublane<W>(key);
+    if (sl == piv) {
+      line[K] = myinv;
+#pragma unroll
+      for (int j = K + 1; j < NP; ++j) line[j] = m[j];
+      line[NP] = st.rhs;
+      st.used = true;
+      st.mycol = K;
+      st.diag = m[K];
+    }
+    __syncwarp();
+    float2 f = make_float2(0.f, 0.f);
+    if (sl != piv && sl < NP) {
+      f = cmulf(m[K], line[K]);
+      const float nfx = -f.x, nfy = -f.y;
+#pragma unroll
+      for (int j = K + 1; j < NP; ++j) {
+        const float2 pj = line[j];
+        m[j].x = fmaf(f.y, pj.y, fmaf(nfx, pj.x, m[j].x));
+        m[j].y = fmaf(nfy, pj.x, fmaf(nfx, pj.y, m[j].y));
+      }
+      const float2 pr = line[NP];
+      st.rhs.x = fmaf(f.y, pr.y, fmaf(nfx, pr.x, st.rhs.x));
+      st.rhs.y = fmaf(nfy, pr.x, fmaf(nfx, pr.y, st.rhs.y));
+    }
+    fm[K] = f;
+    if (fac != nullptr) fac[K * W + sl] = f;
+    if constexpr (K + 1 < NP) GJStepF<NP, W, K + 1>::run(m, st, sl, line0, line1, fac, fm);
+  }
+};
+
+// delta <- T_K delta for the saved steps in order: component i != p_K loses f[K][i] * delta[p_K]
+template <int NP, int W, int K>
+struct CorrStepF {
+  static __device__ __forceinline__ void run(const float2 (&fm)[NP], float2& r, int sl, int base, const int* ptab) {
+    const int src = ptab[K];
+    const float vx = __shfl_sync(0xffffffffu, r.x, base + src);
+    const float vy = __shfl_sync(0xffffffffu, r.y, base + src);
+    if (sl != src) {  // (fm[K] is zero for the pivot lane and the padding lanes anyway)
+      r.x = fmaf(fm[K].y, vy, fmaf(-fm[K].x, vx, r.x));
+      r.y = fmaf(-fm[K].y, vx, fmaf(-fm[K].x, vy, r.y));
+    }
+    if constexpr (K + 1 < NP) CorrStepF<NP, W, K + 1>::run(fm, r, sl, base, ptab);
+  }
+};
+
+template <int NP, int W>
+__global__ void __launch_bounds__(kWarps * 32, 4) solve_fwd_mixed_kernel(SolveParams p) {
+  extern __shared__ double smem[];
+  constexpr int kSpw = 32 / W;
+  const int n = p.n;
+  double* s_const = smem;
+  double* s_vec = s_const + (size_t)p.nsys * 2 * NP * NP;
+  double* s_groups = s_vec + (size_t)p.nsys * 4 * NP;
+  const GroupIndex<W> gi(p);
+  const int sl = gi.sl, q = gi.q;
+  const int lane = threadIdx.x & 31;
+  const int lg = (threadIdx.x >> 5) * kSpw + lane / W;
+  // per lane group: two float2 pivot lines of NP + 1 | the solution by column as double2 [NP] | pivot lane of every step
+  double* gbase = s_groups + (size_t)lg * Smem<NP>::kGroupMixed;
+  float2* line0 = reinterpret_cast<float2*>(gbase);
+  float2* line1 = line0 + (NP + 1);
+  double2* xcol = reinterpret_cast<double2*>(gbase + 2 * (NP + 1));
+  int* ptab = reinterpret_cast<int*>(gbase + 2 * (NP + 1) + 2 * NP);
+
+  load_block_constants<NP>(p, s_const, s_vec);
+  __syncthreads();
+  const double* s_a = s_const + (size_t)q * 2 * NP * NP;
+  const double* s_at = s_a + NP * NP;
+  const int li = q * NP + (sl < NP ? sl : 0);
+  const double my_invg = s_vec[li], my_b = s_vec[p.nsys * NP + li];
+  const int my_delay = (int)s_vec[3 * p.nsys * NP + li];
+  const int my_line = q * n + sl;
+  const int nbits = 32 - __clz((int)__reduce_max_sync(0xffffffffu, (unsigned)(sl < n ? my_delay : 0)));
+  const int base = lane - sl;
+
+  const int64_t iters = (p.k + gi.bin_stride - 1) / gi.bin_stride;
+  int64_t iters_max = iters;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const int64_t other = __shfl_xor_sync(0xffffffffu, iters_max, o);
+    iters_max = other > iters_max ? other : iters_max;
+  }
+  for (int64_t it = 0; it < iters_max; ++it) {
+    int64_t bin = gi.bin0 + it * gi.bin_stride;
+    const bool live_bin = bin < p.k;
+    if (!live_bin) bin = p.k - 1;
+    double2 zm = make_double2(0.0, 0.0);
+    double2 dz = make_double2(0.0, 0.0);
+    if (sl < n) dz = diag_entry(p, bin, my_line, my_invg, my_delay, nbits, &zm);
+    // row `sl` of M in float32 (padded rows / columns: identity)
+    float2 m[NP], fm[NP];
+    {
+      const int lr = sl < NP ? sl : 0;
+#pragma unroll
+      for (int j = 0; j < NP; ++j) {
+        const bool on_diag = (j == sl);
+        const double re = (on_diag ? (sl < n ? dz.x : 1.0) : 0.0) - s_at[j * NP + lr];
+        m[j] = make_float2((float)re, on_diag && sl < n ? (float)dz.y : 0.f);
+      }
+    }
+    const bool save = p.fac != nullptr && live_bin;
+    const int64_t slot = bin * p.nsys + q;
+    GJStateF st;
+    st.rhs = make_float2((float)my_b, 0.f);
+    st.diag = make_float2(1.f, 0.f);
+    st.mycol = -1;
+    st.used = sl >= NP;
+    GJStepF<NP, W, 0>::run(m, st, sl, line0, line1, save ? p.fac + slot * (NP * W) : nullptr, fm);
+    __syncwarp();
+    const int col = st.mycol;
+    const float dn = __frcp_rn(st.diag.x * st.diag.x + st.diag.y * st.diag.y);
+    const float2 dinv = make_float2(st.diag.x * dn, -st.diag.y * dn);
+    const float2 x0 = cmulf(st.rhs, dinv);
+    if (save) {
+      p.rec[slot * W + sl] = make_float4(st.diag.x, st.diag.y, (float)zm.x, (float)zm.y);
+      p.pcol[slot * W + sl] = col;
+    }
+    // ---- float64 residual of row sl:  r = b - (dz x0[sl] - sum_j A[sl][j] x0[j])
+    if (col >= 0) {
+      xcol[col] = make_double2((double)x0.x, (double)x0.y);
+      ptab[col] = sl;
+    }
+    __syncwarp();
+    float2 r = make_float2(0.f, 0.f);
+    if (sl < NP) {
+      const int lr = sl;
+      double ax = 0.0, ay = 0.0;
+#pragma unroll 8
+      for (int j = 0; j < NP; ++j) {
+        const double a = s_at[j * NP + lr];
+        const double2 xj = xcol[j];
+        ax = fma(a, xj.x, ax);
+        ay = fma(a, xj.y, ay);
+      }
+      const double2 xs = xcol[sl];
+      double rx, ry;
+      if (sl < n) {
+        rx = my_b - (dz.x * xs.x - dz.y * xs.y) + ax;
+        ry = -(dz.x * xs.y + dz.y * xs.x) + ay;
+      } else {  // identity padding row: x = b = 0 exactly
+        rx = -xs.x;
+        ry = -xs.y;
+      }
+      r = make_float2((float)rx, (float)ry);
+    }
+    // ---- correction by the saved elimination, then x = x0 + delta in float64
+    CorrStepF<NP, W, 0>::run(fm, r, sl, base, ptab);
+    const float2 delta = cmulf(r, dinv);
+    const double2 xr = make_double2((double)x0.x + (double)delta.x, (double)x0.y + (double)delta.y);
+    __syncwarp();  // xcol / ptab are rewritten below and by the next bin
+    const bool live = col >= 0 && col < n;
+    if (p.x != nullptr && live && live_bin) p.x[bin * p.ntot + q * n + col] = make_float2((float)xr.x, (float)xr.y);
+    if (p.y != nullptr) {
+      if (live) {
+        const double cr = s_vec[2 * p.nsys * NP + q * NP + col];
+        xcol[col] = make_double2(cr * xr.x, cr * xr.y);
+      }
+      __syncwarp();
+      if (p.nsys == 1) {
+        if (sl < p.g && live_bin) {
+          double re = 0.0, im = 0.0;
+          for (int j = 0; j < p.l; ++j) {
+            const double2 v = xcol[sl * p.l + j];
+            re += v.x;
+            im += v.y;
+          }
+          p.y[bin * p.g + sl] = make_float2((float)re, (float)im);
+        }
+      } else if (sl == 0 && live_bin) {
+        double re = 0.0, im = 0.0;
+        for (int j = 0; j < n; ++j) {
+          const double2 v = xcol[j];
+          re += v.x;
+          im += v.y;
+        }
+        p.y[bin * p.g + q] = make_float2((float)re, (float)im);
+      }
+      __syncwarp();
+    }
+  }
 }
 
 // Backward: adjoint solve per bin + accumulation of the parameter gradients. Each lane group writes one row of
@@ -825,6 +1038,17 @@ int launch_fwd(const SolveParams& p, cudaStream_t st) {
 }
 
 template <int NP>
+int launch_fwd_mixed(const SolveParams& p, cudaStream_t st) {
+  constexpr int W = lanes_for(NP);
+  const size_t smem = ((size_t)p.nsys * Smem<NP>::kConstPerSys + (size_t)kWarps * (32 / W) * Smem<NP>::kGroupMixed) * sizeof(double);
+  DGFDN_CUDA(cudaFuncSetAttribute(solve_fwd_mixed_kernel<NP, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int blocks = grid_blocks(p.k * p.nsys, W, blocks_per_sm(solve_fwd_mixed_kernel<NP, W>, smem));
+  solve_fwd_mixed_kernel<NP, W><<<blocks, kWarps * 32, smem, st>>>(p);
+  DGFDN_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int NP>
 int launch_bwd(const SolveParams& p, int* blocks_out, cudaStream_t st) {
   constexpr int W = lanes_for(NP);
   const size_t smem = smem_bytes<NP>(p, true);
@@ -866,6 +1090,12 @@ int launch_bwd_replay(const SolveParams& p, int* blocks_out, cudaStream_t st) {
 
 int dispatch_fwd(const SolveParams& p, cudaStream_t st) {
 #define CALL_FWD(NP) launch_fwd<NP>(p, st)
+  DGFDN_DISPATCH_NP(p.n, CALL_FWD);
+#undef CALL_FWD
+}
+
+int dispatch_fwd_mixed(const SolveParams& p, cudaStream_t st) {
+#define CALL_FWD(NP) launch_fwd_mixed<NP>(p, st)
   DGFDN_DISPATCH_NP(p.n, CALL_FWD);
 #undef CALL_FWD
 }
@@ -950,6 +1180,15 @@ static int solve_fwd_impl(int n, int nsys, int g, int64_t k, const void* z, cons
   p.x = static_cast<float2*>(x);
   p.y = static_cast<float2*>(y);
   bind_factors(p, factors, n, nsys, k);
+  // coupled systems with scalar absorption: float32 elimination + float64 refinement (solve_fwd_mixed_kernel).
+  // Filter absorption (gamma_z), the small sub-FDN systems (group mode) and DGFDN_SOLVE_MIXED=0 take the float64 kernel.
+  static const bool mixed_on = [] {
+    const char* e = getenv("DGFDN_SOLVE_MIXED");
+    return e == nullptr || atoi(e) != 0;
+  }();
+  bool mixed = mixed_on && nsys == 1 && n >= 12 && gamma_z == nullptr;
+  if (const char* e = getenv("DGFDN_SOLVE_MIXED_FORCE")) mixed = atoi(e) != 0 && nsys == 1;
+  if (mixed) return dispatch_fwd_mixed(p, static_cast<cudaStream_t>(stream));
   return dispatch_fwd(p, static_cast<cudaStream_t>(stream));
 }
 
