@@ -738,15 +738,25 @@ __global__ void __launch_bounds__(kWarps * 32) solve_bwd_replay_kernel(SolvePara
     }
     if (sl < NP) xs[sl] = xr;
     const float2* fac = p.fac + slot * (NP * W) + sl;
+    {
+      // The recursion itself runs in float32: the multipliers ARE float32, the group-wide sum is half the shuffles, and
+      // lambda only needs the ~1e-6 this leaves (the gradient gate is 1e-3; the products below accumulate in float64).
+      float2 wf = make_float2((float)w.x, (float)w.y);
 #pragma unroll 4
-    for (int k = NP - 1; k >= 0; --k) {
-      const float2 f = fac[k * W];
-      const double fx = (double)f.x, fy = (double)f.y;
-      const double2 s = group_sum<W>(make_double2(fx * w.x + fy * w.y, fx * w.y - fy * w.x));  // conj(f) w
-      if (col == k) {
-        w.x -= s.x;
-        w.y -= s.y;
+      for (int k = NP - 1; k >= 0; --k) {
+        const float2 f = fac[k * W];
+        float sx = fmaf(f.x, wf.x, f.y * wf.y), sy = fmaf(f.x, wf.y, -f.y * wf.x);  // conj(f) w
+#pragma unroll
+        for (int o = W / 2; o > 0; o >>= 1) {
+          sx += __shfl_xor_sync(0xffffffffu, sx, o);
+          sy += __shfl_xor_sync(0xffffffffu, sy, o);
+        }
+        if (col == k) {
+          wf.x -= sx;
+          wf.y -= sy;
+        }
       }
+      w = make_double2((double)wf.x, (double)wf.y);
     }
     __syncwarp();
     if (sl < n) {  // a dead bin contributes zeros: its w and x are zero
