@@ -485,8 +485,12 @@ __global__ void __launch_bounds__(T::FT, T::MINB) td_fused_kernel(FusedParams p)
           lacc = fmaf(mk.w, fabsf(d23.y), lacc);
           const float2 w01 = MASKED ? make_float2(mk.x * cf2, mk.y * cf2) : make_float2(wcf, wcf);
           const float2 w23 = MASKED ? make_float2(mk.z * cf2, mk.w * cf2) : make_float2(wcf, wcf);
-          const float2 g01 = __fmul2_rn(w01, make_float2(rcp_ftz(x01.x), rcp_ftz(x01.y)));
-          const float2 g23 = __fmul2_rn(w23, make_float2(rcp_ftz(x23.x), rcp_ftz(x23.y)));
+          // 1 / x of a sample pair from ONE reciprocal: r = 1 / (x0 x1), 1 / x0 = r x1, 1 / x1 = r x0 (phase B is bound by
+          // the MUFU pipe: 6 instead of 8 MUFU per segment). x >= eps_f32, so x0 x1 >= 1.4e-14; it overflows for EDC
+          // values above 1.8e19, far outside what squared impulse responses reach.
+          const float r01 = rcp_ftz(x01.x * x01.y), r23 = rcp_ftz(x23.x * x23.y);
+          const float2 g01 = __fmul2_rn(w01, __fmul2_rn(make_float2(r01, r01), make_float2(x01.y, x01.x)));
+          const float2 g23 = __fmul2_rn(w23, __fmul2_rn(make_float2(r23, r23), make_float2(x23.y, x23.x)));
           float4 ge;
           ge.x = __int_as_float(__float_as_int(g01.x) ^ (~__float_as_int(d01.x) & 0x80000000));
           ge.y = __int_as_float(__float_as_int(g01.y) ^ (~__float_as_int(d01.y) & 0x80000000));
