@@ -55,6 +55,12 @@ struct SolveParams {
   float2* fac;   // [bins * nsys][NP][W]
   float4* rec;   // [bins * nsys][W]   (pivot.x, pivot.y, zm.x, zm.y)
   int* pcol;     // [bins * nsys][W]   column this lane was pivot for (-1: padding lane)
+  // FIR coupling (filter_matrix, reference feedback_loop.py:362-373): A(z_k) = sum_p taps[p] z_k^-p, taps [P][N][N] real;
+  // null for a constant A. The adjoint kernel then also writes lambda [K, N] (the tap gradients are a DFT-weighted sum of
+  // lambda x^H over the bins, formed by the caller).
+  const float* taps;
+  int ntaps;
+  float2* lam;
 };
 
 // Shared memory (in doubles). Block-wide constants per system type q: A_eff row-major [NP*NP] and transposed
@@ -228,6 +234,45 @@ __device__ __forceinline__ void build_row(double2 (&m)[NP], const double* s_a, c
   }
 }
 
+// FIR coupling: the taps staged in shared memory as s_taps[p][j * NP + i] = A_eff,p[i][j] (forward) or A_eff,p[j][i] (adjoint),
+// A_eff = A^T when transpose_a; padded rows / columns are zero.
+template <int NP>
+__device__ __forceinline__ void stage_taps(const SolveParams& p, float* s_taps, bool adjoint) {
+  const int n = p.n;
+  for (int i = threadIdx.x; i < p.ntaps * NP * NP; i += blockDim.x) {
+    const int t = i / (NP * NP), rc = i % (NP * NP);
+    const int j = rc / NP, l = rc % NP;  // lane l reads entry (row r, column c) of A_eff
+    const int r = adjoint ? j : l, c = adjoint ? l : j;
+    float v = 0.f;
+    if (r < n && c < n) v = p.transpose_a ? p.taps[((size_t)t * n + c) * n + r] : p.taps[((size_t)t * n + r) * n + c];
+    s_taps[i] = v;
+  }
+}
+
+// Row `sl` of M_k = D_k - sum_p A_p z_k^-p (adjoint = false) or of M_k^H (adjoint = true); zinv = 1 / z_k.
+template <int NP>
+__device__ __forceinline__ void build_row_fir(double2 (&m)[NP], const float* s_taps, int ntaps, int n, int sl, double2 dz,
+                                              double2 zinv, bool adjoint) {
+  const int li = sl < NP ? sl : 0;
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
+    const bool on_diag = (j == sl);
+    m[j] = make_double2(on_diag ? (sl < n ? dz.x : 1.0) : 0.0, on_diag && sl < n ? (adjoint ? -dz.y : dz.y) : 0.0);
+  }
+  double2 w = make_double2(1.0, 0.0);  // z^-p (conjugated in the adjoint)
+  if (adjoint) zinv.y = -zinv.y;
+  for (int t = 0; t < ntaps; ++t) {
+    const float* tp = s_taps + (size_t)t * NP * NP;
+#pragma unroll
+    for (int j = 0; j < NP; ++j) {
+      const double a = (double)tp[j * NP + li];
+      m[j].x = fma(-a, w.x, m[j].x);
+      m[j].y = fma(-a, w.y, m[j].y);
+    }
+    w = cmul(w, zinv);
+  }
+}
+
 // z^{m_i} / gamma_i for this lane's delay line; also returns z^m alone through zm.
 __device__ __forceinline__ double2 diag_entry(const SolveParams& p, int64_t bin, int line, double invg, int delay,
                                               int nbits, double2* zm) {
@@ -270,8 +315,10 @@ __global__ void __launch_bounds__(kWarps * 32, (NP <= 24 ? 3 : 2)) solve_fwd_ker
   const int lg = (threadIdx.x >> 5) * kSpw + (threadIdx.x & 31) / W;  // lane group inside the block
   double2* line0 = reinterpret_cast<double2*>(s_groups + (size_t)lg * Smem<NP>::kGroupFwd);
   double2* line1 = line0 + (NP + 1);
+  float* s_taps = reinterpret_cast<float*>(s_groups + (size_t)kWarps * kSpw * Smem<NP>::kGroupFwd);
 
   load_block_constants<NP>(p, s_const, s_vec);
+  if (p.taps != nullptr) stage_taps<NP>(p, s_taps, false);
   __syncthreads();
   const double* s_a = s_const + (size_t)q * 2 * NP * NP;
   const double* s_at = s_a + NP * NP;
@@ -297,7 +344,10 @@ __global__ void __launch_bounds__(kWarps * 32, (NP <= 24 ? 3 : 2)) solve_fwd_ker
     double2 dz = make_double2(0.0, 0.0);
     if (sl < n) dz = diag_entry(p, bin, my_line, my_invg, my_delay, nbits, &zm);
     double2 m[NP];
-    build_row<NP>(m, s_a, s_at, n, sl, dz, false);
+    if (p.taps != nullptr)
+      build_row_fir<NP>(m, s_taps, p.ntaps, n, sl, dz, fast_cinv(p.z[bin]), false);
+    else
+      build_row<NP>(m, s_a, s_at, n, sl, dz, false);
     int col;
     double2 pivot;
     const bool save = p.fac != nullptr && live_bin;
@@ -571,8 +621,10 @@ __global__ void __launch_bounds__(kWarps * 32, (NP <= 24 ? 3 : 2)) solve_bwd_ker
   double2* lam = line1 + (NP + 1);
   double2* xs = lam + NP;
   double* acc = reinterpret_cast<double*>(xs + NP);
+  float* s_taps = reinterpret_cast<float*>(s_groups + (size_t)kWarps * kSpw * Smem<NP>::kGroupBwd);
 
   load_block_constants<NP>(p, s_const, s_vec);
+  if (p.taps != nullptr) stage_taps<NP>(p, s_taps, true);
   if (sl < NP)
     for (int j = 0; j < NP; ++j) acc[sl + NP * j] = 0.0;
   __syncthreads();
@@ -622,13 +674,17 @@ __global__ void __launch_bounds__(kWarps * 32, (NP <= 24 ? 3 : 2)) solve_bwd_ker
     }
     if (sl < NP) xs[sl] = xr;
     double2 m[NP];
-    build_row<NP>(m, s_a, s_at, n, sl, dz, true);
+    if (p.taps != nullptr)
+      build_row_fir<NP>(m, s_taps, p.ntaps, n, sl, dz, fast_cinv(p.z[bin]), true);
+    else
+      build_row<NP>(m, s_a, s_at, n, sl, dz, true);
     int col;
     const double2 sol = gauss_jordan<NP, W>(m, rhs, sl, line0, line1, &col);
     if (col >= 0) lam[col] = sol;
     __syncwarp();
     if (sl < n) {  // a dead bin contributes zeros: its rhs and x are zero
       const double2 lr = lam[sl];
+      if (p.lam != nullptr && live_bin) p.lam[bin * p.ntot + my_line] = make_float2((float)lr.x, (float)lr.y);
       // dL/dA_eff[i][j] = Re(lambda_i conj(x_j)); the reduce kernel transposes back when A_eff = A^T.
 #pragma unroll 4
       for (int j = 0; j < n; ++j) {
@@ -1032,8 +1088,9 @@ template <int NP>
 size_t smem_bytes(const SolveParams& p, bool bwd) {
   constexpr int W = lanes_for(NP);
   const size_t groups = kWarps * (32 / W);
+  const size_t taps = p.taps != nullptr ? (((size_t)p.ntaps * NP * NP * sizeof(float) + 7) & ~(size_t)7) : 0;
   return ((size_t)p.nsys * Smem<NP>::kConstPerSys + groups * (bwd ? Smem<NP>::kGroupBwd : Smem<NP>::kGroupFwd)) *
-         sizeof(double);
+             sizeof(double) + taps;
 }
 
 template <int NP>
@@ -1181,7 +1238,7 @@ static int64_t bwd_rows_bytes(int n);
 
 static int solve_fwd_impl(int n, int nsys, int g, int64_t k, const void* z, const int32_t* delays, const float* a,
                           int transpose_a, const float* gamma, const void* gamma_z, const float* b, const float* c,
-                          void* x, void* y, void* factors, void* stream) {
+                          void* x, void* y, void* factors, void* stream, const float* taps = nullptr, int ntaps = 0) {
   if (check_common(n, nsys, g, k)) return 1;
   DGFDN_CHECK(z && delays && a && b, "solve_fwd: null input pointer");
   DGFDN_CHECK(y == nullptr || c != nullptr, "solve_fwd: y requested without c");
@@ -1189,6 +1246,12 @@ static int solve_fwd_impl(int n, int nsys, int g, int64_t k, const void* z, cons
   fill_params(p, n, nsys, g, k, z, delays, a, transpose_a, gamma, gamma_z, b, c);
   p.x = static_cast<float2*>(x);
   p.y = static_cast<float2*>(y);
+  if (taps != nullptr) {  // FIR coupling: per-bin complex A(z_k) in the float64 kernel, no saved elimination
+    DGFDN_CHECK(nsys == 1 && ntaps >= 1 && ntaps <= 64 && factors == nullptr, "solve_fir_fwd: 1..64 taps, coupled mode, no factors");
+    p.taps = taps;
+    p.ntaps = ntaps;
+    return dispatch_fwd(p, static_cast<cudaStream_t>(stream));
+  }
   bind_factors(p, factors, n, nsys, k);
   // coupled systems with scalar absorption: float32 elimination + float64 refinement (solve_fwd_mixed_kernel).
   // Filter absorption (gamma_z), the small sub-FDN systems (group mode) and DGFDN_SOLVE_MIXED=0 take the float64 kernel.
@@ -1205,13 +1268,19 @@ static int solve_fwd_impl(int n, int nsys, int g, int64_t k, const void* z, cons
 static int solve_bwd_impl(int n, int nsys, int g, int64_t k, const void* z, const int32_t* delays, const float* a,
                           int transpose_a, const float* gamma, const void* gamma_z, const float* c, const void* x,
                           const void* gy, const void* gx, double* ga, double* gb, double* gc, double* ginvgamma,
-                          void* ws, const void* factors, void* stream) {
+                          void* ws, const void* factors, void* stream, const float* taps = nullptr, int ntaps = 0,
+                          void* lam = nullptr) {
   if (check_common(n, nsys, g, k)) return 1;
   DGFDN_CHECK(z && delays && a && x && ws, "solve_bwd: null input pointer");
   DGFDN_CHECK(gy || gx, "solve_bwd: need gy or gx");
   DGFDN_CHECK(gy == nullptr || c != nullptr, "solve_bwd: gy given without c");
+  DGFDN_CHECK(taps == nullptr || (nsys == 1 && ntaps >= 1 && ntaps <= 64 && factors == nullptr && lam != nullptr),
+              "solve_fir_bwd: 1..64 taps, coupled mode, no factors, lambda output required");
   SolveParams p{};
   fill_params(p, n, nsys, g, k, z, delays, a, transpose_a, gamma, gamma_z, nullptr, c);
+  p.taps = taps;
+  p.ntaps = ntaps;
+  p.lam = static_cast<float2*>(lam);
   p.xin = static_cast<const float2*>(x);
   p.gy = static_cast<const float2*>(gy);
   p.gx = static_cast<const float2*>(gx);
@@ -1232,6 +1301,22 @@ extern "C" int dgfdn_solve_fwd(int n, int g, int64_t k, const void* z, const int
                                int transpose_a, const float* gamma, const void* gamma_z, const float* b,
                                const float* c, void* x, void* y, void* factors, void* stream) {
   return solve_fwd_impl(n, 1, g, k, z, delays, a, transpose_a, gamma, gamma_z, b, c, x, y, factors, stream);
+}
+
+extern "C" int dgfdn_solve_fir_fwd(int n, int g, int ntaps, int64_t k, const void* z, const int32_t* delays,
+                                   const float* taps, int transpose_a, const float* gamma, const void* gamma_z,
+                                   const float* b, const float* c, void* x, void* y, void* stream) {
+  DGFDN_CHECK(taps != nullptr, "solve_fir_fwd: null taps");
+  return solve_fwd_impl(n, 1, g, k, z, delays, taps, transpose_a, gamma, gamma_z, b, c, x, y, nullptr, stream, taps, ntaps);
+}
+
+extern "C" int dgfdn_solve_fir_bwd(int n, int g, int ntaps, int64_t k, const void* z, const int32_t* delays,
+                                   const float* taps, int transpose_a, const float* gamma, const void* gamma_z,
+                                   const float* c, const void* x, const void* gy, const void* gx, void* lam, double* gb,
+                                   double* gc, double* ginvgamma, void* ws, void* stream) {
+  DGFDN_CHECK(taps != nullptr && lam != nullptr, "solve_fir_bwd: null taps / lambda");
+  return solve_bwd_impl(n, 1, g, k, z, delays, taps, transpose_a, gamma, gamma_z, c, x, gy, gx, nullptr, gb, gc, ginvgamma, ws,
+                        nullptr, stream, taps, ntaps, lam);
 }
 
 extern "C" int64_t dgfdn_solve_factors_bytes(int n, int64_t k) {

@@ -273,24 +273,14 @@ class FeedbackLoop(nn.Module):
 
     def _solve_filter_coupling(self, z: torch.Tensor, b: torch.Tensor, c: torch.Tensor, transpose: bool):
         """filter_matrix coupling: the system matrix D(z_k) Gamma^-1 - A(z_k) has a different complex A per bin
-        (reference :362-373, A(z) cast to complex64 like there). No shipped configuration uses this variant and it is
-        not on the kernel hot path: the per-bin matrices are formed and solved by a batched LU on the device
-        (torch.linalg.solve, complex128), differentiable through autograd."""
+        (reference :362-373). K1 builds A(z_k) = sum_p A_p z_k^-p from the taps in shared memory per bin
+        (ops.gfdn_solve_fir); the adjoint hands back lambda and the tap gradients are P small products."""
         taps = self.coupled_feedback_taps(torch.float64)
         self.coupled_feedback_matrix = taps.detach()
-        zc = z.to(device=taps.device, dtype=torch.complex128)
-        p = torch.arange(taps.shape[-1], device=taps.device, dtype=torch.float64)
-        az = torch.einsum('nmp,kp->knm', taps.to(torch.complex128), zc.unsqueeze(-1)**(-p))
-        az = az.to(torch.complex64).to(torch.complex128)
         gamma_z = self.absorption_response(z)
-        d = zc.unsqueeze(-1)**self.delays.to(torch.float64)
-        dd = d / (self.delay_line_gains.to(torch.complex128) if gamma_z is None else gamma_z.to(torch.complex128).transpose(0, 1))
-        m = torch.diag_embed(dd) - az
-        if transpose:
-            m = m.transpose(-1, -2)
-        x = torch.linalg.solve(m, b.reshape(-1).to(torch.complex128).expand(m.shape[0], -1).unsqueeze(-1)).squeeze(-1)
-        y = (x * c.reshape(-1).to(torch.complex128)).reshape(x.shape[0], self.num_groups, -1).sum(-1)
-        return x.to(torch.complex64), y.to(torch.complex64)
+        gamma = None if gamma_z is not None else self.delay_line_gains
+        return ops.gfdn_solve_fir(z, self.delays.to(torch.int32), taps, gamma, b, c, self.num_groups,
+                                  transpose_a=transpose, gamma_z=gamma_z)
 
     def construct_coupling_matrix(self, dtype: Optional[torch.dtype] = None) -> torch.Tensor:
         if self.coupling_matrix_type == CouplingMatrixType.FILTER:

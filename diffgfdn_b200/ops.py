@@ -189,6 +189,80 @@ def gfdn_solve(z: torch.Tensor, delays: torch.Tensor, a: torch.Tensor, gamma: Op
     return _GFDNSolve.apply(z, delays, a, gamma, b, c, num_groups, transpose_a, gamma_z)
 
 
+class _GFDNSolveFIR(torch.autograd.Function):
+    """K1 with FIR coupling: x_k = (diag(z_k^m / gamma) - sum_p A_p z_k^-p)^-1 b (reference feedback_loop.py:362-373 with
+    coupling_matrix_type filter_matrix). taps (N, N, P) real."""
+
+    @staticmethod
+    def forward(ctx, z, delays, taps, gamma, b, c, num_groups, transpose_a, gamma_z):
+        z = _cuda("z", z, C128)
+        delays = _cuda("delays", delays, torch.int32)
+        if taps.dim() != 3 or taps.shape[0] != taps.shape[1]:
+            raise RuntimeError("gfdn_solve_fir: taps must be (N, N, P)")
+        taps_ = _cuda("taps", taps.permute(2, 0, 1), torch.float32)  # (P, N, N)
+        gamma_ = _cuda("gamma", gamma, torch.float32, optional=True)
+        gamma_z_ = _cuda("gamma_z", gamma_z, C64, optional=True)
+        b_ = _cuda("b", b.reshape(-1), torch.float32)
+        c_ = _cuda("c", c.reshape(-1), torch.float32)
+        ntaps, n, _ = taps_.shape
+        k = z.shape[0]
+        if delays.numel() != n or b_.numel() != n or c_.numel() != n:
+            raise RuntimeError("gfdn_solve_fir: inconsistent shapes")
+        x = torch.empty(k, n, dtype=C64, device=z.device)
+        y = torch.empty(k, num_groups, dtype=C64, device=z.device)
+        with torch.cuda.device(z.device):
+            _lib.call("dgfdn_solve_fir_fwd", n, num_groups, ntaps, k, _ptr(z), _ptr(delays), _ptr(taps_), int(transpose_a),
+                      _ptr(gamma_), _ptr(gamma_z_), _ptr(b_), _ptr(c_), _ptr(x), _ptr(y), _stream())
+        ctx.save_for_backward(z, delays, taps_, gamma_, gamma_z_, c_, x)
+        ctx.meta = (n, num_groups, ntaps, k, int(transpose_a), b.shape, c.shape, taps.dtype)
+        return x, y
+
+    @staticmethod
+    def backward(ctx, gx, gy):
+        z, delays, taps_, gamma_, gamma_z_, c_, x = ctx.saved_tensors
+        n, g, ntaps, k, tr, bshape, cshape, tdtype = ctx.meta
+        if gx is None and gy is None:
+            return (None, ) * 9
+        gx_ = _cuda("gx", gx, C64, optional=True)
+        gy_ = _cuda("gy", gy, C64, optional=True)
+        dev = z.device
+        out = torch.empty(3 * n, dtype=torch.float64, device=dev)
+        gb, gc, gig = out[:n], out[n:2 * n], out[2 * n:]
+        lam = torch.empty(k, n, dtype=C64, device=dev)
+        with torch.cuda.device(dev):
+            ws = torch.empty(_lib.load().dgfdn_solve_bwd_ws_bytes(n) // 8, dtype=torch.float64, device=dev)
+            _lib.call("dgfdn_solve_fir_bwd", n, g, ntaps, k, _ptr(z), _ptr(delays), _ptr(taps_), tr, _ptr(gamma_),
+                      _ptr(gamma_z_), _ptr(c_), _ptr(x), _ptr(gy_), _ptr(gx_), _ptr(lam), _ptr(gb), _ptr(gc), _ptr(gig),
+                      _ptr(ws), _stream())
+        g_taps = None
+        if ctx.needs_input_grad[2]:
+            # gtaps[i,j,p] = Re sum_k lambda[k,i] conj(x[k,j]) conj(z_k^-p): P small (N x K) x (K x N) products
+            lam128, xc = lam.to(C128), x.to(C128).conj()
+            zinv = (1.0 / z).conj()
+            w = torch.ones_like(zinv)
+            cols = []
+            for _ in range(ntaps):
+                cols.append(((lam128 * w.unsqueeze(-1)).transpose(0, 1) @ xc).real)
+                w = w * zinv
+            g_taps = torch.stack(cols, dim=-1)  # gradient w.r.t. A_eff: transposed back when the solve ran on A^T
+            if tr:
+                g_taps = g_taps.transpose(0, 1)
+            g_taps = g_taps.to(tdtype)
+        g_gamma = None
+        if gamma_ is not None and ctx.needs_input_grad[3]:
+            g_gamma = (-gig / gamma_.to(torch.float64)**2).to(torch.float32)
+        g_b = gb.to(torch.float32).reshape(bshape) if ctx.needs_input_grad[4] else None
+        g_c = gc.to(torch.float32).reshape(cshape) if ctx.needs_input_grad[5] else None
+        return None, None, g_taps, g_gamma, g_b, g_c, None, None, None
+
+
+def gfdn_solve_fir(z: torch.Tensor, delays: torch.Tensor, taps: torch.Tensor, gamma: Optional[torch.Tensor],
+                   b: torch.Tensor, c: torch.Tensor, num_groups: int, transpose_a: bool = False,
+                   gamma_z: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """gfdn_solve with a FIR feedback matrix A(z) = sum_p taps[..., p] z^-p; differentiable w.r.t. taps, gamma, b, c."""
+    return _GFDNSolveFIR.apply(z, delays, taps, gamma, b, c, num_groups, transpose_a, gamma_z)
+
+
 class _GFDNSolveGroups(torch.autograd.Function):
     """G independent LxL systems per bin: x[k, gL+i] = ((diag(z_k^{m_g}/gamma_g) - M_g)^-1 b_g)[i],
     y[k,g] = sum_i c[gL+i] x[k, gL+i]  -- DiffGFDN.sub_fdn_output (reference model.py:209-252)."""

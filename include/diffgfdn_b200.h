@@ -99,6 +99,20 @@ DGFDN_API int dgfdn_solve_bwd(int n, int g, int64_t k, const void* z, const int3
                     const void* gy, const void* gx, double* ga, double* gb, double* gc, double* ginvgamma,
                     void* ws, const void* factors, void* stream);
 
+/* K1 with FIR coupling (coupling_matrix_type: filter_matrix, feedback_loop.py:90-143, 362-373, 447-453): the feedback matrix is
+ * a polynomial A(z) = sum_p A_p z^-p, so every bin has its own complex M_k = diag(z_k^m / gamma) - sum_p A_p z_k^-p.
+ * taps [P,N,N] float32 (A_p row-major), 1 <= P <= 64; everything else as dgfdn_solve_fwd / dgfdn_solve_bwd (float64
+ * elimination, the adjoint re-eliminates M_k^H). The adjoint also returns lambda [K,N] c64: the tap gradients are
+ *   gtaps[p,i,j] = Re sum_k lambda[k,i] conj(x[k,j]) conj(z_k^-p)        (transposed back if transpose_a)
+ * a P-term DFT-weighted sum of outer products that the caller forms. ws: dgfdn_solve_bwd_ws_bytes(n) bytes. */
+DGFDN_API int dgfdn_solve_fir_fwd(int n, int g, int ntaps, int64_t k, const void* z, const int32_t* delays, const float* taps,
+                        int transpose_a, const float* gamma, const void* gamma_z, const float* b, const float* c,
+                        void* x, void* y, void* stream);
+DGFDN_API int dgfdn_solve_fir_bwd(int n, int g, int ntaps, int64_t k, const void* z, const int32_t* delays, const float* taps,
+                        int transpose_a, const float* gamma, const void* gamma_z, const float* c, const void* x,
+                        const void* gy, const void* gx, void* lam, double* gb, double* gc, double* ginvgamma, void* ws,
+                        void* stream);
+
 /* Group mode of K1: the G independent lossless LxL systems of DiffGFDN.sub_fdn_output (model.py:209-252, quirk Q1:
  * RAW mixing matrices, normally no absorption) solved as G small systems per bin -- four 8x8 systems to a warp --
  * instead of one block-diagonal NxN system.

@@ -107,6 +107,45 @@ def test_solve_backward(n, g, transpose, radius):
     assert rel(cd.grad, c.grad) < 1e-3
 
 
+@pytest.mark.parametrize("n,g,ntaps,transpose,radius", [(12, 3, 4, False, 1.0), (24, 3, 8, False, 1.00002), (27, 3, 3, True, 1.0),
+                                                        (6, 2, 1, False, 1.0)])
+def test_solve_fir_coupling_forward_backward(n, g, ntaps, transpose, radius):
+    """K1 with a FIR feedback matrix A(z_k) = sum_p A_p z_k^-p (filter_matrix coupling, reference feedback_loop.py:362-373):
+    x, y and every gradient (taps, gamma, b, c) against the float64 oracle's dense inverse and its autograd."""
+    from diffgfdn_b200 import ops
+    sy = make_system(n, g, 1024, seed=300 + n, radius=radius)
+    k = sy["z"].numel()
+    gen = torch.Generator().manual_seed(11)
+    taps = torch.stack([sy["a"] * (0.6 ** p) * (1.0 if p == 0 else 0.5) for p in range(ntaps)], dim=-1)
+    taps = (taps + 0.05 * torch.randn(n, n, ntaps, generator=gen)).to(torch.float32)
+    wy = torch.randn(k, g, dtype=torch.complex128, generator=gen)
+    wx = torch.randn(k, n, dtype=torch.complex128, generator=gen)
+    to = taps.to(F64).requires_grad_(True)
+    gam = sy["gamma"].to(F64).requires_grad_(True)
+    b = sy["b"].to(F64).requires_grad_(True)
+    c = sy["c"].to(F64).requires_grad_(True)
+    # the oracle rounds A(z) to complex64 like the reference (:373); compare against the unrounded product here
+    zp = sy["z"].to(torch.complex128).unsqueeze(-1) ** (-torch.arange(ntaps, dtype=F64))
+    az = torch.einsum('nmp,kp->knm', to.to(torch.complex128), zp)
+    d = sy["z"].to(torch.complex128).unsqueeze(-1) ** sy["delays"].to(F64) / gam.to(torch.complex128)
+    pinv = torch.linalg.inv(torch.diag_embed(d) - az)
+    xo = torch.einsum('knm,n->km' if transpose else 'knm,m->kn', pinv, b.to(torch.complex128))
+    yo = (xo * c.to(torch.complex128)).reshape(-1, g, n // g).sum(-1)
+    lo = (yo * wy.conj()).real.sum() + (xo * wx.conj()).real.sum()
+    lo.backward()
+    td, gd, bd, cd = [dev(t).requires_grad_(True) for t in (taps, sy["gamma"], sy["b"], sy["c"])]
+    x, y = ops.gfdn_solve_fir(dev(sy["z"]), dev(sy["delays"]), td, gd, bd, cd, g, transpose_a=transpose)
+    assert rel(x.detach().cpu().to(torch.complex128), xo.detach()) < 2e-6
+    assert rel(y.detach().cpu().to(torch.complex128), yo.detach()) < 2e-6
+    lk = (y.to(torch.complex128) * dev(wy).conj()).real.sum() + (x.to(torch.complex128) * dev(wx).conj()).real.sum()
+    lk.backward()
+    assert abs(float(lk) - float(lo)) < 1e-5 * abs(float(lo)) + 1e-6
+    assert rel(td.grad, to.grad) < 1e-3
+    assert rel(gd.grad, gam.grad) < 1e-3
+    assert rel(bd.grad, b.grad) < 1e-3
+    assert rel(cd.grad, c.grad) < 1e-3
+
+
 @pytest.mark.parametrize("g,l,scale", [(3, 4, 1.0), (3, 8, 1.0), (3, 9, 3.0), (1, 16, 0.2), (5, 1, 1.0), (2, 6, 25.0)])
 def test_skew_expm_forward_backward(g, l, scale):
     """Fused Skew + matrix exponential against torch.matrix_exp in float64 (reference feedback_loop.py:16-36)."""
