@@ -238,7 +238,9 @@ class ShardedEDCStep:
             y = _GatherBins.apply(y_loc, lo, hi, ke, self.pg)
         else:
             _, y = net.feedback_loop.solve(z_edc, net.input_gains.reshape(-1), net.output_gains.reshape(-1))
-        hy = ops.irfft_window(y.transpose(0, 1), self.n_fft, self.t0, self.tn)  # (G, tn)
+        # the graph is cut at y: the backward below runs the chirp-z adjoint first, on its own (see there)
+        y_cut = y.detach().requires_grad_(True)
+        hy = ops.irfft_window(y_cut.transpose(0, 1), self.n_fft, self.t0, self.tn)  # (G, tn)
         # own kernels of the front: position network, 2 x skew-expm (coupled matrix, sparsity term), matrix assembly,
         # coupled solve, chirp-z (pre, mul, post; the 2 cuFFT launches are not counted), colorless branch
         fused_cl = self.use_fused_colorless and net.num_delay_lines_per_group <= 16
@@ -313,7 +315,17 @@ class ShardedEDCStep:
         # consumers itself, so the adjoint solve of the EDC branch does not wait for the tail of the colorless branch
         # two calls: the EDC branch first, so that its nodes are enqueued (and captured) ahead of the colorless tail --
         # the branches share nothing but leaf parameters
-        torch.autograd.backward([hy, s], [ghy, gs])
+        # three calls for the EDC branch: (1) the chirp-z adjoint (a chain of 5-15 us kernels right behind the receiver
+        # kernel), (2) the position network's backward on its stream, gated on (1): its big grid otherwise shares the SMs
+        # with those latency-bound kernels and doubles their time; behind them it overlaps the adjoint solve (FP64 /
+        # shuffle bound against FP32 FMA work), (3) the adjoint solve chain from dL/dy on.
+        torch.autograd.backward([hy], [ghy])
+        after_czt = torch.cuda.Event()
+        after_czt.record(main)
+        side.wait_event(after_czt)
+        with torch.cuda.stream(side):
+            torch.autograd.backward([s], [gs])
+        torch.autograd.backward([y], [y_cut.grad])
         with torch.cuda.stream(side2):
             torch.autograd.backward([aux], [torch.ones_like(aux)])
         main.wait_stream(side)  # the engine joins the streams of the leaves; this makes the join explicit for capture
