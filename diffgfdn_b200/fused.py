@@ -319,10 +319,13 @@ class ShardedEDCStep:
         # kernel), (2) the position network's backward on its stream, gated on (1): its big grid otherwise shares the SMs
         # with those latency-bound kernels and doubles their time; behind them it overlaps the adjoint solve (FP64 /
         # shuffle bound against FP32 FMA work), (3) the adjoint solve chain from dL/dy on.
+        # (With the per-bin work sharded over the ranks the adjoint chain is short and the position network's backward is
+        # what finishes last: it then starts as soon as dL/ds exists. Measured at N = 8: 1.84 ms ungated, 1.87 ms gated.)
         torch.autograd.backward([hy], [ghy])
-        after_czt = torch.cuda.Event()
-        after_czt.record(main)
-        side.wait_event(after_czt)
+        if not self.shard_bins:
+            after_czt = torch.cuda.Event()
+            after_czt.record(main)
+            side.wait_event(after_czt)
         with torch.cuda.stream(side):
             torch.autograd.backward([s], [gs])
         torch.autograd.backward([y], [y_cut.grad])
