@@ -39,6 +39,14 @@ SIGNATURES = {
     "dgfdn_solve_fir_bwd": (c_int, [c_int, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                                     c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                     c_void_p, c_void_p]),
+    "dgfdn_peer_state_bytes": (c_int64, []),
+    "dgfdn_peer_flags_bytes": (c_int64, []),
+    "dgfdn_peer_push": (c_int, [c_int, c_int, c_int, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_int64,
+                                c_void_p]),
+    "dgfdn_peer_gather": (c_int, [c_int, c_int, c_int, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_void_p,
+                                  c_int64, c_void_p]),
+    "dgfdn_peer_reduce": (c_int, [c_int, c_int, c_int, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_void_p,
+                                  c_int64, c_void_p]),
     "dgfdn_solve_colorless_ws_bytes": (c_int64, [c_int]),
     "dgfdn_solve_colorless": (c_int, [c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                       c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -15,7 +15,7 @@ INCLUDE = os.path.join(ROOT, "include")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libdiffgfdn_b200.so")
 SOURCES = ["common.cu", "expm.cu", "solve.cu", "project.cu", "czt.cu", "edc.cu", "edc_td.cu", "edc_td_fused.cu", "edc_td_sliced.cu", "colorless.cu", "render.cu",
-           "mlp.cu", "svf.cu", "edr.cu", "assemble.cu"]
+           "mlp.cu", "svf.cu", "edr.cu", "assemble.cu", "peer.cu"]
 
 
 def _nvcc():

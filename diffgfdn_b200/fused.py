@@ -44,24 +44,25 @@ C64 = torch.complex64
 
 
 class _GatherBins(torch.autograd.Function):
-    """y (K, G) from this rank's bin slice y_loc = y[lo:hi]: an all-gather of equal (padded) slices over NCCL, a
-    zero-padded SUM all-reduce on other backends. The caller all-reduces the gradient of everything downstream
-    (dL/dhy) BEFORE the backward, so the backward is the slice of the total gradient."""
+    """y (K, G) from this rank's bin slice y_loc = y[lo:hi] (slices of `per` bins, the last ones shorter): over NVLink
+    peer memory (PeerExchange) when the ranks share a node, else an all-gather of the padded slices over NCCL, else (other
+    backends) a zero-padded SUM all-reduce. The caller sums the gradient of everything downstream (dL/dhy) over the ranks
+    BEFORE the backward, so the backward is the slice of the total gradient."""
 
     @staticmethod
-    def forward(ctx, y_loc, lo, hi, k, group):
+    def forward(ctx, y_loc, lo, hi, k, per, group, peer):
         world = dist.get_world_size(group)
-        per = (k + world - 1) // world
         ctx.lo, ctx.hi = lo, hi
-        if dist.get_backend(group) == "nccl":
-            # equal slices of `per` bins (the last ranks' slices are padded): one all-gather into a (world * per, G)
-            # buffer, no zero fill and half the traffic of the all-reduce formulation
-            buf = torch.empty(world * per, y_loc.shape[1], dtype=y_loc.dtype, device=y_loc.device)
+        if peer is not None or dist.get_backend(group) == "nccl":
             mine = y_loc
             if hi - lo < per:
                 mine = torch.zeros(per, y_loc.shape[1], dtype=y_loc.dtype, device=y_loc.device)
                 mine[:hi - lo] = y_loc
-            dist.all_gather_into_tensor(torch.view_as_real(buf), torch.view_as_real(mine.contiguous()), group=group)
+            mine = mine.contiguous()
+            if peer is not None:
+                return peer.all_gather("y", mine)[:k]
+            buf = torch.empty(world * per, y_loc.shape[1], dtype=y_loc.dtype, device=y_loc.device)
+            dist.all_gather_into_tensor(torch.view_as_real(buf), torch.view_as_real(mine), group=group)
             return buf[:k]
         y = torch.zeros(k, y_loc.shape[1], dtype=y_loc.dtype, device=y_loc.device)
         y[lo:hi] = y_loc
@@ -70,7 +71,7 @@ class _GatherBins(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gy):
-        return gy[ctx.lo:ctx.hi].contiguous(), None, None, None, None
+        return gy[ctx.lo:ctx.hi].contiguous(), None, None, None, None, None, None
 
 
 def _p(t):
@@ -107,6 +108,9 @@ class ShardedEDCStep:
         self._mask_count = None
         self.events = None  # set to a dict of lists to collect per-kernel CUDA events (bench.py)
         self.use_side_stream = os.environ.get("DGFDN_SIDE_STREAM", "1") != "0"
+        # exchanges of the multi-GPU step over NVLink peer memory (diffgfdn_b200/peer.py) instead of NCCL; set up at attach()
+        self.use_peer = world_size > 1 and os.environ.get("DGFDN_PEER", "1") != "0"
+        self.peer = None
         self.use_fused_colorless = os.environ.get("DGFDN_FUSED_COLORLESS", "1") != "0"
         self._side = None
         self._side2 = None
@@ -177,6 +181,7 @@ class ShardedEDCStep:
             self._bufs = dict(gh=torch.empty(r, self.tn, dtype=torch.float32, device=dev),
                               ws=ops.td_contract_workspace(g, r, self.tn, dev),
                               row_sum=torch.empty(self.rows, dtype=torch.float64, device=dev))
+        self._setup_peer()
 
     def set_mask(self, mask: Optional[torch.Tensor]):
         """Fixed 0/1 sample mask of the EDC loss (reference losses.py:221-238 draws one per call; here it is an
@@ -235,7 +240,7 @@ class ShardedEDCStep:
             ke = z_edc.shape[0]
             lo, hi = self._bin_slice(ke)
             _, y_loc = net.feedback_loop.solve(z_edc[lo:hi], net.input_gains.reshape(-1), net.output_gains.reshape(-1))
-            y = _GatherBins.apply(y_loc, lo, hi, ke, self.pg)
+            y = _GatherBins.apply(y_loc, lo, hi, ke, self._bins_per_rank(ke), self.pg, self.peer)
         else:
             _, y = net.feedback_loop.solve(z_edc, net.input_gains.reshape(-1), net.output_gains.reshape(-1))
         # the graph is cut at y: the backward below runs the chirp-z adjoint first, on its own (see there)
@@ -308,9 +313,14 @@ class ShardedEDCStep:
                 per_group = ops.colorless_loss_per_group(h_sub, self.asym)
             spectral = self.w_spec * per_group.sum() * share  # this rank's share: the ranks' values add up to the loss
             aux = spectral + sparsity.to(spectral.dtype) / self.world_size
+        gs_ready = torch.cuda.Event()  # dL/ds (and dL/dhy of this rank) are complete on the main stream
+        gs_ready.record(main)
         edc = (self._bufs["loss_sum"][0] if self.use_fused else self._bufs["row_sum"].sum()) * coef
         if self.shard_bins:  # every rank needs the TOTAL dL/dhy for the adjoint solve of its bins
-            dist.all_reduce(ghy, op=dist.ReduceOp.SUM, group=self.pg)
+            if self.peer is not None:
+                self.peer.all_reduce_("ghy", ghy)
+            else:
+                dist.all_reduce(ghy, op=dist.ReduceOp.SUM, group=self.pg)
         # no join before the backward: the engine runs each node on its forward's stream and orders producers and
         # consumers itself, so the adjoint solve of the EDC branch does not wait for the tail of the colorless branch
         # two calls: the EDC branch first, so that its nodes are enqueued (and captured) ahead of the colorless tail --
@@ -326,6 +336,8 @@ class ShardedEDCStep:
             after_czt = torch.cuda.Event()
             after_czt.record(main)
             side.wait_event(after_czt)
+        else:
+            side.wait_event(gs_ready)  # (the engine takes the gradients handed to backward() as ready on the CALLING stream)
         with torch.cuda.stream(side):
             torch.autograd.backward([s], [gs])
         torch.autograd.backward([y], [y_cut.grad])
@@ -422,11 +434,38 @@ class ShardedEDCStep:
             ev.setdefault("td_contract", []).append((marks[1], marks[2]))
         self.kernel_launches += 3  # td_edc_step, td_contract, td_contract_reduce
 
-    def _bin_slice(self, k: int):
-        """Contiguous bins [lo, hi) of this rank out of k (ranks at the end may get one bin less)."""
+    def _bins_per_rank(self, k: int) -> int:
+        """Bins of a rank's slice: ceil(k / world) rounded up to an even count (16-byte granularity of complex64 x G rows
+        for the peer-memory exchange); the last ranks' slices are shorter."""
         per = (k + self.world_size - 1) // self.world_size
+        return per + (per & 1)
+
+    def _bin_slice(self, k: int):
+        """Contiguous bins [lo, hi) of this rank out of k."""
+        per = self._bins_per_rank(k)
         lo = min(k, self.rank * per)
         return lo, min(k, lo + per)
+
+    def _setup_peer(self):
+        """One symmetric buffer per rank with a channel per exchange of the step (y slices, dL/dhy, gradient bucket)."""
+        if not self.use_peer or self.peer is not None:
+            return
+        try:
+            if dist.get_backend(self.pg) != "nccl":
+                raise RuntimeError("ranks do not own one GPU each")
+            from .peer import PeerExchange
+            g = self.net.num_groups
+            n_grad = sum(p.numel() for p in self.net.parameters() if p.requires_grad)
+            channels = {"grads": 4 * ((n_grad + 3) // 4 * 4)}
+            if self.shard_bins:
+                ke = self.k if self.net.feedback_loop.delay_line_gain_response is not None else self.kx
+                channels["y"] = self._bins_per_rank(ke) * g * 8
+                channels["ghy"] = g * self.tn * 4
+            self.peer = PeerExchange(self.pg, self.dev, channels)
+        except Exception as exc:  # NCCL carries the exchanges then (same results, a library collective per exchange)
+            import warnings
+            warnings.warn(f"ShardedEDCStep: peer-memory exchange unavailable ({exc}); using NCCL collectives")
+            self.use_peer = False
 
     @staticmethod
     def _sparsity(a: torch.Tensor) -> torch.Tensor:
@@ -506,8 +545,15 @@ class ShardedEDCStep:
         for p in params:
             if p.grad is None:
                 p.grad = torch.zeros_like(p)
-        flat = torch.cat([p.grad.reshape(-1).to(torch.float32) for p in params])
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.pg)
+        parts = [p.grad.reshape(-1).to(torch.float32) for p in params]
+        n = sum(t.numel() for t in parts)
+        if self.peer is not None and (n + 3) // 4 * 4 > n:  # the peer exchange moves 16-byte units
+            parts.append(torch.zeros((n + 3) // 4 * 4 - n, dtype=torch.float32, device=parts[0].device))
+        flat = torch.cat(parts)
+        if self.peer is not None:
+            self.peer.all_reduce_("grads", flat)
+        else:
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.pg)
         views, off = [], 0
         for p in params:
             n = p.numel()

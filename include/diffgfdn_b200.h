@@ -330,6 +330,29 @@ DGFDN_API int dgfdn_render_groups(int bands, int n, int g, int64_t t, const int3
 DGFDN_API int dgfdn_render_mix(int bands, int g, int64_t t, int64_t listeners, int64_t positions, int64_t hop,
                      const float* s, const int32_t* traj, const float* q, float* out, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Exchange steps of the bin-sharded multi-GPU step over NVLink peer memory (csrc/peer.cu): every rank of the node owns one
+ * symmetric buffer (same layout everywhere) and holds the device pointers of all of them (peer_ptrs[world], host array;
+ * P2P mappings from the caller, e.g. torch's symmetric-memory rendezvous). Layout of a buffer: flags at flags_off
+ * (dgfdn_peer_flags_bytes() bytes, zero before first use), and per channel two data regions (parity of the channel's sequence
+ * number) of region_bytes at data_off, the slot of source rank r at r * slot_stride inside a region.
+ *   dgfdn_peer_push    stores src (nbytes) into this rank's slot in EVERY rank's buffer, then raises this rank's flag there;
+ *   dgfdn_peer_gather  waits for every rank's flag of the channel's current sequence number, out <- the world slots in rank order;
+ *   dgfdn_peer_reduce  the same wait, out[i] = sum over the slots in rank order (float32; deterministic, identical on all ranks).
+ * Replaces dist.all_gather_into_tensor / dist.all_reduce for the three small exchanges of a step (no counterpart in the
+ * reference, which is single-process). state: dgfdn_peer_state_bytes() bytes of zeroed local device memory, one per
+ * buffer. All sizes / offsets multiples of 16 bytes. Stream ordered, no host synchronisation (CUDA-graph capturable). */
+DGFDN_API int64_t dgfdn_peer_state_bytes(void);
+DGFDN_API int64_t dgfdn_peer_flags_bytes(void);
+DGFDN_API int dgfdn_peer_push(int world, int rank, int channel, const void* const* peer_ptrs, int64_t flags_off, int64_t data_off,
+                    int64_t region_bytes, int64_t slot_stride, void* state, const void* src, int64_t nbytes, void* stream);
+DGFDN_API int dgfdn_peer_gather(int world, int rank, int channel, const void* const* peer_ptrs, int64_t flags_off,
+                      int64_t data_off, int64_t region_bytes, int64_t slot_stride, void* state, void* out, int64_t nbytes,
+                      void* stream);
+DGFDN_API int dgfdn_peer_reduce(int world, int rank, int channel, const void* const* peer_ptrs, int64_t flags_off,
+                      int64_t data_off, int64_t region_bytes, int64_t slot_stride, void* state, void* out, int64_t nbytes,
+                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif

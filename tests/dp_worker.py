@@ -48,6 +48,7 @@ def run_step(net, max_ms, z, pos, early, target, world, total, pg=None, graph=Fa
         out = step.step()
     torch.cuda.synchronize()
     flat = torch.cat([p.grad.reshape(-1).float() for p in net.parameters()])
+    run_step.peer_active = step.peer is not None  # exchanges over NVLink peer memory (else NCCL / gloo collectives)
     return {k: float(v) for k, v in out.items()}, flat.cpu()
 
 
@@ -66,9 +67,10 @@ def main():
     net, max_ms, z, pos, early, target = make_problem(rows, nfft, dev)
     per = (rows + world - 1) // world
     sl = slice(rank * per, min(rows, (rank + 1) * per))
-    kw = dict(shard_bins=True) if mode == "strong" else {}
-    losses, flat = run_step(net, max_ms, z, pos[sl], early[sl], target[sl], world, rows, graph=(mode == "graph"), **kw)
-    torch.save(dict(losses=losses, flat=flat, backend=dist.get_backend()), os.path.join(out_dir, f"rank{rank}.pt"))
+    kw = dict(shard_bins=True) if mode in ("strong", "strong_graph") else {}
+    losses, flat = run_step(net, max_ms, z, pos[sl], early[sl], target[sl], world, rows, graph=mode.endswith("graph"), **kw)
+    torch.save(dict(losses=losses, flat=flat, backend=dist.get_backend(), peer=run_step.peer_active),
+               os.path.join(out_dir, f"rank{rank}.pt"))
     dist.barrier()
     dist.destroy_process_group()
 

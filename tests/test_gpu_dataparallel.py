@@ -26,25 +26,32 @@ def _launch(tmp_path, rows, nfft, mode, world=2):
     return [torch.load(os.path.join(tmp_path, f"rank{r}.pt")) for r in range(world)]
 
 
-@pytest.mark.parametrize("mode", ["weak", "strong", "graph"])
-def test_two_ranks_equal_one_rank_on_the_concatenation(tmp_path, mode):
+@pytest.mark.parametrize("peer", ["1", "0"])
+@pytest.mark.parametrize("mode", ["weak", "strong", "graph", "strong_graph"])
+def test_two_ranks_equal_one_rank_on_the_concatenation(tmp_path, mode, peer, monkeypatch):
     """mode weak: every rank solves all bins (K1 replicated); strong: K1 sharded over bins with all-gather of y /
-    reduce of the adjoint right-hand sides; graph: the weak step captured in a CUDA graph (all-reduce inside)."""
+    reduce of the adjoint right-hand sides; graph / strong_graph: the step captured in a CUDA graph (exchanges inside).
+    peer 1: the exchanges run over NVLink peer memory (csrc/peer.cu) when every rank has its own GPU, 0: NCCL."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import dp_worker
-    if mode == "graph" and torch.cuda.device_count() < 2:
-        pytest.skip("a captured all-reduce needs NCCL, i.e. one GPU per rank")
+    if mode.endswith("graph") and torch.cuda.device_count() < 2:
+        pytest.skip("a captured exchange needs one GPU per rank")
+    if peer == "1" and torch.cuda.device_count() < 2:
+        pytest.skip("peer memory needs one GPU per rank")
+    monkeypatch.setenv("DGFDN_PEER", peer)
     rows, nfft = 10, 4096
     net, max_ms, z, pos, early, target = dp_worker.make_problem(rows, nfft, torch.device("cuda"))
     losses1, flat1 = dp_worker.run_step(net, max_ms, z, pos, early, target, 1, rows)
     ranks = _launch(tmp_path, rows, nfft, mode)
     edc = sum(r["losses"]["edc_loss"] for r in ranks)  # per-rank partial of the global mean
     assert abs(edc - losses1["edc_loss"]) < 1e-5 * abs(losses1["edc_loss"])
-    if mode == "strong":  # bin-sharded colorless branch: the ranks' shares add up
+    if torch.cuda.device_count() >= 2:
+        assert all(r["peer"] == (peer == "1") for r in ranks), [r["peer"] for r in ranks]
+    if mode.startswith("strong"):  # bin-sharded colorless branch: the ranks' shares add up
         spec = sum(r["losses"]["spectral_loss"] for r in ranks)
         assert abs(spec - losses1["spectral_loss"]) < 1e-5 * abs(losses1["spectral_loss"])
     for r in ranks:
-        if mode != "strong":
+        if not mode.startswith("strong"):
             assert abs(r["losses"]["spectral_loss"] - losses1["spectral_loss"]) < 1e-5 * abs(losses1["spectral_loss"])
         err = float((r["flat"] - flat1).abs().max() / flat1.abs().max())
         assert err < 1e-4, (mode, r["backend"], err)
