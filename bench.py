@@ -707,6 +707,9 @@ def main():
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": args.scaling, "vs_baseline": None, "dtype": "f32 storage / f64 per-bin solve and scans",
             "data": "synthetic", "config": workload_config(args), "loss": loss_val, "clocks": clocks.summary(),
+            "exchanges": ("none (one rank)" if world == 1 else
+                          "own push / wait kernels over NVLink peer memory (csrc/peer.cu), inside the captured graph"
+                          if step.peer is not None else "NCCL collectives inside the captured graph"),
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
                          "traffic": traffic, "peak_source": how, "kernel": td_name,

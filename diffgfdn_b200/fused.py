@@ -241,6 +241,7 @@ class ShardedEDCStep:
             lo, hi = self._bin_slice(ke)
             _, y_loc = net.feedback_loop.solve(z_edc[lo:hi], net.input_gains.reshape(-1), net.output_gains.reshape(-1))
             y = _GatherBins.apply(y_loc, lo, hi, ke, self._bins_per_rank(ke), self.pg, self.peer)
+            self.kernel_launches += 2 if self.peer is not None else 0  # push + wait-and-gather
         else:
             _, y = net.feedback_loop.solve(z_edc, net.input_gains.reshape(-1), net.output_gains.reshape(-1))
         # the graph is cut at y: the backward below runs the chirp-z adjoint first, on its own (see there)
@@ -319,6 +320,7 @@ class ShardedEDCStep:
         if self.shard_bins:  # every rank needs the TOTAL dL/dhy for the adjoint solve of its bins
             if self.peer is not None:
                 self.peer.all_reduce_("ghy", ghy)
+                self.kernel_launches += 2  # push + wait-and-add
             else:
                 dist.all_reduce(ghy, op=dist.ReduceOp.SUM, group=self.pg)
         # no join before the backward: the engine runs each node on its forward's stream and orders producers and
@@ -552,6 +554,7 @@ class ShardedEDCStep:
         flat = torch.cat(parts)
         if self.peer is not None:
             self.peer.all_reduce_("grads", flat)
+            self.kernel_launches += 2
         else:
             dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.pg)
         views, off = [], 0
