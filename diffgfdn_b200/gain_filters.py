@@ -120,8 +120,10 @@ class SVF_from_MLP(nn.Module):
         self.compress_pole_factor = compress_pole_factor
         self.device = device
         if self.encoding_type != FeatureEncodingType.SINE:
-            raise NotImplementedError("only the sinusoidal position encoding is on the B200 hot path "
-                                      "(no shipped config uses the meshgrid encoding)")
+            # unreachable in the reference too: its collate function never puts 'mesh_2D' into a batch
+            # (dataloader.py:674-704), which the meshgrid branch of forward() reads (gain_filters.py:353, 511)
+            raise NotImplementedError("meshgrid position encoding: the reference's own batches never carry 'mesh_2D', so "
+                                      "that branch cannot run there either; only the sinusoidal encoding is built")
         self.svf_cutoff_freqs = svf_cutoff_frequencies(sample_rate)
         self.num_biquads = self.svf_cutoff_freqs.numel()
         self.encoder = SinusoidalEncoding(num_fourier_features)
@@ -195,8 +197,10 @@ class Gains_from_MLP(nn.Module):
         self.encoding_type = encoding_type
         self.device = device
         if self.encoding_type != FeatureEncodingType.SINE:
-            raise NotImplementedError("only the sinusoidal position encoding is on the B200 hot path "
-                                      "(no shipped config uses the meshgrid encoding)")
+            # unreachable in the reference too: its collate function never puts 'mesh_2D' into a batch
+            # (dataloader.py:674-704), which the meshgrid branch of forward() reads (gain_filters.py:353, 511)
+            raise NotImplementedError("meshgrid position encoding: the reference's own batches never carry 'mesh_2D', so "
+                                      "that branch cannot run there either; only the sinusoidal encoding is built")
         self.encoder = SinusoidalEncoding(num_fourier_features)
         self.mlp = MLP(3 * num_fourier_features * 2, num_hidden_layers, num_neurons, self.num_groups,
                        num_biquads_in_cascade=1, num_params=1)

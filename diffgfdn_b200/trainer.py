@@ -38,7 +38,10 @@ class Trainer:
         self.subband_filter_freq_resp = None
         self.use_directional_fdn = getattr(self.net, "ambi_order", None) is not None
         if self.use_reg_loss:
-            raise NotImplementedError("reg_loss belongs to the SVF output filters (out of scope this round)")
+            # the reference's own branch cannot run: its trainer calls torch.cat(tensor, tensor) at construction
+            # (trainer.py:89-100) and the loss reads net.biquad_cascade, which VarReceiverPos models do not have (:290-293)
+            raise NotImplementedError("use_reg_loss: the reference's reg_loss branch raises at trainer construction "
+                                      "(torch.cat on a tensor, trainer.py:99); there is no behaviour to mirror")
         self.init_scheduler(trainer_config)
         if self.net.common_decay_times is None:
             max_ir_len_ms = 2000
