@@ -549,11 +549,12 @@ class ShardedEDCStep:
                 p.grad = torch.zeros_like(p)
         parts = [p.grad.reshape(-1).to(torch.float32) for p in params]
         n = sum(t.numel() for t in parts)
-        if self.peer is not None and (n + 3) // 4 * 4 > n:  # the peer exchange moves 16-byte units
+        peer = getattr(self, "peer", None)
+        if peer is not None and (n + 3) // 4 * 4 > n:  # the peer exchange moves 16-byte units
             parts.append(torch.zeros((n + 3) // 4 * 4 - n, dtype=torch.float32, device=parts[0].device))
         flat = torch.cat(parts)
-        if self.peer is not None:
-            self.peer.all_reduce_("grads", flat)
+        if peer is not None:
+            peer.all_reduce_("grads", flat)
             self.kernel_launches += 2
         else:
             dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.pg)
