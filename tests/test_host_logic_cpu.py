@@ -97,3 +97,20 @@ def test_geq_absorption_design_matches_the_reference_cascades():
     wb = 2 * np.pi * g["bands"] / fs
     want = 20 * np.log10((10.0**(-3.0 / fs / g["t60"]))[None, :]**g["delays"][:, None])  # (delays, bands)
     assert np.abs(cascade_db(got, wb) - want).max() < 0.5  # a graphic equaliser meets its band targets to a fraction of a dB
+
+
+def test_bin_slices_of_the_sharded_step_cover_every_bin_once():
+    """shard_bins: rank r solves bins [r * per, min(k, (r + 1) * per)), per = ceil(k / world) rounded up to an even count
+    (16-byte units of the complex64 x G rows moved by the peer-memory gather)."""
+    from diffgfdn_b200.fused import ShardedEDCStep
+    for k, world in [(65537, 8), (65537, 2), (131073, 4), (2049, 2), (7, 8), (16, 3), (1, 2)]:
+        seen = []
+        for rank in range(world):
+            step = ShardedEDCStep.__new__(ShardedEDCStep)
+            step.world_size, step.rank = world, rank
+            per = step._bins_per_rank(k)
+            lo, hi = step._bin_slice(k)
+            assert per % 2 == 0 and per * world >= k and 0 <= lo <= hi <= k and hi - lo <= per
+            assert lo == min(k, rank * per)
+            seen.extend(range(lo, hi))
+        assert seen == list(range(k))
