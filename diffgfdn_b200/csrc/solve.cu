@@ -859,7 +859,7 @@ struct ReplayStep {
 // products. Replaces solve_fwd(groups) + colorless_fwd + colorless_bwd + solve_bwd(groups): the second elimination,
 // the H_sub round trip and three launches disappear. loss_part[sgid] holds the group's partial sum of the loss terms.
 template <int NP, int W>
-__global__ void __launch_bounds__(kWarps * 32, 3) solve_colorless_kernel(SolveParams p, int asym, double* loss_part) {
+__global__ void __launch_bounds__(kWarps * 32, (NP <= 8 ? 4 : 3)) solve_colorless_kernel(SolveParams p, int asym, double* loss_part) {
   extern __shared__ double smem[];
   constexpr int kSpw = 32 / W;
   const int n = p.n;
