@@ -71,9 +71,10 @@ struct Smem {
   static constexpr size_t kConstPerSys = 2 * (size_t)NP * NP + 4 * NP;
   static constexpr size_t kGroupFwd = 2 * 2 * (NP + 1);
   static constexpr size_t kGroupBwd = kGroupFwd + 4 * NP + (size_t)NP * NP;
-  // mixed-precision forward: two float2 pivot lines (NP + 1) | solution by column, double2 [NP] | pivot lane per step, int [NP]
+  // mixed-precision forward: two float2 pivot lines (NP + 1 entries, pitch NP + 2: 16-byte aligned for 128-bit accesses) |
+  // solution by column, double2 [NP] | pivot lane per step, int [NP]
   // (an even number of doubles: the double2 part stays 16-byte aligned from group to group)
-  static constexpr size_t kGroupMixed = (2 * (NP + 1) + 2 * NP + (NP + 1) / 2 + 2) & ~(size_t)1;
+  static constexpr size_t kGroupMixed = (2 * (NP + 2) + 2 * NP + (NP + 1) / 2 + 2) & ~(size_t)1;
 };
 
 __device__ __forceinline__ double fast_rcp(double d) {
@@ -401,6 +402,12 @@ __global__ void __launch_bounds__(kWarps * 32, (NP <= 24 ? 3 : 2)) solve_fwd_ker
 // elimination (the multipliers are still in registers): delta = E^-1 T_N ... T_1 r, one shuffle + one complex FMA per
 // step. x = x0 + delta is then accurate to ~(cond(M) eps_32)^2 -- the same multipliers, stored as float32, are what the
 // adjoint replay (solve_bwd_replay_kernel) has always used. DGFDN_SOLVE_MIXED=0 keeps the all-float64 kernel.
+__device__ __forceinline__ float rcp_nr(float d) {  // rcp.approx + one Newton step (~1 ulp; IEEE rounding is not needed here)
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
+  return fmaf(r, fmaf(-d, r, 1.0f), r);
+}
+
 struct GJStateF {
   float2 rhs;
   float2 diag;
@@ -408,37 +415,51 @@ struct GJStateF {
   bool used;
 };
 
+// The float32 row is held as NP / 2 float4 (two complex entries each): the pivot lane publishes its row with 128-bit
+// stores straight from those register quads. (Held as float2 pairs, the compiler still fused the stores into 128-bit ones
+// and paid two MOVs per entry to pack them -- 12 % of the kernel's instructions, in a branch only one lane takes.)
+__device__ __forceinline__ float2 row_get(const float4& q, int j) { return (j & 1) ? make_float2(q.z, q.w) : make_float2(q.x, q.y); }
+
 template <int NP, int W, int K>
 struct GJStepF {
-  static __device__ __forceinline__ void run(float2 (&m)[NP], GJStateF& st, int sl, float2* line0, float2* line1, float2* fac,
+  static __device__ __forceinline__ void run(float4 (&m4)[NP / 2], GJStateF& st, int sl, float2* line0, float2* line1, float2* fac,
                                              float2 (&fm)[NP]) {
-    float2* line = (K & 1) ? line1 : line0;
+    float2* line = (K & 1) ? line1 : line0;  // NP + 1 complex entries, 16-byte aligned
     unsigned key = 0u;
-    const float nrm = m[K].x * m[K].x + m[K].y * m[K].y;
+    const float2 mk = row_get(m4[K / 2], K);
+    const float nrm = mk.x * mk.x + mk.y * mk.y;
     if (!st.used)  // monotone in |m|^2 for non-negative floats; the low bits carry the lane
       key = 0x80000000u | ((__float_as_uint(nrm) >> 1) & ~(unsigned)(W - 1)) | (unsigned)(W - 1 - sl);
-    const float rn = __frcp_rn(nrm);  // every lane inverts its own candidate while the search is in flight
-    const float2 myinv = make_float2(m[K].x * rn, -m[K].y * rn);
+    const float rn = rcp_nr(nrm);  // every lane inverts its own candidate while the search is in flight
+    const float2 myinv = make_float2(mk.x * rn, -mk.y * rn);
     const int piv = pivot_sublane<W>(key);
     if (sl == piv) {
       line[K] = myinv;
+      if constexpr ((K & 1) == 0) line[K + 1] = make_float2(m4[K / 2].z, m4[K / 2].w);  // the other half of K's quad
 #pragma unroll
-      for (int j = K + 1; j < NP; ++j) line[j] = m[j];
+      for (int q = K / 2 + 1; q < NP / 2; ++q) reinterpret_cast<float4*>(line)[q] = m4[q];
       line[NP] = st.rhs;
       st.used = true;
       st.mycol = K;
-      st.diag = m[K];
+      st.diag = mk;
     }
     __syncwarp();
     float2 f = make_float2(0.f, 0.f);
     if (sl != piv && sl < NP) {
-      f = cmulf(m[K], line[K]);
+      f = cmulf(mk, line[K]);
       const float nfx = -f.x, nfy = -f.y;
+      if constexpr ((K & 1) == 0) {
+        const float2 pj = line[K + 1];
+        m4[K / 2].z = fmaf(f.y, pj.y, fmaf(nfx, pj.x, m4[K / 2].z));
+        m4[K / 2].w = fmaf(nfy, pj.x, fmaf(nfx, pj.y, m4[K / 2].w));
+      }
 #pragma unroll
-      for (int j = K + 1; j < NP; ++j) {
-        const float2 pj = line[j];
-        m[j].x = fmaf(f.y, pj.y, fmaf(nfx, pj.x, m[j].x));
-        m[j].y = fmaf(nfy, pj.x, fmaf(nfx, pj.y, m[j].y));
+      for (int q = K / 2 + 1; q < NP / 2; ++q) {
+        const float4 pq = reinterpret_cast<const float4*>(line)[q];
+        m4[q].x = fmaf(f.y, pq.y, fmaf(nfx, pq.x, m4[q].x));
+        m4[q].y = fmaf(nfy, pq.x, fmaf(nfx, pq.y, m4[q].y));
+        m4[q].z = fmaf(f.y, pq.w, fmaf(nfx, pq.z, m4[q].z));
+        m4[q].w = fmaf(nfy, pq.z, fmaf(nfx, pq.w, m4[q].w));
       }
       const float2 pr = line[NP];
       st.rhs.x = fmaf(f.y, pr.y, fmaf(nfx, pr.x, st.rhs.x));
@@ -446,7 +467,7 @@ struct GJStepF {
     }
     fm[K] = f;
     if (fac != nullptr) fac[K * W + sl] = f;
-    if constexpr (K + 1 < NP) GJStepF<NP, W, K + 1>::run(m, st, sl, line0, line1, fac, fm);
+    if constexpr (K + 1 < NP) GJStepF<NP, W, K + 1>::run(m4, st, sl, line0, line1, fac, fm);
   }
 };
 
@@ -480,9 +501,9 @@ __global__ void __launch_bounds__(kWarps * 32, 4) solve_fwd_mixed_kernel(SolvePa
   // per lane group: two float2 pivot lines of NP + 1 | the solution by column as double2 [NP] | pivot lane of every step
   double* gbase = s_groups + (size_t)lg * Smem<NP>::kGroupMixed;
   float2* line0 = reinterpret_cast<float2*>(gbase);
-  float2* line1 = line0 + (NP + 1);
-  double2* xcol = reinterpret_cast<double2*>(gbase + 2 * (NP + 1));
-  int* ptab = reinterpret_cast<int*>(gbase + 2 * (NP + 1) + 2 * NP);
+  float2* line1 = line0 + (NP + 2);
+  double2* xcol = reinterpret_cast<double2*>(gbase + 2 * (NP + 2));
+  int* ptab = reinterpret_cast<int*>(gbase + 2 * (NP + 2) + 2 * NP);
 
   load_block_constants<NP>(p, s_const, s_vec);
   __syncthreads();
@@ -510,14 +531,19 @@ __global__ void __launch_bounds__(kWarps * 32, 4) solve_fwd_mixed_kernel(SolvePa
     double2 dz = make_double2(0.0, 0.0);
     if (sl < n) dz = diag_entry(p, bin, my_line, my_invg, my_delay, nbits, &zm);
     // row `sl` of M in float32 (padded rows / columns: identity)
-    float2 m[NP], fm[NP];
+    float4 m4[NP / 2];
+    float2 fm[NP];
     {
       const int lr = sl < NP ? sl : 0;
 #pragma unroll
       for (int j = 0; j < NP; ++j) {
         const bool on_diag = (j == sl);
-        const double re = (on_diag ? (sl < n ? dz.x : 1.0) : 0.0) - s_at[j * NP + lr];
-        m[j] = make_float2((float)re, on_diag && sl < n ? (float)dz.y : 0.f);
+        const float re = (float)((on_diag ? (sl < n ? dz.x : 1.0) : 0.0) - s_at[j * NP + lr]);
+        const float im = on_diag && sl < n ? (float)dz.y : 0.f;
+        if (j & 1)
+          m4[j / 2].z = re, m4[j / 2].w = im;
+        else
+          m4[j / 2].x = re, m4[j / 2].y = im;
       }
     }
     const bool save = p.fac != nullptr && live_bin;
@@ -527,10 +553,10 @@ __global__ void __launch_bounds__(kWarps * 32, 4) solve_fwd_mixed_kernel(SolvePa
     st.diag = make_float2(1.f, 0.f);
     st.mycol = -1;
     st.used = sl >= NP;
-    GJStepF<NP, W, 0>::run(m, st, sl, line0, line1, save ? p.fac + slot * (NP * W) : nullptr, fm);
+    GJStepF<NP, W, 0>::run(m4, st, sl, line0, line1, save ? p.fac + slot * (NP * W) : nullptr, fm);
     __syncwarp();
     const int col = st.mycol;
-    const float dn = __frcp_rn(st.diag.x * st.diag.x + st.diag.y * st.diag.y);
+    const float dn = rcp_nr(st.diag.x * st.diag.x + st.diag.y * st.diag.y);
     const float2 dinv = make_float2(st.diag.x * dn, -st.diag.y * dn);
     const float2 x0 = cmulf(st.rhs, dinv);
     if (save) {
