@@ -85,7 +85,7 @@ class ShardedEDCStep:
                  edc_weight: float = 1.0, spectral_weight: float = 1.0, sparsity_weight: float = 1.0,
                  asym_spectral: bool = True, mixing_time_ms: float = 20.0, world_size: int = 1,
                  total_receivers: Optional[int] = None, process_group=None, e2e_tile_rows: int = 128,
-                 shard_bins: bool = False):
+                 shard_bins: bool = False, subband_filter: Optional[torch.Tensor] = None):
         self.net = net
         self.dev = net.device
         self.crit = edc_loss(max_ir_len_ms, net.sample_rate, mixing_time_ms=mixing_time_ms)
@@ -101,6 +101,10 @@ class ShardedEDCStep:
         # dL/dhy summed before the adjoint -- two small all-reduces (8 K G and 4 G tn bytes) on the critical path
         self.shard_bins = bool(shard_bins) and world_size > 1
         self.rank = dist.get_rank(process_group) if self.shard_bins else 0
+        # Sub-band training (reference trainer.py:457-461, 804: H * subband_filter_freq_resp before the losses): the band
+        # filter F[k] is receiver independent, so it folds into y[k,g] before the inverse DFT of the G rows and into the
+        # early responses d when their windows are (re)built -- nothing per receiver and bin is added.
+        self.subband_filter = None if subband_filter is None else subband_filter.to(net.device, C64).reshape(-1)
         self.kernel_launches = 0
         self.h2d_bytes = 0
         self._bufs = None
@@ -210,7 +214,12 @@ class ShardedEDCStep:
     @torch.no_grad()
     def precompute_early_window(self, early_response: torch.Tensor) -> torch.Tensor:
         """hd = irfft(d, n=K)[mix:max_len] of the early (direct-path) responses, (B, tn) float32. d is an input of
-        the data set ('target_early_response'), constant over training, so its window is too."""
+        the data set ('target_early_response'), constant over training, so its window is too. With a sub-band filter
+        the model response is (sum_g s y_g + d) F, so d is filtered here."""
+        if self.subband_filter is not None:
+            f = self.subband_filter
+            early_response = torch.cat([early_response[r0:r0 + 1024].to(self.dev, C64) * f[:early_response.shape[1]]
+                                        for r0 in range(0, early_response.shape[0], 1024)])
         return self._window_rows(early_response, False)
 
     # ---- one step ----------------------------------------------------------------------------------------
@@ -246,7 +255,8 @@ class ShardedEDCStep:
             _, y = net.feedback_loop.solve(z_edc, net.input_gains.reshape(-1), net.output_gains.reshape(-1))
         # the graph is cut at y: the backward below runs the chirp-z adjoint first, on its own (see there)
         y_cut = y.detach().requires_grad_(True)
-        hy = ops.irfft_window(y_cut.transpose(0, 1), self.n_fft, self.t0, self.tn)  # (G, tn)
+        y_f = y_cut if self.subband_filter is None else y_cut * self.subband_filter[:y_cut.shape[0]].unsqueeze(-1)
+        hy = ops.irfft_window(y_f.transpose(0, 1), self.n_fft, self.t0, self.tn)  # (G, tn)
         # own kernels of the front: position network, 2 x skew-expm (coupled matrix, sparsity term), matrix assembly,
         # coupled solve, chirp-z (pre, mul, post; the 2 cuFFT launches are not counted), colorless branch
         fused_cl = self.use_fused_colorless and net.num_delay_lines_per_group <= 16

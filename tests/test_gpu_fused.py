@@ -27,12 +27,14 @@ def setup(nfft=4096, rows=11, seed=0):
     return net, t60, unit_circle_grid(nfft).cuda(), pos, early, target
 
 
-def module_path(net, t60, z, pos, early, target):
+def module_path(net, t60, z, pos, early, target, subband=None):
     from diffgfdn_b200 import ops
     from diffgfdn_b200.losses import edc_loss
     net.zero_grad()
     data = dict(z_values=z, listener_position=pos, norm_listener_position=pos, target_early_response=early)
     H, (Hs, _) = net(data)
+    if subband is not None:  # reference trainer.py:457-461: H * subband_filter_freq_resp before the losses
+        H = H * subband
     edc = 10.0 * edc_loss(max(t60) * 1e3, 32000.0)(target, H)
     spec = ops.colorless_loss_per_group(Hs, True).sum()
     a = net.feedback_loop.ortho_param(net.feedback_loop.M[2])
@@ -67,6 +69,49 @@ def test_fused_step_equals_module_path(tile, td_fused, monkeypatch):
         assert err < 1e-3, (k, err)
     # only the bins irfft(X, n=K) reads (0..K/2, quirk Q3) cross the bus
     assert step.h2d_bytes == 2 * pos.shape[0] * (z.numel() // 2 + 1) * 8
+
+
+def test_fused_step_with_subband_filter_equals_module_path():
+    """Sub-band training (reference trainer.py:457-461): the band filter folded into y and into the early windows gives
+    the losses and gradients of H * F through the module path."""
+    from diffgfdn_b200.fused import ShardedEDCStep
+    net, t60, z, pos, early, target = setup(rows=7, seed=3)
+    k = z.numel()
+    w = torch.linspace(0, np.pi, k, device="cuda")
+    band = (torch.exp(-((w - 0.9) / 0.5)**2) * torch.exp(-1j * 40.0 * w)).to(torch.complex64)  # band-pass with a delay
+    edc_ref, g_ref = module_path(net, t60, z, pos, early, target, subband=band)
+    step = ShardedEDCStep(net, max(t60) * 1e3, tile_rows=4, edc_weight=10.0, subband_filter=band)
+    step.attach(z, pos, None, None)
+    step.attach(z, pos, step.precompute_early_window(early), step.precompute_target_db(target))
+    out = step.step()
+    assert abs(float(out["edc_loss"]) - edc_ref) < 1e-4 * abs(edc_ref)
+    g_fused = {k_: p.grad.clone() for k_, p in net.named_parameters()}
+    # float64 oracle on the same parameters: the judge between the two float32-storage paths. dL/dalpha is a cancelling
+    # sum of O(1) terms of dL/dA (DESIGN.md section 8); behind this band-pass the complex64 x / y / H both paths store
+    # leave it with ~7e-3 of noise (the same figure with the float64 kernels: DGFDN_SOLVE_MIXED=0, DGFDN_SOLVE_REPLAY=0),
+    # the other parameters stay within 2e-3
+    from oracle import gfdn_oracle as O
+    names = [k_ for k_, _ in net.named_parameters()]
+    po = {k_: v.detach().cpu().to(torch.float64).requires_grad_(k_ in names) for k_, v in net.state_dict().items()
+          if v.dtype.is_floating_point}
+    delays = net.delays.cpu().to(torch.float64)
+    a = O.coupled_feedback_matrix(po["feedback_loop.M"], po["feedback_loop.alpha"])
+    gamma = O.decay_times_to_gain_per_sample(t60, delays.tolist(), 32000.0, 3)
+    b, c = po["input_gains"].reshape(-1), po["output_gains"].reshape(-1)
+    s = O.gains_from_mlp(pos.cpu().to(torch.float64), po, 4, 3)
+    H = O.omni_response(z.cpu(), delays, gamma, a, b, c, s, early.cpu().to(torch.complex128)) * band.cpu().to(torch.complex128)
+    edc = O.edc_loss(target.cpu().to(torch.complex128), H, max(t60) * 1e3, 32000.0)
+    hs, _ = O.sub_fdn_output(z.cpu(), delays, po["feedback_loop.M"], b, c)
+    spec, spars = O.colorless_losses(hs, po["feedback_loop.M"], 1.0, 1.0, asym=True)
+    (10.0 * edc + spec + spars).backward()
+    assert abs(float(out["edc_loss"]) - 10.0 * float(edc)) < 1e-4 * abs(edc_ref)
+    for k_ in names:
+        ref = po[k_].grad
+        tol = 2e-2 if k_ == "feedback_loop.alpha" else 5e-3  # (band-passed responses: smaller gradients over the same float32 noise)
+        err = float((g_fused[k_].cpu().double() - ref).abs().max() / ref.abs().max())
+        assert err < tol, (k_, err)
+        err_m = float((g_ref[k_].cpu().double() - ref).abs().max() / ref.abs().max())
+        assert err_m < tol, (k_, err_m)
 
 
 def test_graph_replay_equals_eager_step():
