@@ -486,6 +486,10 @@ class ShardedEDCStep:
 
     # ---- end-to-end mode: inputs come from pinned host memory every step ---------------------------------
     def _stream_tiles(self, host_d, host_target, s_d, hy_d, ghy, gs, coef, stream):
+        if self.subband_filter is not None:
+            raise RuntimeError("step(host_d, host_target): the host-streamed mode rebuilds the early windows from the raw "
+                               "early responses; with a sub-band filter use the resident mode (precompute_early_window "
+                               "applies the filter) or hand over early responses that are already band filtered")
         dev = self.dev
         r = max(1, min(self.e2e_tile_rows, self.rows))
         kx, tn, g = self.kx, self.tn, self.net.num_groups
