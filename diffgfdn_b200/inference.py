@@ -212,3 +212,33 @@ class GFDNAuraliser:
         finally:
             torch.backends.cuda.matmul.allow_tf32 = keep
         return out
+
+
+def srir_to_brir(srirs: torch.Tensor, hrir_sh: torch.Tensor, rotations: torch.Tensor) -> torch.Tensor:
+    """Spatial (ambisonic) RIRs -> binaural RIRs for a set of head orientations (reference sofa_parser.py:452-505
+    `convert_srir_to_brir`). srirs (R, C, T) with C = (order + 1)^2 SH channels; hrir_sh (C, 2, Th): the SH representation
+    of the HRIR set (the reference gets it from the SOFA file through spaudiopy); rotations (O, C, C): the real SH rotation
+    matrices of the NEGATED head orientations (spaudiopy `sh_rotation_matrix`, sofa_parser.py:488-493). Both are inputs
+    here like the other third-party filter designs. Returns (R, O, nfft, 2) with nfft = next power of two >= T.
+
+        BRTF[r,o,f,e] = sum_n conj(HRTF_sh[n,e,f]) sum_m Rot[o,n,m] SRTF[r,m,f]
+
+    The reference loops over receivers and orientations on the host; this is one batched contraction between two real
+    FFTs on whatever device the inputs live on (cuFFT + a cuBLAS complex GEMM per batch: plain library work, no own kernel)."""
+    if srirs.dim() != 3 or hrir_sh.dim() != 3 or rotations.dim() != 3:
+        raise RuntimeError("srir_to_brir: srirs (R, C, T), hrir_sh (C, 2, Th), rotations (O, C, C)")
+    c = srirs.shape[1]
+    if hrir_sh.shape[0] != c or hrir_sh.shape[1] != 2 or tuple(rotations.shape[1:]) != (c, c):
+        raise RuntimeError("srir_to_brir: inconsistent number of SH channels")
+    nfft = _next_pow2(srirs.shape[-1])
+    rtf = torch.fft.rfft(srirs, n=nfft, dim=-1)  # (R, C, F)
+    htf = torch.fft.rfft(hrir_sh.to(srirs.device, srirs.dtype), n=nfft, dim=-1)  # (C, 2, F)
+    rot = rotations.to(srirs.device, srirs.dtype)
+    # fold the HRTFs into the (real) rotation first: W[o,e,m,f] = sum_n conj(H[n,e,f]) Rot[o,n,m] is receiver independent.
+    # Real and imaginary parts are contracted as real tensors (plain GEMMs; no complex-einsum code path is involved).
+    wr = torch.einsum('nef,onm->oemf', htf.real, rot)
+    wi = -torch.einsum('nef,onm->oemf', htf.imag, rot)
+    ar, ai = rtf.real, rtf.imag
+    re = torch.einsum('oemf,rmf->rofe', wr, ar) - torch.einsum('oemf,rmf->rofe', wi, ai)
+    im = torch.einsum('oemf,rmf->rofe', wr, ai) + torch.einsum('oemf,rmf->rofe', wi, ar)
+    return torch.fft.irfft(torch.complex(re, im), n=nfft, dim=2)

@@ -82,3 +82,21 @@ def filter_overlap_add(stimulus_ext: np.ndarray, rirs: np.ndarray, hop: int, fad
         else:
             prev_tail[:len(y)] = y
     return out
+
+
+def convert_srir_to_brir(srirs: np.ndarray, hrir_sh: np.ndarray, rotations: np.ndarray) -> np.ndarray:
+    """sofa_parser.py:452-505 with the two third-party inputs made explicit: hrir_sh = hrtf_reader.
+    get_spherical_harmonic_representation(order) (C, 2, Th) and rotations[o] = spaudiopy sh_rotation_matrix(order,
+    -azimuth_o, -elevation_o, 0, 'real') (:488-493). Same loops and einsum as the reference. Returns (R, O, nfft, 2)."""
+    num_receivers = srirs.shape[0]
+    nfft = 2**int(np.ceil(np.log2(srirs.shape[-1])))  #                        :466
+    ambi_rtfs = np.fft.rfft(srirs, nfft, axis=-1)  #                            :470
+    ambi_hrtfs = np.fft.rfft(hrir_sh, n=nfft, axis=-1)  #                       :473
+    brirs = np.zeros((num_receivers, rotations.shape[0], nfft, 2))
+    for r in range(num_receivers):
+        cur = ambi_rtfs[r]  # (C, F)
+        for o in range(rotations.shape[0]):
+            rotated = cur.T @ rotations[o].T  #                                 :495  (F, C)
+            brtf = np.einsum('nrf, fn -> fr', np.conj(ambi_hrtfs), rotated)  #  :498
+            brirs[r, o] = np.fft.irfft(brtf, n=nfft, axis=0)  #                 :501
+    return brirs

@@ -84,3 +84,20 @@ def test_auraliser_from_trained_models_matches_irfft_of_the_model_response():
     aur = GFDNAuraliser.from_models([net])
     h = aur.static_rirs(s.unsqueeze(0), nfft).double()
     assert float((h - h_ref).abs().max() / h_ref.abs().max()) < 1e-4
+
+
+def test_srir_to_brir_on_the_device_matches_the_reference_loops():
+    """SH -> binaural step (reference sofa_parser.py:452-505) in float32 on the GPU against the restatement with the
+    reference's own loops; 1e-5 of peak."""
+    from diffgfdn_b200.inference import srir_to_brir
+    rng = np.random.default_rng(9)
+    r, order, t, th, o = 5, 2, 1000, 128, 6
+    c = (order + 1)**2
+    srirs = rng.standard_normal((r, c, t)) * np.exp(-np.arange(t) / 150.0)
+    hrir_sh = rng.standard_normal((c, 2, th)) * np.exp(-np.arange(th) / 20.0)
+    rot = np.stack([np.linalg.qr(rng.standard_normal((c, c)))[0] for _ in range(o)])
+    want = A.convert_srir_to_brir(srirs, hrir_sh, rot)
+    got = srir_to_brir(torch.tensor(srirs, dtype=torch.float32).cuda(), torch.tensor(hrir_sh, dtype=torch.float32).cuda(),
+                       torch.tensor(rot, dtype=torch.float32).cuda())
+    assert got.is_cuda and tuple(got.shape) == want.shape
+    assert np.abs(got.cpu().numpy() - want).max() < 1e-5 * np.abs(want).max()

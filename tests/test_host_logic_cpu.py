@@ -114,3 +114,20 @@ def test_bin_slices_of_the_sharded_step_cover_every_bin_once():
             assert lo == min(k, rank * per)
             seen.extend(range(lo, hi))
         assert seen == list(range(k))
+
+
+def test_srir_to_brir_matches_the_reference_loops():
+    """SH -> binaural step of the auralisation chain (reference sofa_parser.py:452-505) against its restatement with the
+    reference's loops and einsum (oracle/auralisation_oracle.py); device-agnostic torch code, float64 here."""
+    from diffgfdn_b200.inference import srir_to_brir
+    from oracle import auralisation_oracle as A
+    rng = np.random.default_rng(5)
+    r, order, t, th, o = 3, 2, 300, 64, 4
+    c = (order + 1)**2
+    srirs = rng.standard_normal((r, c, t)) * np.exp(-np.arange(t) / 60.0)
+    hrir_sh = rng.standard_normal((c, 2, th)) * np.exp(-np.arange(th) / 10.0)
+    rot = np.stack([np.linalg.qr(rng.standard_normal((c, c)))[0] for _ in range(o)])
+    want = A.convert_srir_to_brir(srirs, hrir_sh, rot)
+    got = srir_to_brir(torch.tensor(srirs), torch.tensor(hrir_sh), torch.tensor(rot)).numpy()
+    assert got.shape == want.shape == (r, o, 512, 2)
+    assert np.abs(got - want).max() < 1e-12 * np.abs(want).max()
